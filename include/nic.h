@@ -1,0 +1,186 @@
+/*
+ * nic.h — C ABI of libnic.so: the B200 (sm_100a) implementation of the per-texel decode / training-step
+ * hot path of 21K1113/Neural_Image_Compression_V2.
+ *
+ * The reference has no FFI of its own (pure Python/PyTorch); the seam this ABI replaces is the set of
+ * module-level functions that `train_models`, `decode_image` and `process_images` call
+ * (Projects/image_compression.py:233-269, 313-345, 380-396).  Each entry point below cites the reference
+ * interface it stands in for.  `INTEGRATION.md` shows the ctypes binding a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch), borrowed for the duration of the stream
+ *     work the call enqueues; the library never frees caller memory.  Scratch lives in the NicHandle.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - return value: 0 = success, < 0 = NicStatus library error, > 0 = cudaError_t.  Nothing throws.
+ *   - there is NO CPU fallback: a device that is not compute capability 10.x yields NIC_ERR_DEVICE.
+ *   - a handle is bound to one device and is not thread-safe; use one handle per rank.
+ *   - grids keep the reference layout: float32, contiguous, channel-major `[C, y, x]` (2-D) or
+ *     `[C, z, y, x]` (3-D), where x is the FIRST image axis (Projects/fp_def.py:81-86, 96-103).
+ *   - a step's samples are ordered n = block*Bx*By*Bz + ix*By*Bz + iy*Bz + iz (meshgrid 'ij',
+ *     Projects/fp_def.py:124,161), blocks = crops (training) or decode blocks.
+ */
+#ifndef NIC_H_
+#define NIC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIC_ABI_VERSION 1
+
+typedef enum NicStatus {
+  NIC_OK = 0,
+  NIC_ERR_ARG = -1,          /* null pointer / negative size / inconsistent descriptor            */
+  NIC_ERR_UNSUPPORTED = -2,  /* configuration outside what the kernels are built for              */
+  NIC_ERR_DEVICE = -3,       /* not an sm_100 device, or handle bound to another device           */
+  NIC_ERR_BOUNDS = -4,       /* a host-known origin would index outside the grids                 */
+  NIC_ERR_ALIGN = -5,        /* pointer not aligned as documented                                 */
+  NIC_ERR_SCRATCH = -6       /* scratch allocation failed                                         */
+} NicStatus;
+
+/* COMPRESSION_METHOD of Projects/var2.py:51-55 (2 = 2-D atlas, handled by the caller as method 1). */
+enum { NIC_METHOD_2D = 1, NIC_METHOD_3D = 3, NIC_METHOD_3D_V2 = 4 };
+/* positional encodings: Projects/utils.py:211-227 (triangular) and :198-208 (sinusoidal). */
+enum { NIC_PE_TRIANGULAR = 0, NIC_PE_SINUSOIDAL = 1 };
+/* arithmetic of the decoder MLP. F32 = reference-exact erf GELU on CUDA cores (1e-5 parity path);
+ * F16 / BF16 = tcgen05 tensor-core path, fp32 accumulate, tanh-form GELU (+-1 LSB on 8-bit output). */
+enum { NIC_PREC_F32 = 0, NIC_PREC_F16 = 1, NIC_PREC_BF16 = 2 };
+/* element types of outputs */
+enum { NIC_DT_F32 = 0, NIC_DT_F16 = 1, NIC_DT_BF16 = 2, NIC_DT_U8 = 3 };
+
+/* Geometry of one gather problem: which grids, which texels.  Mirrors the arguments of
+ * fp_def.create_g0_g1 / create_g0_g1_3d / create_g0_g1_3d_v2 (Projects/fp_def.py:115,148,187) plus the
+ * crop loop of create_decoder_input_* (Projects/image_compression.py:71-167). */
+typedef struct NicGeom {
+  int32_t method;        /* NIC_METHOD_*                                                            */
+  int32_t channels;      /* C, FEATURE_PYRAMID_CHANNELS                                             */
+  int32_t pe_channels;   /* PE_CHANNELS per axis                                                    */
+  int32_t pe_kind;       /* NIC_PE_*                                                                */
+  int32_t step_log2;     /* log2(step_number) = mip - 2(fl+1)  (image_compression.py:79)            */
+  int32_t mip_level;     /* value written to the LOD column                                         */
+  int32_t g0_nodes[3];   /* nodes of G0 along image axes x,y,z (z ignored in 2-D)                   */
+  int32_t g1_nodes[3];   /* nodes of G1 along x,y,z                                                 */
+  int32_t block[3];      /* texels per block along x,y,z (reference: a cube of sample_number)       */
+  int32_t num_blocks;    /* crops per step, or decode blocks                                        */
+  int32_t origin0[3];    /* origin of block 0 when `origins` is NULL (single-block decode)          */
+  int32_t reserved;
+  float pe_div[8];       /* sinusoidal div_term (utils.py:202), float32 as torch evaluates it        */
+} NicGeom;
+
+/* The decoder MLP of ColorDecoder (Projects/image_compression.py:54-68), nn.Linear layout [out,in]. */
+typedef struct NicMlp {
+  int32_t cin, hidden, cout, reserved;
+  const float* w1; const float* b1;   /* [hidden, cin], [hidden]    */
+  const float* w2; const float* b2;   /* [hidden, hidden], [hidden] */
+  const float* w3; const float* b3;   /* [cout, hidden], [cout]     */
+} NicMlp;
+
+/* Gradients / mutable views of the same six tensors. */
+typedef struct NicMlpGrad {
+  float* w1; float* b1; float* w2; float* b2; float* w3; float* b3;
+} NicMlpGrad;
+
+typedef struct NicHandle NicHandle;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------- */
+int nic_abi_version(void);
+/* Binds a handle to CUDA device `device`; fails with NIC_ERR_DEVICE unless it is compute capability 10.x. */
+int nic_create(int device, NicHandle** out);
+int nic_destroy(NicHandle* h);
+/* Message for the last non-zero status returned on this handle (or a generic one when h is NULL). */
+const char* nic_last_error_string(const NicHandle* h);
+const char* nic_status_string(int status);
+/* Number of kernel launches this handle has enqueued so far (bench.py reports it as `gpu_launches`). */
+int64_t nic_launch_count(const NicHandle* h);
+
+/* ---- decoder input (K1) ------------------------------------------------------------------------------- */
+/* Width of the decoder input for a geometry: C*(corners+1) + PE*D + 1 (Projects/var2.py:114-118). */
+int nic_cin(const NicGeom* g);
+/* Replaces create_decoder_input_2d/3d/3d_v2 and finally_decode_input_* (image_compression.py:71-211):
+ * writes X [N, Cin] row-major, N = num_blocks*Bx*By*Bz.  `origins` = int64 [num_blocks, D] device pointer
+ * (the reference's `coord` tensor) or NULL to use g->origin0.  x_dtype: NIC_DT_F32 (bit-exact with the
+ * reference for triangular PE), NIC_DT_F16 or NIC_DT_BF16 (rounded once from the fp32 value). */
+int nic_gather(NicHandle* h, const NicGeom* g, const float* g0, const float* g1, const int64_t* origins,
+               void* x, int x_dtype, void* stream);
+/* Transpose of nic_gather for autograd (the reference's 64 index_put(accumulate) calls,
+ * image_compression.py:265): dX [N, Cin] fp32 -> accumulates into dG0 / dG1 (grid-shaped, fp32). */
+int nic_scatter(NicHandle* h, const NicGeom* g, const float* dx, const int64_t* origins, float* dg0, float* dg1,
+                void* stream);
+
+/* Stand-alone positional encodings, utils.triangular_positional_encoding (utils.py:211-223) and
+ * utils.positional_encoding (utils.py:198-208): coord [dim, n] fp32 -> out [pe_channels*dim, n] fp32.
+ * pe_div: HOST pointer to pe_channels/2 floats (sinusoidal div_term), ignored for the triangular kind. */
+int nic_positional_encoding(NicHandle* h, const float* coord, int dim, int64_t n, int pe_channels, int pe_kind,
+                            const float* pe_div, float* out, void* stream);
+
+/* ---- decoder MLP on a materialised input (ColorDecoder.forward, image_compression.py:66-68) ------------ */
+/* out [N, cout] fp32 = sigmoid(W3 gelu(W2 gelu(W1 x + b1) + b2) + b3); x [N, cin] fp32 row-major with row
+ * stride `ldx` elements.  If z1/z2 are non-NULL the pre-activations [N, hidden] are saved for backward. */
+int nic_mlp_forward(NicHandle* h, const NicMlp* m, const float* x, int64_t ldx, int64_t n, float* out, float* z1,
+                    float* z2, void* stream);
+/* Backward of the above given dOut [N, cout]: accumulates weight/bias gradients into `gm` and, when dx is
+ * non-NULL, writes dX [N, cin]. */
+int nic_mlp_backward(NicHandle* h, const NicMlp* m, const float* x, int64_t ldx, int64_t n, const float* z1,
+                     const float* z2, const float* out, const float* dout, const NicMlpGrad* gm, float* dx,
+                     void* stream);
+
+/* ---- fused decode (K2): gather -> MLP -> output, X never materialised ---------------------------------- */
+/* Replaces finally_decode_input_* + arc_decoder(...) inside decode_image (image_compression.py:313-345).
+ * out: [N, cout] row-major in out_dtype (NIC_DT_F32, or NIC_DT_U8 = floor(v*255+.5), models.py:29-40).
+ * precision: NIC_PREC_F32 (reference-exact) or NIC_PREC_F16/BF16 (tcgen05). */
+int nic_decode(NicHandle* h, const NicGeom* g, const float* g0, const float* g1, const int64_t* origins,
+               const NicMlp* m, void* out, int out_dtype, int precision, void* stream);
+
+/* ---- fused training forward+backward (K3+K4) ----------------------------------------------------------- */
+/* One step of train_models up to loss.backward() (image_compression.py:239-265).
+ *   targets [N, cout] fp32; noise: NULL (no noise), or [N, Cin] fp32 injected tensor (parity tests), or use
+ *   in-kernel Philox when noise == NULL and noise_bits > 0: X += (U[0,1) - .5) / 2^noise_bits with
+ *   (seed, step) as the Philox key/offset.
+ *   Writes: loss_sum[0] += sum((out-target)^2) (caller divides by N*cout), gradients ACCUMULATED into
+ *   gm / dg0 / dg1 (caller zeroes them), already scaled by 2/(N*cout*loss_scale_den) where loss_scale_den
+ *   lets data-parallel callers pass the GLOBAL sample count (0 = use local N).
+ *   dg0/dg1 may both be NULL (grids frozen, image_compression.py:227-231): the grid scatter is skipped.
+ *   out (optional, may be NULL): decoder output [N, cout] fp32. */
+int nic_train_step(NicHandle* h, const NicGeom* g, const float* g0, const float* g1, const int64_t* origins,
+                   const NicMlp* m, const float* targets, const float* noise, int noise_bits, uint64_t seed,
+                   uint64_t step, int64_t global_n, const NicMlpGrad* gm, float* dg0, float* dg1,
+                   float* loss_sum, float* out, int precision, void* stream);
+
+/* ---- optimiser (K5): torch.optim.Adam + CosineAnnealingLR + fp_quantize_clamp -------------------------- */
+/* One fused Adam update of `count` tensors (image_compression.py:266-269, 361-365).  For tensor i:
+ *   m,v,p updated with step count t[i] (>=1), lr[i] already cosine-scheduled by the caller, betas/eps
+ *   torch defaults unless overridden; if clamp[i] != 0 the result is clamped to [clamp_lo, clamp_hi]
+ *   (fp_quantize_clamp, fp_def.py:227-232).  grad_scale multiplies the gradient first (1/world for DP);
+ *   if zero_grad != 0 the gradient buffer is zeroed after use. */
+typedef struct NicAdamTensor {
+  float* p; float* g; float* m; float* v;
+  int64_t numel;
+  float lr; int32_t t;
+  int32_t clamp; float clamp_lo, clamp_hi;
+} NicAdamTensor;
+int nic_adam_step(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                  float grad_scale, int zero_grad, void* stream);
+
+/* ---- quantisers (K6) ------------------------------------------------------------------------------------ */
+/* models.quantize4fp (models.py:55-57): dst = floor(src*(2^b-1)+.5)/(2^b-1), separate fp32 mul and add. */
+int nic_quantize4fp(NicHandle* h, const float* src, float* dst, int64_t n, int bits, void* stream);
+/* models.save4fp (models.py:61-64): code = floor(src*(2^b-1)+.5) + 2^(b-1) - 1 -> uint8, one code per byte. */
+int nic_quantize_pack(NicHandle* h, const float* src, uint8_t* codes, int64_t n, int bits, void* stream);
+/* models.load4fp (models.py:68-71) with the intended float result (the reference call site passes uint8 and
+ * wraps, image_compression.py:396): dst = (code - 2^(b-1) + 1)/(2^b-1). */
+int nic_unpack(NicHandle* h, const uint8_t* codes, float* dst, int64_t n, int bits, void* stream);
+/* fp_quantize_clamp / models.quantize_clamp (fp_def.py:227-232, models.py:48-51): in-place clamp. */
+int nic_clamp(NicHandle* h, float* p, int64_t n, float lo, float hi, void* stream);
+/* models.quantize_to_bit + astype(uint8) (models.py:29-40, image_compression.py:406-407):
+ * dst = (uint8) floor(src*(2^b-1)+.5) for src in [0,1]. */
+int nic_output_to_u8(NicHandle* h, const float* src, uint8_t* dst, int64_t n, int bits, void* stream);
+/* Sum of squared differences of two 8-bit images, for utils.calculate_psnr (utils.py:117-130):
+ * sse[0] += sum((a-b)^2) as float64. */
+int nic_sse_u8(NicHandle* h, const uint8_t* a, const uint8_t* b, int64_t n, double* sse, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIC_H_ */

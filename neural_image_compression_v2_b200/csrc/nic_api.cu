@@ -1,0 +1,336 @@
+// nic_api.cu — the C ABI of libnic.so (include/nic.h): argument validation, geometry flattening, dispatch.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "nic_internal.cuh"
+
+using namespace nic;
+
+struct NicHandle : public Handle {};
+
+static thread_local char g_err[256] = "no error";
+
+static int fail(NicHandle* h, int code, const char* fmt, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) {
+    strncpy(h->err, buf, sizeof(h->err) - 1);
+    h->err[sizeof(h->err) - 1] = 0;
+  }
+  strncpy(g_err, buf, sizeof(g_err) - 1);
+  return code;
+}
+
+static int cuda_fail(NicHandle* h, int e, const char* what) {
+  if (e == 0) return 0;
+  if (e < 0) return fail(h, e, "%s: %s", what, nic_status_string(e));
+  return fail(h, e, "%s: CUDA error %d (%s)", what, e, cudaGetErrorString((cudaError_t)e));
+}
+
+extern "C" {
+
+int nic_abi_version(void) { return NIC_ABI_VERSION; }
+
+const char* nic_status_string(int status) {
+  switch (status) {
+    case NIC_OK: return "ok";
+    case NIC_ERR_ARG: return "invalid argument";
+    case NIC_ERR_UNSUPPORTED: return "unsupported configuration";
+    case NIC_ERR_DEVICE: return "not an sm_100 device (no CPU or other-GPU fallback exists)";
+    case NIC_ERR_BOUNDS: return "origin would index outside the grids";
+    case NIC_ERR_ALIGN: return "misaligned pointer";
+    case NIC_ERR_SCRATCH: return "scratch allocation failed";
+    default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown status";
+  }
+}
+
+const char* nic_last_error_string(const NicHandle* h) { return h ? h->err : g_err; }
+
+int nic_create(int device, NicHandle** out) {
+  if (!out) return fail(nullptr, NIC_ERR_ARG, "nic_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, NIC_ERR_DEVICE, "nic_create: no CUDA device visible (%s)", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, NIC_ERR_ARG, "nic_create: device %d out of range", device);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, (int)e, "nic_create: cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, NIC_ERR_DEVICE, "nic_create: device %d is sm_%d%d; libnic.so is built for sm_100a only", device,
+                prop.major, prop.minor);
+  NicHandle* h = new (std::nothrow) NicHandle();
+  if (!h) return fail(nullptr, NIC_ERR_SCRATCH, "nic_create: out of host memory");
+  memset(static_cast<Handle*>(h), 0, sizeof(Handle));
+  h->device = device;
+  h->sms = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  strcpy(h->err, "no error");
+  *out = h;
+  return NIC_OK;
+}
+
+int nic_destroy(NicHandle* h) {
+  if (!h) return NIC_OK;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(h->device);
+  if (h->tc_weights) cudaFree(h->tc_weights);
+  if (h->adam_desc) cudaFree(h->adam_desc);
+  cudaSetDevice(cur);
+  delete h;
+  return NIC_OK;
+}
+
+int64_t nic_launch_count(const NicHandle* h) { return h ? h->launches : 0; }
+
+int nic_cin(const NicGeom* g) {
+  if (!g) return NIC_ERR_ARG;
+  int dim = g->method == NIC_METHOD_2D ? 2 : 3;
+  int corners = g->method == NIC_METHOD_3D ? 8 : 4;
+  return g->channels * (corners + 1) + g->pe_channels * dim + 1;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ helpers
+static int flatten_geom(NicHandle* h, const NicGeom* g, bool have_origins, DevGeom* d) {
+  if (!g) return fail(h, NIC_ERR_ARG, "geometry is NULL");
+  if (g->method != NIC_METHOD_2D && g->method != NIC_METHOD_3D && g->method != NIC_METHOD_3D_V2)
+    return fail(h, NIC_ERR_UNSUPPORTED, "method %d (expected 1, 3 or 4)", g->method);
+  memset(d, 0, sizeof(*d));
+  d->method = g->method;
+  d->dim = g->method == NIC_METHOD_2D ? 2 : 3;
+  d->ncorner0 = g->method == NIC_METHOD_3D ? 8 : 4;
+  d->C = g->channels;
+  d->PE = g->pe_channels;
+  d->pe_kind = g->pe_kind;
+  if (d->C < 1 || d->PE < 0 || d->PE > NIC_MAX_PE) return fail(h, NIC_ERR_UNSUPPORTED, "channels %d / pe_channels %d", d->C, d->PE);
+  if (g->pe_kind != NIC_PE_TRIANGULAR && g->pe_kind != NIC_PE_SINUSOIDAL) return fail(h, NIC_ERR_ARG, "pe_kind %d", g->pe_kind);
+  d->cin = d->C * (d->ncorner0 + 1) + d->PE * d->dim + 1;
+  if (d->cin > NIC_MAX_CIN) return fail(h, NIC_ERR_UNSUPPORTED, "decoder input width %d > %d", d->cin, NIC_MAX_CIN);
+  d->mip = g->mip_level;
+  d->lod = (float)g->mip_level;
+  if (g->step_log2 < -24 || g->step_log2 > 24) return fail(h, NIC_ERR_ARG, "step_log2 %d", g->step_log2);
+  d->step = ldexpf(1.0f, g->step_log2);
+  d->interp = g->step_log2 != 1;                 // fp_def.py:136: int(1 // (step/2)) != 1
+  d->nblocks = g->num_blocks;
+  if (g->num_blocks < 0) return fail(h, NIC_ERR_ARG, "num_blocks %d", g->num_blocks);
+  d->per_block = 1;
+  for (int a = 0; a < 3; ++a) {
+    bool used = a < d->dim;
+    d->n0[a] = used ? g->g0_nodes[a] : 1;
+    d->n1[a] = used ? g->g1_nodes[a] : 1;
+    d->B[a] = used ? g->block[a] : 1;
+    d->origin0[a] = used ? g->origin0[a] : 0;
+    if (used && (d->n0[a] < 2 || d->n1[a] < 2)) return fail(h, NIC_ERR_ARG, "grid axis %d has < 2 nodes", a);
+    if (d->B[a] < 0) return fail(h, NIC_ERR_ARG, "block extent %d on axis %d", d->B[a], a);
+    d->per_block *= d->B[a];
+  }
+  d->N = d->per_block * d->nblocks;
+  for (int i = 0; i < NIC_MAX_PE; ++i) d->pe_div[i] = g->pe_div[i];
+  if (!have_origins) {
+    if (d->nblocks > 1) return fail(h, NIC_ERR_ARG, "origins is NULL but num_blocks = %d", d->nblocks);
+    // host-known origin: reproduce the reference's IndexError instead of clamping silently
+    for (int a = 0; a < d->dim && d->N > 0; ++a) {
+      double last = (double)(d->origin0[a] + d->B[a] - 1) * (double)d->step;
+      long long i0 = (long long)floor(last), i1 = (long long)floor(last / 2);
+      if (d->origin0[a] < 0 || i0 + 1 >= d->n0[a] || i1 + 1 >= d->n1[a])
+        return fail(h, NIC_ERR_BOUNDS, "axis %d: origin %d + block %d at step %g reaches node %lld/%lld of %d/%d", a,
+                    d->origin0[a], d->B[a], (double)d->step, i0 + 1, i1 + 1, d->n0[a], d->n1[a]);
+    }
+  }
+  return NIC_OK;
+}
+
+static int flatten_mlp(NicHandle* h, const NicMlp* m, MlpDev* d, int expect_cin) {
+  if (!m || !m->w1 || !m->b1 || !m->w2 || !m->b2 || !m->w3 || !m->b3) return fail(h, NIC_ERR_ARG, "MLP descriptor has NULL tensors");
+  if (expect_cin > 0 && m->cin != expect_cin) return fail(h, NIC_ERR_ARG, "MLP cin %d != geometry cin %d", m->cin, expect_cin);
+  if (m->cin < 1 || m->cin > NIC_MAX_CIN) return fail(h, NIC_ERR_UNSUPPORTED, "MLP cin %d", m->cin);
+  if (m->cout < 1 || m->cout > NIC_MAX_COUT) return fail(h, NIC_ERR_UNSUPPORTED, "MLP cout %d", m->cout);
+  if (m->hidden != 64 && m->hidden != 32) return fail(h, NIC_ERR_UNSUPPORTED, "MLP hidden %d (32 or 64)", m->hidden);
+  d->cin = m->cin; d->hidden = m->hidden; d->cout = m->cout;
+  d->w1 = m->w1; d->b1 = m->b1; d->w2 = m->w2; d->b2 = m->b2; d->w3 = m->w3; d->b3 = m->b3;
+  return NIC_OK;
+}
+
+struct DeviceGuard {
+  int prev;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define NIC_ENTER(h)                                         \
+  if (!(h)) return fail(nullptr, NIC_ERR_ARG, "handle is NULL"); \
+  DeviceGuard guard_((h)->device);                           \
+  cudaStream_t st = (cudaStream_t)stream
+
+extern "C" {
+
+int nic_gather(NicHandle* h, const NicGeom* g, const float* g0, const float* g1, const int64_t* origins, void* x,
+               int x_dtype, void* stream) {
+  NIC_ENTER(h);
+  DevGeom d;
+  int rc = flatten_geom(h, g, origins != nullptr, &d);
+  if (rc) return rc;
+  if (!g0 || !g1 || (!x && d.N > 0)) return fail(h, NIC_ERR_ARG, "nic_gather: NULL pointer");
+  return cuda_fail(h, launch_gather(h, d, g0, g1, (const long long*)origins, x, x_dtype, st), "nic_gather");
+}
+
+int nic_scatter(NicHandle* h, const NicGeom* g, const float* dx, const int64_t* origins, float* dg0, float* dg1,
+                void* stream) {
+  NIC_ENTER(h);
+  DevGeom d;
+  int rc = flatten_geom(h, g, origins != nullptr, &d);
+  if (rc) return rc;
+  if ((!dx && d.N > 0) || !dg0 || !dg1) return fail(h, NIC_ERR_ARG, "nic_scatter: NULL pointer");
+  return cuda_fail(h, launch_scatter(h, d, dx, (const long long*)origins, dg0, dg1, st), "nic_scatter");
+}
+
+int nic_positional_encoding(NicHandle* h, const float* coord, int dim, int64_t n, int pe_channels, int pe_kind,
+                            const float* pe_div, float* out, void* stream) {
+  NIC_ENTER(h);
+  if (dim < 1 || dim > 3 || n < 0 || pe_channels < 0 || pe_channels > NIC_MAX_PE) return fail(h, NIC_ERR_ARG, "nic_positional_encoding: dim %d pe %d", dim, pe_channels);
+  if (pe_kind != NIC_PE_TRIANGULAR && pe_kind != NIC_PE_SINUSOIDAL) return fail(h, NIC_ERR_ARG, "nic_positional_encoding: kind %d", pe_kind);
+  if (pe_kind == NIC_PE_SINUSOIDAL && !pe_div) return fail(h, NIC_ERR_ARG, "nic_positional_encoding: pe_div is NULL");
+  if (n > 0 && (!coord || !out)) return fail(h, NIC_ERR_ARG, "nic_positional_encoding: NULL pointer");
+  return cuda_fail(h, launch_pe(h, coord, dim, n, pe_channels, pe_kind, pe_div, out, st), "nic_positional_encoding");
+}
+
+int nic_mlp_forward(NicHandle* h, const NicMlp* m, const float* x, int64_t ldx, int64_t n, float* out, float* z1,
+                    float* z2, void* stream) {
+  NIC_ENTER(h);
+  MlpDev md;
+  int rc = flatten_mlp(h, m, &md, 0);
+  if (rc) return rc;
+  if (n < 0 || ldx < md.cin) return fail(h, NIC_ERR_ARG, "nic_mlp_forward: n %lld ldx %lld", (long long)n, (long long)ldx);
+  if (n > 0 && (!x || !out)) return fail(h, NIC_ERR_ARG, "nic_mlp_forward: NULL pointer");
+  if ((((uintptr_t)z1 | (uintptr_t)z2) & 15) != 0) return fail(h, NIC_ERR_ALIGN, "nic_mlp_forward: z1/z2 must be 16-byte aligned");
+  return cuda_fail(h, launch_mlp_forward_f32(h, nullptr, md, nullptr, nullptr, nullptr, x, ldx, n, out, NIC_DT_F32, z1, z2, st),
+                   "nic_mlp_forward");
+}
+
+int nic_mlp_backward(NicHandle* h, const NicMlp* m, const float* x, int64_t ldx, int64_t n, const float* z1,
+                     const float* z2, const float* out, const float* dout, const NicMlpGrad* gm, float* dx,
+                     void* stream) {
+  NIC_ENTER(h);
+  MlpDev md;
+  int rc = flatten_mlp(h, m, &md, 0);
+  if (rc) return rc;
+  if (!gm || !gm->w1 || !gm->b1 || !gm->w2 || !gm->b2 || !gm->w3 || !gm->b3) return fail(h, NIC_ERR_ARG, "nic_mlp_backward: NULL gradient tensor");
+  if (n < 0 || ldx < md.cin) return fail(h, NIC_ERR_ARG, "nic_mlp_backward: n %lld ldx %lld", (long long)n, (long long)ldx);
+  if (n > 0 && (!x || !z1 || !z2 || !out || !dout)) return fail(h, NIC_ERR_ARG, "nic_mlp_backward: NULL pointer");
+  MlpGradDev gd = {gm->w1, gm->b1, gm->w2, gm->b2, gm->w3, gm->b3};
+  return cuda_fail(h, launch_mlp_backward_f32(h, md, gd, x, ldx, n, z1, z2, out, dout, dx, st), "nic_mlp_backward");
+}
+
+int nic_decode(NicHandle* h, const NicGeom* g, const float* g0, const float* g1, const int64_t* origins,
+               const NicMlp* m, void* out, int out_dtype, int precision, void* stream) {
+  NIC_ENTER(h);
+  DevGeom d;
+  int rc = flatten_geom(h, g, origins != nullptr, &d);
+  if (rc) return rc;
+  MlpDev md;
+  rc = flatten_mlp(h, m, &md, d.cin);
+  if (rc) return rc;
+  if (!g0 || !g1 || (!out && d.N > 0)) return fail(h, NIC_ERR_ARG, "nic_decode: NULL pointer");
+  if (out_dtype != NIC_DT_F32 && out_dtype != NIC_DT_U8) return fail(h, NIC_ERR_ARG, "nic_decode: out_dtype %d", out_dtype);
+  if (precision == NIC_PREC_F32)
+    return cuda_fail(h, launch_mlp_forward_f32(h, &d, md, g0, g1, (const long long*)origins, nullptr, 0, d.N, out, out_dtype,
+                                               nullptr, nullptr, st), "nic_decode(f32)");
+  if (precision == NIC_PREC_F16 || precision == NIC_PREC_BF16)
+    return cuda_fail(h, launch_decode_tc(h, d, md, g0, g1, (const long long*)origins, out, out_dtype, precision, st),
+                     "nic_decode(tensor core)");
+  return fail(h, NIC_ERR_ARG, "nic_decode: precision %d", precision);
+}
+
+int nic_train_step(NicHandle* h, const NicGeom* g, const float* g0, const float* g1, const int64_t* origins,
+                   const NicMlp* m, const float* targets, const float* noise, int noise_bits, uint64_t seed,
+                   uint64_t step, int64_t global_n, const NicMlpGrad* gm, float* dg0, float* dg1, float* loss_sum,
+                   float* out, int precision, void* stream) {
+  NIC_ENTER(h);
+  DevGeom d;
+  int rc = flatten_geom(h, g, origins != nullptr, &d);
+  if (rc) return rc;
+  MlpDev md;
+  rc = flatten_mlp(h, m, &md, d.cin);
+  if (rc) return rc;
+  if (!g0 || !g1 || !gm || !gm->w1 || !gm->b1 || !gm->w2 || !gm->b2 || !gm->w3 || !gm->b3 || (!targets && d.N > 0))
+    return fail(h, NIC_ERR_ARG, "nic_train_step: NULL pointer");
+  if ((dg0 == nullptr) != (dg1 == nullptr)) return fail(h, NIC_ERR_ARG, "nic_train_step: dg0 and dg1 must both be set or both NULL");
+  if (noise_bits < 0 || noise_bits > 24) return fail(h, NIC_ERR_ARG, "nic_train_step: noise_bits %d", noise_bits);
+  if (precision != NIC_PREC_F32) return fail(h, NIC_ERR_UNSUPPORTED, "nic_train_step: only NIC_PREC_F32 is built in this round");
+  long long denom = (global_n > 0 ? global_n : d.N) * (long long)md.cout;
+  float grad_scale = denom > 0 ? (float)(1.0 / (double)denom) : 0.f;
+  MlpGradDev gd = {gm->w1, gm->b1, gm->w2, gm->b2, gm->w3, gm->b3};
+  return cuda_fail(h, launch_train_f32(h, d, md, gd, g0, g1, (const long long*)origins, targets, noise, noise_bits, seed, step,
+                                       grad_scale, dg0, dg1, loss_sum, out, st), "nic_train_step");
+}
+
+int nic_adam_step(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                  float grad_scale, int zero_grad, void* stream) {
+  NIC_ENTER(h);
+  if (count < 0 || (count > 0 && !tensors)) return fail(h, NIC_ERR_ARG, "nic_adam_step: count %d", count);
+  for (int i = 0; i < count; ++i) {
+    const NicAdamTensor& t = tensors[i];
+    if (t.numel < 0 || t.t < 1 || (t.numel > 0 && (!t.p || !t.g || !t.m || !t.v)))
+      return fail(h, NIC_ERR_ARG, "nic_adam_step: tensor %d invalid (numel %lld, t %d)", i, (long long)t.numel, t.t);
+  }
+  return cuda_fail(h, launch_adam(h, tensors, count, beta1, beta2, eps, grad_scale, zero_grad, st), "nic_adam_step");
+}
+
+static int check_bits(NicHandle* h, int bits, const char* who) {
+  if (bits < 1 || bits > 8) return fail(h, NIC_ERR_ARG, "%s: bits %d (1..8)", who, bits);
+  return NIC_OK;
+}
+
+int nic_quantize4fp(NicHandle* h, const float* src, float* dst, int64_t n, int bits, void* stream) {
+  NIC_ENTER(h);
+  if (int rc = check_bits(h, bits, "nic_quantize4fp")) return rc;
+  if (n < 0 || (n > 0 && (!src || !dst))) return fail(h, NIC_ERR_ARG, "nic_quantize4fp: bad buffer");
+  return cuda_fail(h, launch_quantize4fp(h, src, dst, n, bits, st), "nic_quantize4fp");
+}
+
+int nic_quantize_pack(NicHandle* h, const float* src, uint8_t* codes, int64_t n, int bits, void* stream) {
+  NIC_ENTER(h);
+  if (int rc = check_bits(h, bits, "nic_quantize_pack")) return rc;
+  if (n < 0 || (n > 0 && (!src || !codes))) return fail(h, NIC_ERR_ARG, "nic_quantize_pack: bad buffer");
+  return cuda_fail(h, launch_quantize_pack(h, src, codes, n, bits, st), "nic_quantize_pack");
+}
+
+int nic_unpack(NicHandle* h, const uint8_t* codes, float* dst, int64_t n, int bits, void* stream) {
+  NIC_ENTER(h);
+  if (int rc = check_bits(h, bits, "nic_unpack")) return rc;
+  if (n < 0 || (n > 0 && (!codes || !dst))) return fail(h, NIC_ERR_ARG, "nic_unpack: bad buffer");
+  return cuda_fail(h, launch_unpack(h, codes, dst, n, bits, st), "nic_unpack");
+}
+
+int nic_clamp(NicHandle* h, float* p, int64_t n, float lo, float hi, void* stream) {
+  NIC_ENTER(h);
+  if (n < 0 || (n > 0 && !p) || !(lo <= hi)) return fail(h, NIC_ERR_ARG, "nic_clamp: bad arguments");
+  return cuda_fail(h, launch_clamp(h, p, n, lo, hi, st), "nic_clamp");
+}
+
+int nic_output_to_u8(NicHandle* h, const float* src, uint8_t* dst, int64_t n, int bits, void* stream) {
+  NIC_ENTER(h);
+  if (int rc = check_bits(h, bits, "nic_output_to_u8")) return rc;
+  if (n < 0 || (n > 0 && (!src || !dst))) return fail(h, NIC_ERR_ARG, "nic_output_to_u8: bad buffer");
+  return cuda_fail(h, launch_output_to_u8(h, src, dst, n, bits, st), "nic_output_to_u8");
+}
+
+int nic_sse_u8(NicHandle* h, const uint8_t* a, const uint8_t* b, int64_t n, double* sse, void* stream) {
+  NIC_ENTER(h);
+  if (n < 0 || !sse || (n > 0 && (!a || !b))) return fail(h, NIC_ERR_ARG, "nic_sse_u8: bad buffer");
+  return cuda_fail(h, launch_sse_u8(h, a, b, n, sse, st), "nic_sse_u8");
+}
+
+}  // extern "C"

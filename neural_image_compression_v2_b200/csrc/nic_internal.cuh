@@ -1,0 +1,163 @@
+// nic_internal.cuh — host-side handle, device-side parameter blocks and the launch prototypes that tie
+// nic_api.cu (the C ABI) to the kernel translation units.
+#pragma once
+#include "nic_common.cuh"
+
+#define NIC_MAX_CIN 160     // widest decoder input the fp32 kernels accept (method 3: 9C + 3PE + 1 = 127 at C=12)
+#define NIC_MAX_COUT 16     // widest decoder output
+
+namespace nic {
+
+struct MlpDev {
+  int cin, hidden, cout;
+  const float *w1, *b1, *w2, *b2, *w3, *b3;
+};
+struct MlpGradDev {
+  float *w1, *b1, *w2, *b2, *w3, *b3;
+};
+
+struct Handle {
+  int device;
+  int sms;
+  int cc_major, cc_minor;
+  long long launches;
+  char err[256];
+  // scratch owned by the handle (device memory)
+  void* tc_weights;          // packed f16/bf16 UMMA operand images of the decoder weights
+  size_t tc_weights_bytes;
+  void* adam_desc;           // device copy of NicAdamTensor descriptors
+  size_t adam_desc_bytes;
+};
+
+// ---------------------------------------------------------------------------------------------- typed stores
+__device__ __forceinline__ void store_as(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_as(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void store_as(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+// decoder outputs: float as is, uint8 = floor(v*255 + .5) (models.quantize_to_bit, models.py:29-40)
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(uint8_t* p, float v) {
+  float q = quant_round(v, 255.0f);
+  *p = (uint8_t)(q < 0.f ? 0.f : (q > 255.f ? 255.f : q));
+}
+
+// ---------------------------------------------------------------------------------------------- row iterator
+// Calls f(col, value) for every decoder-input column of one texel in reference column order
+// (image_compression.py:94-96): G0 corners | sum of weighted G1 corners | PE per axis | LOD.
+template <class F>
+__device__ __forceinline__ void for_each_input(const DevGeom& g, const float* __restrict__ g0,
+                                               const float* __restrict__ g1, const AxisCoord* ax, F&& f) {
+  const int C = g.C;
+  const long long ps0 = plane_size(g.n0, g.dim), ps1 = plane_size(g.n1, g.dim);
+  int col = 0;
+  for (int j = 0; j < g.ncorner0; ++j) {
+    const int8_t* d = g.dim == 2 ? kCorner2D[j] : (g.method == NIC_METHOD_3D ? kCorner3D[j] : kCorner3Dv2[j]);
+    const float* p = g0 + node_index(g.n0, g.dim, ax[0].i0 + d[2], ax[1].i0 + d[1], ax[2].i0 + d[0]);
+    for (int c = 0; c < C; ++c) f(col++, __ldg(p + (long long)c * ps0));
+  }
+  const int nc1 = g.dim == 2 ? 4 : 8;
+  long long idx1[8];
+  float fac[8][3];
+  for (int j = 0; j < nc1; ++j) {
+    const int8_t* d = g.dim == 2 ? kCorner2D[j] : kCorner3D[j];
+    idx1[j] = node_index(g.n1, g.dim, ax[0].i1 + d[2], ax[1].i1 + d[1], ax[2].i1 + d[0]);
+    g1_factors(g, j, ax, fac[j]);
+  }
+  for (int c = 0; c < C; ++c) {
+    const float* plane = g1 + (long long)c * ps1;
+    float acc = 0.f;
+    for (int j = 0; j < nc1; ++j) {
+      float v = __ldg(plane + idx1[j]);
+      if (g.interp) {
+        v = __fmul_rn(__fmul_rn(v, fac[j][0]), fac[j][1]);
+        if (g.dim == 3) v = __fmul_rn(v, fac[j][2]);
+      }
+      acc = j == 0 ? v : __fadd_rn(acc, v);
+    }
+    f(col++, acc);
+  }
+  for (int a = 0; a < g.dim; ++a)
+    for (int r = 0; r < g.PE; ++r) f(col++, pe_value(g, ax[a].u1, r));
+  f(col, g.lod);
+}
+
+// Transpose of one grid column of the gather: adds v (d loss / d X[col]) into the grid gradients.
+__device__ __forceinline__ void scatter_column(const DevGeom& g, float* __restrict__ dg0, float* __restrict__ dg1,
+                                               const AxisCoord* ax, int col, float v) {
+  const int C = g.C;
+  const int n0c = g.ncorner0 * C;
+  if (col < n0c) {
+    int j = col / C, c = col - j * C;
+    const int8_t* d = g.dim == 2 ? kCorner2D[j] : (g.method == NIC_METHOD_3D ? kCorner3D[j] : kCorner3Dv2[j]);
+    long long idx = node_index(g.n0, g.dim, ax[0].i0 + d[2], ax[1].i0 + d[1], ax[2].i0 + d[0]);
+    atomicAdd(dg0 + (long long)c * plane_size(g.n0, g.dim) + idx, v);
+    return;
+  }
+  int c = col - n0c;
+  if (c >= C) return;
+  float* plane = dg1 + (long long)c * plane_size(g.n1, g.dim);
+  const int nc1 = g.dim == 2 ? 4 : 8;
+  for (int j = 0; j < nc1; ++j) {
+    const int8_t* d = g.dim == 2 ? kCorner2D[j] : kCorner3D[j];
+    float f[3];
+    g1_factors(g, j, ax, f);
+    float w = f[0] * f[1] * f[2];
+    if (w != 0.f) atomicAdd(plane + node_index(g.n1, g.dim, ax[0].i1 + d[2], ax[1].i1 + d[1], ax[2].i1 + d[0]), w * v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32(unsigned long long seed, unsigned long long offset,
+                                            unsigned long long counter) {
+  unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+  unsigned int c0 = (unsigned int)counter, c1 = (unsigned int)(counter >> 32);
+  unsigned int c2 = (unsigned int)offset, c3 = (unsigned int)(offset >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Quantisation noise of image_compression.py:250: (U[0,1) - 0.5) / 2^bits for element `idx` of step `step`.
+// Element idx uses word idx%4 of Philox block idx/4 (key = seed, high counter words = step).
+__device__ __forceinline__ float philox_noise(unsigned long long seed, unsigned long long step,
+                                              unsigned long long idx, int bits) {
+  uint4 r = philox4x32(seed, step, idx >> 2);
+  unsigned int w = (idx & 3) == 0 ? r.x : ((idx & 3) == 1 ? r.y : ((idx & 3) == 2 ? r.z : r.w));
+  float u = (float)(w >> 8) * (1.0f / 16777216.0f);
+  return (u - 0.5f) * exp2f(-(float)bits);
+}
+
+// ---------------------------------------------------------------------------------------------- launchers
+int launch_gather(Handle* h, const DevGeom& g, const float* g0, const float* g1, const long long* origins, void* x,
+                  int x_dtype, cudaStream_t st);
+int launch_scatter(Handle* h, const DevGeom& g, const float* dx, const long long* origins, float* dg0, float* dg1,
+                   cudaStream_t st);
+int launch_pe(Handle* h, const float* coord, int dim, long long n, int PE, int kind, const float* div_host, float* out,
+              cudaStream_t st);
+int launch_mlp_forward_f32(Handle* h, const DevGeom* g, const MlpDev& m, const float* g0, const float* g1,
+                           const long long* origins, const float* x, long long ldx, long long N, void* out,
+                           int out_dtype, float* z1, float* z2, cudaStream_t st);
+int launch_mlp_backward_f32(Handle* h, const MlpDev& m, const MlpGradDev& gm, const float* x, long long ldx,
+                            long long N, const float* z1, const float* z2, const float* out, const float* dout,
+                            float* dx, cudaStream_t st);
+int launch_train_f32(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradDev& gm, const float* g0,
+                     const float* g1, const long long* origins, const float* targets, const float* noise,
+                     int noise_bits, unsigned long long seed, unsigned long long step, float grad_scale, float* dg0,
+                     float* dg1, float* loss_sum, float* out_save, cudaStream_t st);
+int launch_decode_tc(Handle* h, const DevGeom& g, const MlpDev& m, const float* g0, const float* g1,
+                     const long long* origins, void* out, int out_dtype, int precision, cudaStream_t st);
+int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                float grad_scale, int zero_grad, cudaStream_t st);
+int launch_quantize4fp(Handle* h, const float* src, float* dst, long long n, int bits, cudaStream_t st);
+int launch_quantize_pack(Handle* h, const float* src, uint8_t* codes, long long n, int bits, cudaStream_t st);
+int launch_unpack(Handle* h, const uint8_t* codes, float* dst, long long n, int bits, cudaStream_t st);
+int launch_clamp(Handle* h, float* p, long long n, float lo, float hi, cudaStream_t st);
+int launch_output_to_u8(Handle* h, const float* src, uint8_t* dst, long long n, int bits, cudaStream_t st);
+int launch_sse_u8(Handle* h, const uint8_t* a, const uint8_t* b, long long n, double* sse, cudaStream_t st);
+
+}  // namespace nic

@@ -1,0 +1,162 @@
+// nic_optim.cu — K5 fused multi-tensor Adam (+ clamp, + grad zeroing) and K6 quantise / pack / unpack kernels.
+// Reference: torch.optim.Adam as configured at Projects/image_compression.py:361-365, fp_quantize_clamp
+// (Projects/fp_def.py:227-232) and the quantiser family of Projects/models.py:29-71.
+// HBM-bound elementwise work: 28 B/param for Adam (read p,g,m,v; write p,m,v), vectorised 16-byte accesses.
+#include "nic_internal.cuh"
+
+namespace nic {
+
+#define NIC_ADAM_BATCH 24
+struct AdamBatch {
+  NicAdamTensor t[NIC_ADAM_BATCH];
+  int count;
+  float beta1, beta2, eps, grad_scale;
+  int zero_grad;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float beta1, float beta2, float eps,
+                                         float gscale, float step_size, float bc2_sqrt, int clamp, float lo, float hi) {
+  float gr = g * gscale;
+  m = m + (gr - m) * (1.0f - beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * beta2 + (1.0f - beta2) * gr * gr;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  float denom = sqrtf(v) / bc2_sqrt + eps;           // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+  float np = p - step_size * (m / denom);            // param.addcdiv_(exp_avg, denom, value=-step_size)
+  if (clamp) np = fminf(fmaxf(np, lo), hi);          // fp_quantize_clamp after the step
+  p = np;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(AdamBatch b) {
+  const NicAdamTensor& t = b.t[blockIdx.y];
+  // bias corrections in double on every thread is cheap next to the memory traffic and keeps torch's values
+  const double bc1 = 1.0 - pow((double)b.beta1, (double)t.t);
+  const double bc2 = 1.0 - pow((double)b.beta2, (double)t.t);
+  const float step_size = (float)((double)t.lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const long long n4 = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0) ? t.numel / 4 : 0;
+  float4* p4 = reinterpret_cast<float4*>(t.p);
+  float4* g4 = reinterpret_cast<float4*>(t.g);
+  float4* m4 = reinterpret_cast<float4*>(t.m);
+  float4* v4 = reinterpret_cast<float4*>(t.v);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+    adam_one(p.x, g.x, m.x, v.x, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    adam_one(p.y, g.y, m.y, v.y, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    adam_one(p.z, g.z, m.z, v.z, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    adam_one(p.w, g.w, m.w, v.w, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    p4[i] = p; m4[i] = m; v4[i] = v;
+    if (b.zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.numel; i += stride) {
+    float p = t.p[i], g = t.g[i], m = t.m[i], v = t.v[i];
+    adam_one(p, g, m, v, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    t.p[i] = p; t.m[i] = m; t.v[i] = v;
+    if (b.zero_grad) t.g[i] = 0.f;
+  }
+}
+
+int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                float grad_scale, int zero_grad, cudaStream_t st) {
+  for (int base = 0; base < count; base += NIC_ADAM_BATCH) {
+    AdamBatch b;
+    b.count = count - base < NIC_ADAM_BATCH ? count - base : NIC_ADAM_BATCH;
+    b.beta1 = beta1; b.beta2 = beta2; b.eps = eps; b.grad_scale = grad_scale; b.zero_grad = zero_grad;
+    long long maxn = 0;
+    for (int i = 0; i < b.count; ++i) {
+      b.t[i] = tensors[base + i];
+      if (b.t[i].numel > maxn) maxn = b.t[i].numel;
+    }
+    if (maxn == 0) continue;
+    long long blocks = (maxn / 4 + 255) / 256 + 1;
+    long long cap = (long long)h->sms * 8;
+    dim3 grid((unsigned)(blocks > cap ? cap : blocks), (unsigned)b.count);
+    adam_kernel<<<grid, 256, 0, st>>>(b);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return NIC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ quantisers
+enum { Q_QUANT = 0, Q_PACK = 1, Q_UNPACK = 2, Q_CLAMP = 3, Q_OUT8 = 4 };
+
+template <int OP>
+__global__ void __launch_bounds__(256) quant_kernel(const float* __restrict__ src, const uint8_t* __restrict__ csrc,
+                                                    float* __restrict__ dst, uint8_t* __restrict__ cdst, long long n,
+                                                    float scale, float offset, float lo, float hi) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (OP == Q_QUANT) {
+      dst[i] = __fdiv_rn(quant_round(src[i], scale), scale);                 // models.py:55-57
+    } else if (OP == Q_PACK) {
+      float c = __fsub_rn(__fadd_rn(quant_round(src[i], scale), offset), 1.0f);   // models.py:61-64: + 2^(b-1) - 1
+      cdst[i] = (uint8_t)fminf(fmaxf(c, 0.f), 255.f);
+    } else if (OP == Q_UNPACK) {
+      float z = __fadd_rn(__fsub_rn((float)csrc[i], offset), 1.0f);          // models.py:68-71: - 2^(b-1) + 1
+      dst[i] = __fdiv_rn(z, scale);
+    } else if (OP == Q_CLAMP) {
+      dst[i] = fminf(fmaxf(dst[i], lo), hi);                                 // models.py:48-51
+    } else {
+      float q = quant_round(src[i], scale);                                  // models.py:29-40 (+ astype uint8)
+      cdst[i] = (uint8_t)fminf(fmaxf(q, 0.f), scale);
+    }
+  }
+}
+
+template <int OP>
+static int launch_q(Handle* h, const float* src, const uint8_t* csrc, float* dst, uint8_t* cdst, long long n,
+                    float scale, float offset, float lo, float hi, cudaStream_t st) {
+  if (n == 0) return NIC_OK;
+  long long blocks = (n + 255) / 256, cap = (long long)h->sms * 16;
+  quant_kernel<OP><<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, st>>>(src, csrc, dst, cdst, n, scale, offset, lo, hi);
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
+int launch_quantize4fp(Handle* h, const float* src, float* dst, long long n, int bits, cudaStream_t st) {
+  return launch_q<Q_QUANT>(h, src, nullptr, dst, nullptr, n, (float)((1 << bits) - 1), 0.f, 0.f, 0.f, st);
+}
+int launch_quantize_pack(Handle* h, const float* src, uint8_t* codes, long long n, int bits, cudaStream_t st) {
+  return launch_q<Q_PACK>(h, src, nullptr, nullptr, codes, n, (float)((1 << bits) - 1), (float)(1 << (bits - 1)), 0.f, 0.f, st);
+}
+int launch_unpack(Handle* h, const uint8_t* codes, float* dst, long long n, int bits, cudaStream_t st) {
+  return launch_q<Q_UNPACK>(h, nullptr, codes, dst, nullptr, n, (float)((1 << bits) - 1), (float)(1 << (bits - 1)), 0.f, 0.f, st);
+}
+int launch_clamp(Handle* h, float* p, long long n, float lo, float hi, cudaStream_t st) {
+  return launch_q<Q_CLAMP>(h, nullptr, nullptr, p, nullptr, n, 0.f, 0.f, lo, hi, st);
+}
+int launch_output_to_u8(Handle* h, const float* src, uint8_t* dst, long long n, int bits, cudaStream_t st) {
+  return launch_q<Q_OUT8>(h, src, nullptr, nullptr, dst, n, (float)((1 << bits) - 1), 0.f, 0.f, 0.f, st);
+}
+
+// sum of squared differences of two 8-bit images (integer-exact per thread, double at the end)
+__global__ void __launch_bounds__(256) sse_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                     long long n, double* __restrict__ sse) {
+  unsigned long long acc = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int d = (int)a[i] - (int)b[i];
+    acc += (unsigned long long)(d * d);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  __shared__ unsigned long long red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(sse, (double)t);
+  }
+}
+
+int launch_sse_u8(Handle* h, const uint8_t* a, const uint8_t* b, long long n, double* sse, cudaStream_t st) {
+  if (n == 0) return NIC_OK;
+  long long blocks = (n + 255) / 256, cap = (long long)h->sms * 8;
+  sse_u8_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, st>>>(a, b, n, sse);
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace nic

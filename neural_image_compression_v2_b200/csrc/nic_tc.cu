@@ -1,0 +1,446 @@
+// nic_tc.cu — K2, the fused tensor-core decode: gather -> Linear/GELU/Linear/GELU/Linear/Sigmoid -> output,
+// with all three layer GEMMs on tcgen05.mma (sm_100a) and every activation resident in TMEM / registers.
+// Reference behaviour: finally_decode_input_* + ColorDecoder.forward inside decode_image
+// (Projects/image_compression.py:54-68, 170-211, 313-327).
+//
+// Shape of the computation per CTA (128 threads, one thread per texel row, 4 CTAs resident per SM so one
+// CTA's epilogue overlaps another's MMA):
+//   tile of 128 texels:
+//     gather   : each thread builds its decoder-input row (fp32), packs it to 16-bit pairs and writes it with
+//                tcgen05.st into TMEM columns [A, A+KX/2)  -> operand A of layer 1 (A-from-TMEM, "TS" MMA).
+//     layer 1  : KX/16 x tcgen05.mma (M=128, N=64, K=16)  A = TMEM, B = W1' in shared memory, D1 -> TMEM.
+//     epilogue : tcgen05.ld D1 -> packed tanh-GELU (x + x*tanh(u); the 1/2 is folded into W2') -> tcgen05.st H1.
+//     layer 2  : 5 x tcgen05.mma, A = H1 (TMEM, K = 64 + bias column block), B = W2'.
+//     epilogue : same -> H2.
+//     layer 3  : 5 x tcgen05.mma (N = 16), B = W3'.   epilogue: sigmoid, quantise, store.
+//   Biases ride in the K dimension: the row carries a constant 1 and the matching column of W' holds the bias
+//   (for layer 1 that column also absorbs the LOD input, which is constant for a launch).
+//   TMEM map (128 columns per CTA): [0,64) accumulator D (fp32), [64,64+KX/2) operand A (16-bit pairs).
+//
+// Algorithmic work: 2*(Cin*64 + 64*64 + 64*Cout) FLOP/texel (17,920 for the 2-D default); tensor-bound roofline.
+#include "nic_internal.cuh"
+
+namespace nic {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// tcgen05.commit: the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread is done.
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]   (kind::f16: f16 or bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): in 16-byte units the
+// canonical layout is ((8,n),2):((1,SBO),LBO) — 8 rows x 16 B form a 128-byte core matrix, SBO steps to the next
+// 8-row group, LBO to the next 8-element K chunk.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B format fmt (0 f16, 1 bf16), both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// tcgen05.ld / st, shape 32x32b: thread i of warp w touches TMEM lane 32*(w%4)+i, one 32-bit column per register.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ 16-bit math
+template <int FMT> struct Pair;   // FMT 0 = f16, 1 = bf16
+template <> struct Pair<0> {
+  using T2 = __half2;
+  static __device__ __forceinline__ T2 pack(float a, float b) { return __floats2half2_rn(a, b); }
+  static __device__ __forceinline__ T2 cst(float a) { return __float2half2_rn(a); }
+  static __device__ __forceinline__ T2 tanh2(T2 x) {
+    uint32_t r, v = *reinterpret_cast<uint32_t*>(&x);
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(v));
+    return *reinterpret_cast<T2*>(&r);
+  }
+};
+template <> struct Pair<1> {
+  using T2 = __nv_bfloat162;
+  static __device__ __forceinline__ T2 pack(float a, float b) { return __floats2bfloat162_rn(a, b); }
+  static __device__ __forceinline__ T2 cst(float a) { return __float2bfloat162_rn(a); }
+  static __device__ __forceinline__ T2 tanh2(T2 x) {
+    uint32_t r, v = *reinterpret_cast<uint32_t*>(&x);
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(v));
+    return *reinterpret_cast<T2*>(&r);
+  }
+};
+
+// 2*GELU_tanh on a packed pair: x + x*tanh(x*(c1 + c2*x^2)); the factor 1/2 lives in the next layer's weights.
+template <int FMT>
+__device__ __forceinline__ uint32_t gelu2x_pair(float a, float b) {
+  using P = Pair<FMT>;
+  typename P::T2 x = P::pack(a, b);
+  typename P::T2 x2 = __hmul2(x, x);
+  typename P::T2 p = __hfma2(x2, P::cst(0.0356774081f), P::cst(0.7978845608f));
+  typename P::T2 t = P::tanh2(__hmul2(p, x));
+  typename P::T2 h = __hfma2(x, t, x);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------ weight images
+// Operand-B images in global memory, already in the shared-memory UMMA layout (K-major, no swizzle):
+//   byte offset of element (n, k) = (k/8)*LBO + (n/8)*128 + (n%8)*16 + (k%8)*2,  LBO = (Nrows/8)*128.
+// W1': [64 x KX]  col k < cin-1: W1[n][k];  col cin-1: b1[n] + lod*W1[n][cin-1];  rest 0.
+// W2': [64 x 80]  col k < 64: W2[n][k]/2;   col 64: b2[n];  rest 0.
+// W3': [16 x 80]  row n < cout: col k < 64: W3[n][k]/2; col 64: b3[n];  rest 0.
+template <int FMT>
+__device__ __forceinline__ uint16_t to16(float v) {
+  if (FMT == 0) {
+    __half h = __float2half_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__host__ __device__ constexpr int b_image_bytes(int nrows, int k) { return nrows * k * 2; }
+
+template <int FMT>
+__global__ void pack_weights_kernel(MlpDev m, float lod, int KX, uint16_t* __restrict__ img) {
+  const int H = 64;
+  const int n1 = H * KX, n2 = H * 80, n3 = 16 * 80;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += gridDim.x * blockDim.x) {
+    int which = i < n1 ? 0 : (i < n1 + n2 ? 1 : 2);
+    int local = which == 0 ? i : (which == 1 ? i - n1 : i - n1 - n2);
+    int nrows = which == 2 ? 16 : H;
+    // decode the position inside the image: [k/8][n/8][n%8][k%8]
+    int kc = local / (nrows * 8);
+    int rem = local - kc * nrows * 8;
+    int n = rem / 8, ke = rem - n * 8;
+    int k = kc * 8 + ke;
+    float v = 0.f;
+    if (which == 0) {
+      if (k < m.cin - 1) v = m.w1[n * m.cin + k];
+      else if (k == m.cin - 1) v = m.b1[n] + lod * m.w1[n * m.cin + k];
+    } else if (which == 1) {
+      if (k < H) v = 0.5f * m.w2[n * H + k];
+      else if (k == H) v = m.b2[n];
+    } else if (n < m.cout) {
+      if (k < H) v = 0.5f * m.w3[n * H + k];
+      else if (k == H) v = m.b3[n];
+    }
+    img[i] = to16<FMT>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gather to registers
+// Decoder-input row of one texel for C = 12, PE = 6 with every index a compile-time constant (the row lives in
+// registers).  Column cin-1 (the LOD input) becomes the constant 1 that carries the layer-1 bias.
+template <int METHOD>
+struct RowShape {
+  static constexpr int DIM = METHOD == NIC_METHOD_2D ? 2 : 3;
+  static constexpr int NC0 = METHOD == NIC_METHOD_3D ? 8 : 4;
+  static constexpr int NC1 = METHOD == NIC_METHOD_2D ? 4 : 8;
+  static constexpr int C = 12, PE = 6;
+  static constexpr int CIN = C * (NC0 + 1) + PE * DIM + 1;    // 73 / 127 / 79
+  static constexpr int KX = (CIN + 15) / 16 * 16;            // 80 / 128 / 80
+};
+
+template <int METHOD>
+__device__ __forceinline__ void gather_row_regs(const DevGeom& g, const float* __restrict__ g0,
+                                                const float* __restrict__ g1, const AxisCoord* ax, float* xf) {
+  using S = RowShape<METHOD>;
+  const long long ps0 = plane_size(g.n0, S::DIM), ps1 = plane_size(g.n1, S::DIM);
+#pragma unroll
+  for (int j = 0; j < S::NC0; ++j) {
+    const int8_t* d = S::DIM == 2 ? kCorner2D[j] : (METHOD == NIC_METHOD_3D ? kCorner3D[j] : kCorner3Dv2[j]);
+    const float* p = g0 + node_index(g.n0, S::DIM, ax[0].i0 + d[2], ax[1].i0 + d[1], ax[2].i0 + d[0]);
+#pragma unroll
+    for (int c = 0; c < S::C; ++c) xf[j * S::C + c] = __ldg(p + (long long)c * ps0);
+  }
+  float w[S::NC1];
+  const float* p1[S::NC1];
+#pragma unroll
+  for (int j = 0; j < S::NC1; ++j) {
+    const int8_t* d = S::DIM == 2 ? kCorner2D[j] : kCorner3D[j];
+    p1[j] = g1 + node_index(g.n1, S::DIM, ax[0].i1 + d[2], ax[1].i1 + d[1], ax[2].i1 + d[0]);
+    float f[3];
+    g1_factors(g, j, ax, f);
+    w[j] = f[0] * f[1] * f[2];
+  }
+#pragma unroll
+  for (int c = 0; c < S::C; ++c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < S::NC1; ++j) acc = fmaf(__ldg(p1[j] + (long long)c * ps1), w[j], acc);
+    xf[S::NC0 * S::C + c] = acc;
+  }
+#pragma unroll
+  for (int a = 0; a < S::DIM; ++a)
+#pragma unroll
+    for (int r = 0; r < S::PE; ++r) xf[(S::NC0 + 1) * S::C + a * S::PE + r] = pe_value(g, ax[a].u1, r);
+  xf[S::CIN - 1] = 1.0f;
+#pragma unroll
+  for (int k = S::CIN; k < S::KX; ++k) xf[k] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+constexpr int TC_THREADS = 128;
+constexpr int TC_TMEM_COLS = 128;
+constexpr int TC_COL_D = 0;     // accumulator columns [0, 64)
+constexpr int TC_COL_A = 64;    // operand-A columns   [64, 64 + KX/2)
+constexpr int TC_K2 = 80;       // K of layers 2/3: 64 hidden + the bias block
+
+template <int METHOD, int FMT, typename OutT>
+__global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, const float* __restrict__ g0,
+                                                                  const float* __restrict__ g1,
+                                                                  const long long* __restrict__ origins,
+                                                                  const uint4* __restrict__ wimg, int cout,
+                                                                  OutT* __restrict__ out) {
+  using S = RowShape<METHOD>;
+  constexpr int KX = S::KX;
+  constexpr int W1_BYTES = b_image_bytes(64, KX), W2_BYTES = b_image_bytes(64, TC_K2), W3_BYTES = b_image_bytes(16, TC_K2);
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* sW1 = smem_raw;
+  uint8_t* sW2 = sW1 + W1_BYTES;
+  uint8_t* sW3 = sW2 + W2_BYTES;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sW3 + W3_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // ---- one-time setup: TMEM allocation, barrier, weight images -> shared memory
+  if (warp == 0) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  if (tid == 0) mbar_init(mbar, 1);
+  {
+    uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+    constexpr int NV = (W1_BYTES + W2_BYTES + W3_BYTES) / 16;
+    for (int i = tid; i < NV; i += TC_THREADS) dst[i] = __ldg(wimg + i);
+  }
+  fence_async_smem();            // weights (generic-proxy stores) -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t tD = tmem + TC_COL_D, tA = tmem + TC_COL_A;
+
+  constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
+  constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
+  const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  uint32_t phase = 0;
+
+  const long long ntiles = (g.N + TC_THREADS - 1) / TC_THREADS;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long n = tile * TC_THREADS + tid;
+    const bool live = n < g.N;
+    // ---- gather: the row of this thread's texel -> 16-bit pairs -> TMEM operand A
+    {
+      Texel t = texel_of(g, live ? n : g.N - 1, origins);
+      AxisCoord ax[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) ax[a] = axis_coord(t.p[a], g.step);
+      float xf[KX];
+      gather_row_regs<METHOD>(g, g0, g1, ax, xf);
+      uint32_t xp[KX / 2];
+#pragma unroll
+      for (int i = 0; i < KX / 2; ++i) {
+        auto v = Pair<FMT>::pack(xf[2 * i], xf[2 * i + 1]);
+        xp[i] = *reinterpret_cast<uint32_t*>(&v);
+      }
+#pragma unroll
+      for (int i = 0; i + 16 <= KX / 2; i += 16) tmem_st16(tA + lane_base + i, xp + i);
+      if ((KX / 2) % 16 == 8) tmem_st8(tA + lane_base + (KX / 2 - 8), xp + (KX / 2 - 8));
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    // ---- layer 1
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kc = 0; kc < KX / 16; ++kc)
+        mma_ts(tD, tA + kc * 8, make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
+      tc_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue of layers 1 and 2: D -> 2*gelu -> H (operand A of the next layer), bias block [1, 0, ...]
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t acc[32];
+        tmem_ld32(tD + lane_base + half * 32, acc);
+        tc_wait_ld();
+        uint32_t hp[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hp[i] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+        tmem_st16(tA + lane_base + half * 16, hp);
+      }
+      {
+        uint32_t ones[8];
+        auto one = Pair<FMT>::pack(1.0f, 0.0f);
+        ones[0] = *reinterpret_cast<uint32_t*>(&one);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) ones[i] = 0u;
+        tmem_st8(tA + lane_base + 32, ones);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        if (layer == 0) {
+#pragma unroll
+          for (int kc = 0; kc < TC_K2 / 16; ++kc)
+            mma_ts(tD, tA + kc * 8, make_smem_desc(aW2 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
+        } else {
+#pragma unroll
+          for (int kc = 0; kc < TC_K2 / 16; ++kc)
+            mma_ts(tD, tA + kc * 8, make_smem_desc(aW3 + kc * 2 * LBO_16, LBO_16, SBO), IDESC_16, kc > 0);
+        }
+        tc_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+    // ---- output: sigmoid, optional 8-bit quantisation
+    {
+      uint32_t acc[16];
+      tmem_ld16(tD + lane_base, acc);
+      tc_wait_ld();
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < cout) {
+            float z = __uint_as_float(acc[c]);
+            float v = __fdividef(1.0f, 1.0f + __expf(-z));
+            store_out(out + n * cout + c, v);
+          }
+      }
+    }
+    // the next tile's tcgen05.st / mma reuse the A and D columns: order them after this tile's tcgen05.ld
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TC_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+template <int METHOD, int FMT, typename OutT>
+static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float* g0, const float* g1,
+                       const long long* origins, OutT* out, cudaStream_t st) {
+  using S = RowShape<METHOD>;
+  constexpr int IMG = b_image_bytes(64, S::KX) + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2);
+  if (h->tc_weights_bytes < (size_t)IMG) {
+    if (h->tc_weights) cudaFree(h->tc_weights);
+    h->tc_weights = nullptr;
+    h->tc_weights_bytes = 0;
+    if (cudaMalloc(&h->tc_weights, 64 * 1024) != cudaSuccess) return NIC_ERR_SCRATCH;
+    h->tc_weights_bytes = 64 * 1024;
+  }
+  pack_weights_kernel<FMT><<<16, 256, 0, st>>>(m, g.lod, S::KX, (uint16_t*)h->tc_weights);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  // 56 KB of dynamic shared memory per CTA caps residency at 4 CTAs/SM = 4 x 128 TMEM columns = all 512.
+  size_t smem = 56 * 1024;
+  auto kern = decode_tc_kernel<METHOD, FMT, OutT>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  long long ntiles = (g.N + TC_THREADS - 1) / TC_THREADS;
+  long long cap = (long long)h->sms * 4;
+  int grid = (int)(ntiles < cap ? ntiles : cap);
+  kern<<<grid, TC_THREADS, smem, st>>>(g, g0, g1, origins, (const uint4*)h->tc_weights, m.cout, out);
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
+template <int METHOD>
+static int launch_tc_m(Handle* h, const DevGeom& g, const MlpDev& m, const float* g0, const float* g1,
+                       const long long* origins, void* out, int out_dtype, int precision, cudaStream_t st) {
+  if (precision == NIC_PREC_F16) {
+    if (out_dtype == NIC_DT_U8) return launch_tc_t<METHOD, 0, uint8_t>(h, g, m, g0, g1, origins, (uint8_t*)out, st);
+    return launch_tc_t<METHOD, 0, float>(h, g, m, g0, g1, origins, (float*)out, st);
+  }
+  if (out_dtype == NIC_DT_U8) return launch_tc_t<METHOD, 1, uint8_t>(h, g, m, g0, g1, origins, (uint8_t*)out, st);
+  return launch_tc_t<METHOD, 1, float>(h, g, m, g0, g1, origins, (float*)out, st);
+}
+
+int launch_decode_tc(Handle* h, const DevGeom& g, const MlpDev& m, const float* g0, const float* g1,
+                     const long long* origins, void* out, int out_dtype, int precision, cudaStream_t st) {
+  if (g.N == 0) return NIC_OK;
+  if (g.C != 12 || g.PE != 6 || m.hidden != 64 || m.cout > 16) return NIC_ERR_UNSUPPORTED;
+  switch (g.method) {
+    case NIC_METHOD_2D: return launch_tc_m<NIC_METHOD_2D>(h, g, m, g0, g1, origins, out, out_dtype, precision, st);
+    case NIC_METHOD_3D: return launch_tc_m<NIC_METHOD_3D>(h, g, m, g0, g1, origins, out, out_dtype, precision, st);
+    case NIC_METHOD_3D_V2: return launch_tc_m<NIC_METHOD_3D_V2>(h, g, m, g0, g1, origins, out, out_dtype, precision, st);
+  }
+  return NIC_ERR_UNSUPPORTED;
+}
+
+}  // namespace nic

@@ -1,0 +1,98 @@
+"""Feature-pyramid operations — host-side mirror of the reference's `Projects/fp_def.py` (same names,
+argument order and return layouts).  Level tables are host integers; everything that touches grid values
+runs in libnic.so."""
+from collections import defaultdict
+
+import torch
+
+from . import _lib as L
+from .models import load4fp, quantize4fp, save4fp
+
+
+def return_2_power(base_size):
+    """fp_def.py:8-15."""
+    count = 0
+    x = base_size
+    while x != 1:
+        x = x // 2
+        count += 1
+    return count
+
+
+def return_pyramid_levels(base_size):
+    """fp_def.py:18-21."""
+    return (return_2_power(base_size) + 1) // 2
+
+
+def create_pyramid_mip_levels(image_size, base_size):
+    """fp_def.py:24-34 — mip level -> pyramid level."""
+    count = return_2_power(image_size)
+    table = defaultdict(int)
+    levels = return_pyramid_levels(base_size)
+    for i in range(count + 1):
+        table[i] = min(max((i // 2) - 1, 0), levels - 1)
+    return table
+
+
+def _create(base_size, channels, num_bits, device, dtype, no_mip, dim):
+    if dtype != torch.float32:
+        raise TypeError("grids are float32 (the reference's MLP_NUM_DTYPE=16 path diverges within two steps)")
+    levels = 1 if no_mip else return_pyramid_levels(base_size)
+    q_min = -(pow(2, num_bits) - 1) / pow(2, num_bits + 1)
+    q_max = 1 / 2
+    pyramid = []
+    for i in range(levels * 2):
+        size = base_size // (2 ** i)
+        shape = (channels,) + (size + 1,) * dim
+        pyramid.append(((q_max - q_min) * torch.rand(shape, device=device, dtype=dtype) + q_min).requires_grad_(True))
+    return pyramid, levels
+
+
+def create_pyramid(base_size, channels, num_bits, device, dtype, no_mip=False):
+    """fp_def.py:37-56 — 2*levels learnable grids `[C, s+1, s+1]`, U[q_min, 1/2]."""
+    return _create(base_size, channels, num_bits, device, dtype, no_mip, 2)
+
+
+def create_pyramid_3d(base_size, channels, num_bits, device, dtype, no_mip=False):
+    """fp_def.py:59-78."""
+    return _create(base_size, channels, num_bits, device, dtype, no_mip, 3)
+
+
+def fp_quantize_clamp(fp, fl, num_bits):
+    """fp_def.py:227-232 — clamp the two active grids in place."""
+    q_min = -(pow(2, num_bits) - 1) / pow(2, num_bits + 1)
+    lib = L.load_library()
+    with torch.no_grad():
+        for g in (fp[fl * 2], fp[fl * 2 + 1]):
+            if not g.is_contiguous() or g.dtype != torch.float32:
+                raise TypeError("grids must be contiguous float32")
+            h = L.handle(g.device)
+            L.check(h, lib.nic_clamp(h, L.ptr(g), g.numel(), q_min, 0.5, L.stream_ptr(g.device)))
+
+
+def fp_quantize(fp, fl, num_bits):
+    """fp_def.py:235-239."""
+    with torch.no_grad():
+        fp[fl * 2] = quantize4fp(fp[fl * 2], num_bits)
+        fp[fl * 2 + 1] = quantize4fp(fp[fl * 2 + 1], num_bits)
+
+
+def fp_all_quantize(fp, num_bits):
+    """fp_def.py:242-247."""
+    return [quantize4fp(g, num_bits) for g in fp]
+
+
+def fp_savable(fp, num_bits, dtype=torch.uint8):
+    """fp_def.py:250-255 — uint8 codes, bit-exact with models.save4fp."""
+    return [save4fp(g, num_bits, dtype) for g in fp]
+
+
+def fp_load(compressed_fp, num_bits, dtype=torch.float32):
+    """fp_def.py:258-263 (float result; see models.load4fp about the reference's dtype bug)."""
+    return [load4fp(g, num_bits, dtype) for g in compressed_fp]
+
+
+def fp_freeze(fp):
+    """fp_def.py:266-268."""
+    for g in fp:
+        g.requires_grad = False

@@ -1,0 +1,421 @@
+"""Host-side mirror of the hot-path functions of the reference's `Projects/image_compression.py`.
+
+Same function names, argument order, return shapes and `state_dict` keys as the reference, so a maintainer
+can swap the imports.  Each function cites the reference lines it replaces.  All arithmetic
+runs in libnic.so on a B200; tensors must live on a CUDA device (there is no CPU fallback).
+
+Two ways to drive the path:
+  * the reference's own two-call sequence — `create_decoder_input_*` / `finally_decode_input_*` followed by
+    `decoder(x)`, `loss.backward()` and a torch optimiser — works unchanged through autograd Functions;
+  * the fused entry points `decode(...)` and `FusedTrainer.step(...)`, which never materialise X.
+"""
+import ctypes as C
+import math
+import random
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import var2
+from .fp_def import create_pyramid_mip_levels, fp_all_quantize, fp_freeze, fp_quantize_clamp
+from .models import quantize4fp
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def _method():
+    return {1: L.METHOD_2D, 2: L.METHOD_2D, 3: L.METHOD_3D, 4: L.METHOD_3D_V2}[var2.COMPRESSION_METHOD]
+
+
+def _pe_kind(method):
+    """2-D: TF_USE_TRI_PE chooses (fp_def.py:132-135); method 3 always triangular (:169); method 4 always
+    sinusoidal (:208)."""
+    if method == L.METHOD_2D:
+        return L.PE_TRIANGULAR if var2.TF_USE_TRI_PE else L.PE_SINUSOIDAL
+    return L.PE_TRIANGULAR if method == L.METHOD_3D else L.PE_SINUSOIDAL
+
+
+def feature_pyramid_mip_levels():
+    """The reference's global `feature_pyramid_mip_levels_dict` (image_compression.py:360)."""
+    return create_pyramid_mip_levels(var2.IMAGE_SIZE, var2.FEATURE_PYRAMID_SIZE)
+
+
+def _step_log2(mip_level, fl):
+    """image_compression.py:79 — step_number = 2^(mip - 2(fl+1))."""
+    return mip_level - (fl + 1) * 2
+
+
+def _check_grid(g):
+    if not g.is_cuda:
+        raise L.NicError(-3, "grids must be CUDA tensors (no CPU fallback)")
+    if g.dtype != torch.float32 or not g.is_contiguous():
+        raise TypeError("grids must be contiguous float32")
+    return g
+
+
+class _GatherFn(torch.autograd.Function):
+    """X = gather(G0, G1): fp_def.create_g0_g1* + the torch.cat of image_compression.py:90-100.  Backward is the
+    scatter-add the reference gets from autograd's index_put(accumulate) (image_compression.py:265)."""
+
+    @staticmethod
+    def forward(ctx, g0, g1, coord, geom):
+        g0d, g1d = _check_grid(g0.detach()), _check_grid(g1.detach())
+        n = geom.num_blocks * geom.block[0] * geom.block[1] * geom.block[2]
+        x = torch.empty((n, L.cin_of(geom)), dtype=torch.float32, device=g0.device)
+        h = L.handle(g0.device)
+        L.check(h, L.load_library().nic_gather(h, C.byref(geom), L.ptr(g0d), L.ptr(g1d), L.ptr(coord), L.ptr(x),
+                                               L.DT_F32, L.stream_ptr(g0.device)))
+        ctx.geom, ctx.coord, ctx.shapes = geom, coord, (g0.shape, g1.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        dx = dx.contiguous()
+        dg0 = torch.zeros(ctx.shapes[0], dtype=torch.float32, device=dx.device)
+        dg1 = torch.zeros(ctx.shapes[1], dtype=torch.float32, device=dx.device)
+        h = L.handle(dx.device)
+        L.check(h, L.load_library().nic_scatter(h, C.byref(ctx.geom), L.ptr(dx), L.ptr(ctx.coord), L.ptr(dg0),
+                                                L.ptr(dg1), L.stream_ptr(dx.device)))
+        return dg0, dg1, None, None
+
+
+class _MlpFn(torch.autograd.Function):
+    """ColorDecoder.forward on a materialised input (image_compression.py:57-68), exact-erf GELU in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, w3, b3):
+        if not x.is_cuda:
+            raise L.NicError(-3, "decoder input must be a CUDA tensor (no CPU fallback)")
+        params = [p.detach().contiguous() for p in (w1, b1, w2, b2, w3, b3)]
+        xd = x.detach()
+        if xd.dtype != torch.float32:
+            raise TypeError("decoder input must be float32")
+        if xd.dim() != 2:
+            raise ValueError("decoder input must be [N, Cin]")
+        if xd.stride(1) != 1:
+            xd = xd.contiguous()
+        m = L.make_mlp(params)
+        if xd.shape[1] != m.cin:
+            raise ValueError(f"decoder input has {xd.shape[1]} columns, decoder expects {m.cin}")
+        n = xd.shape[0]
+        need_grad = any(ctx.needs_input_grad)
+        out = torch.empty((n, m.cout), dtype=torch.float32, device=x.device)
+        z1 = torch.empty((n, m.hidden), dtype=torch.float32, device=x.device) if need_grad else None
+        z2 = torch.empty((n, m.hidden), dtype=torch.float32, device=x.device) if need_grad else None
+        h = L.handle(x.device)
+        L.check(h, L.load_library().nic_mlp_forward(h, C.byref(m), L.ptr(xd), xd.stride(0), n, L.ptr(out), L.ptr(z1),
+                                                    L.ptr(z2), L.stream_ptr(x.device)))
+        if need_grad:
+            ctx.save_for_backward(xd, z1, z2, out, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xd, z1, z2, out, *params = ctx.saved_tensors
+        m = L.make_mlp(params)
+        grads = [torch.zeros_like(p) for p in params]
+        gm = L.make_mlp_grad(grads)
+        dx = torch.empty((xd.shape[0], m.cin), dtype=torch.float32, device=xd.device) if ctx.needs_input_grad[0] else None
+        h = L.handle(xd.device)
+        L.check(h, L.load_library().nic_mlp_backward(h, C.byref(m), L.ptr(xd), xd.stride(0), xd.shape[0], L.ptr(z1),
+                                                     L.ptr(z2), L.ptr(out), L.ptr(dout.contiguous()), C.byref(gm),
+                                                     L.ptr(dx), L.stream_ptr(xd.device)))
+        return (dx, *grads)
+
+
+# ------------------------------------------------------------------------------------------------ decoder
+class _FusedSequential(nn.Sequential):
+    """nn.Sequential(Linear, GELU, Linear, GELU, Linear, Sigmoid) whose forward is one fused CUDA kernel."""
+
+    def forward(self, x):
+        lin = [self[0], self[2], self[4]]
+        return _MlpFn.apply(x, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)
+
+
+class ColorDecoder(nn.Module):
+    """image_compression.py:54-68 — same construction and `state_dict` keys (`decoder.{0,2,4}.{weight,bias}`)."""
+
+    def __init__(self, in_channels=None, hidden=None, out_channels=None):
+        super().__init__()
+        cin = var2.DECODER_INPUT_CHANNELS if in_channels is None else in_channels
+        hid = var2.HIDDEN_LAYER_CHANNELS if hidden is None else hidden
+        cout = var2.OUTPUT_CHANNELS if out_channels is None else out_channels
+        self.decoder = _FusedSequential(nn.Linear(cin, hid), nn.GELU(), nn.Linear(hid, hid), nn.GELU(),
+                                        nn.Linear(hid, cout), nn.Sigmoid())
+
+    def forward(self, x):
+        return self.decoder(x)
+
+    def parameters_list(self):
+        d = self.decoder
+        return [d[0].weight, d[0].bias, d[2].weight, d[2].bias, d[4].weight, d[4].bias]
+
+
+# ------------------------------------------------------------------------------------------------ decoder inputs
+def _create_decoder_input(fp, coord, num_crops, fl, mip_level, method):
+    g0, g1 = fp[fl * 2], fp[fl * 2 + 1]
+    dim = 2 if method == L.METHOD_2D else 3
+    # image_compression.py:78 hard-codes 8 in 2-D; :110/:144 use CROP_MIP_LEVEL in 3-D
+    sample_number = pow(2, max(0, (8 if dim == 2 else var2.CROP_MIP_LEVEL) - mip_level))
+    coord = L.origins_tensor(coord, g0.device, dim)[:num_crops].contiguous()
+    geom = L.make_geom(method, g0, g1, sample_number, num_crops, _step_log2(mip_level, fl), mip_level,
+                       var2.PE_CHANNELS, _pe_kind(method))
+    return _GatherFn.apply(g0, g1, coord, geom)
+
+
+def create_decoder_input_2d(fp, coord, num_crops, fl, mip_level):
+    """image_compression.py:71-100 -> X [num_crops * S^2, Cin]."""
+    return _create_decoder_input(fp, coord, num_crops, fl, mip_level, L.METHOD_2D)
+
+
+def create_decoder_input_3d(fp, coord, num_crops, fl, mip_level):
+    """image_compression.py:103-134."""
+    return _create_decoder_input(fp, coord, num_crops, fl, mip_level, L.METHOD_3D)
+
+
+def create_decoder_input_3d_v2(fp, coord, num_crops, fl, mip_level):
+    """image_compression.py:137-167."""
+    return _create_decoder_input(fp, coord, num_crops, fl, mip_level, L.METHOD_3D_V2)
+
+
+def _finally_decode_input(fp, image_size, mip_level, origin, method):
+    fl = feature_pyramid_mip_levels()[mip_level]
+    g0, g1 = fp[fl * 2], fp[fl * 2 + 1]
+    geom = L.make_geom(method, g0, g1, image_size, 1, _step_log2(mip_level, fl), mip_level, var2.PE_CHANNELS,
+                       _pe_kind(method), origin0=origin)
+    return _GatherFn.apply(g0, g1, None, geom)
+
+
+def finally_decode_input_2d(fp, image_size, mip_level, x=0, y=0):
+    """image_compression.py:170-181."""
+    return _finally_decode_input(fp, image_size, mip_level, (x, y), L.METHOD_2D)
+
+
+def finally_decode_input_3d(fp, image_size, mip_level, x=0, y=0, z=0):
+    """image_compression.py:184-196."""
+    return _finally_decode_input(fp, image_size, mip_level, (x, y, z), L.METHOD_3D)
+
+
+def finally_decode_input_3d_v2(fp, image_size, mip_level, x=0, y=0, z=0):
+    """image_compression.py:199-211."""
+    return _finally_decode_input(fp, image_size, mip_level, (x, y, z), L.METHOD_3D_V2)
+
+
+# ------------------------------------------------------------------------------------------------ fused decode
+def decode(fp, decoder, mip_level=0, size=None, origin=None, precision=None, out_dtype=torch.float32, out=None,
+           method=None, level_table=None):
+    """Fused gather + MLP for one block: the body of decode_image's single-shot branch
+    (image_compression.py:313-327) without materialising X.
+
+    size: texels per axis (int) or per-axis tuple (x, y[, z]); default IMAGE_SIZE >> mip_level.
+    origin: block origin in texels of this mip level.  precision: "f32" | "f16" | "bf16" (default
+    var2.DECODE_PRECISION).  out_dtype: torch.float32 or torch.uint8 (floor(v*255+.5)).
+    Returns [Sx, Sy(, Sz), Cout]."""
+    method = _method() if method is None else method
+    dim = 2 if method == L.METHOD_2D else 3
+    table = feature_pyramid_mip_levels() if level_table is None else level_table
+    fl = table[mip_level]
+    g0, g1 = _check_grid(fp[fl * 2].detach()), _check_grid(fp[fl * 2 + 1].detach())
+    if size is None:
+        size = var2.IMAGE_SIZE // pow(2, mip_level)
+    block = (size,) * dim if isinstance(size, int) else tuple(size)
+    params = [p.detach().contiguous() for p in decoder.parameters_list()]
+    m = L.make_mlp(params)
+    geom = L.make_geom(method, g0, g1, block, 1, _step_log2(mip_level, fl), mip_level, var2.PE_CHANNELS,
+                       _pe_kind(method), origin0=origin)
+    prec = L.PRECISIONS[(precision or var2.DECODE_PRECISION).lower()]
+    if out_dtype not in (torch.float32, torch.uint8):
+        raise TypeError("out_dtype must be torch.float32 or torch.uint8")
+    shape = block + (m.cout,)
+    if out is None:
+        out = torch.empty(shape, dtype=out_dtype, device=g0.device)
+    elif tuple(out.shape) != shape or out.dtype != out_dtype or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous {out_dtype} tensor of shape {shape}")
+    h = L.handle(g0.device)
+    L.check(h, L.load_library().nic_decode(h, C.byref(geom), L.ptr(g0), L.ptr(g1), None, C.byref(m), L.ptr(out),
+                                           L.DT_U8 if out_dtype == torch.uint8 else L.DT_F32, prec,
+                                           L.stream_ptr(g0.device)))
+    return out
+
+
+def decode_image(fp, arc_decoder, mip_level, pr=True, div_size=10, precision=None):
+    """image_compression.py:307-346 — full-frame decode; <= 2^div_size-texel tiles when the frame is larger.
+    Differences from the reference, both deliberate: the tiled result is assembled on the device (the
+    reference assembles it in a CPU tensor, :329), and 3-D tiling passes all three origins (the reference's
+    3-D tiled branch passes only x,y, :338-340)."""
+    with torch.no_grad():
+        power = var2.MAX_MIP_LEVEL - mip_level
+        div_slice = pow(2, max(power - div_size, 0))
+        div_count = pow(div_slice, 2)
+        decode_size = var2.IMAGE_SIZE // pow(2, mip_level)
+        dim = var2.FP_DIMENSION
+        fused = isinstance(arc_decoder, ColorDecoder)
+
+        def one(size, origin):
+            if fused:
+                return decode(fp, arc_decoder, mip_level, size, origin, precision)
+            method = _method()
+            x = _finally_decode_input(fp, size, mip_level, origin, method)
+            return arc_decoder(x).reshape((size,) * dim + (-1,))
+
+        if div_count == 1:
+            out = one(decode_size, (0,) * dim)
+            if pr:
+                print(torch.Size([out.numel() // out.shape[-1], out.shape[-1]]))
+            return out
+        if dim != 2:
+            raise NotImplementedError("tiled decode is 2-D only, as in the reference (image_compression.py:329-345)")
+        result = torch.zeros(decode_size, decode_size, var2.OUTPUT_CHANNELS, dtype=torch.float32, device=fp[0].device)
+        sample_number = var2.IMAGE_SIZE // pow(2, mip_level + max(power - div_size, 0))
+        for i in range(div_count):
+            x, y = i % div_slice, i // div_slice
+            tile = one(sample_number, (sample_number * x, sample_number * y))
+            if pr:
+                print(torch.Size([tile.numel() // tile.shape[-1], tile.shape[-1]]))
+            result[sample_number * x:sample_number * (x + 1), sample_number * y:sample_number * (y + 1), :] = tile
+        return result
+
+
+# ------------------------------------------------------------------------------------------------ crop sampler
+def random_crop_dataset(datasets, crop_size, num_crops, uniform_distribution, dim=2):
+    """image_compression.py:26-50 — host RNG LOD draw + integer crop origins; targets `[NC, S^D, C]`."""
+    if uniform_distribution:
+        lod = random.randint(0, var2.MAX_MIP_LEVEL)
+    else:
+        lod = int(math.floor(-math.log2(random.random()) / 2))
+        if lod > var2.MAX_MIP_LEVEL:
+            lod = var2.MAX_MIP_LEVEL
+    dataset = datasets[lod]
+    data_size = dataset.shape[1]
+    re_crop_size = max(1, crop_size // pow(2, lod))
+    coord = torch.randint(0, data_size - re_crop_size + 1, (num_crops, dim))
+    crops = []
+    for c in coord.tolist():
+        sl = (slice(None),) + tuple(slice(c[a], c[a] + re_crop_size) for a in range(dim))
+        crops.append(dataset[sl].reshape(dataset.shape[0], -1).T)
+    return torch.stack(crops), coord.to(dataset.device), lod
+
+
+# ------------------------------------------------------------------------------------------------ fused training
+class FusedTrainer:
+    """The body of train_models (image_compression.py:215-269) as fused CUDA launches per step:
+    one forward+backward kernel (gather, noise, MLP, MSE, backward, grid-gradient scatter), an optional
+    single NCCL all-reduce of the flat gradient buffer (data parallel), and one fused Adam (+ cosine LR,
+    + clamp of the active grids, + gradient zeroing).
+
+    Semantics kept from the reference: Adam defaults with lr 0.01 (grids) / 0.005 (decoder) and
+    CosineAnnealingLR(T_max=NUM_EPOCHS) (:361-365); per-tensor Adam step counts — grids of inactive levels
+    are skipped entirely; noise on every input column while epoch < 0.95 N (:248-254); freeze +
+    quantise the grids once epoch > 0.95 N (:227-231); clamp of the two active grids after each step (:269).
+    """
+
+    def __init__(self, fp, decoder, num_epochs=None, fp_bits=None, lr_fp=0.01, lr_mlp=0.005, betas=(0.9, 0.999),
+                 eps=1e-8, method=None, level_table=None, process_group=None, seed=0):
+        self.fp = [_check_grid(g.detach()) for g in fp]
+        self.decoder = decoder
+        self.params = [p.detach() for p in decoder.parameters_list()]
+        self.num_epochs = var2.NUM_EPOCHS if num_epochs is None else num_epochs
+        self.bits = var2.FP_BITS if fp_bits is None else fp_bits
+        self.lr_fp, self.lr_mlp, self.betas, self.eps = lr_fp, lr_mlp, betas, eps
+        self.method = _method() if method is None else method
+        self.dim = 2 if self.method == L.METHOD_2D else 3
+        self.table = feature_pyramid_mip_levels() if level_table is None else level_table
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.seed = seed
+        self.epoch = 0
+        self.frozen = False
+        dev = self.fp[0].device
+        self.device = dev
+        # one flat gradient buffer per pyramid level: [dG0 | dG1 | dW1 db1 dW2 db2 dW3 db3 | loss] -> one all-reduce
+        self._flat = {}
+        self.state = {}          # id -> (m, v, t)
+        self.q_min = -(pow(2, self.bits) - 1) / pow(2, self.bits + 1)
+
+    # -- buffers
+    def _level_buffers(self, fl):
+        if fl not in self._flat:
+            sizes = [self.fp[2 * fl].numel(), self.fp[2 * fl + 1].numel()] + [p.numel() for p in self.params] + [4]
+            offs, total = [], 0
+            for s in sizes:
+                offs.append(total)
+                total += (s + 3) // 4 * 4          # keep every view 16-byte aligned
+            flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+            views = [flat[o:o + s] for o, s in zip(offs, sizes)]
+            self._flat[fl] = (flat, views)
+        return self._flat[fl]
+
+    def _adam_state(self, key, like):
+        if key not in self.state:
+            self.state[key] = [torch.zeros_like(like), torch.zeros_like(like), 0]
+        return self.state[key]
+
+    def lr_scale(self, epoch):
+        """CosineAnnealingLR closed form, eta_min = 0 (image_compression.py:365)."""
+        return (1.0 + math.cos(math.pi * epoch / self.num_epochs)) / 2.0 if self.num_epochs > 0 else 1.0
+
+    def step(self, coord, targets, lod, noise=None, out=None):
+        """One training step.  coord [NC, D] crop origins (int64), targets [NC, S^D, Cout] or [N, Cout] float32,
+        lod = mip level of this step.  noise: None -> in-kernel Philox noise while epoch < .95 N;
+        a tensor [N, Cin] -> injected noise (parity tests); False -> no noise.  Returns the loss (0-dim
+        device tensor, mean over N*Cout, averaged over ranks when data parallel)."""
+        lib = L.load_library()
+        epoch = self.epoch
+        if epoch > self.num_epochs * 0.95 and not self.frozen:       # image_compression.py:227-231
+            for i, g in enumerate(self.fp):
+                g.copy_(quantize4fp(g, self.bits))
+            self.frozen = True
+        fl = self.table[lod]
+        g0, g1 = self.fp[2 * fl], self.fp[2 * fl + 1]
+        sample_number = pow(2, max(0, (8 if self.dim == 2 else var2.CROP_MIP_LEVEL) - lod))
+        coord = L.origins_tensor(coord, self.device, self.dim)
+        nc = coord.shape[0]
+        geom = L.make_geom(self.method, g0, g1, sample_number, nc, _step_log2(lod, fl), lod, var2.PE_CHANNELS,
+                           _pe_kind(self.method))
+        m = L.make_mlp(self.params)
+        n = nc * sample_number ** self.dim
+        targets = targets.detach().to(torch.float32).reshape(n, m.cout).contiguous()
+        flat, views = self._level_buffers(fl)
+        gm = L.make_mlp_grad(views[2:8])
+        noise_bits, noise_t = 0, None
+        if epoch < self.num_epochs * 0.95 and noise is not False:   # image_compression.py:248-254
+            if torch.is_tensor(noise):
+                noise_t = noise.detach().to(torch.float32).contiguous()
+                if tuple(noise_t.shape) != (n, m.cin):
+                    raise ValueError(f"noise must be [{n}, {m.cin}]")
+            else:
+                noise_bits = self.bits
+        h = L.handle(self.device)
+        st = L.stream_ptr(self.device)
+        rank = torch.distributed.get_rank(self.pg) if self.world > 1 else 0
+        L.check(h, lib.nic_train_step(h, C.byref(geom), L.ptr(g0), L.ptr(g1), L.ptr(coord), C.byref(m), L.ptr(targets),
+                                      L.ptr(noise_t), noise_bits, self.seed + 7919 * rank, epoch, n * self.world,
+                                      C.byref(gm), L.ptr(None if self.frozen else views[0]),
+                                      L.ptr(None if self.frozen else views[1]), L.ptr(views[8]), L.ptr(out),
+                                      L.PREC_F32, st))
+        if self.world > 1:                                           # the one exchange step of the path
+            torch.distributed.all_reduce(flat, group=self.pg)
+        loss = views[8][0] / float(n * self.world * m.cout)
+        # Adam on the tensors that received a gradient this step (per-tensor step counts)
+        scale = self.lr_scale(epoch)
+        entries = []
+        if not self.frozen:
+            for j, (g, dg) in enumerate(((g0, views[0]), (g1, views[1]))):
+                entries.append((("g", 2 * fl + j), g.view(-1), dg, self.lr_fp * scale, True))
+        for i, p in enumerate(self.params):
+            entries.append((("p", i), p.view(-1), views[2 + i], self.lr_mlp * scale, False))
+        arr = (L.NicAdamTensor * len(entries))()
+        for k, (key, p, g, lr, clamp) in enumerate(entries):
+            stt = self._adam_state(key, p)
+            stt[2] += 1
+            a = arr[k]
+            a.p, a.g, a.m, a.v = p.data_ptr(), g.data_ptr(), stt[0].data_ptr(), stt[1].data_ptr()
+            a.numel, a.lr, a.t = p.numel(), lr, stt[2]
+            a.clamp, a.clamp_lo, a.clamp_hi = int(clamp), self.q_min, 0.5
+        loss = loss.clone()                     # views[8] is zeroed below
+        L.check(h, lib.nic_adam_step(h, arr, len(entries), self.betas[0], self.betas[1], self.eps, 1.0, 1, st))
+        views[8].zero_()
+        self.epoch += 1
+        return loss
