@@ -85,6 +85,7 @@ int nic_destroy(NicHandle* h) {
   cudaGetDevice(&cur);
   cudaSetDevice(h->device);
   if (h->tc_weights) cudaFree(h->tc_weights);
+  if (h->tc_shadow) cudaFree(h->tc_shadow);
   if (h->adam_desc) cudaFree(h->adam_desc);
   cudaSetDevice(cur);
   delete h;

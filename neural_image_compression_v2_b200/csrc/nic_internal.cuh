@@ -25,6 +25,8 @@ struct Handle {
   // scratch owned by the handle (device memory)
   void* tc_weights;          // packed f16/bf16 UMMA operand images of the decoder weights
   size_t tc_weights_bytes;
+  void* tc_shadow;           // 16-bit channel-last shadows of the two active grids
+  size_t tc_shadow_bytes;
   void* adam_desc;           // device copy of NicAdamTensor descriptors
   size_t adam_desc_bytes;
 };

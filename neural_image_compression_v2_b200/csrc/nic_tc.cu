@@ -195,9 +195,41 @@ __global__ void pack_weights_kernel(MlpDev m, float lod, int KX, uint16_t* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------ shadow grids
+// The tensor-core path reads 16-bit, channel-LAST copies of the two active grids, transposed so that the fast texel
+// axis is contiguous: shadow[((x*Ny + y)*Nz + z)*C + c] = grid[c][z][y][x]  (2-D: Nz = 1, shadow[(x*Ny + y)*C + c]).
+// One node = C*2 bytes (24 B at C = 12) -> a corner is three 8-byte loads that land in the operand registers as is.
+// Written once per decode call by relayout_kernel (coalesced both ways through shared memory).
+template <int FMT>
+__global__ void __launch_bounds__(256) relayout_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C,
+                                                       int nx, int nf, int no, long long sf, long long so,
+                                                       long long plane) {
+  // tile: 32 nodes along x  x  32 nodes along the output-fast axis f, all channels; blockIdx.z = the other axis
+  extern __shared__ uint16_t tile[];           // [C][32][33]
+  const int x0 = blockIdx.x * 32, f0 = blockIdx.y * 32, o = blockIdx.z;
+  for (int i = threadIdx.x; i < C * 1024; i += blockDim.x) {
+    int c = i >> 10, r = i & 1023, fi = r >> 5, xi = r & 31;
+    int x = x0 + xi, f = f0 + fi;
+    float v = (x < nx && f < nf) ? __ldg(src + (long long)c * plane + (long long)f * sf + (long long)o * so + x) : 0.f;
+    tile[(c * 32 + fi) * 33 + xi] = to16<FMT>(v);
+  }
+  __syncthreads();
+  const int fw = nf - f0 < 32 ? nf - f0 : 32;   // valid nodes along f in this tile
+  for (int xi = 0; xi < 32 && x0 + xi < nx; ++xi) {
+    uint16_t* row = dst + (((long long)(x0 + xi) * no + o) * nf + f0) * C;
+    for (int i = threadIdx.x; i < fw * C; i += blockDim.x) {
+      int fi = i / C, c = i - fi * C;
+      row[i] = tile[(c * 32 + fi) * 33 + xi];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ gather to registers
-// Decoder-input row of one texel for C = 12, PE = 6 with every index a compile-time constant (the row lives in
-// registers).  Column cin-1 (the LOD input) becomes the constant 1 that carries the layer-1 bias.
+// Decoder-input row of one texel for C = 12, PE = 6, built directly as packed 16-bit pairs (the operand-A registers):
+//   pairs [6j, 6j+6)         corner j of G0 (raw copy of the shadow node)
+//   pairs [6*NC0, 6*NC0+6)   sum_j w_j * G1 corner j   (packed fma; w_j exact in f16)
+//   then 3 pairs per axis    positional encoding (shared-memory LUT for the triangular kind)
+//   half CIN-1               constant 1 carrying the layer-1 bias (+ LOD), remaining halves 0.
 template <int METHOD>
 struct RowShape {
   static constexpr int DIM = METHOD == NIC_METHOD_2D ? 2 : 3;
@@ -208,42 +240,94 @@ struct RowShape {
   static constexpr int KX = (CIN + 15) / 16 * 16;            // 80 / 128 / 80
 };
 
-template <int METHOD>
-__device__ __forceinline__ void gather_row_regs(const DevGeom& g, const float* __restrict__ g0,
-                                                const float* __restrict__ g1, const AxisCoord* ax, float* xf) {
+static long long plane_size_host(const int* n, int dim) {
+  return dim == 2 ? (long long)n[0] * n[1] : (long long)n[0] * n[1] * n[2];
+}
+
+struct ShadowGeom {
+  const uint2* s0;   // shadow of G0, 3 x uint2 per node
+  const uint2* s1;   // shadow of G1
+};
+
+__device__ __forceinline__ int node_lin(const int* n, int dim, int x, int y, int z) {
+  // shadow order: x slowest, then y, then z (2-D: x, y)
+  return dim == 2 ? x * n[1] + y : (x * n[1] + y) * n[2] + z;
+}
+
+template <int METHOD, int FMT>
+__device__ __forceinline__ void gather_row_packed(const DevGeom& g, const ShadowGeom& sg, const int* p,
+                                                  const uint4* __restrict__ pe_lut, int lut_mask, uint32_t* xp) {
   using S = RowShape<METHOD>;
-  const long long ps0 = plane_size(g.n0, S::DIM), ps1 = plane_size(g.n1, S::DIM);
+  using P = Pair<FMT>;
+  AxisCoord ax[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    ax[a] = axis_coord(p[a], g.step);
+    // memory safety for device-supplied origins (host-known origins are validated): keep i, i+1 inside the grid
+    ax[a].i0 = clampi(ax[a].i0, 0, g.n0[a] - 2 < 0 ? 0 : g.n0[a] - 2);
+    ax[a].i1 = clampi(ax[a].i1, 0, g.n1[a] - 2 < 0 ? 0 : g.n1[a] - 2);
+  }
+  // ---- G0 corners: raw copies
 #pragma unroll
   for (int j = 0; j < S::NC0; ++j) {
     const int8_t* d = S::DIM == 2 ? kCorner2D[j] : (METHOD == NIC_METHOD_3D ? kCorner3D[j] : kCorner3Dv2[j]);
-    const float* p = g0 + node_index(g.n0, S::DIM, ax[0].i0 + d[2], ax[1].i0 + d[1], ax[2].i0 + d[0]);
+    int dz = S::DIM == 3 ? d[0] : 0;
+    const uint2* node = sg.s0 + 3 * node_lin(g.n0, S::DIM, ax[0].i0 + d[2], ax[1].i0 + d[1], ax[2].i0 + dz);
 #pragma unroll
-    for (int c = 0; c < S::C; ++c) xf[j * S::C + c] = __ldg(p + (long long)c * ps0);
+    for (int q = 0; q < 3; ++q) {
+      uint2 v = __ldg(node + q);
+      xp[6 * j + 2 * q] = v.x;
+      xp[6 * j + 2 * q + 1] = v.y;
+    }
   }
-  float w[S::NC1];
-  const float* p1[S::NC1];
+  // ---- G1: weighted sum of corners
+  typename P::T2 acc[6];
 #pragma unroll
   for (int j = 0; j < S::NC1; ++j) {
     const int8_t* d = S::DIM == 2 ? kCorner2D[j] : kCorner3D[j];
-    p1[j] = g1 + node_index(g.n1, S::DIM, ax[0].i1 + d[2], ax[1].i1 + d[1], ax[2].i1 + d[0]);
+    int dz = S::DIM == 3 ? d[0] : 0;
+    const uint2* node = sg.s1 + 3 * node_lin(g.n1, S::DIM, ax[0].i1 + d[2], ax[1].i1 + d[1], ax[2].i1 + dz);
     float f[3];
     g1_factors(g, j, ax, f);
-    w[j] = f[0] * f[1] * f[2];
+    float w = f[0] * f[1];
+    if (S::DIM == 3) w *= f[2];
+    typename P::T2 w2 = P::cst(w);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      uint2 v = __ldg(node + q);
+      typename P::T2 a = *reinterpret_cast<typename P::T2*>(&v.x), b = *reinterpret_cast<typename P::T2*>(&v.y);
+      acc[2 * q] = j == 0 ? __hmul2(a, w2) : __hfma2(a, w2, acc[2 * q]);
+      acc[2 * q + 1] = j == 0 ? __hmul2(b, w2) : __hfma2(b, w2, acc[2 * q + 1]);
+    }
   }
 #pragma unroll
-  for (int c = 0; c < S::C; ++c) {
-    float acc = 0.f;
+  for (int q = 0; q < 6; ++q) xp[6 * S::NC0 + q] = *reinterpret_cast<uint32_t*>(&acc[q]);
+  // ---- positional encoding: 3 pairs per axis
+  constexpr int PE0 = 6 * (S::NC0 + 1);
 #pragma unroll
-    for (int j = 0; j < S::NC1; ++j) acc = fmaf(__ldg(p1[j] + (long long)c * ps1), w[j], acc);
-    xf[S::NC0 * S::C + c] = acc;
+  for (int a = 0; a < S::DIM; ++a) {
+    if (g.pe_kind == NIC_PE_TRIANGULAR) {
+      uint4 e = pe_lut[p[a] & lut_mask];       // the encoding is periodic in the texel coordinate (period 16/step)
+      xp[PE0 + 3 * a] = e.x;
+      xp[PE0 + 3 * a + 1] = e.y;
+      xp[PE0 + 3 * a + 2] = e.z;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        float arg = __fmul_rn(ax[a].u1, g.pe_div[q]);
+        auto v = P::pack(sinf(arg), cosf(arg));
+        xp[PE0 + 3 * a + q] = *reinterpret_cast<uint32_t*>(&v);
+      }
+    }
   }
+  // ---- bias carrier and padding.  CIN - 1 is even for all three methods: the 1 sits in the low half of its pair.
+  static_assert((S::CIN - 1) % 2 == 0, "bias column must be the low half of a pair");
+  {
+    auto one = P::pack(1.0f, 0.0f);
+    xp[(S::CIN - 1) / 2] = *reinterpret_cast<uint32_t*>(&one);
 #pragma unroll
-  for (int a = 0; a < S::DIM; ++a)
-#pragma unroll
-    for (int r = 0; r < S::PE; ++r) xf[(S::NC0 + 1) * S::C + a * S::PE + r] = pe_value(g, ax[a].u1, r);
-  xf[S::CIN - 1] = 1.0f;
-#pragma unroll
-  for (int k = S::CIN; k < S::KX; ++k) xf[k] = 0.f;
+    for (int i = (S::CIN - 1) / 2 + 1; i < S::KX / 2; ++i) xp[i] = 0u;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -252,31 +336,45 @@ constexpr int TC_TMEM_COLS = 128;
 constexpr int TC_COL_D = 0;     // accumulator columns [0, 64)
 constexpr int TC_COL_A = 64;    // operand-A columns   [64, 64 + KX/2)
 constexpr int TC_K2 = 80;       // K of layers 2/3: 64 hidden + the bias block
+constexpr int TC_LUT_MAX = 256; // positional-encoding LUT entries (period 16/step texels)
 
 template <int METHOD, int FMT, typename OutT>
-__global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, const float* __restrict__ g0,
-                                                                  const float* __restrict__ g1,
+__global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, ShadowGeom sg,
                                                                   const long long* __restrict__ origins,
                                                                   const uint4* __restrict__ wimg, int cout,
-                                                                  OutT* __restrict__ out) {
+                                                                  int lut_n, OutT* __restrict__ out) {
   using S = RowShape<METHOD>;
+  using P = Pair<FMT>;
   constexpr int KX = S::KX;
   constexpr int W1_BYTES = b_image_bytes(64, KX), W2_BYTES = b_image_bytes(64, TC_K2), W3_BYTES = b_image_bytes(16, TC_K2);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sW1 = smem_raw;
   uint8_t* sW2 = sW1 + W1_BYTES;
   uint8_t* sW3 = sW2 + W2_BYTES;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sW3 + W3_BYTES);
+  uint4* sLut = reinterpret_cast<uint4*>(sW3 + W3_BYTES);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sLut + TC_LUT_MAX);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  // ---- one-time setup: TMEM allocation, barrier, weight images -> shared memory
+  // ---- one-time setup: TMEM allocation, barrier, weight images and PE LUT -> shared memory
   if (warp == 0) tmem_alloc(tmem_slot, TC_TMEM_COLS);
   if (tid == 0) mbar_init(mbar, 1);
   {
     uint4* dst = reinterpret_cast<uint4*>(smem_raw);
     constexpr int NV = (W1_BYTES + W2_BYTES + W3_BYTES) / 16;
     for (int i = tid; i < NV; i += TC_THREADS) dst[i] = __ldg(wimg + i);
+    for (int i = tid; i < lut_n; i += TC_THREADS) {
+      float u1 = __fmul_rn(__fmul_rn((float)i, g.step), 0.5f);
+      uint4 e;
+      auto v0 = P::pack(pe_triangular(u1, 0, 6), pe_triangular(u1, 1, 6));
+      auto v1 = P::pack(pe_triangular(u1, 2, 6), pe_triangular(u1, 3, 6));
+      auto v2 = P::pack(pe_triangular(u1, 4, 6), pe_triangular(u1, 5, 6));
+      e.x = *reinterpret_cast<uint32_t*>(&v0);
+      e.y = *reinterpret_cast<uint32_t*>(&v1);
+      e.z = *reinterpret_cast<uint32_t*>(&v2);
+      e.w = 0u;
+      sLut[i] = e;
+    }
   }
   fence_async_smem();            // weights (generic-proxy stores) -> visible to the tensor core (async proxy)
   tc_fence_before();
@@ -295,20 +393,11 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, con
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long n = tile * TC_THREADS + tid;
     const bool live = n < g.N;
-    // ---- gather: the row of this thread's texel -> 16-bit pairs -> TMEM operand A
+    // ---- gather: the row of this thread's texel as 16-bit pairs -> TMEM operand A
     {
       Texel t = texel_of(g, live ? n : g.N - 1, origins);
-      AxisCoord ax[3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) ax[a] = axis_coord(t.p[a], g.step);
-      float xf[KX];
-      gather_row_regs<METHOD>(g, g0, g1, ax, xf);
       uint32_t xp[KX / 2];
-#pragma unroll
-      for (int i = 0; i < KX / 2; ++i) {
-        auto v = Pair<FMT>::pack(xf[2 * i], xf[2 * i + 1]);
-        xp[i] = *reinterpret_cast<uint32_t*>(&v);
-      }
+      gather_row_packed<METHOD, FMT>(g, sg, t.p, sLut, lut_n - 1, xp);
 #pragma unroll
       for (int i = 0; i + 16 <= KX / 2; i += 16) tmem_st16(tA + lane_base + i, xp + i);
       if ((KX / 2) % 16 == 8) tmem_st8(tA + lane_base + (KX / 2 - 8), xp + (KX / 2 - 8));
@@ -330,19 +419,19 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, con
     // ---- epilogue of layers 1 and 2: D -> 2*gelu -> H (operand A of the next layer), bias block [1, 0, ...]
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t acc[32];
-        tmem_ld32(tD + lane_base + half * 32, acc);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        uint32_t acc[16];
+        tmem_ld16(tD + lane_base + q * 16, acc);
         tc_wait_ld();
-        uint32_t hp[16];
+        uint32_t hp[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) hp[i] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-        tmem_st16(tA + lane_base + half * 16, hp);
+        for (int i = 0; i < 8; ++i) hp[i] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+        tmem_st8(tA + lane_base + q * 8, hp);
       }
-      {
+      if (layer == 0) {          // the bias block survives layer 2's epilogue, which rewrites columns [0, 32) only
         uint32_t ones[8];
-        auto one = Pair<FMT>::pack(1.0f, 0.0f);
+        auto one = P::pack(1.0f, 0.0f);
         ones[0] = *reinterpret_cast<uint32_t*>(&one);
 #pragma unroll
         for (int i = 1; i < 8; ++i) ones[i] = 0u;
@@ -353,15 +442,11 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, con
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        if (layer == 0) {
+        const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
+        const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
 #pragma unroll
-          for (int kc = 0; kc < TC_K2 / 16; ++kc)
-            mma_ts(tD, tA + kc * 8, make_smem_desc(aW2 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
-        } else {
-#pragma unroll
-          for (int kc = 0; kc < TC_K2 / 16; ++kc)
-            mma_ts(tD, tA + kc * 8, make_smem_desc(aW3 + kc * 2 * LBO_16, LBO_16, SBO), IDESC_16, kc > 0);
-        }
+        for (int kc = 0; kc < TC_K2 / 16; ++kc)
+          mma_ts(tD, tA + kc * 8, make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
         tc_commit(mbar);
       }
       mbar_wait(mbar, phase);
@@ -391,31 +476,70 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, con
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
+static int ensure_scratch(void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return NIC_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  size_t sz = (need + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+  if (cudaMalloc(ptr, sz) != cudaSuccess) return NIC_ERR_SCRATCH;
+  *have = sz;
+  return NIC_OK;
+}
+
+template <int FMT>
+static int launch_relayout(Handle* h, const DevGeom& g, const float* src, const int* nodes, uint16_t* dst, cudaStream_t st) {
+  const int dim = g.dim;
+  const int nx = nodes[0], nf = dim == 2 ? nodes[1] : nodes[2], no = dim == 2 ? 1 : nodes[1];
+  const long long sf = dim == 2 ? nx : (long long)nodes[1] * nx, so = dim == 2 ? 0 : nx;
+  const long long plane = (long long)nx * nodes[1] * (dim == 2 ? 1 : nodes[2]);
+  dim3 grid((nx + 31) / 32, (nf + 31) / 32, no);
+  size_t smem = (size_t)g.C * 32 * 33 * sizeof(uint16_t);
+  relayout_kernel<FMT><<<grid, 256, smem, st>>>(src, dst, g.C, nx, nf, no, sf, so, plane);
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
 template <int METHOD, int FMT, typename OutT>
 static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float* g0, const float* g1,
                        const long long* origins, OutT* out, cudaStream_t st) {
   using S = RowShape<METHOD>;
   constexpr int IMG = b_image_bytes(64, S::KX) + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2);
-  if (h->tc_weights_bytes < (size_t)IMG) {
-    if (h->tc_weights) cudaFree(h->tc_weights);
-    h->tc_weights = nullptr;
-    h->tc_weights_bytes = 0;
-    if (cudaMalloc(&h->tc_weights, 64 * 1024) != cudaSuccess) return NIC_ERR_SCRATCH;
-    h->tc_weights_bytes = 64 * 1024;
-  }
+  int rc = ensure_scratch(&h->tc_weights, &h->tc_weights_bytes, 64 * 1024);
+  if (rc) return rc;
+  // 16-bit channel-last shadows of the two active grids
+  const long long nodes0 = plane_size_host(g.n0, g.dim), nodes1 = plane_size_host(g.n1, g.dim);
+  const size_t b0 = ((size_t)nodes0 * g.C * 2 + 255) & ~(size_t)255, b1 = ((size_t)nodes1 * g.C * 2 + 255) & ~(size_t)255;
+  rc = ensure_scratch(&h->tc_shadow, &h->tc_shadow_bytes, b0 + b1);
+  if (rc) return rc;
+  uint16_t* s0 = (uint16_t*)h->tc_shadow;
+  uint16_t* s1 = (uint16_t*)((uint8_t*)h->tc_shadow + b0);
+  cudaError_t e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
+  if (e != cudaSuccess) return (int)e;
+  e = (cudaError_t)launch_relayout<FMT>(h, g, g1, g.n1, s1, st);
+  if (e != cudaSuccess) return (int)e;
   pack_weights_kernel<FMT><<<16, 256, 0, st>>>(m, g.lod, S::KX, (uint16_t*)h->tc_weights);
   h->launches++;
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
+  // positional-encoding LUT length: the triangular encoding has period 16/step texels
+  int lut_n = 1;
+  {
+    float period = 16.0f / g.step;
+    while (lut_n < period && lut_n < TC_LUT_MAX) lut_n <<= 1;
+    if (g.pe_kind == NIC_PE_TRIANGULAR && (float)lut_n < period) return NIC_ERR_UNSUPPORTED;
+  }
   // 56 KB of dynamic shared memory per CTA caps residency at 4 CTAs/SM = 4 x 128 TMEM columns = all 512.
   size_t smem = 56 * 1024;
+  static_assert(IMG + TC_LUT_MAX * 16 + 64 <= 56 * 1024, "shared memory budget");
   auto kern = decode_tc_kernel<METHOD, FMT, OutT>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   long long ntiles = (g.N + TC_THREADS - 1) / TC_THREADS;
   long long cap = (long long)h->sms * 4;
   int grid = (int)(ntiles < cap ? ntiles : cap);
-  kern<<<grid, TC_THREADS, smem, st>>>(g, g0, g1, origins, (const uint4*)h->tc_weights, m.cout, out);
+  ShadowGeom sg = {(const uint2*)s0, (const uint2*)s1};
+  kern<<<grid, TC_THREADS, smem, st>>>(g, sg, origins, (const uint4*)h->tc_weights, m.cout, lut_n, out);
   h->launches++;
   return (int)cudaGetLastError();
 }
