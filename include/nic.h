@@ -95,6 +95,11 @@ const char* nic_status_string(int status);
 /* Number of kernel launches this handle has enqueued so far (bench.py reports it as `gpu_launches`). */
 int64_t nic_launch_count(const NicHandle* h);
 
+/* Tuning / testing knobs.  NIC_OPT_DISABLE_FAST2D = 1 forces the general tensor-core decode kernel even when the
+ * geometry qualifies for the aligned full-resolution 2-D fast path (both must give the same image). */
+enum { NIC_OPT_DISABLE_FAST2D = 1 };
+int nic_set_option(NicHandle* h, int option, int value);
+
 /* ---- decoder input (K1) ------------------------------------------------------------------------------- */
 /* Width of the decoder input for a geometry: C*(corners+1) + PE*D + 1 (Projects/var2.py:114-118). */
 int nic_cin(const NicGeom* g);

@@ -57,6 +57,7 @@ SYMBOLS = {
     "nic_last_error_string": (C.c_char_p, [_P]),
     "nic_status_string": (C.c_char_p, [_I]),
     "nic_launch_count": (_L, [_P]),
+    "nic_set_option": (_I, [_P, _I, _I]),
     "nic_cin": (_I, [C.POINTER(NicGeom)]),
     "nic_gather": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, _P, _I, _P]),
     "nic_scatter": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, _P, _P]),
@@ -113,6 +114,14 @@ def handle(device):
             raise NicError(rc, lib.nic_last_error_string(None).decode())
         _handles[idx] = h
     return _handles[idx]
+
+
+OPT_DISABLE_FAST2D = 1
+
+
+def set_option(device, option, value):
+    h = handle(device)
+    check(h, load_library().nic_set_option(h, option, int(value)))
 
 
 def check(h, rc):

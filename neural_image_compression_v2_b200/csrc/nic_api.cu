@@ -94,6 +94,12 @@ int nic_destroy(NicHandle* h) {
 
 int64_t nic_launch_count(const NicHandle* h) { return h ? h->launches : 0; }
 
+int nic_set_option(NicHandle* h, int option, int value) {
+  if (!h) return fail(nullptr, NIC_ERR_ARG, "handle is NULL");
+  if (option == NIC_OPT_DISABLE_FAST2D) { h->disable_fast2d = value != 0; return NIC_OK; }
+  return fail(h, NIC_ERR_ARG, "nic_set_option: unknown option %d", option);
+}
+
 int nic_cin(const NicGeom* g) {
   if (!g) return NIC_ERR_ARG;
   int dim = g->method == NIC_METHOD_2D ? 2 : 3;
@@ -138,6 +144,18 @@ static int flatten_geom(NicHandle* h, const NicGeom* g, bool have_origins, DevGe
     d->per_block *= d->B[a];
   }
   d->N = d->per_block * d->nblocks;
+  {
+    long long divs[3] = {d->per_block, (long long)d->B[1] * d->B[2], d->B[2]};
+    for (int i = 0; i < 3; ++i) {
+      unsigned long long dv = divs[i] > 0 ? (unsigned long long)divs[i] : 1ull;
+      unsigned sh = 0;
+      while ((1ull << sh) < dv) ++sh;
+      if (dv >= (1ull << 31)) { d->fd_mul[i] = 0; d->fd_shift[i] = 0; continue; }   // quotient is 0 for n < 2^31
+      unsigned long long num = 1ull << (31 + sh);
+      d->fd_mul[i] = (unsigned)((num + dv - 1) / dv);
+      d->fd_shift[i] = sh;
+    }
+  }
   for (int i = 0; i < NIC_MAX_PE; ++i) d->pe_div[i] = g->pe_div[i];
   if (!have_origins) {
     if (d->nblocks > 1) return fail(h, NIC_ERR_ARG, "origins is NULL but num_blocks = %d", d->nblocks);

@@ -28,6 +28,8 @@ struct DevGeom {
   float pe_div[NIC_MAX_PE];
   long long per_block;                            // B[0]*B[1]*B[2]
   long long N;                                    // nblocks*per_block
+  // exact division of n < 2^31 by per_block, B[1]*B[2] and B[2]: q = (n * mul) >> (31 + shift)
+  unsigned fd_mul[3], fd_shift[3];
 };
 
 // corner tables, (dz,dy,dx) as the reference orders them
@@ -103,6 +105,31 @@ __device__ __forceinline__ Texel texel_of(const DevGeom& g, long long n, const l
   t.p[0] = o[0] + ix;
   t.p[1] = o[1] + iy;
   t.p[2] = o[2] + iz;
+  return t;
+}
+
+// n / d for n < 2^31 with mul = ceil(2^(31+shift) / d), shift = ceil(log2 d): one wide multiply and a shift.
+__device__ __forceinline__ unsigned fastdiv31(unsigned n, unsigned mul, unsigned shift) {
+  return (unsigned)(((unsigned long long)n * mul) >> (31 + shift));
+}
+
+// texel_of for N < 2^31 without 64-bit division (the tensor-core kernels' per-tile index math).
+__device__ __forceinline__ Texel texel_of_fast(const DevGeom& g, unsigned n, const long long* origins) {
+  Texel t;
+  unsigned b = fastdiv31(n, g.fd_mul[0], g.fd_shift[0]);
+  unsigned r = n - b * (unsigned)g.per_block;
+  unsigned ix = fastdiv31(r, g.fd_mul[1], g.fd_shift[1]);
+  unsigned r2 = r - ix * (unsigned)(g.B[1] * g.B[2]);
+  unsigned iy = fastdiv31(r2, g.fd_mul[2], g.fd_shift[2]);
+  unsigned iz = r2 - iy * (unsigned)g.B[2];
+  t.b = (int)b;
+  int o[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    o[a] = origins ? (a < g.dim ? (int)origins[(long long)b * g.dim + a] : 0) : (b == 0 ? g.origin0[a] : 0);
+  t.p[0] = o[0] + (int)ix;
+  t.p[1] = o[1] + (int)iy;
+  t.p[2] = o[2] + (int)iz;
   return t;
 }
 

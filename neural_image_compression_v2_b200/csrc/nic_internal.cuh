@@ -27,6 +27,7 @@ struct Handle {
   size_t tc_weights_bytes;
   void* tc_shadow;           // 16-bit channel-last shadows of the two active grids
   size_t tc_shadow_bytes;
+  int disable_fast2d;        // testing knob: force the general tensor-core kernel
   void* adam_desc;           // device copy of NicAdamTensor descriptors
   size_t adam_desc_bytes;
 };

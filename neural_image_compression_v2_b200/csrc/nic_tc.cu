@@ -50,6 +50,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires)
+// instead of burning issue slots in a spin loop.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITS_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONES_%=;\n\t"
+      "bra WAITS_%=;\n\t"
+      "DONES_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
 // tcgen05.commit: the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread is done.
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -61,6 +72,15 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -77,8 +97,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B format fmt (0 f16, 1 bf16), both K-major.
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int b_mn_major = 0) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // tcgen05.ld / st, shape 32x32b: thread i of warp w touches TMEM lane 32*(w%4)+i, one 32-bit column per register.
@@ -331,12 +352,35 @@ __device__ __forceinline__ void gather_row_packed(const DevGeom& g, const Shadow
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-constexpr int TC_THREADS = 128;
+constexpr int TC_ROWS = 128;    // texels per tile = MMA M = TMEM lanes
+constexpr int TC_THREADS = 256; // 8 warps: warps w and w+4 share TMEM lane quarter w and split the columns
 constexpr int TC_TMEM_COLS = 128;
 constexpr int TC_COL_D = 0;     // accumulator columns [0, 64)
 constexpr int TC_COL_A = 64;    // operand-A columns   [64, 64 + KX/2)
 constexpr int TC_K2 = 80;       // K of layers 2/3: 64 hidden + the bias block
 constexpr int TC_LUT_MAX = 256; // positional-encoding LUT entries (period 16/step texels)
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+
+// stores registers [lo, lo+n) of a row to operand-A columns [lo, lo+n) with the widest tcgen05.st shapes
+template <int N>
+__device__ __forceinline__ void store_row_part(uint32_t taddr, const uint32_t* r) {
+  if constexpr (N >= 16) {
+    tmem_st16(taddr, r);
+    store_row_part<N - 16>(taddr + 16, r + 16);
+  } else if constexpr (N >= 8) {
+    tmem_st8(taddr, r);
+    store_row_part<N - 8>(taddr + 8, r + 8);
+  } else if constexpr (N >= 4) {
+    tmem_st4(taddr, r);
+    store_row_part<N - 4>(taddr + 4, r + 4);
+  } else {
+    static_assert(N == 0, "row parts are multiples of 4 registers");
+  }
+}
 
 template <int METHOD, int FMT, typename OutT>
 __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, ShadowGeom sg,
@@ -346,6 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
   using S = RowShape<METHOD>;
   using P = Pair<FMT>;
   constexpr int KX = S::KX;
+  constexpr int HALF = KX / 4;   // operand-A registers per warp group
   constexpr int W1_BYTES = b_image_bytes(64, KX), W2_BYTES = b_image_bytes(64, TC_K2), W3_BYTES = b_image_bytes(16, TC_K2);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sW1 = smem_raw;
@@ -356,6 +401,8 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int grp = warp >> 2;                 // 0: columns [0, 32) of D / first half of the row; 1: the rest
+  const int row = tid & (TC_ROWS - 1);       // texel row of the tile = TMEM lane
   // ---- one-time setup: TMEM allocation, barrier, weight images and PE LUT -> shared memory
   if (warp == 0) tmem_alloc(tmem_slot, TC_TMEM_COLS);
   if (tid == 0) mbar_init(mbar, 1);
@@ -381,7 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t tD = tmem + TC_COL_D, tA = tmem + TC_COL_A;
 
   constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
@@ -389,47 +436,54 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
   const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
   uint32_t phase = 0;
 
-  const long long ntiles = (g.N + TC_THREADS - 1) / TC_THREADS;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long n = tile * TC_THREADS + tid;
-    const bool live = n < g.N;
-    // ---- gather: the row of this thread's texel as 16-bit pairs -> TMEM operand A
+  const unsigned ntiles = (unsigned)((g.N + TC_ROWS - 1) / TC_ROWS);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const unsigned n = tile * TC_ROWS + row;
+    const bool live = n < (unsigned)g.N;
+    // ---- gather: each warp group builds and stores its half of the row (the other half is dead code per branch)
     {
-      Texel t = texel_of(g, live ? n : g.N - 1, origins);
+      Texel t = texel_of_fast(g, live ? n : (unsigned)g.N - 1, origins);
       uint32_t xp[KX / 2];
-      gather_row_packed<METHOD, FMT>(g, sg, t.p, sLut, lut_n - 1, xp);
-#pragma unroll
-      for (int i = 0; i + 16 <= KX / 2; i += 16) tmem_st16(tA + lane_base + i, xp + i);
-      if ((KX / 2) % 16 == 8) tmem_st8(tA + lane_base + (KX / 2 - 8), xp + (KX / 2 - 8));
+      if (grp == 0) {
+        gather_row_packed<METHOD, FMT>(g, sg, t.p, sLut, lut_n - 1, xp);
+        store_row_part<HALF>(tA + lane_base, xp);
+      } else {
+        gather_row_packed<METHOD, FMT>(g, sg, t.p, sLut, lut_n - 1, xp);
+        store_row_part<HALF>(tA + lane_base + HALF, xp + HALF);
+      }
     }
     tc_wait_st();
     tc_fence_before();
     __syncthreads();
     // ---- layer 1
-    if (tid == 0) {
-      tc_fence_after();
+    if (warp == 0) {               // one warp issues and waits for the MMAs; the others sleep at the barrier below
+      if (tid == 0) {
+        tc_fence_after();
 #pragma unroll
-      for (int kc = 0; kc < KX / 16; ++kc)
-        mma_ts(tD, tA + kc * 8, make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
-      tc_commit(mbar);
+        for (int kc = 0; kc < KX / 16; ++kc)
+          mma_ts(tD, tA + kc * 8, make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
+        tc_commit(mbar);
+      }
+      __syncwarp();
+      mbar_wait(mbar, phase);
     }
-    mbar_wait(mbar, phase);
     phase ^= 1;
+    __syncthreads();
     tc_fence_after();
     // ---- epilogue of layers 1 and 2: D -> 2*gelu -> H (operand A of the next layer), bias block [1, 0, ...]
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
         uint32_t acc[16];
-        tmem_ld16(tD + lane_base + q * 16, acc);
+        tmem_ld16(tD + lane_base + grp * 32 + q * 16, acc);
         tc_wait_ld();
         uint32_t hp[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) hp[i] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-        tmem_st8(tA + lane_base + q * 8, hp);
+        tmem_st8(tA + lane_base + grp * 16 + q * 8, hp);
       }
-      if (layer == 0) {          // the bias block survives layer 2's epilogue, which rewrites columns [0, 32) only
+      if (layer == 0 && grp == 1) {   // the bias block survives layer 2's epilogue, which rewrites columns [0, 32) only
         uint32_t ones[8];
         auto one = P::pack(1.0f, 0.0f);
         ones[0] = *reinterpret_cast<uint32_t*>(&one);
@@ -440,21 +494,25 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
       tc_wait_st();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
-        const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
+      if (warp == 0) {
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
+          const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
 #pragma unroll
-        for (int kc = 0; kc < TC_K2 / 16; ++kc)
-          mma_ts(tD, tA + kc * 8, make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
-        tc_commit(mbar);
+          for (int kc = 0; kc < TC_K2 / 16; ++kc)
+            mma_ts(tD, tA + kc * 8, make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
+          tc_commit(mbar);
+        }
+        __syncwarp();
+        mbar_wait(mbar, phase);
       }
-      mbar_wait(mbar, phase);
       phase ^= 1;
+      __syncthreads();
       tc_fence_after();
     }
-    // ---- output: sigmoid, optional 8-bit quantisation
-    {
+    // ---- output (warp group 0): sigmoid, optional 8-bit quantisation.  Group 1 moves on to the next gather.
+    if (grp == 0) {
       uint32_t acc[16];
       tmem_ld16(tD + lane_base, acc);
       tc_wait_ld();
@@ -464,7 +522,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
           if (c < cout) {
             float z = __uint_as_float(acc[c]);
             float v = __fdividef(1.0f, 1.0f + __expf(-z));
-            store_out(out + n * cout + c, v);
+            store_out(out + (size_t)n * cout + c, v);
           }
       }
     }
@@ -473,6 +531,332 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TC_TMEM_COLS);
+}
+
+// ================================================================================================ 2-D fast path
+// Full-resolution 2-D decode (step 1/4, interpolation on, triangular PE, block aligned to 8 x 16 texels): layer 1 is
+// re-associated so that NO per-texel input is ever built.  For a tile of 8 x 16 texels:
+//   z1 = W1[:, 0:48] * (G0 corners of the texel's cell)          -> the 128 rows alias 8 cell rows (descriptor SBO = 0)
+//      + sum_nodes tent(node, texel) * R[node]                   R[node] = W1[:, 48:60] * G1[node]   (per-node table)
+//      + LUTx[px mod 64] + LUTy[py mod 64]                       LUT = W1[:, 60:72] * PE(p) (+ bias and LOD in LUTx)
+// The last two lines are ONE constant 128 x 32 selector/weight matrix (tent weights, one-hot x, one-hot y) that stays
+// in TMEM for the life of the CTA, times per-tile table rows that are addressed in shared memory as an MN-major B
+// operand.  Row m of a tile is texel (cell = m % 8, within-cell index = m / 8).
+constexpr int F_TX = 8, F_TY = 16;                 // tile extent in texels (x = first image axis)
+constexpr int F_COL_SEL = 104;                     // TMEM columns [104, 120): the selector matrix (32 halves / row)
+constexpr int F_W1G0 = b_image_bytes(64, 48);      // 6144
+constexpr int F_LUT = 64 * 64 * 2;                 // 8192 per axis
+constexpr int F_IMG = F_W1G0 + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2) + 2 * F_LUT;
+
+// R[node][n] = sum_c W1[n][4C + c] * G1[c][node], stored [x][y][64] 16-bit (128 B per node).  One thread per node:
+// 12 coalesced loads, 64 x 12 fma against weights broadcast from shared memory, one 128-byte row out.
+template <int FMT>
+__global__ void __launch_bounds__(128) g1_rows_kernel(MlpDev m, const float* __restrict__ g1, int nx, int ny,
+                                                      uint16_t* __restrict__ R) {
+  constexpr int C = 12;
+  __shared__ float w[C * 64];                 // [c][n]
+  for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) w[(i % C) * 64 + i / C] = m.w1[(i / C) * m.cin + 4 * C + (i % C)];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= nx) return;
+  const size_t nodes = (size_t)nx * ny, node = (size_t)y * nx + x;
+  float acc[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float g = __ldg(g1 + c * nodes + node);
+    const float4* wr = reinterpret_cast<const float4*>(w + c * 64);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      float4 ww = wr[q];
+      acc[4 * q] = fmaf(g, ww.x, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(g, ww.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(g, ww.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(g, ww.w, acc[4 * q + 3]);
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(R + ((size_t)x * ny + y) * 64);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 v;
+    v.x = to16<FMT>(acc[8 * q]) | ((uint32_t)to16<FMT>(acc[8 * q + 1]) << 16);
+    v.y = to16<FMT>(acc[8 * q + 2]) | ((uint32_t)to16<FMT>(acc[8 * q + 3]) << 16);
+    v.z = to16<FMT>(acc[8 * q + 4]) | ((uint32_t)to16<FMT>(acc[8 * q + 5]) << 16);
+    v.w = to16<FMT>(acc[8 * q + 6]) | ((uint32_t)to16<FMT>(acc[8 * q + 7]) << 16);
+    dst[q] = v;
+  }
+}
+
+// Weight images of the fast path: [W1g0 K-major 64x48][W2' 64x80][W3' 16x80][LUTx][LUTy]; LUT element (n, k = p mod 64)
+// at (k/8)*1024 + (n/8)*128 + (k%8)*16 + (n%8)*2  (MN-major B operand, 8 k-rows x 8 n per 128-byte block).
+template <int FMT>
+__global__ void pack_fast_kernel(MlpDev m, float lod, float step, uint16_t* __restrict__ img) {
+  const int H = 64, C = 12, PE = 6;
+  const int n1 = H * 48, n2 = H * 80, n3 = 16 * 80, nl = 64 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3 + 2 * nl; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < n1 + n2 + n3) {
+      int which = i < n1 ? 0 : (i < n1 + n2 ? 1 : 2);
+      int local = which == 0 ? i : (which == 1 ? i - n1 : i - n1 - n2);
+      int nrows = which == 2 ? 16 : H;
+      int kc = local / (nrows * 8), rem = local - kc * nrows * 8;
+      int n = rem / 8, k = kc * 8 + (rem - n * 8);
+      if (which == 0) v = m.w1[n * m.cin + k];
+      else if (which == 1) v = k < H ? 0.5f * m.w2[n * H + k] : (k == H ? m.b2[n] : 0.f);
+      else if (n < m.cout) v = k < H ? 0.5f * m.w3[n * H + k] : (k == H ? m.b3[n] : 0.f);
+    } else {
+      int local = i - (n1 + n2 + n3);
+      int axis = local / nl;
+      local -= axis * nl;
+      int kg = local / 512, rem = local - kg * 512;       // 512 elements per k-group: [n/8][k%8][n%8]
+      int ng = rem / 64, r2 = rem - ng * 64;
+      int k = kg * 8 + r2 / 8, n = ng * 8 + (r2 & 7);
+      float u1 = __fmul_rn(__fmul_rn((float)k, step), 0.5f);
+      float acc = axis == 0 ? m.b1[n] + lod * m.w1[n * m.cin + (m.cin - 1)] : 0.f;
+      for (int r = 0; r < PE; ++r) acc = fmaf(m.w1[n * m.cin + 5 * C + axis * PE + r], pe_triangular(u1, r, PE), acc);
+      v = acc;
+    }
+    img[i] = to16<FMT>(v);
+  }
+}
+
+// Fast-path kernel: 512 threads (16 warps: lane quarter = warp % 4, 16-column slice = warp / 4), two tiles in flight
+// per CTA in ping-pong so one tile's MMAs run under the other tile's epilogue; 2 CTAs per SM (256 TMEM columns each).
+//   TMEM: D0 [0,64) D1 [64,128) A0 [128,168) A1 [168,208) SEL [208,224).
+constexpr int F_THREADS = 512;
+constexpr int F_TMEM_COLS = 256;
+constexpr int F_COL_D = 0, F_COL_A = 128, F_COL_S = 208;
+constexpr int F_STAGE = 4096;                      // per-slot staging: [slot][Ag0 1 KB | G1 rows 1 KB]
+
+template <int FMT, typename OutT>
+__global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, const uint2* __restrict__ shadow0,
+                                                                   const uint4* __restrict__ R,
+                                                                   const uint4* __restrict__ wimg, int cout,
+                                                                   unsigned tiles_y, unsigned fd_mul, unsigned fd_shift,
+                                                                   OutT* __restrict__ out) {
+  using P = Pair<FMT>;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* sW = smem_raw + F_STAGE;                 // weight images + LUTs sit ABOVE the staging buffers (LBO = distance)
+  uint8_t* sW1 = sW;
+  uint8_t* sW2 = sW1 + F_W1G0;
+  uint8_t* sW3 = sW2 + b_image_bytes(64, TC_K2);
+  uint8_t* sLx = sW3 + b_image_bytes(16, TC_K2);
+  uint8_t* sLy = sLx + F_LUT;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sLy + F_LUT);       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int cs = warp >> 2;                          // which 16 accumulator columns this thread owns
+  const int row = tid & (TC_ROWS - 1);
+  if (warp == 0) tmem_alloc(tmem_slot, F_TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar + 1, 1);
+  }
+  {
+    uint4* dst = reinterpret_cast<uint4*>(sW);
+    for (int i = tid; i < F_IMG / 16; i += F_THREADS) dst[i] = __ldg(wimg + i);
+    for (int i = tid; i < F_STAGE / 16; i += F_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+
+  // ---- this thread's texel inside a tile: row m = cell + 8 * within
+  const int cell = row & 7, within = row >> 3;
+  const int lx = 4 * (cell >> 2) + (within >> 2), ly = 4 * (cell & 3) + (within & 3);
+  // ---- constants in TMEM: selector rows (slice-1 warps), bias blocks of both A slots (slice-0 warps)
+  if (cs == 1) {
+    float kx = (float)lx * 0.125f, ky = (float)(ly & 7) * 0.125f;
+    int cy1 = ly >> 3;
+    float sel[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sel[i] = 0.f;
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+      for (int iy = 0; iy < 3; ++iy) {
+        float wx = ix ? kx : 1.0f - kx;
+        float wy = iy == cy1 ? 1.0f - ky : (iy == cy1 + 1 ? ky : 0.f);
+        sel[ix * 3 + iy] = wx * wy;
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sel[8 + j] = j == lx ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sel[16 + j] = j == ly ? 1.f : 0.f;
+    uint32_t sp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      auto v = P::pack(sel[2 * i], sel[2 * i + 1]);
+      sp[i] = *reinterpret_cast<uint32_t*>(&v);
+    }
+    tmem_st16(tmem + F_COL_S + lane_base, sp);
+  } else if (cs == 0) {
+    uint32_t ones[8];
+    auto one = P::pack(1.0f, 0.0f);
+    ones[0] = *reinterpret_cast<uint32_t*>(&one);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) ones[i] = 0u;
+    tmem_st8(tmem + F_COL_A + lane_base + 32, ones);
+    tmem_st8(tmem + F_COL_A + 40 + lane_base + 32, ones);
+  }
+  tc_wait_st();
+
+  constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
+  constexpr uint32_t IDESC_64_BMN = make_idesc(FMT, 128, 64, 1);
+  constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
+  const uint32_t aStage = smem_u32(smem_raw), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  const uint32_t aLx = smem_u32(sLx), aLy = smem_u32(sLy);
+  const int ny0 = g.n0[1], ny1 = g.n1[1];
+  const unsigned ntiles = (unsigned)(g.B[0] / F_TX) * tiles_y;
+  const unsigned npairs = (ntiles + 1) >> 1;
+  uint32_t ph0 = 0, ph1 = 0;
+
+  // ---- staging: thread t < 288 fetches one piece of tile (t >= 144) of the pair
+  const int st_slot = tid >= 144, st_t = tid - 144 * st_slot;
+  const bool st_active = tid < 288;
+  uint4 pre = make_uint4(0, 0, 0, 0);
+  auto tile_origin = [&](unsigned tile, int& px0, int& py0, int& bx0, int& by0) {
+    unsigned tx = fastdiv31(tile, fd_mul, fd_shift), ty = tile - tx * tiles_y;
+    bx0 = (int)tx * F_TX;
+    by0 = (int)ty * F_TY;
+    px0 = g.origin0[0] + bx0;
+    py0 = g.origin0[1] + by0;
+  };
+  auto prefetch = [&](unsigned pair) {
+    unsigned tile = 2 * pair + st_slot;
+    if (!st_active || tile >= ntiles) return;
+    int px0, py0, bx0, by0;
+    tile_origin(tile, px0, py0, bx0, by0);
+    if (st_t < 96) {
+      int c8 = st_t / 12, piece = st_t - c8 * 12;
+      int seg = piece >= 6, off = piece - seg * 6;
+      int nx_ = (px0 >> 2) + (c8 >> 2) + seg, ny_ = (py0 >> 2) + (c8 & 3);
+      uint2 v = __ldg(shadow0 + ((size_t)nx_ * ny0 + ny_) * 3 + off);      // nodes (x, y) and (x, y + 1) are contiguous
+      pre.x = v.x;
+      pre.y = v.y;
+    } else {
+      int t2 = st_t - 96, r6 = t2 >> 3, piece = t2 & 7;
+      int nx_ = (px0 >> 3) + r6 / 3, ny_ = (py0 >> 3) + r6 % 3;
+      pre = __ldg(R + ((size_t)nx_ * ny1 + ny_) * 8 + piece);
+    }
+  };
+  auto commit_stage = [&]() {
+    if (!st_active) return;
+    uint8_t* base = smem_raw + st_slot * 2048;
+    if (st_t < 96) {
+      int c8 = st_t / 12, piece = st_t - c8 * 12;
+      int seg = piece >= 6, off = piece - seg * 6;
+      int k = seg * 24 + off * 4;
+      *reinterpret_cast<uint2*>(base + (k >> 3) * 128 + c8 * 16 + (k & 7) * 2) = make_uint2(pre.x, pre.y);
+    } else {
+      int t2 = st_t - 96, r6 = t2 >> 3, piece = t2 & 7;
+      *reinterpret_cast<uint4*>(base + 1024 + piece * 128 + r6 * 16) = pre;
+    }
+  };
+  // layer 1 of the tile in `slot`: 3 aliased-cell MMAs (G0) + [G1 rows | LUTx] + [LUTy]
+  auto issue_layer1 = [&](int slot, unsigned tile) {
+    int px0, py0, bx0, by0;
+    tile_origin(tile, px0, py0, bx0, by0);
+    const uint32_t tD = tmem + F_COL_D + slot * 64, tS = tmem + F_COL_S;
+    const uint32_t aAg0 = aStage + slot * 2048, aG1 = aAg0 + 1024;
+#pragma unroll
+    for (int kc = 0; kc < 3; ++kc)
+      mma_ss(tD, make_smem_desc(aAg0 + kc * 256, 128, 0), make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
+    const uint32_t lx_grp = aLx + ((px0 & 63) >> 3) * 1024;
+    mma_ts(tD, tS, make_smem_desc(aG1, lx_grp - aG1, SBO), IDESC_64_BMN, 1);
+    mma_ts(tD, tS + 8, make_smem_desc(aLy + ((py0 & 63) >> 3) * 1024, 1024, SBO), IDESC_64_BMN, 1);
+    tc_commit(mbar + slot);
+  };
+  auto issue_layer23 = [&](int slot, int layer) {
+    const uint32_t tD = tmem + F_COL_D + slot * 64, tA = tmem + F_COL_A + slot * 40;
+    const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
+    const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
+#pragma unroll
+    for (int kc = 0; kc < TC_K2 / 16; ++kc)
+      mma_ts(tD, tA + kc * 8, make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
+    tc_commit(mbar + slot);
+  };
+  // epilogue of one hidden layer: this thread's 16 accumulator columns -> 8 packed activations
+  auto epilogue = [&](int slot) {
+    uint32_t acc[16];
+    tmem_ld16(tmem + F_COL_D + slot * 64 + lane_base + cs * 16, acc);
+    tc_wait_ld();
+    uint32_t hp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hp[i] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+    tmem_st8(tmem + F_COL_A + slot * 40 + lane_base + cs * 8, hp);
+    tc_wait_st();
+    tc_fence_before();
+  };
+  auto output = [&](int slot, unsigned tile) {
+    if (cs != 0) return;
+    int px0, py0, bx0, by0;
+    tile_origin(tile, px0, py0, bx0, by0);
+    uint32_t acc[16];
+    tmem_ld16(tmem + F_COL_D + slot * 64 + lane_base, acc);
+    tc_wait_ld();
+    const size_t n = (size_t)(bx0 + lx) * g.B[1] + (by0 + ly);
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < cout) store_out(out + n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+    tc_fence_before();
+  };
+
+  prefetch(blockIdx.x);
+  for (unsigned pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const unsigned tA_ = 2 * pair, tB_ = 2 * pair + 1;
+    const bool hasB = tB_ < ntiles;
+    commit_stage();
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_layer1(0, tA_);
+      if (hasB) issue_layer1(1, tB_);
+    }
+    prefetch(pair + gridDim.x);                 // next pair's operands: in flight during this pair's epilogues
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+      mbar_wait_sleep(mbar, ph0);
+      ph0 ^= 1;
+      tc_fence_after();
+      epilogue(0);
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        issue_layer23(0, layer);
+      }
+      if (hasB) {
+        mbar_wait_sleep(mbar + 1, ph1);
+        ph1 ^= 1;
+        tc_fence_after();
+        epilogue(1);
+      }
+      __syncthreads();
+      if (hasB && tid == 0) {
+        tc_fence_after();
+        issue_layer23(1, layer);
+      }
+    }
+    mbar_wait_sleep(mbar, ph0);
+    ph0 ^= 1;
+    tc_fence_after();
+    output(0, tA_);
+    if (hasB) {
+      mbar_wait_sleep(mbar + 1, ph1);
+      ph1 ^= 1;
+      tc_fence_after();
+      output(1, tB_);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, F_TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
@@ -500,10 +884,61 @@ static int launch_relayout(Handle* h, const DevGeom& g, const float* src, const 
   return (int)cudaGetLastError();
 }
 
+static bool fast2d_eligible(const DevGeom& g, const long long* origins) {
+  return g.method == NIC_METHOD_2D && g.step == 0.25f && g.interp && g.pe_kind == NIC_PE_TRIANGULAR && !origins &&
+         g.nblocks == 1 && g.B[0] % F_TX == 0 && g.B[1] % F_TY == 0 && g.origin0[0] % F_TX == 0 &&
+         g.origin0[1] % F_TY == 0 && g.B[0] > 0 && g.B[1] > 0;
+}
+
+template <int FMT, typename OutT>
+static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const float* g0, const float* g1, OutT* out,
+                         cudaStream_t st) {
+  int rc = ensure_scratch(&h->tc_weights, &h->tc_weights_bytes, 64 * 1024);
+  if (rc) return rc;
+  const long long nodes0 = plane_size_host(g.n0, 2), nodes1 = plane_size_host(g.n1, 2);
+  const size_t b0 = ((size_t)nodes0 * g.C * 2 + 255) & ~(size_t)255, b1 = (size_t)nodes1 * 128;
+  rc = ensure_scratch(&h->tc_shadow, &h->tc_shadow_bytes, b0 + b1);
+  if (rc) return rc;
+  uint16_t* s0 = (uint16_t*)h->tc_shadow;
+  uint16_t* R = (uint16_t*)((uint8_t*)h->tc_shadow + b0);
+  cudaError_t e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
+  if (e != cudaSuccess) return (int)e;
+  {
+    dim3 grid_r((g.n1[0] + 127) / 128, g.n1[1]);
+    g1_rows_kernel<FMT><<<grid_r, 128, 0, st>>>(m, g1, g.n1[0], g.n1[1], R);
+    h->launches++;
+    pack_fast_kernel<FMT><<<32, 256, 0, st>>>(m, g.lod, g.step, (uint16_t*)h->tc_weights);
+    h->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  // 100 KB of dynamic shared memory per CTA caps residency at 2 CTAs/SM = 2 x 256 TMEM columns = all 512.
+  size_t smem = 100 * 1024;
+  static_assert(F_STAGE + F_IMG + 64 <= 100 * 1024, "shared memory budget");
+  auto kern = decode_tc2d_kernel<FMT, OutT>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  unsigned tiles_y = (unsigned)(g.B[1] / F_TY);
+  long long ntiles = (long long)(g.B[0] / F_TX) * tiles_y;
+  if (ntiles >= (1ll << 31)) return NIC_ERR_UNSUPPORTED;
+  unsigned sh = 0;
+  while ((1ull << sh) < tiles_y) ++sh;
+  unsigned mul = (unsigned)(((1ull << (31 + sh)) + tiles_y - 1) / tiles_y);
+  long long npairs = (ntiles + 1) / 2, cap = (long long)h->sms * 2;
+  int grid = (int)(npairs < cap ? npairs : cap);
+  kern<<<grid, F_THREADS, smem, st>>>(g, (const uint2*)s0, (const uint4*)R, (const uint4*)h->tc_weights, m.cout, tiles_y,
+                                      mul, sh, out);
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
 template <int METHOD, int FMT, typename OutT>
 static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float* g0, const float* g1,
                        const long long* origins, OutT* out, cudaStream_t st) {
   using S = RowShape<METHOD>;
+  if constexpr (METHOD == NIC_METHOD_2D) {
+    if (fast2d_eligible(g, origins) && !h->disable_fast2d) return launch_fast2d<FMT, OutT>(h, g, m, g0, g1, out, st);
+  }
   constexpr int IMG = b_image_bytes(64, S::KX) + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2);
   int rc = ensure_scratch(&h->tc_weights, &h->tc_weights_bytes, 64 * 1024);
   if (rc) return rc;
@@ -535,7 +970,8 @@ static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float
   auto kern = decode_tc_kernel<METHOD, FMT, OutT>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  long long ntiles = (g.N + TC_THREADS - 1) / TC_THREADS;
+  if (g.N >= (1ll << 31) - TC_ROWS) return NIC_ERR_UNSUPPORTED;     // 32-bit sample index in the kernel
+  long long ntiles = (g.N + TC_ROWS - 1) / TC_ROWS;
   long long cap = (long long)h->sms * 4;
   int grid = (int)(ntiles < cap ? ntiles : cap);
   ShadowGeom sg = {(const uint2*)s0, (const uint2*)s1};

@@ -286,6 +286,40 @@ def test_decode_vs_oracle_512_and_tiled_equals_single():
     assert within1 >= 0.999 and dpsnr <= 0.05, (within1, same, worst, dpsnr)
 
 
+def test_fast2d_path_matches_general_kernel():
+    """The aligned full-resolution 2-D fast path (aliased-cell MMA + selector matrix) against the general tensor-core
+    kernel and the oracle, on blocks that are / are not eligible for it."""
+    n = nic()
+    ic, L = n.image_compression, n._lib
+    size = 512
+    configure(IMAGE_SIZE=size)
+    grids = I.make_grids(size, 2, seed=94, no_mip=True, quantized=True)
+    params = I.make_mlp(73, seed=95, gain=2.0)
+    fp, dec = [T(a) for a in grids], make_decoder(params)
+    table = O.create_pyramid_mip_levels(size, size // 4)
+    ref = O.decode_block(grids, params, size, 0, table, 1)
+    ref8 = O.quantize_to_bit(ref, 8).astype(np.uint8)
+    for prec in ("f16", "bf16"):
+        fast = ic.decode(fp, dec, 0, precision=prec).cpu().numpy()
+        L.set_option(dev(), L.OPT_DISABLE_FAST2D, 1)
+        try:
+            gen = ic.decode(fp, dec, 0, precision=prec).cpu().numpy()
+        finally:
+            L.set_option(dev(), L.OPT_DISABLE_FAST2D, 0)
+        tol = 4e-3 if prec == "f16" else 2.5e-2
+        assert np.abs(fast - ref).max() < tol and np.abs(gen - ref).max() < tol, (np.abs(fast - ref).max(), np.abs(gen - ref).max())
+        for o in (fast, gen):
+            within1, same, worst = lsb_stats(np.floor(o.astype(np.float64) * 255 + 0.5).astype(np.uint8), ref8)
+            assert within1 >= 0.999, (prec, within1, same, worst)
+    # an eligible sub-block at a non-zero aligned origin, and a non-eligible (unaligned) one, agree with the full frame
+    whole = ic.decode(fp, dec, 0, precision="f16", out_dtype=torch.uint8)
+    a = ic.decode(fp, dec, 0, size=(64, 128), origin=(200, 304), precision="f16", out_dtype=torch.uint8)      # fast path
+    assert torch.equal(a, whole[200:264, 304:432])
+    b = ic.decode(fp, dec, 0, size=(64, 128), origin=(201, 300), precision="f16", out_dtype=torch.uint8)      # general path
+    d = (b.int() - whole[201:265, 300:428].int()).abs()
+    assert int(d.max()) <= 1 and float((d == 0).float().mean()) > 0.97
+
+
 def test_decode_4096_properties():
     """BASELINE config 2 shape (4096^2 full frame): properties that do not need the oracle at full size."""
     ic = nic().image_compression
@@ -299,7 +333,11 @@ def test_decode_4096_properties():
     # (a) any sub-block decoded on its own equals the same region of the full frame (tile independence)
     for (x0, y0, sx, sy) in ((0, 0, 128, 128), (4096 - 96, 4096 - 160, 96, 160), (1000, 2000, 333, 77)):
         part = ic.decode(fp, dec, 0, size=(sx, sy), origin=(x0, y0), precision="f16", out_dtype=torch.uint8)
-        assert torch.equal(part, whole[x0:x0 + sx, y0:y0 + sy])
+        if x0 % 8 == 0 and y0 % 16 == 0 and sx % 8 == 0 and sy % 16 == 0:      # same (aligned fast-path) kernel: bit-equal
+            assert torch.equal(part, whole[x0:x0 + sx, y0:y0 + sy])
+        else:                                   # general kernel vs fast path: same image within the 1-LSB tolerance
+            d = (part.int() - whole[x0:x0 + sx, y0:y0 + sy].int()).abs()
+            assert int(d.max()) <= 1 and float((d == 0).float().mean()) > 0.97
     # (b) a 256^2 window agrees with the oracle within the tensor-core tolerance
     table = O.create_pyramid_mip_levels(size, size // 4)
     ref = O.decode_block(grids, params, 256, 0, table, 1, origin=(1792, 3840))
@@ -457,5 +495,6 @@ def test_philox_noise_distribution_and_determinism():
         return float(tr.step(torch.tensor([[0, 0]]), tg, 2)), float(tr.step(torch.tensor([[0, 0]]), tg, 2, noise=False))
 
     a, b, c = run(1), run(1), run(2)
-    assert a == b and a[0] != c[0]
+    # same (seed, step) -> same noise; the loss sum itself is reduced with float atomics, so equal to rounding only
+    assert all(abs(x - y) <= 1e-5 * abs(x) for x, y in zip(a, b)) and abs(a[0] - c[0]) > 1e-5 * a[0]
     assert abs(a[0] - c[0]) < 0.05 * a[0]          # noise of +-2^-9 perturbs the loss only slightly
