@@ -26,6 +26,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 SIZE = 4096                      # BASELINE.json configs[1]
 FLOP_PER_TEXEL = 2 * (73 * 64 + 64 * 64 + 64 * 3)      # 17,920
 METRIC, UNIT = "decoded Gtexel/s (4096x4096 RGB full-frame decode)", "Gtexel/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of decode_tc2d_kernel per launch, from the committed ncu --set full capture
+NCU_TRAFFIC_BYTES = 59308032 + 15698688
+NCU_TRAFFIC_SOURCE = "profiles/r01e_decode_tc2d_pingpong_metrics.txt"
 
 
 def peaks():
@@ -76,51 +79,57 @@ def synthetic_model(seed=0):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_decode_rate(rows, threads):
-    """Times the oracle port (numpy restatement of the reference algorithm) on a slab of `rows` x 4096 texels."""
+CPU_TILE = 1024                  # decode_image's own tile size for large frames (image_compression.py:310-312)
+
+
+def cpu_setup(threads):
+    import torch
     from oracle import nic_oracle as O
-    try:
-        import torch
-        torch.set_num_threads(threads)
-    except Exception:
-        pass
+    from oracle import nic_oracle_torch as OT
+    torch.set_num_threads(threads)
     grids, params = synthetic_model()
+    fp = [torch.tensor(g) for g in grids]
+    dec = OT.make_decoder(params)
     table = O.create_pyramid_mip_levels(SIZE, SIZE // 4)
-    chunk = 64
+    return OT, fp, dec, table
+
+
+def cpu_decode_tiles(ctx, tiles, first=0):
+    """Decodes `tiles` 1024x1024 tiles of the 4096^2 frame with the torch-CPU port of the reference path
+    (oracle/nic_oracle_torch.py: the reference's own op sequence incl. the 8-bit output quantiser).  Returns
+    (texels, seconds)."""
+    import torch
+    OT, fp, dec, table = ctx
+    n = SIZE // CPU_TILE
     t0 = time.perf_counter()
-    done = 0
-    for r0 in range(0, rows, chunk):
-        blk = min(chunk, rows - r0)
-        # a [blk, 4096] slab = blk single-row blocks would be slow in numpy; decode it as (blk x 4096) via two 1-D meshes
-        xin = slab_input(O, grids, r0, blk)
-        out = O.mlp_forward(xin, params)
-        _ = O.quantize_to_bit(out, 8).astype(np.uint8)
-        done += blk * SIZE
-    dt = time.perf_counter() - t0
-    return done / dt / 1e9, done, dt
+    for i in range(first, first + tiles):
+        x, y = (i % (n * n)) % n, (i % (n * n)) // n
+        out = OT.decode_block(fp, dec, CPU_TILE, 0, table, 1, origin=(CPU_TILE * x, CPU_TILE * y))
+        _ = torch.floor(out * 255 + 0.5).to(torch.uint8)
+    return tiles * CPU_TILE * CPU_TILE, time.perf_counter() - t0
 
 
-def slab_input(O, grids, r0, rows):
-    """Decoder input of the texel slab [r0, r0+rows) x [0, 4096) following oracle.decoder_input_one, for a
-    non-square block (the reference only decodes squares; the arithmetic per texel is identical)."""
-    F32 = np.float32
-    ax_x = O._axis_vectors(r0, rows, 0.25)
-    ax_y = O._axis_vectors(0, SIZE, 0.25)
-    mesh = lambda a, b: [m.reshape(-1) for m in np.meshgrid(a, b, indexing="ij")]
-    x0, y0 = mesh(ax_x[1], ax_y[1])
-    x1, y1 = mesh(ax_x[3], ax_y[3])
-    ux, uy = mesh(ax_x[2], ax_y[2])
-    kx, ky = mesh(ax_x[4], ax_y[4])
-    g0, g1 = grids[0], grids[1]
-    rows_ = [g0[:, y0 + dy, x0 + dx] for dy, dx in O._CORNERS_2D]
-    one = F32(1)
-    wx = [one - kx, one - kx, kx, kx]
-    wy = [one - ky, ky, one - ky, ky]
-    g1c = [(g1[:, y1 + dy, x1 + dx] * wx[j]) * wy[j] for j, (dy, dx) in enumerate(O._CORNERS_2D)]
-    rows_.append(((g1c[0] + g1c[1]) + g1c[2]) + g1c[3])
-    rows_.append(O.triangular_positional_encoding(np.stack([ux, uy]), 6))
-    rows_.append(np.zeros((1, x0.shape[0]), dtype=F32))
-    return np.ascontiguousarray(np.concatenate(rows_, axis=0).T)
+def cpu_train_rate(threads, steps=2):
+    """Msamples/s of the torch-CPU port of train_models' body at config 1 (8 crops of 256^2 on a 512^2 image)."""
+    import torch
+    import inputs as I
+    from oracle import nic_oracle as O
+    from oracle import nic_oracle_torch as OT
+    torch.set_num_threads(threads)
+    size = 512
+    table = O.create_pyramid_mip_levels(size, size // 4)
+    tr = OT.Trainer(I.make_grids(size, 2, seed=3, no_mip=True), OT.make_decoder(I.make_mlp(73, seed=4)), 1000, 8, 1, table)
+    img = torch.tensor(I.make_image(size, 2, seed=5))
+    g = torch.Generator().manual_seed(6)
+    dt = 0.0
+    for s in range(steps + 1):
+        coord = torch.randint(0, size - 256 + 1, (8, 2), generator=g)
+        tg = torch.stack([img[:, c[0]:c[0] + 256, c[1]:c[1] + 256].reshape(3, -1).T for c in coord.tolist()])
+        t0 = time.perf_counter()
+        tr.step(coord, tg, 0)
+        if s > 0:
+            dt += time.perf_counter() - t0
+    return steps * 8 * 256 * 256 / dt / 1e6
 
 
 def run_reference(args):
@@ -128,30 +137,112 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = args.cpu_rows
-    for _ in range(min(args.warmup, 1)):
-        cpu_decode_rate(16, threads)
-    rates, tot_t = [], 0.0
-    for _ in range(max(1, min(args.steps, 3))):
-        r, done, dt = cpu_decode_rate(rows, threads)
-        rates.append(r)
+    ctx = cpu_setup(threads)
+    tiles = args.cpu_tiles
+    for w in range(min(args.warmup, 2)):
+        cpu_decode_tiles(ctx, 1, w)
+    done, tot_t = 0, 0.0
+    for k in range(args.steps):
+        d, dt = cpu_decode_tiles(ctx, tiles, k * tiles)
+        done += d
         tot_t += dt
-    v = float(np.mean(rates))
+    v = done / tot_t / 1e9
+    sample = f"{tiles} tiles of {CPU_TILE}x{CPU_TILE} texels of the 4096^2 frame per step"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(rates),
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * tot_t / len(rates), "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "decode_4096x4096_rgb", "sample": f"{rows}x4096 texel slab of the frame per step"},
+        "config": {"workload": "decode_4096x4096_rgb", "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{rows}x4096 texel slab per step, numpy port of the reference algorithm (oracle/nic_oracle.py)"},
+                         "sample": sample + "; torch-CPU port of the reference op sequence (oracle/nic_oracle_torch.py)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def bench_train(args, nic, ic, var2, dev, world, rank, dist, barrier):
+    """Fused training step at BASELINE config 1 shape: 512^2 image, 8 crops of 256^2 per rank per step (weak DP),
+    Philox noise on, one all-reduce of the flat gradient buffer when world > 1, fused Adam + clamp."""
+    import torch
+    import inputs as I
+    from neural_image_compression_v2_b200 import _lib as L
+    size, nc, crop = 512, 8, 256
+    var2.update(IMAGE_SIZE=size)
+    fp = [torch.tensor(g, device=dev) for g in I.make_grids(size, 2, seed=3, no_mip=True)]
+    dec = ic.ColorDecoder(73, 64, 3).to(dev)
+    with torch.no_grad():
+        for p, v in zip(dec.parameters_list(), I.make_mlp(73, seed=4)):
+            p.copy_(torch.tensor(v))
+    tr = ic.FusedTrainer(fp, dec, num_epochs=100000, fp_bits=8, seed=1, precision=args.train_prec)
+    img = torch.tensor(I.make_image(size, 2, seed=5), device=dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    batches = []
+    for _ in range(4):
+        coord = torch.randint(0, size - crop + 1, (nc, 2), generator=g)
+        tg = torch.stack([img[:, c[0]:c[0] + crop, c[1]:c[1] + crop].reshape(3, -1).T for c in coord.tolist()]).contiguous()
+        batches.append((coord.to(dev), tg))
+    steps = max(args.steps, 10)
+    for i in range(max(args.warmup, 3)):
+        tr.step(*batches[i % 4], 0)
+    barrier()
+    L.set_option(dev, L.OPT_TIME_KERNELS, 1)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(steps):
+        loss = tr.step(*batches[i % 4], 0)
+    e.record()
+    barrier()
+    kms, kn = L.kernel_time_ms(dev)
+    L.set_option(dev, L.OPT_TIME_KERNELS, 0)
+    ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    n = nc * crop * crop
+    rate = world * n * steps / (float(ms.item()) * 1e-3) / 1e6
+    tf_peak = peaks()[0]
+    kernel_tflops = 3 * FLOP_PER_TEXEL * n * kn / (kms * 1e-3) / 1e12 if kms > 0 else None
+    return {"value": rate, "unit": "Msamples/s", "samples_per_step": world * n, "ms_per_step": float(ms.item()) / steps,
+            "precision": args.train_prec, "loss": float(loss), "workload": "train_512x512_8x256x256_crops",
+            "kernel_ms": kms / max(kn, 1), "kernel_tflops": kernel_tflops,
+            "roofline_frac": (kernel_tflops / tf_peak) if kernel_tflops else None, "flop_per_sample": 3 * FLOP_PER_TEXEL}
+
+
+def bench_gather(args, nic, ic, var2, dev, fp):
+    """K1 alone: materialise X [N, 73] in 16-bit for the whole 4096^2 frame (HBM-write-bound)."""
+    import ctypes as C
+    import torch
+    from neural_image_compression_v2_b200 import _lib as L
+    var2.update(IMAGE_SIZE=SIZE)
+    n = SIZE * SIZE
+    x = torch.empty((n, 73), dtype=torch.float16, device=dev)
+    geom = L.make_geom(L.METHOD_2D, fp[0], fp[1], SIZE, 1, -2, 0, 6, L.PE_TRIANGULAR)
+    h, lib = L.handle(dev), L.load_library()
+
+    def run():
+        L.check(h, lib.nic_gather(h, C.byref(geom), L.ptr(fp[0]), L.ptr(fp[1]), None, L.ptr(x), L.DT_F16, L.stream_ptr(dev)))
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    L.set_option(dev, L.OPT_TIME_KERNELS, 1)
+    reps = 5
+    for _ in range(reps):
+        run()
+    torch.cuda.synchronize()
+    kms, kn = L.kernel_time_ms(dev)
+    L.set_option(dev, L.OPT_TIME_KERNELS, 0)
+    bytes_per_texel = 73 * 2 + 12 * 4 * (1 / 16 + 1 / 64)
+    gbs = bytes_per_texel * n * kn / (kms * 1e-3) / 1e9
+    hbm = peaks()[1]
+    del x
+    return {"value": gbs, "unit": "GB/s", "frac_of_hbm_peak": gbs / hbm, "peak": hbm, "kernel_ms": kms / max(kn, 1),
+            "bytes_per_texel": bytes_per_texel, "workload": "gather_4096x4096_f16_X", "gtexel_s": n * kn / (kms * 1e-3) / 1e9}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import neural_image_compression_v2_b200 as nic
+    from neural_image_compression_v2_b200 import _lib as L
     from neural_image_compression_v2_b200 import image_compression as ic
     from neural_image_compression_v2_b200 import fp_def, var2
 
@@ -187,6 +278,7 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = nic.launch_count(dev)
+    L.set_option(dev, L.OPT_TIME_KERNELS, 1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for s, e in ev:
@@ -195,6 +287,8 @@ def run_ours(args):
         step()
         e.record()
     barrier()
+    kernel_ms, kernel_n = L.kernel_time_ms(dev)
+    L.set_option(dev, L.OPT_TIME_KERNELS, 0)
     launches = nic.launch_count(dev) - l0
     clocks = sampler.stop() if sampler else None
     ms = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], dtype=torch.float64, device=dev)
@@ -207,19 +301,12 @@ def run_ours(args):
     codes = [c.cpu().pin_memory() for c in fp_def.fp_savable(fp, 8)]
     host_params = [p.detach().cpu().pin_memory() for p in dec.parameters_list()]
     host_out = torch.empty((SIZE, SIZE, 3), dtype=torch.uint8).pin_memory()
-    dcodes = [torch.empty_like(c, device=dev) for c in codes]
     h2d = sum(c.numel() for c in codes) + sum(p.numel() * 4 for p in host_params)
     d2h = host_out.numel()
+    pipe = ic.HostDecodePipeline(SIZE, dev, precision=args.prec)
 
     def e2e_step():
-        for d, c in zip(dcodes, codes):
-            d.copy_(c, non_blocking=True)
-        with torch.no_grad():
-            for p, hp in zip(dec.parameters_list(), host_params):
-                p.copy_(hp, non_blocking=True)
-        f = fp_def.fp_load(dcodes, 8)
-        ic.decode(f, dec, 0, precision=args.prec, out_dtype=torch.uint8, out=out)
-        host_out.copy_(out, non_blocking=True)
+        pipe.decode_frame(codes, host_params, host_out)
 
     for _ in range(2):
         e2e_step()
@@ -235,10 +322,19 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * texels / (float(ms2.item()) / k2 * 1e-3) / 1e9
+    # the e2e frame is the frame: compare with the resident-path output
+    e2e_ok = bool(torch.equal(host_out.to(dev), out))
+
+    extras = {}
+    if not args.no_extras:
+        extras["gather"] = bench_gather(args, nic, ic, var2, dev, fp)
+        del fp, out, flush
+        extras["train"] = bench_train(args, nic, ic, var2, dev, world, rank, dist, barrier)
 
     if rank == 0:
         tf_peak, hbm_peak, src = peaks()
-        achieved = FLOP_PER_TEXEL * texels / (ms_per_step * 1e-3) / 1e12
+        kms = kernel_ms / max(kernel_n, 1)
+        achieved = FLOP_PER_TEXEL * texels / (kms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -246,15 +342,25 @@ def run_ours(args):
             "config": {"workload": "decode_4096x4096_rgb", "frames_per_step": world, "grids": "[12,1025,1025]+[12,513,513] 8-bit",
                        "decoder": "73-64-64-3", "output": "uint8", "l2": "flushed between timed iterations (256 MB write)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                         "traffic": None, "peak_source": f"{src} bf16_tflops (burst: kernel timed alone)",
-                         "flop_per_texel": FLOP_PER_TEXEL},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                         "traffic": NCU_TRAFFIC_BYTES, "peak_source": f"{src} bf16_tflops (burst: kernel timed alone)",
+                         "flop_per_texel": FLOP_PER_TEXEL, "kernel": "decode_tc2d_kernel", "kernel_ms": kms,
+                         "kernel_share_of_step": kms / ms_per_step,
+                         "traffic_source": NCU_TRAFFIC_SOURCE},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "matches_resident_output": e2e_ok},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu:
-            r, done, dt = cpu_decode_rate(args.cpu_rows, os.cpu_count() or 1)
-            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"{args.cpu_rows}x4096 texel slab ({dt:.1f} s), numpy port of the reference algorithm"}
+            threads = os.cpu_count() or 1
+            ctx = cpu_setup(threads)
+            cpu_decode_tiles(ctx, 1)
+            done, dt = cpu_decode_tiles(ctx, args.cpu_tiles * 4, 1)
+            line["cpu_baseline"] = {"value": done / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_tiles * 4} tiles of {CPU_TILE}x{CPU_TILE} texels ({dt:.1f} s), torch-CPU "
+                                              "port of the reference op sequence (oracle/nic_oracle_torch.py)"}
+            if "train" in line:
+                line["train"]["cpu_value"] = cpu_train_rate(threads)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -267,8 +373,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--prec", default="f16", choices=["f16", "bf16", "f32"])
-    ap.add_argument("--cpu-rows", type=int, default=512)
+    ap.add_argument("--train-prec", default="f32", choices=["f16", "bf16", "f32"])
+    ap.add_argument("--cpu-tiles", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the gather and training side benchmarks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

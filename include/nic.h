@@ -97,8 +97,17 @@ int64_t nic_launch_count(const NicHandle* h);
 
 /* Tuning / testing knobs.  NIC_OPT_DISABLE_FAST2D = 1 forces the general tensor-core decode kernel even when the
  * geometry qualifies for the aligned full-resolution 2-D fast path (both must give the same image). */
-enum { NIC_OPT_DISABLE_FAST2D = 1 };
+/* NIC_OPT_REUSE_PREPARED = 1: the caller asserts that grids and decoder weights have not changed since the previous
+ * tensor-core nic_decode on this handle; if that call prepared its private tables (shadow grids, per-node G1 rows,
+ * packed weights) for the same pointers, node counts, step, mip level and precision, they are reused instead of being
+ * rebuilt (decoding one frame as several row bands).  Off by default: every call rebuilds from the caller's tensors. */
+enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3 };
 int nic_set_option(NicHandle* h, int option, int value);
+/* With NIC_OPT_TIME_KERNELS = 1 every nic_decode / nic_train_step / nic_gather call brackets its DOMINANT kernel
+ * (not the small preparation kernels) with CUDA events on the call's stream.  This call synchronises on the recorded
+ * events, adds up their durations, returns the sum (milliseconds) and the number of bracketed launches, and clears
+ * the list.  bench.py uses it for the roofline fraction of the dominant kernel. */
+int nic_kernel_time_ms(NicHandle* h, double* total_ms, int64_t* launches);
 
 /* ---- decoder input (K1) ------------------------------------------------------------------------------- */
 /* Width of the decoder input for a geometry: C*(corners+1) + PE*D + 1 (Projects/var2.py:114-118). */

@@ -13,7 +13,8 @@ Importing the package does not need a GPU; calling anything that computes does (
 """
 from . import _lib, fp_def, models, utils, var2  # noqa: F401
 from . import image_compression  # noqa: F401
+from . import parallel  # noqa: F401
 from ._lib import NicError, launch_count, load_library  # noqa: F401
 
-__all__ = ["_lib", "fp_def", "models", "utils", "var2", "image_compression", "NicError", "launch_count",
+__all__ = ["_lib", "fp_def", "models", "utils", "var2", "image_compression", "parallel", "NicError", "launch_count",
            "load_library"]

@@ -58,6 +58,7 @@ SYMBOLS = {
     "nic_status_string": (C.c_char_p, [_I]),
     "nic_launch_count": (_L, [_P]),
     "nic_set_option": (_I, [_P, _I, _I]),
+    "nic_kernel_time_ms": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "nic_cin": (_I, [C.POINTER(NicGeom)]),
     "nic_gather": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, _P, _I, _P]),
     "nic_scatter": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, _P, _P]),
@@ -117,6 +118,16 @@ def handle(device):
 
 
 OPT_DISABLE_FAST2D = 1
+OPT_TIME_KERNELS = 2
+OPT_REUSE_PREPARED = 3
+
+
+def kernel_time_ms(device):
+    """(sum of the dominant kernels' durations in ms, launches bracketed) since the last call; see nic.h."""
+    h = handle(device)
+    ms, n = C.c_double(0.0), C.c_int64(0)
+    check(h, load_library().nic_kernel_time_ms(h, C.byref(ms), C.byref(n)))
+    return float(ms.value), int(n.value)
 
 
 def set_option(device, option, value):

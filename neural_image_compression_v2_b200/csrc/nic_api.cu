@@ -87,6 +87,8 @@ int nic_destroy(NicHandle* h) {
   if (h->tc_weights) cudaFree(h->tc_weights);
   if (h->tc_shadow) cudaFree(h->tc_shadow);
   if (h->adam_desc) cudaFree(h->adam_desc);
+  for (int i = 0; i < 2 * NIC_MAX_TIMED; ++i)
+    if (h->timed_ev[i]) cudaEventDestroy(h->timed_ev[i]);
   cudaSetDevice(cur);
   delete h;
   return NIC_OK;
@@ -97,7 +99,25 @@ int64_t nic_launch_count(const NicHandle* h) { return h ? h->launches : 0; }
 int nic_set_option(NicHandle* h, int option, int value) {
   if (!h) return fail(nullptr, NIC_ERR_ARG, "handle is NULL");
   if (option == NIC_OPT_DISABLE_FAST2D) { h->disable_fast2d = value != 0; return NIC_OK; }
+  if (option == NIC_OPT_REUSE_PREPARED) { h->reuse_prepared = value != 0; return NIC_OK; }
+  if (option == NIC_OPT_TIME_KERNELS) { h->time_kernels = value != 0; h->timed_count = 0; return NIC_OK; }
   return fail(h, NIC_ERR_ARG, "nic_set_option: unknown option %d", option);
+}
+
+int nic_kernel_time_ms(NicHandle* h, double* total_ms, int64_t* launches) {
+  if (!h || !total_ms || !launches) return fail(h, NIC_ERR_ARG, "nic_kernel_time_ms: NULL argument");
+  double sum = 0.0;
+  for (int i = 0; i < h->timed_count; ++i) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(h->timed_ev[2 * i + 1]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->timed_ev[2 * i], h->timed_ev[2 * i + 1]);
+    if (e != cudaSuccess) return fail(h, (int)e, "nic_kernel_time_ms: %s", cudaGetErrorString(e));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = h->timed_count;
+  h->timed_count = 0;
+  return NIC_OK;
 }
 
 int nic_cin(const NicGeom* g) {

@@ -81,6 +81,7 @@ int launch_gather(Handle* h, const DevGeom& g, const float* g0, const float* g1,
   long long total = g.N * g.cin;
   if (total == 0) return NIC_OK;
   int grid = grid_for(total, 256, h->sms, 8);
+  KernelTimer timer(h, st);
   switch (x_dtype) {
     case NIC_DT_F32: gather_flat_kernel<float><<<grid, 256, 0, st>>>(g, g0, g1, origins, (float*)x, total); break;
     case NIC_DT_F16: gather_flat_kernel<__half><<<grid, 256, 0, st>>>(g, g0, g1, origins, (__half*)x, total); break;

@@ -354,7 +354,10 @@ static int launch_fwd_t(Handle* h, const DevGeom& g, const MlpDev& m, const floa
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   long long blocks = (N + 127) / 128, cap = (long long)h->sms * 3;
-  kern<<<(int)(blocks > cap ? cap : blocks), 128, smem, st>>>(g, m, g0, g1, origins, x, ldx, N, out, out_u8, z1, z2);
+  {
+    KernelTimer timer(h, st);
+    kern<<<(int)(blocks > cap ? cap : blocks), 128, smem, st>>>(g, m, g0, g1, origins, x, ldx, N, out, out_u8, z1, z2);
+  }
   h->launches++;
   return (int)cudaGetLastError();
 }
@@ -387,8 +390,11 @@ static int launch_bwd_t(Handle* h, const DevGeom& g, const MlpDev& m, const MlpG
   if (e != cudaSuccess) return (int)e;
   long long ntiles = (N + T - 1) / T;
   int grid = (int)(ntiles < h->sms ? ntiles : h->sms);
-  kern<<<grid, T, smem, st>>>(g, m, gm, g0, g1, origins, x, ldx, N, z1, z2, out, dout, dx, targets, noise,
-                              noise_bits, seed, step, grad_scale, dg0, dg1, loss_sum, out_save);
+  {
+    KernelTimer timer(h, st);
+    kern<<<grid, T, smem, st>>>(g, m, gm, g0, g1, origins, x, ldx, N, z1, z2, out, dout, dx, targets, noise,
+                                noise_bits, seed, step, grad_scale, dg0, dg1, loss_sum, out_save);
+  }
   h->launches++;
   return (int)cudaGetLastError();
 }

@@ -28,8 +28,38 @@ struct Handle {
   void* tc_shadow;           // 16-bit channel-last shadows of the two active grids
   size_t tc_shadow_bytes;
   int disable_fast2d;        // testing knob: force the general tensor-core kernel
+  int reuse_prepared;        // NIC_OPT_REUSE_PREPARED
+  struct PreparedKey {       // what the tables in tc_weights / tc_shadow were last built from
+    const void *g0, *g1, *w1, *b1, *w2, *b2, *w3, *b3;
+    int n0[3], n1[3], method, pe_kind, mip, fmt, fast, valid;
+    float step;
+  } prepared;
   void* adam_desc;           // device copy of NicAdamTensor descriptors
   size_t adam_desc_bytes;
+  // NIC_OPT_TIME_KERNELS: event pairs around the dominant kernel of each call (ring of NIC_MAX_TIMED pairs)
+  int time_kernels;
+  int timed_count;
+  cudaEvent_t timed_ev[2 * 256];
+};
+#define NIC_MAX_TIMED 256
+
+// Brackets the dominant kernel of a call with events when NIC_OPT_TIME_KERNELS is on (no-op otherwise).
+struct KernelTimer {
+  Handle* h;
+  cudaStream_t st;
+  int slot;
+  KernelTimer(Handle* h_, cudaStream_t st_) : h(h_), st(st_), slot(-1) {
+    if (!h->time_kernels || h->timed_count >= NIC_MAX_TIMED) return;
+    slot = h->timed_count;
+    for (int i = 0; i < 2; ++i)
+      if (!h->timed_ev[2 * slot + i] && cudaEventCreate(&h->timed_ev[2 * slot + i]) != cudaSuccess) { slot = -1; return; }
+    cudaEventRecord(h->timed_ev[2 * slot], st);
+  }
+  ~KernelTimer() {
+    if (slot < 0) return;
+    cudaEventRecord(h->timed_ev[2 * slot + 1], st);
+    h->timed_count = slot + 1;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------- typed stores

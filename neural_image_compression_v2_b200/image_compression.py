@@ -238,6 +238,85 @@ def decode(fp, decoder, mip_level=0, size=None, origin=None, precision=None, out
     return out
 
 
+def decode_points(fp, decoder, coords, mip_level=0, precision=None, out_dtype=torch.float32, method=None,
+                  level_table=None):
+    """Random-access decode: coords `[Q, D]` integer texel coordinates of mip `mip_level` -> `[Q, Cout]`.
+    Each query is a 1-texel block whose origin is the query (the `coord` mechanism of create_decoder_input_*,
+    image_compression.py:71-167, with sample_number = 1); used for LUT look-ups (BASELINE config 4)."""
+    method = _method() if method is None else method
+    dim = 2 if method == L.METHOD_2D else 3
+    table = feature_pyramid_mip_levels() if level_table is None else level_table
+    fl = table[mip_level]
+    g0, g1 = _check_grid(fp[fl * 2].detach()), _check_grid(fp[fl * 2 + 1].detach())
+    coords = L.origins_tensor(coords, g0.device, dim)
+    params = [p.detach().contiguous() for p in decoder.parameters_list()]
+    m = L.make_mlp(params)
+    q = coords.shape[0]
+    if q >= 2 ** 31 - 128:
+        raise ValueError("at most 2^31 - 129 queries per call; split the batch")
+    geom = L.make_geom(method, g0, g1, 1, q, _step_log2(mip_level, fl), mip_level, var2.PE_CHANNELS, _pe_kind(method))
+    prec = L.PRECISIONS[(precision or var2.DECODE_PRECISION).lower()]
+    out = torch.empty((q, m.cout), dtype=out_dtype, device=g0.device)
+    h = L.handle(g0.device)
+    L.check(h, L.load_library().nic_decode(h, C.byref(geom), L.ptr(g0), L.ptr(g1), L.ptr(coords), C.byref(m), L.ptr(out),
+                                           L.DT_U8 if out_dtype == torch.uint8 else L.DT_F32, prec,
+                                           L.stream_ptr(g0.device)))
+    return out
+
+
+class HostDecodePipeline:
+    """End-to-end decode of one 2-D frame from HOST buffers to a HOST buffer (what `process_images` does with a saved
+    model, image_compression.py:393-407): pinned H2D of the uint8 grid codes and the decoder, `fp_load`, fused decode in
+    row bands, and the D2H of each 8-bit band on a second stream while the next band decodes.  The preparation tables
+    (shadow grids, per-node G1 rows, packed weights) are built by the first band and reused by the others
+    (NIC_OPT_REUSE_PREPARED)."""
+
+    def __init__(self, size, device, precision="f16", bands=4, bits=8):
+        self.size, self.device, self.precision, self.bits = size, torch.device(device), precision, bits
+        self.bands = [(r0, n) for r0, n in (_band(size, b, bands) for b in range(bands)) if n > 0]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.decoder = None
+        self.dcodes = None
+        self.out = None
+
+    def decode_frame(self, codes, host_params, host_out, mip_level=0):
+        from .fp_def import fp_load
+        dev = self.device
+        if self.dcodes is None:
+            self.dcodes = [torch.empty(c.shape, dtype=torch.uint8, device=dev) for c in codes]
+            self.decoder = ColorDecoder(host_params[0].shape[1], host_params[0].shape[0], host_params[4].shape[0]).to(dev)
+            self.out = torch.empty((self.size, self.size, host_params[4].shape[0]), dtype=torch.uint8, device=dev)
+        for d, c in zip(self.dcodes, codes):
+            d.copy_(c, non_blocking=True)
+        with torch.no_grad():
+            for p, hp in zip(self.decoder.parameters_list(), host_params):
+                p.copy_(hp, non_blocking=True)
+        fp = fp_load(self.dcodes, self.bits)
+        main = torch.cuda.current_stream(dev)
+        try:
+            for i, (r0, n) in enumerate(self.bands):
+                L.set_option(dev, L.OPT_REUSE_PREPARED, int(i > 0))
+                band = self.out[r0:r0 + n]
+                decode(fp, self.decoder, mip_level, size=(n, self.size), origin=(r0, 0), precision=self.precision,
+                       out_dtype=torch.uint8, out=band)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                self.copy_stream.wait_event(ready)
+                with torch.cuda.stream(self.copy_stream):
+                    host_out[r0:r0 + n].copy_(band, non_blocking=True)
+        finally:
+            L.set_option(dev, L.OPT_REUSE_PREPARED, 0)
+        done = torch.cuda.Event()
+        done.record(self.copy_stream)
+        main.wait_event(done)            # the frame is complete (in host memory) when the caller's stream gets here
+        return host_out
+
+
+def _band(size, b, bands):
+    from .parallel import shard_rows
+    return shard_rows(size, b, bands)
+
+
 def decode_image(fp, arc_decoder, mip_level, pr=True, div_size=10, precision=None):
     """image_compression.py:307-346 — full-frame decode; <= 2^div_size-texel tiles when the frame is larger.
     Differences from the reference, both deliberate: the tiled result is assembled on the device (the
@@ -310,7 +389,7 @@ class FusedTrainer:
     """
 
     def __init__(self, fp, decoder, num_epochs=None, fp_bits=None, lr_fp=0.01, lr_mlp=0.005, betas=(0.9, 0.999),
-                 eps=1e-8, method=None, level_table=None, process_group=None, seed=0):
+                 eps=1e-8, method=None, level_table=None, process_group=None, seed=0, precision="f32"):
         self.fp = [_check_grid(g.detach()) for g in fp]
         self.decoder = decoder
         self.params = [p.detach() for p in decoder.parameters_list()]
@@ -325,6 +404,7 @@ class FusedTrainer:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self.seed = seed
+        self.precision = L.PRECISIONS[precision.lower()]     # "f32" reference-exact; "f16"/"bf16" tcgen05 path
         self.epoch = 0
         self.frozen = False
         dev = self.fp[0].device
@@ -394,7 +474,7 @@ class FusedTrainer:
                                       L.ptr(noise_t), noise_bits, self.seed + 7919 * rank, epoch, n * self.world,
                                       C.byref(gm), L.ptr(None if self.frozen else views[0]),
                                       L.ptr(None if self.frozen else views[1]), L.ptr(views[8]), L.ptr(out),
-                                      L.PREC_F32, st))
+                                      self.precision, st))
         if self.world > 1:                                           # the one exchange step of the path
             torch.distributed.all_reduce(flat, group=self.pg)
         loss = views[8][0] / float(n * self.world * m.cout)
