@@ -70,7 +70,7 @@ __device__ __forceinline__ float pe_triangular(float u, int r, int PE) {
   int q = PE - 1 - r;          // = 2*octave + i
   if (q <= 0 || q >= 2 * (PE / 2)) return 0.0f;
   int octave = q >> 1, i = q & 1;
-  float x = __fdiv_rn(u, (float)(1 << octave));
+  float x = __fmul_rn(u, __int_as_float((127 - octave) << 23));   // u / 2^octave, exact (power-of-two divisor)
   return tri_wave(x, i ? 0.0f : 0.5f);
 }
 

@@ -80,6 +80,7 @@ int launch_gather(Handle* h, const DevGeom& g, const float* g0, const float* g1,
                   int x_dtype, cudaStream_t st) {
   long long total = g.N * g.cin;
   if (total == 0) return NIC_OK;
+  if (gather_tile_eligible(g, x) && !h->disable_fast2d) return launch_gather_tile(h, g, g0, g1, origins, x, x_dtype, st);
   int grid = grid_for(total, 256, h->sms, 8);
   KernelTimer timer(h, st);
   switch (x_dtype) {

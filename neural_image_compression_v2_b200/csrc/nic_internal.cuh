@@ -168,6 +168,9 @@ __device__ __forceinline__ float philox_noise(unsigned long long seed, unsigned 
 // ---------------------------------------------------------------------------------------------- launchers
 int launch_gather(Handle* h, const DevGeom& g, const float* g0, const float* g1, const long long* origins, void* x,
                   int x_dtype, cudaStream_t st);
+bool gather_tile_eligible(const DevGeom& g, const void* x);
+int launch_gather_tile(Handle* h, const DevGeom& g, const float* g0, const float* g1, const long long* origins, void* x,
+                       int x_dtype, cudaStream_t st);
 int launch_scatter(Handle* h, const DevGeom& g, const float* dx, const long long* origins, float* dg0, float* dg1,
                    cudaStream_t st);
 int launch_pe(Handle* h, const float* coord, int dim, long long n, int PE, int kind, const float* div_host, float* out,

@@ -155,6 +155,44 @@ def test_gather_vs_oracle_larger_and_ragged():
     assert torch.equal(x16, x32.to(torch.float16)) and torch.equal(xb16, x32.to(torch.bfloat16))
 
 
+def test_gather_tile_kernel_equals_flat_kernel():
+    """K1's TMA-staged tile kernel (rows of 128 texels, 2-D, step <= 1) is bit-identical to the flat kernel for fp32,
+    f16 and bf16 X, for a full frame, for crops with device origins (training shape) and at steps 1/4, 1/2 and 1."""
+    import ctypes as C
+    n = nic()
+    L = n._lib
+    size = 512
+    grids = I.make_grids(size, 2, seed=78)
+    fp = [T(a) for a in grids]
+    h, lib = L.handle(dev()), L.load_library()
+    rng = np.random.default_rng(79)
+    cases = [  # (fl, mip, block, num_blocks, origins)
+        (0, 0, (512, 512), 1, None), (0, 0, (40, 384), 1, (9, 128)), (0, 1, (256, 256), 1, None), (0, 2, (128, 128), 1, None),
+        (0, 0, (256, 256), 3, rng.integers(0, 257, (3, 2))), (0, 1, (128, 128), 5, rng.integers(0, 129, (5, 2))),
+        (0, 2, (64, 128), 1, (64, 0))]
+    for fl, mip, block, nb, org in cases:
+        g0, g1 = fp[2 * fl], fp[2 * fl + 1]
+        o0 = org if (org is not None and nb == 1 and not isinstance(org, np.ndarray)) else None
+        geom = L.make_geom(L.METHOD_2D, g0, g1, block, nb, mip - 2 * (fl + 1), mip, 6, L.PE_TRIANGULAR, origin0=o0)
+        coords = T(org, torch.int64) if isinstance(org, np.ndarray) else None
+        N = nb * block[0] * block[1]
+        for dt, td in ((L.DT_F32, torch.float32), (L.DT_F16, torch.float16), (L.DT_BF16, torch.bfloat16)):
+            outs = []
+            for flat in (0, 1):
+                x = torch.full((N, 73), -7.0, dtype=td, device=dev())
+                L.set_option(dev(), L.OPT_DISABLE_FAST2D, flat)
+                try:
+                    L.check(h, lib.nic_gather(h, C.byref(geom), L.ptr(g0), L.ptr(g1), L.ptr(coords), L.ptr(x), dt, L.stream_ptr(dev())))
+                finally:
+                    L.set_option(dev(), L.OPT_DISABLE_FAST2D, 0)
+                outs.append(x)
+            assert torch.equal(outs[0], outs[1]), (fl, mip, block, nb, td)
+    # and against the oracle for the training shape
+    coord = rng.integers(0, 257, (2, 2))
+    X = n.image_compression.create_decoder_input_2d(fp, T(coord, torch.int64), 2, 0, 0).cpu().numpy()
+    assert np.array_equal(X, O.create_decoder_input(grids, coord, 0, 0, 1))
+
+
 def test_gather_scatter_adjoint():
     """<gather(G), dX> == <G, scatter(dX)> on the grid columns (linearity / transpose property)."""
     ic = nic().image_compression
