@@ -45,37 +45,47 @@ template <> struct Pack16<__nv_bfloat16> {
   }
 };
 
-// Row of texel `t` (73 fp32 values in registers) -> staging buffer.
-template <typename OutT>
-__device__ __forceinline__ void write_row(OutT* stage, int t, int par, const float* v);
-
-template <>
-__device__ __forceinline__ void write_row<float>(float* stage, int t, int, const float* v) {
-  float* row = stage + t * GT_CIN;
+// Streaming row writers: pieces of the row (12 channels of a corner, 6 encoding rows, the LOD) go to the staging
+// buffer as soon as they are produced, so a thread never holds the whole 73-value row in registers.
+template <typename OutT> struct RowWriter;
+template <> struct RowWriter<float> {
+  float* row;
+  __device__ __forceinline__ RowWriter(float* stage, int t, int) : row(stage + t * GT_CIN) {}
+  template <int N> __device__ __forceinline__ void put(const float* v, int base) {
 #pragma unroll
-  for (int c = 0; c < GT_CIN; ++c) row[c] = v[c];
-}
-
-template <typename OutT>
-__device__ __forceinline__ void write_row16(OutT* stage, int t, int par, const float* v) {
-  using P = Pack16<OutT>;
-  uint32_t* words = reinterpret_cast<uint32_t*>(stage) + (t >> 1) * GT_CIN;     // texel pair (2m, 2m+1) = 73 words
-  if (par == 0) {
-#pragma unroll
-    for (int k = 0; k < 36; ++k) words[k] = P::two(v[2 * k], v[2 * k + 1]);
-    reinterpret_cast<uint16_t*>(words + 36)[0] = P::one(v[72]);
-  } else {
-    reinterpret_cast<uint16_t*>(words + 36)[1] = P::one(v[0]);
-#pragma unroll
-    for (int k = 0; k < 36; ++k) words[37 + k] = P::two(v[2 * k + 1], v[2 * k + 2]);
+    for (int i = 0; i < N; ++i) row[base + i] = v[i];
   }
-}
-template <>
-__device__ __forceinline__ void write_row<__half>(__half* stage, int t, int par, const float* v) { write_row16(stage, t, par, v); }
-template <>
-__device__ __forceinline__ void write_row<__nv_bfloat16>(__nv_bfloat16* stage, int t, int par, const float* v) {
-  write_row16(stage, t, par, v);
-}
+  __device__ __forceinline__ void last(float v) { row[GT_CIN - 1] = v; }
+};
+// 16-bit rows are 146 bytes: the rows of a texel pair (2m, 2m+1) form 73 aligned words.  Even texels pair columns
+// (even, even+1) and end with a lone low half (column 72); odd texels start with a lone high half (column 0) and pair
+// (even-1, even), which needs a one-value carry between pieces.  Parity is warp-uniform.
+template <typename OutT> struct RowWriter16 {
+  using P = Pack16<OutT>;
+  uint32_t* words;
+  int par;
+  float carry;
+  __device__ __forceinline__ RowWriter16(OutT* stage, int t, int par_)
+      : words(reinterpret_cast<uint32_t*>(stage) + (t >> 1) * GT_CIN), par(par_), carry(0.f) {}
+  template <int N> __device__ __forceinline__ void put(const float* v, int base) {   // N and base even
+    if (par == 0) {
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) words[base / 2 + i] = P::two(v[2 * i], v[2 * i + 1]);
+    } else {
+      if (base == 0) reinterpret_cast<uint16_t*>(words + 36)[1] = P::one(v[0]);
+      else words[36 + base / 2] = P::two(carry, v[0]);
+#pragma unroll
+      for (int i = 1; i < N / 2; ++i) words[36 + base / 2 + i] = P::two(v[2 * i - 1], v[2 * i]);
+      carry = v[N - 1];
+    }
+  }
+  __device__ __forceinline__ void last(float v) {
+    if (par == 0) reinterpret_cast<uint16_t*>(words + 36)[0] = P::one(v);
+    else words[GT_CIN - 1] = P::two(carry, v);
+  }
+};
+template <> struct RowWriter<__half> : RowWriter16<__half> { using RowWriter16<__half>::RowWriter16; };
+template <> struct RowWriter<__nv_bfloat16> : RowWriter16<__nv_bfloat16> { using RowWriter16<__nv_bfloat16>::RowWriter16; };
 
 // Triangular encoding rows of coordinate u for PE = 6 (utils.py:211-223):
 // [tri(u/4, 0), tri(u/4, .5), tri(u/2, 0), tri(u/2, .5), tri(u, 0), 0]; the divisions are exact (powers of two).
@@ -89,34 +99,44 @@ __device__ __forceinline__ void pe6_triangular(float u, float* out) {
   out[5] = 0.0f;
 }
 
+// One CTA iteration = a SUPER-TILE of GT_R x-rows by 128 y-texels: the GT_R rows share one staged patch of grid nodes
+// (NX0 x NP0 nodes of G0, NX1 x NP1 of G1), which divides the global-load / L1-lookup cost per texel by GT_R; each
+// row of 128 texels is then built in a double-buffered staging area and leaves with its own bulk store.
+constexpr int GT_R = 4;
+
 template <typename OutT>
 __global__ void __launch_bounds__(GT_T) gather_tile_kernel(DevGeom g, const float* __restrict__ g0,
                                                            const float* __restrict__ g1,
                                                            const long long* __restrict__ origins, OutT* __restrict__ x,
-                                                           int np0, int np1, unsigned ntiles, unsigned tiles_per_row) {
+                                                           int nx0, int nx1, int np0, int np1, unsigned ntiles,
+                                                           unsigned tiles_per_row) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int STAGE_BYTES = GT_T * GT_CIN * (int)sizeof(OutT);
-  float* patch0 = reinterpret_cast<float*>(smem_raw + 2 * STAGE_BYTES);      // [2][np0][C]
-  float* patch1 = patch0 + 2 * np0 * GT_C;                                  // [2][np1][C]
-  float* pex = patch1 + 2 * np1 * GT_C;                                     // [8]: encoding of the tile's x coordinate
+  float* patch0 = reinterpret_cast<float*>(smem_raw + 2 * STAGE_BYTES);      // [nx0][np0][C]
+  float* patch1 = patch0 + nx0 * np0 * GT_C;                                // [nx1][np1][C]
+  float* pex = patch1 + nx1 * np1 * GT_C;                                   // [GT_R][8]: x encodings of the rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // 16-bit rows: warp-uniform texel parity (see header); fp32 rows: thread = texel, lanes stride 73 words (== 9 mod 32)
   const int par = sizeof(OutT) == 2 ? (warp & 1) : 0;
   const int t = sizeof(OutT) == 2 ? 64 * (warp >> 1) + 2 * lane + par : tid;
   const long long ps0 = (long long)g.n0[0] * g.n0[1], ps1 = (long long)g.n1[0] * g.n1[1];
-  const unsigned rows_per_block = (unsigned)g.B[0] * tiles_per_row;
+  const unsigned xgroups = (unsigned)g.B[0] / GT_R;
+  const unsigned tiles_per_block = xgroups * tiles_per_row;
 
-  // Patch staging: thread -> one (channel, x-node) column of the patch (24 columns), walking the y nodes with stride 5
-  // (threads 120..127 idle here).  No runtime division; the first PRE loads per grid are PREFETCHED into registers one
-  // tile ahead (the whole patch at step 1/4: 34 and 18 nodes), hiding their latency behind the previous tile's build.
-  constexpr int PRE0 = 7, PRE1 = 4, YS = 5;
-  const int combo = tid % 24, yn0 = tid / 24, pc = combo >> 1, pxn = combo & 1;
-  const bool stager = tid < 24 * YS;
+  // Patch staging: thread -> one (channel, x-node) column of the patch, walking the y nodes with a fixed stride (no
+  // runtime division).  Lanes run over x-nodes first (adjacent addresses), then channels.  The first PRE loads per grid
+  // are PREFETCHED into registers one super-tile ahead, hiding their latency behind the previous rows' build.
+  constexpr int PRE0 = 12, PRE1 = 6;
+  const int ncol0 = GT_C * nx0, ncol1 = GT_C * nx1;            // <= 128 (launcher guarantees)
+  const int ys0 = GT_T / ncol0, ys1 = GT_T / ncol1;            // y stride of a staging thread
+  const int col0 = tid % ncol0, yA0 = tid / ncol0, c0_ = col0 / nx0, xn0_ = col0 - c0_ * nx0;
+  const int col1 = tid % ncol1, yA1 = tid / ncol1, c1_ = col1 / nx1, xn1_ = col1 - c1_ * nx1;
+  const bool stager0 = yA0 < ys0, stager1 = yA1 < ys1;
   float pre0[PRE0], pre1[PRE1];
-  auto tile_coords = [&](unsigned tile, AxisCoord& ax, AxisCoord& ay_first, int& py0) {
-    const unsigned b = tile / rows_per_block, r = tile - b * rows_per_block;
-    const unsigned ix = r / tiles_per_row, iy0 = (r - ix * tiles_per_row) * GT_T;
+  auto tile_coords = [&](unsigned tile, int& px0, int& py0) {
+    const unsigned b = tile / tiles_per_block, r = tile - b * tiles_per_block;
+    const unsigned xg = r / tiles_per_row, iy0 = (r - xg * tiles_per_row) * GT_T;
     int ox, oy;
     if (origins) {
       ox = (int)origins[2 * (long long)b];
@@ -125,148 +145,161 @@ __global__ void __launch_bounds__(GT_T) gather_tile_kernel(DevGeom g, const floa
       ox = g.origin0[0];
       oy = g.origin0[1];
     }
+    px0 = ox + (int)xg * GT_R;
     py0 = oy + (int)iy0;
-    ax = axis_coord(ox + (int)ix, g.step);
-    ay_first = axis_coord(py0, g.step);
   };
-  auto load0 = [&](int yn, const AxisCoord& ax, const AxisCoord& ayf) -> float {
-    const int gx = clampi(ax.i0 + pxn, 0, g.n0[0] - 1), gy = clampi(ayf.i0 + yn, 0, g.n0[1] - 1);
-    return __ldg(g0 + pc * ps0 + (long long)gy * g.n0[0] + gx);
+  auto load0 = [&](int yn, const AxisCoord& axf, const AxisCoord& ayf) -> float {
+    const int gx = clampi(axf.i0 + xn0_, 0, g.n0[0] - 1), gy = clampi(ayf.i0 + yn, 0, g.n0[1] - 1);
+    return __ldg(g0 + c0_ * ps0 + (long long)gy * g.n0[0] + gx);
   };
-  auto load1 = [&](int yn, const AxisCoord& ax, const AxisCoord& ayf) -> float {
-    const int gx = clampi(ax.i1 + pxn, 0, g.n1[0] - 1), gy = clampi(ayf.i1 + yn, 0, g.n1[1] - 1);
-    return __ldg(g1 + pc * ps1 + (long long)gy * g.n1[0] + gx);
+  auto load1 = [&](int yn, const AxisCoord& axf, const AxisCoord& ayf) -> float {
+    const int gx = clampi(axf.i1 + xn1_, 0, g.n1[0] - 1), gy = clampi(ayf.i1 + yn, 0, g.n1[1] - 1);
+    return __ldg(g1 + c1_ * ps1 + (long long)gy * g.n1[0] + gx);
   };
   auto prefetch = [&](unsigned tile) {
-    if (tile >= ntiles || !stager) return;
-    AxisCoord ax, ayf;
-    int py0;
-    tile_coords(tile, ax, ayf, py0);
+    if (tile >= ntiles) return;
+    int px0, py0;
+    tile_coords(tile, px0, py0);
+    const AxisCoord axf = axis_coord(px0, g.step), ayf = axis_coord(py0, g.step);
+    if (stager0) {
 #pragma unroll
-    for (int k = 0; k < PRE0; ++k)
-      if (yn0 + k * YS < np0) pre0[k] = load0(yn0 + k * YS, ax, ayf);
+      for (int k = 0; k < PRE0; ++k)
+        if (yA0 + k * ys0 < np0) pre0[k] = load0(yA0 + k * ys0, axf, ayf);
+    }
+    if (stager1) {
 #pragma unroll
-    for (int k = 0; k < PRE1; ++k)
-      if (yn0 + k * YS < np1) pre1[k] = load1(yn0 + k * YS, ax, ayf);
+      for (int k = 0; k < PRE1; ++k)
+        if (yA1 + k * ys1 < np1) pre1[k] = load1(yA1 + k * ys1, axf, ayf);
+    }
   };
 
   prefetch(blockIdx.x);
-  unsigned it = 0;
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    OutT* stage = reinterpret_cast<OutT*>(smem_raw + (it & 1) * STAGE_BYTES);
-    AxisCoord ax, ay_first;
-    int py0;
-    tile_coords(tile, ax, ay_first, py0);
-    // the bulk store that used this staging buffer two tiles ago must have finished READING it; every thread must be
-    // done with the previous tile's patches
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncthreads();
-    // ---- stage the grid nodes of this tile, channel-last: patch[(xn * np + yn) * C + c]
-    if (stager) {
-      float* col0 = patch0 + pxn * np0 * GT_C + pc;
-      float* col1 = patch1 + pxn * np1 * GT_C + pc;
+  unsigned nstore = 0;                   // bulk stores issued so far by this CTA (staging buffer = nstore & 1)
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int px0, py0;
+    tile_coords(tile, px0, py0);
+    const AxisCoord ax_first = axis_coord(px0, g.step), ay_first = axis_coord(py0, g.step);
+    __syncthreads();                     // every thread is done with the previous super-tile's patches
+    // ---- stage the grid nodes of this super-tile, channel-last: patch[(xn * np + yn) * C + c]
+    if (stager0) {
+      float* colp = patch0 + xn0_ * np0 * GT_C + c0_;
 #pragma unroll
       for (int k = 0; k < PRE0; ++k)
-        if (yn0 + k * YS < np0) col0[(yn0 + k * YS) * GT_C] = pre0[k];
+        if (yA0 + k * ys0 < np0) colp[(yA0 + k * ys0) * GT_C] = pre0[k];
+      for (int yb = yA0 + PRE0 * ys0; yb < np0; yb += 8 * ys0) {        // larger patches (step > 1/4): unrolled chunks
+        float tmp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (yb + k * ys0 < np0) tmp[k] = load0(yb + k * ys0, ax_first, ay_first);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (yb + k * ys0 < np0) colp[(yb + k * ys0) * GT_C] = tmp[k];
+      }
+    }
+    if (stager1) {
+      float* colp = patch1 + xn1_ * np1 * GT_C + c1_;
 #pragma unroll
       for (int k = 0; k < PRE1; ++k)
-        if (yn0 + k * YS < np1) col1[(yn0 + k * YS) * GT_C] = pre1[k];
-      for (int yb = yn0 + PRE0 * YS; yb < np0; yb += 8 * YS) {       // larger patches (step > 1/4): unrolled chunks
+        if (yA1 + k * ys1 < np1) colp[(yA1 + k * ys1) * GT_C] = pre1[k];
+      for (int yb = yA1 + PRE1 * ys1; yb < np1; yb += 8 * ys1) {
         float tmp[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (yb + k * YS < np0) tmp[k] = load0(yb + k * YS, ax, ay_first);
+          if (yb + k * ys1 < np1) tmp[k] = load1(yb + k * ys1, ax_first, ay_first);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (yb + k * YS < np0) col0[(yb + k * YS) * GT_C] = tmp[k];
+          if (yb + k * ys1 < np1) colp[(yb + k * ys1) * GT_C] = tmp[k];
       }
-      for (int yb = yn0 + PRE1 * YS; yb < np1; yb += 8 * YS) {
-        float tmp[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (yb + k * YS < np1) tmp[k] = load1(yb + k * YS, ax, ay_first);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (yb + k * YS < np1) col1[(yb + k * YS) * GT_C] = tmp[k];
-      }
-    } else if (tid < 24 * YS + GT_PE) {
-      pex[tid - 24 * YS] = pe_value(g, ax.u1, tid - 24 * YS);     // the tile's x encoding, shared by its 128 texels
+    }
+    if (tid >= GT_T - GT_R * GT_PE) {      // the last 24 threads: x encodings of the GT_R rows, shared by their texels
+      const int e = tid - (GT_T - GT_R * GT_PE), row = e / GT_PE, rr = e - row * GT_PE;
+      pex[row * 8 + rr] = pe_value(g, axis_coord(px0 + row, g.step).u1, rr);
     }
     __syncthreads();
-    prefetch(tile + gridDim.x);        // next tile's nodes: in flight while this tile's rows are built
-    // ---- this thread's row, in reference column order (image_compression.py:94-96)
-    {
-      const AxisCoord ay = axis_coord(py0 + t, g.step);
-      const int y0 = ay.i0 - ay_first.i0, y1 = ay.i1 - ay_first.i1;
-      float v[GT_CIN];
-      // G0 corners (dy,dx) = (0,0) (1,0) (0,1) (1,1): raw copies
+    prefetch(tile + gridDim.x);        // next super-tile's nodes: in flight while this one's rows are built
+    const AxisCoord ay = axis_coord(py0 + t, g.step);
+    const int y0 = ay.i0 - ay_first.i0, y1 = ay.i1 - ay_first.i1;
+    const float ky = ay.k, wy0 = __fsub_rn(1.0f, ky);
+    float pey[GT_PE];
+    if (g.pe_kind == NIC_PE_TRIANGULAR) {
+      pe6_triangular(ay.u1, pey);
+    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int dy = j & 1, dx = j >> 1;
-        const float4* node = reinterpret_cast<const float4*>(patch0 + (dx * np0 + y0 + dy) * GT_C);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          float4 f = node[q];
-          v[12 * j + 4 * q] = f.x;
-          v[12 * j + 4 * q + 1] = f.y;
-          v[12 * j + 4 * q + 2] = f.z;
-          v[12 * j + 4 * q + 3] = f.w;
-        }
-      }
-      // G1: ((g*wx)*wy) per corner, summed ((c0+c1)+c2)+c3 (fp_def.py:136-144, image_compression.py:95)
+      for (int rr = 0; rr < GT_PE; ++rr) pey[rr] = pe_sinusoidal(ay.u1, rr, g.pe_div);
+    }
+    const unsigned b = tile / tiles_per_block, r = tile - b * tiles_per_block;
+    const unsigned xg = r / tiles_per_row, run = r - xg * tiles_per_row;
+#pragma unroll 1
+    for (int row = 0; row < GT_R; ++row, ++nstore) {
+      OutT* stage = reinterpret_cast<OutT*>(smem_raw + (nstore & 1) * STAGE_BYTES);
+      // the bulk store that used this staging buffer two rows ago must have finished READING it
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+      // ---- this thread's row, in reference column order (image_compression.py:94-96), streamed piece by piece
       {
-        const float kx = ax.k, ky = ay.k;
-        const float wx0 = __fsub_rn(1.0f, kx), wy0 = __fsub_rn(1.0f, ky);
+        const AxisCoord ax = axis_coord(px0 + row, g.step);
+        const int x0 = ax.i0 - ax_first.i0, x1 = ax.i1 - ax_first.i1;
+        RowWriter<OutT> w(stage, t, par);
+        // G0 corners (dy,dx) = (0,0) (1,0) (0,1) (1,1): raw copies
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int dy = j & 1, dx = j >> 1;
-          const float wx = dx ? kx : wx0, wy = dy ? ky : wy0;
-          const float4* node = reinterpret_cast<const float4*>(patch1 + (dx * np1 + y1 + dy) * GT_C);
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const float4 f = node[q];
-            float e0 = f.x, e1 = f.y, e2 = f.z, e3 = f.w;
-            if (g.interp) {
-              e0 = __fmul_rn(__fmul_rn(e0, wx), wy);
-              e1 = __fmul_rn(__fmul_rn(e1, wx), wy);
-              e2 = __fmul_rn(__fmul_rn(e2, wx), wy);
-              e3 = __fmul_rn(__fmul_rn(e3, wx), wy);
-            }
-            v[48 + 4 * q] = j == 0 ? e0 : __fadd_rn(v[48 + 4 * q], e0);
-            v[48 + 4 * q + 1] = j == 0 ? e1 : __fadd_rn(v[48 + 4 * q + 1], e1);
-            v[48 + 4 * q + 2] = j == 0 ? e2 : __fadd_rn(v[48 + 4 * q + 2], e2);
-            v[48 + 4 * q + 3] = j == 0 ? e3 : __fadd_rn(v[48 + 4 * q + 3], e3);
-          }
+          const float4* node = reinterpret_cast<const float4*>(patch0 + ((x0 + dx) * np0 + y0 + dy) * GT_C);
+          const float4 f0 = node[0], f1 = node[1], f2 = node[2];
+          const float v[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+          w.template put<12>(v, 12 * j);
         }
-      }
-      // positional encodings of u1 along x (shared) then y, then the LOD column
+        // G1: ((g*wx)*wy) per corner, summed ((c0+c1)+c2)+c3 (fp_def.py:136-144, image_compression.py:95)
+        {
+          const float kx = ax.k, wx0 = __fsub_rn(1.0f, kx);
+          float acc[12];
 #pragma unroll
-      for (int rr = 0; rr < GT_PE; ++rr) v[60 + rr] = pex[rr];
-      if (g.pe_kind == NIC_PE_TRIANGULAR) {
-        pe6_triangular(ay.u1, v + 66);
-      } else {
+          for (int j = 0; j < 4; ++j) {
+            const int dy = j & 1, dx = j >> 1;
+            const float wx = dx ? kx : wx0, wy = dy ? ky : wy0;
+            const float4* node = reinterpret_cast<const float4*>(patch1 + ((x1 + dx) * np1 + y1 + dy) * GT_C);
+            const float4 f0 = node[0], f1 = node[1], f2 = node[2];
+            float e[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
 #pragma unroll
-        for (int rr = 0; rr < GT_PE; ++rr) v[66 + rr] = pe_sinusoidal(ay.u1, rr, g.pe_div);
+            for (int c = 0; c < 12; ++c) {
+              if (g.interp) e[c] = __fmul_rn(__fmul_rn(e[c], wx), wy);
+              acc[c] = j == 0 ? e[c] : __fadd_rn(acc[c], e[c]);
+            }
+          }
+          w.template put<12>(acc, 48);
+        }
+        // positional encodings of u1 along x (shared by the row) then y, then the LOD column
+        {
+          float pe[GT_PE];
+#pragma unroll
+          for (int rr = 0; rr < GT_PE; ++rr) pe[rr] = pex[row * 8 + rr];
+          w.template put<GT_PE>(pe, 60);
+          w.template put<GT_PE>(pey, 66);
+        }
+        w.last(g.lod);
       }
-      v[72] = g.lod;
-      write_row<OutT>(stage, t, par, v);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> visible to the bulk copy
-    __syncthreads();
-    if (tid == 0) {
-      OutT* dst = x + (size_t)tile * GT_T * GT_CIN;                    // tiles are consecutive spans of X
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(gt_smem_u32(stage)),
-                   "r"(STAGE_BYTES)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the bulk copy
+      __syncthreads();
+      if (tid == 0) {
+        // sample index of this row's first texel: block b, x row xg*GT_R + row, y run `run`
+        const size_t n0 = (size_t)b * (size_t)g.per_block + ((size_t)xg * GT_R + row) * (size_t)g.B[1] + (size_t)run * GT_T;
+        OutT* dst = x + n0 * GT_CIN;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(gt_smem_u32(stage)),
+                     "r"(STAGE_BYTES)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     }
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 bool gather_tile_eligible(const DevGeom& g, const void* x) {
+  // x-nodes a group of GT_R rows can touch: floor((GT_R-1)*step) + 3 (unaligned start); 12 * nx staging columns <= 128
+  const int nx0 = (int)floorf((GT_R - 1) * g.step) + 3;
   return g.method == NIC_METHOD_2D && g.C == GT_C && g.PE == GT_PE && g.step <= 1.0f && g.step >= 1.0f / 1024.0f &&
-         g.B[1] > 0 && g.B[1] % GT_T == 0 && g.N > 0 && g.N < (1ll << 31) && (((uintptr_t)x) & 15) == 0;
+         GT_C * nx0 <= GT_T && g.B[1] > 0 && g.B[1] % GT_T == 0 && g.B[0] % GT_R == 0 && g.N > 0 && g.N < (1ll << 31) &&
+         (((uintptr_t)x) & 15) == 0;
 }
 
 template <typename OutT>
@@ -274,19 +307,25 @@ static int launch_gather_tile_t(Handle* h, const DevGeom& g, const float* g0, co
                                 OutT* x, cudaStream_t st) {
   // nodes a run of T texels can touch along y: floor((T-1)*step) + 2 cells' corners, +1 for an unaligned start
   const int np0 = (int)floorf((GT_T - 1) * g.step) + 3, np1 = (int)floorf((GT_T - 1) * g.step * 0.5f) + 3;
-  const size_t smem = 2 * (size_t)GT_T * GT_CIN * sizeof(OutT) + ((size_t)2 * (np0 + np1) * GT_C + 8) * sizeof(float);
+  const int nx0 = (int)floorf((GT_R - 1) * g.step) + 3, nx1 = (int)floorf((GT_R - 1) * g.step * 0.5f) + 3;
+  const size_t smem = 2 * (size_t)GT_T * GT_CIN * sizeof(OutT) +
+                      ((size_t)(nx0 * np0 + nx1 * np1) * GT_C + 8 * GT_R) * sizeof(float);
+  if (smem > 200 * 1024) return NIC_ERR_UNSUPPORTED;
   auto kern = gather_tile_kernel<OutT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const unsigned tiles_per_row = (unsigned)(g.B[1] / GT_T);
-  const unsigned ntiles = (unsigned)(g.N / GT_T);
-  int per_sm = (int)((200 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  const unsigned ntiles = (unsigned)(g.N / (GT_T * GT_R));
+  int per_sm = 8;
+  {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GT_T, smem) == cudaSuccess && occ > 0) per_sm = occ;
+  }
   long long cap = (long long)h->sms * per_sm;
   int grid = (int)(ntiles < cap ? ntiles : cap);
   {
     KernelTimer timer(h, st);
-    kern<<<grid, GT_T, smem, st>>>(g, g0, g1, origins, x, np0, np1, ntiles, tiles_per_row);
+    kern<<<grid, GT_T, smem, st>>>(g, g0, g1, origins, x, nx0, nx1, np0, np1, ntiles, tiles_per_row);
   }
   h->launches++;
   return (int)cudaGetLastError();
