@@ -86,6 +86,7 @@ int nic_destroy(NicHandle* h) {
   cudaSetDevice(h->device);
   if (h->tc_weights) cudaFree(h->tc_weights);
   if (h->tc_shadow) cudaFree(h->tc_shadow);
+  if (h->tc_gscratch) cudaFree(h->tc_gscratch);
   if (h->adam_desc) cudaFree(h->adam_desc);
   for (int i = 0; i < 2 * NIC_MAX_TIMED; ++i)
     if (h->timed_ev[i]) cudaEventDestroy(h->timed_ev[i]);
@@ -307,10 +308,19 @@ int nic_train_step(NicHandle* h, const NicGeom* g, const float* g0, const float*
     return fail(h, NIC_ERR_ARG, "nic_train_step: NULL pointer");
   if ((dg0 == nullptr) != (dg1 == nullptr)) return fail(h, NIC_ERR_ARG, "nic_train_step: dg0 and dg1 must both be set or both NULL");
   if (noise_bits < 0 || noise_bits > 24) return fail(h, NIC_ERR_ARG, "nic_train_step: noise_bits %d", noise_bits);
-  if (precision != NIC_PREC_F32) return fail(h, NIC_ERR_UNSUPPORTED, "nic_train_step: only NIC_PREC_F32 is built in this round");
+  if (precision != NIC_PREC_F32 && precision != NIC_PREC_F16 && precision != NIC_PREC_BF16)
+    return fail(h, NIC_ERR_ARG, "nic_train_step: precision %d", precision);
   long long denom = (global_n > 0 ? global_n : d.N) * (long long)md.cout;
   float grad_scale = denom > 0 ? (float)(1.0 / (double)denom) : 0.f;
   MlpGradDev gd = {gm->w1, gm->b1, gm->w2, gm->b2, gm->w3, gm->b3};
+  if (precision != NIC_PREC_F32) {
+    int trc = launch_train_tc(h, d, md, gd, g0, g1, (const long long*)origins, targets, noise, noise_bits, seed, step, grad_scale,
+                              dg0, dg1, loss_sum, out, precision, st);
+    if (trc == NIC_ERR_UNSUPPORTED)
+      return fail(h, trc, "nic_train_step: the tensor-core step covers the 2-D method with C=12, PE=6, hidden 64 and crop origins; "
+                          "use NIC_PREC_F32 for this configuration");
+    return cuda_fail(h, trc, "nic_train_step(tensor core)");
+  }
   return cuda_fail(h, launch_train_f32(h, d, md, gd, g0, g1, (const long long*)origins, targets, noise, noise_bits, seed, step,
                                        grad_scale, dg0, dg1, loss_sum, out, st), "nic_train_step");
 }

@@ -27,6 +27,8 @@ struct Handle {
   size_t tc_weights_bytes;
   void* tc_shadow;           // 16-bit channel-last shadows of the two active grids
   size_t tc_shadow_bytes;
+  void* tc_gscratch;         // channel-last fp32 grid-gradient scratch of the tensor-core training step (kept zero)
+  size_t tc_gscratch_bytes;
   int disable_fast2d;        // testing knob: force the general tensor-core kernel
   int reuse_prepared;        // NIC_OPT_REUSE_PREPARED
   struct PreparedKey {       // what the tables in tc_weights / tc_shadow were last built from
@@ -187,6 +189,10 @@ int launch_train_f32(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGrad
                      float* dg1, float* loss_sum, float* out_save, cudaStream_t st);
 int launch_decode_tc(Handle* h, const DevGeom& g, const MlpDev& m, const float* g0, const float* g1,
                      const long long* origins, void* out, int out_dtype, int precision, cudaStream_t st);
+int launch_train_tc(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradDev& gm, const float* g0, const float* g1,
+                    const long long* origins, const float* targets, const float* noise, int noise_bits,
+                    unsigned long long seed, unsigned long long step, float grad_scale, float* dg0, float* dg1,
+                    float* loss_sum, float* out_save, int precision, cudaStream_t st);
 int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
                 float grad_scale, int zero_grad, cudaStream_t st);
 int launch_quantize4fp(Handle* h, const float* src, float* dst, long long n, int bits, cudaStream_t st);

@@ -1,0 +1,250 @@
+// nic_tc_common.cuh — tcgen05 / TMEM / mbarrier PTX wrappers, UMMA descriptors, packed 16-bit math and the shadow-grid
+// relayout shared by the tensor-core kernels (nic_tc.cu: decode, nic_train_tc.cu: training step).
+#pragma once
+#include <cstring>
+
+#include "nic_internal.cuh"
+
+namespace nic {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires)
+// instead of burning issue slots in a spin loop.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITS_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONES_%=;\n\t"
+      "bra WAITS_%=;\n\t"
+      "DONES_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
+// tcgen05.commit: the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread is done.
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]   (kind::f16: f16 or bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): in 16-byte units the
+// canonical layout is ((8,n),2):((1,SBO),LBO) — 8 rows x 16 B form a 128-byte core matrix, SBO steps to the next
+// 8-row group, LBO to the next 8-element K chunk.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B format fmt (0 f16, 1 bf16), both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int b_mn_major = 0) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// tcgen05.ld / st, shape 32x32b: thread i of warp w touches TMEM lane 32*(w%4)+i, one 32-bit column per register.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ 16-bit math
+template <int FMT> struct Pair;   // FMT 0 = f16, 1 = bf16
+template <> struct Pair<0> {
+  using T2 = __half2;
+  static __device__ __forceinline__ T2 pack(float a, float b) { return __floats2half2_rn(a, b); }
+  static __device__ __forceinline__ T2 cst(float a) { return __float2half2_rn(a); }
+  static __device__ __forceinline__ T2 tanh2(T2 x) {
+    uint32_t r, v = *reinterpret_cast<uint32_t*>(&x);
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(v));
+    return *reinterpret_cast<T2*>(&r);
+  }
+};
+template <> struct Pair<1> {
+  using T2 = __nv_bfloat162;
+  static __device__ __forceinline__ T2 pack(float a, float b) { return __floats2bfloat162_rn(a, b); }
+  static __device__ __forceinline__ T2 cst(float a) { return __float2bfloat162_rn(a); }
+  static __device__ __forceinline__ T2 tanh2(T2 x) {
+    uint32_t r, v = *reinterpret_cast<uint32_t*>(&x);
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(v));
+    return *reinterpret_cast<T2*>(&r);
+  }
+};
+
+// 2*GELU_tanh on a packed pair: x + x*tanh(x*(c1 + c2*x^2)); the factor 1/2 lives in the next layer's weights.
+template <int FMT>
+__device__ __forceinline__ uint32_t gelu2x_pair(float a, float b) {
+  using P = Pair<FMT>;
+  typename P::T2 x = P::pack(a, b);
+  typename P::T2 x2 = __hmul2(x, x);
+  typename P::T2 p = __hfma2(x2, P::cst(0.0356774081f), P::cst(0.7978845608f));
+  typename P::T2 t = P::tanh2(__hmul2(p, x));
+  typename P::T2 h = __hfma2(x, t, x);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int FMT>
+__device__ __forceinline__ uint16_t to16(float v) {
+  if (FMT == 0) {
+    __half h = __float2half_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__host__ __device__ constexpr int b_image_bytes(int nrows, int k) { return nrows * k * 2; }
+
+// ------------------------------------------------------------------------------------------------ shadow grids
+// The tensor-core path reads 16-bit, channel-LAST copies of the two active grids, transposed so that the fast texel
+// axis is contiguous: shadow[((x*Ny + y)*Nz + z)*C + c] = grid[c][z][y][x]  (2-D: Nz = 1, shadow[(x*Ny + y)*C + c]).
+// One node = C*2 bytes (24 B at C = 12) -> a corner is three 8-byte loads that land in the operand registers as is.
+// Written once per decode call by relayout_kernel (coalesced both ways through shared memory).
+template <int FMT>
+__global__ void __launch_bounds__(256) relayout_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C,
+                                                       int nx, int nf, int no, long long sf, long long so,
+                                                       long long plane) {
+  // tile: 32 nodes along x  x  32 nodes along the output-fast axis f, all channels; blockIdx.z = the other axis
+  extern __shared__ uint16_t tile[];           // [C][32][33]
+  const int x0 = blockIdx.x * 32, f0 = blockIdx.y * 32, o = blockIdx.z;
+  for (int i = threadIdx.x; i < C * 1024; i += blockDim.x) {
+    int c = i >> 10, r = i & 1023, fi = r >> 5, xi = r & 31;
+    int x = x0 + xi, f = f0 + fi;
+    float v = (x < nx && f < nf) ? __ldg(src + (long long)c * plane + (long long)f * sf + (long long)o * so + x) : 0.f;
+    tile[(c * 32 + fi) * 33 + xi] = to16<FMT>(v);
+  }
+  __syncthreads();
+  const int fw = nf - f0 < 32 ? nf - f0 : 32;   // valid nodes along f in this tile
+  for (int xi = 0; xi < 32 && x0 + xi < nx; ++xi) {
+    uint16_t* row = dst + (((long long)(x0 + xi) * no + o) * nf + f0) * C;
+    for (int i = threadIdx.x; i < fw * C; i += blockDim.x) {
+      int fi = i / C, c = i - fi * C;
+      row[i] = tile[(c * 32 + fi) * 33 + xi];
+    }
+  }
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+
+// stores registers [lo, lo+n) of a row to operand-A columns [lo, lo+n) with the widest tcgen05.st shapes
+template <int N>
+__device__ __forceinline__ void store_row_part(uint32_t taddr, const uint32_t* r) {
+  if constexpr (N >= 16) {
+    tmem_st16(taddr, r);
+    store_row_part<N - 16>(taddr + 16, r + 16);
+  } else if constexpr (N >= 8) {
+    tmem_st8(taddr, r);
+    store_row_part<N - 8>(taddr + 8, r + 8);
+  } else if constexpr (N >= 4) {
+    tmem_st4(taddr, r);
+    store_row_part<N - 4>(taddr + 4, r + 4);
+  } else {
+    static_assert(N == 0, "row parts are multiples of 4 registers");
+  }
+}
+
+static inline long long plane_size_host(const int* n, int dim) {
+  return dim == 2 ? (long long)n[0] * n[1] : (long long)n[0] * n[1] * n[2];
+}
+
+static inline int ensure_scratch(void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return NIC_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  size_t sz = (need + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+  if (cudaMalloc(ptr, sz) != cudaSuccess) return NIC_ERR_SCRATCH;
+  *have = sz;
+  return NIC_OK;
+}
+
+template <int FMT>
+static inline int launch_relayout(Handle* h, const DevGeom& g, const float* src, const int* nodes, uint16_t* dst, cudaStream_t st) {
+  const int dim = g.dim;
+  const int nx = nodes[0], nf = dim == 2 ? nodes[1] : nodes[2], no = dim == 2 ? 1 : nodes[1];
+  const long long sf = dim == 2 ? nx : (long long)nodes[1] * nx, so = dim == 2 ? 0 : nx;
+  const long long plane = (long long)nx * nodes[1] * (dim == 2 ? 1 : nodes[2]);
+  dim3 grid((nx + 31) / 32, (nf + 31) / 32, no);
+  size_t smem = (size_t)g.C * 32 * 33 * sizeof(uint16_t);
+  relayout_kernel<FMT><<<grid, 256, smem, st>>>(src, dst, g.C, nx, nf, no, sf, so, plane);
+  h->launches++;
+  return (int)cudaGetLastError();
+}
+
+
+}  // namespace nic

@@ -1,0 +1,659 @@
+// nic_train_tc.cu — K3 + K4 on tensor cores: one fused training step (gather, quantisation noise, decoder forward, MSE,
+// full backward, weight-gradient sums, grid-gradient scatter) with EVERY GEMM on tcgen05.mma (sm_100a).
+// Reference behaviour: the body of train_models up to loss.backward() (Projects/image_compression.py:239-265) on the
+// 2-D path (create_decoder_input_2d :71-100, fp_def.create_g0_g1 fp_def.py:115-145, ColorDecoder :54-68).
+//
+// Per CTA (persistent, 256 threads = 2 warpgroups, one CTA per SM), per tile of 128 samples (= MMA M = TMEM lanes):
+//   activations live in shared memory as [sample-group of 8][feature-group of 8][8 samples][8 features] 16-bit core
+//   matrices.  ONE copy serves three operand views (no transposes are ever materialised):
+//     * K-major A  (M = samples,  K = features)  for the forward GEMMs and the delta-propagation GEMMs,
+//     * MN-major A (M = features, K = samples)   for the weight-gradient GEMMs (the reduction runs over the samples),
+//     * MN-major B (N = features, K = samples)   likewise;
+//   the delta-propagation GEMMs take small transposed weight images (K-major B) packed next to the forward ones.
+//   forward : Z1 = X~ W1'^T           (5 MMAs K=16)  -> h1' = 2 gelu(z1), g1' = d h1'/d z1 (registers)   -> H1
+//             Z2 = [H1|1] W2'^T       (5)            -> h2', g2'                                        -> H2
+//             Z3 = [H2|1] W3'^T       (5, N=16)      -> out = sigmoid, loss, dz3 = S (out - t) out (1 - out) -> DZ[0:16)
+//   backward: dH2 = dZ3 W3'           (1)   and  D3 += DZ^T [H2|1]   (8 MMAs, M=128 N=80 K=128: dW3', db3 in rows 0..2)
+//             dZ2 = dH2 * g2' -> DZ[16:80)
+//             dH1 = dZ2 W2'           (4)   and  D2 += DZ^T [H1|1]   (8: dW2', db2 in rows 16..79)
+//             dZ1 = dH1 * g1' -> DZ[16:80)
+//             dX  = dZ1 W1'           (4)   and  D1 += DZ^T X~       (8: dW1', db1 in rows 16..79)
+//             dX -> warp-aggregated red.global.add.v4.f32 into channel-last fp32 scratch grids (K4)
+//   D1, D2, D3 (fp32, TMEM) accumulate over ALL tiles of the CTA and are flushed once per launch with atomics.
+//   Biases ride in K (a constant-1 feature); the 1/2 of GELU is folded into the next layer's weights; dz3 carries a
+//   power-of-two loss scale S so that f16 deltas stay normal; S and the 2/(N*Cout) of the MSE mean are applied at the flush.
+//   GELU is the tanh form in forward AND backward (the gradient of the function actually evaluated).
+//   Noise: X~ = x + (U - 1/2) / 2^bits on all Cin columns (image_compression.py:248-251), Philox4x32-10 keyed by
+//   (seed), counter (sample, block, step); 16-bit uniforms, two per word.
+// Algorithmic work: 3 * 2 * (Cin*64 + 64*64 + 64*Cout) = 53,760 FLOP/sample; tensor-bound roofline.
+#include "nic_tc_common.cuh"
+
+namespace nic {
+
+constexpr int TT_ROWS = 128, TT_THREADS = 256;
+constexpr int TT_CIN = 73, TT_K1 = 80, TT_H = 64, TT_K2 = 80;
+constexpr int TT_SG80 = 10 * 128;          // sample-group stride of an 80-feature activation buffer (bytes)
+constexpr int TT_SG128 = 16 * 128;         // ... of the 128-feature delta buffer
+constexpr int TT_W1 = 64 * 80 * 2, TT_W2 = 64 * 80 * 2, TT_W3 = 16 * 80 * 2;
+constexpr int TT_ACT = 16 * TT_SG80;       // 20480
+constexpr int TT_DZ = 16 * TT_SG128;       // 32768
+constexpr int TT_W1T = 64 * 64 * 2, TT_W2T = 64 * 64 * 2, TT_W3T = 64 * 16 * 2;   // transposed images for the delta GEMMs
+constexpr int TT_WIMG = TT_W1 + TT_W2 + TT_W3 + TT_W1T + TT_W2T + TT_W3T;
+constexpr int TT_OFF_W1 = 0, TT_OFF_W2 = TT_OFF_W1 + TT_W1, TT_OFF_W3 = TT_OFF_W2 + TT_W2;
+constexpr int TT_OFF_W1T = TT_OFF_W3 + TT_W3, TT_OFF_W2T = TT_OFF_W1T + TT_W1T, TT_OFF_W3T = TT_OFF_W2T + TT_W2T;
+constexpr int TT_OFF_X = TT_OFF_W3T + TT_W3T, TT_OFF_H1 = TT_OFF_X + TT_ACT, TT_OFF_H2 = TT_OFF_H1 + TT_ACT;
+constexpr int TT_OFF_DZ = TT_OFF_H2 + TT_ACT, TT_OFF_MISC = TT_OFF_DZ + TT_DZ;
+constexpr int TT_SMEM = TT_OFF_MISC + 256;
+constexpr int TT_TMEM_COLS = 512;
+constexpr int TT_COL_D = 0, TT_COL_D1 = 64, TT_COL_D2 = 144, TT_COL_D3 = 224;
+constexpr float TT_LOSS_SCALE = 64.0f;
+
+// Instruction descriptor with explicit operand majors (bit 15: A is MN-major, bit 16: B is MN-major).
+__host__ __device__ constexpr uint32_t tt_idesc(int fmt, int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Training weight images (K-major B, no swizzle): element (n, k) at (k/8)*(NR/8)*128 + (n/8)*128 + (n%8)*16 + (k%8)*2.
+//   W1' [64 x 80]: k < 73: W1[n][k]; k = 73: b1[n]; rest 0      (the LOD column is a real, noisy input in training)
+//   W2' [64 x 80]: k < 64: W2[n][k]/2; k = 64: b2[n]
+//   W3' [16 x 80]: n < cout: k < 64: W3[n][k]/2; k = 64: b3[n]
+template <int FMT>
+__global__ void pack_train_weights_kernel(MlpDev m, uint16_t* __restrict__ img) {
+  // forward images, then the transposed ones used as K-major B of the delta-propagation GEMMs:
+  //   W1T' [64 x 64]: (n = input column < 64, k = hidden j) = W1[j][n]        (dX = dZ1 W1; only grid columns are needed)
+  //   W2T' [64 x 64]: (n = k_in, k = j) = W2[j][k_in] / 2                     (dH1' = dZ2 W2')
+  //   W3T' [64 x 16]: (n = h, k = c)    = W3[c][h] / 2 for c < cout           (dH2' = dZ3 W3')
+  const int n1 = 64 * 80, n2 = 64 * 80, n3 = 16 * 80, n4 = 64 * 64, n5 = 64 * 64, n6 = 64 * 16;
+  const int off[7] = {0, n1, n1 + n2, n1 + n2 + n3, n1 + n2 + n3 + n4, n1 + n2 + n3 + n4 + n5, n1 + n2 + n3 + n4 + n5 + n6};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < off[6]; i += gridDim.x * blockDim.x) {
+    int which = 0;
+    while (i >= off[which + 1]) ++which;
+    const int local = i - off[which];
+    const int nrows = which == 2 ? 16 : 64;
+    const int kc = local / (nrows * 8), rem = local - kc * nrows * 8;
+    const int n = rem / 8, k = kc * 8 + (rem - n * 8);
+    float v = 0.f;
+    if (which == 0) v = k < m.cin ? m.w1[n * m.cin + k] : (k == m.cin ? m.b1[n] : 0.f);
+    else if (which == 1) v = k < 64 ? 0.5f * m.w2[n * 64 + k] : (k == 64 ? m.b2[n] : 0.f);
+    else if (which == 2) { if (n < m.cout) v = k < 64 ? 0.5f * m.w3[n * 64 + k] : (k == 64 ? m.b3[n] : 0.f); }
+    else if (which == 3) v = m.w1[k * m.cin + n];
+    else if (which == 4) v = 0.5f * m.w2[k * 64 + n];
+    else if (k < m.cout) v = 0.5f * m.w3[k * 64 + n];
+    img[i] = to16<FMT>(v);
+  }
+}
+
+// dg[c][y][x] += scale * s[(x*ny + y)*C + c];  s <- 0   (channel-last fp32 scratch -> the caller's channel-major grid)
+__global__ void __launch_bounds__(256) grad_relayout_add_kernel(float* __restrict__ s, float* __restrict__ dg, int C, int nx,
+                                                                int ny, float scale) {
+  extern __shared__ float tile_f[];            // [C][32][33]
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  const int yw = ny - y0 < 32 ? ny - y0 : 32;
+  for (int xi = 0; xi < 32 && x0 + xi < nx; ++xi) {
+    float* row = s + ((size_t)(x0 + xi) * ny + y0) * C;
+    for (int i = threadIdx.x; i < yw * C; i += blockDim.x) {
+      int yi = i / C, c = i - yi * C;
+      tile_f[(c * 32 + yi) * 33 + xi] = row[i];
+      row[i] = 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 1024; i += blockDim.x) {
+    int c = i >> 10, r = i & 1023, yi = r >> 5, xi = r & 31;
+    int x = x0 + xi, y = y0 + yi;
+    if (x < nx && y < ny) {
+      float v = tile_f[(c * 32 + yi) * 33 + xi];
+      if (v != 0.f) dg[((size_t)c * ny + y) * nx + x] += scale * v;
+    }
+  }
+}
+
+// (h', g') for a pair: h' = 2 gelu_tanh(x) = x + x t,  g' = d h'/dx = (1 + t) + x (1 - t^2)(c1 + 3 c2 x^2),
+// t = tanh(x (c1 + c2 x^2)).  Packed 16-bit math; the activation feeds the next MMA, the derivative stays in registers.
+template <int FMT>
+__device__ __forceinline__ void gelu2x_pair_grad(float a, float b, uint32_t& h_out, uint32_t& g_out) {
+  using P = Pair<FMT>;
+  typename P::T2 x = P::pack(a, b);
+  typename P::T2 x2 = __hmul2(x, x);
+  typename P::T2 p = __hfma2(x2, P::cst(0.0356774081f), P::cst(0.7978845608f));
+  typename P::T2 t = P::tanh2(__hmul2(p, x));
+  typename P::T2 h = __hfma2(x, t, x);
+  typename P::T2 q = __hfma2(x2, P::cst(3.0f * 0.0356774081f), P::cst(0.7978845608f));
+  typename P::T2 s = __hfma2(__hneg2(t), t, P::cst(1.0f));
+  typename P::T2 gd = __hfma2(__hmul2(x, s), q, __hadd2(t, P::cst(1.0f)));
+  h_out = *reinterpret_cast<uint32_t*>(&h);
+  g_out = *reinterpret_cast<uint32_t*>(&gd);
+}
+
+template <int FMT>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  if (FMT == 0) return __half22float2(*reinterpret_cast<__half2*>(&v));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+}
+
+// (U - 1/2) * amp for the two 16-bit halves of a Philox word; U = (u16 + 1/2) / 65536.
+__device__ __forceinline__ float2 noise_pair(uint32_t w, float amp) {
+  float lo = ((float)(w & 0xFFFFu) - 32767.5f) * (1.0f / 65536.0f);
+  float hi = ((float)(w >> 16) - 32767.5f) * (1.0f / 65536.0f);
+  return make_float2(lo * amp, hi * amp);
+}
+
+
+// Segmented warp reduction for the scatter: lanes whose `key` (grid node) is equal and contiguous are summed into the
+// first lane of the run; runs are also cut every 2^steps lanes so that `steps` shuffle rounds always suffice.
+// Returns true on the lanes that must issue the atomic.
+__device__ __forceinline__ bool seg_reduce4(int key, int steps, int lane, float* v) {
+  const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
+  const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+  const int L = 1 << steps, sub = (lane - start) & (L - 1);
+  for (int d = 1; d < L; d <<= 1) {
+    const int kd = __shfl_down_sync(0xffffffffu, key, d);
+    const bool same = lane + d < 32 && kd == key && sub + d < L;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float o = __shfl_down_sync(0xffffffffu, v[e], d);
+      if (same) v[e] += o;
+    }
+  }
+  return sub == 0;
+}
+
+struct TrainArgs {
+  const uint2* s0;            // 16-bit channel-last shadow of G0: [x][y][12]
+  const uint2* s1;            // ... of G1
+  const long long* origins;   // [nblocks, 2]
+  const uint4* wimg;          // packed W1' W2' W3'
+  const float* targets;       // [N, cout]
+  const float* noise;         // optional injected noise [N, cin]
+  float* dgs0;                // channel-last fp32 gradient scratch of G0 (NULL: grids frozen)
+  float* dgs1;
+  float* loss_sum;
+  float* out_save;
+  MlpGradDev gm;
+  float noise_amp;            // 2^-bits, 0 = no in-kernel noise
+  unsigned long long seed, step;
+  float flush_scale;          // 2 / (N_global * cout) / S
+  int cout;
+  int steps0, steps1;         // segmented-reduction depths of the scatter (lanes sharing a G0 / G1 node)
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, TrainArgs a) {
+  using P = Pair<FMT>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sX = smem + TT_OFF_X;
+  uint8_t* sH1 = smem + TT_OFF_H1;
+  uint8_t* sH2 = smem + TT_OFF_H2;
+  uint8_t* sDZ = smem + TT_OFF_DZ;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TT_OFF_MISC);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  float* sRed = reinterpret_cast<float*>(smem + TT_OFF_MISC + 32);      // [8] loss partials
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2;                       // column half of the epilogues / row half of the gather
+  const int row = tid & (TT_ROWS - 1);            // sample of the tile = TMEM lane
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  // byte offset of this sample's 16-byte chunk inside a feature group, for the two buffer widths
+  const int roff80 = (row >> 3) * TT_SG80 + (row & 7) * 16, roff128 = (row >> 3) * TT_SG128 + (row & 7) * 16;
+
+  if (warp == 0) tmem_alloc(tmem_slot, TT_TMEM_COLS);
+  if (tid == 0) mbar_init(mbar, 1);
+  {
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < TT_WIMG / 16; i += TT_THREADS) dst[i] = __ldg(a.wimg + i);
+    // zero the activation / delta buffers once (padding features must be finite), then the constant-1 bias features
+    uint4* act = reinterpret_cast<uint4*>(smem + TT_OFF_X);
+    for (int i = tid; i < (3 * TT_ACT + TT_DZ) / 16; i += TT_THREADS) act[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  if (wg == 0) {
+    auto one = P::pack(1.0f, 0.0f);
+    const uint32_t o = *reinterpret_cast<uint32_t*>(&one);
+    *reinterpret_cast<uint4*>(sH1 + roff80 + 8 * 128) = make_uint4(o, 0, 0, 0);     // feature 64 = 1
+    *reinterpret_cast<uint4*>(sH2 + roff80 + 8 * 128) = make_uint4(o, 0, 0, 0);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t aW1 = smem_u32(smem + TT_OFF_W1), aW2 = smem_u32(smem + TT_OFF_W2), aW3 = smem_u32(smem + TT_OFF_W3);
+  const uint32_t aW1T = smem_u32(smem + TT_OFF_W1T), aW2T = smem_u32(smem + TT_OFF_W2T), aW3T = smem_u32(smem + TT_OFF_W3T);
+  const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aDZ = smem_u32(sDZ);
+  constexpr uint32_t ID_F64 = tt_idesc(FMT, 128, 64, 0, 0), ID_F16 = tt_idesc(FMT, 128, 16, 0, 0);
+  constexpr uint32_t ID_B64 = tt_idesc(FMT, 128, 64, 0, 0);        // delta propagation: A K-major, B = transposed image
+  constexpr uint32_t ID_G80 = tt_idesc(FMT, 128, 80, 1, 1);        // weight gradients: both operands MN-major
+  constexpr uint32_t WG64 = 8 * 128, WG16 = 2 * 128;               // k-group strides of the 64-row / 16-row weight images
+  uint32_t phase = 0;
+  float loss_local = 0.f;
+  unsigned tiles_done = 0;
+
+  // hand the tensor core a batch of MMAs and wait for them
+  auto run_mmas = [&](auto&& issue) {
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue();
+      tc_commit(mbar);
+    }
+    mbar_wait_sleep(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+  };
+  // weight-gradient GEMM: Dacc[128 x 80] (+)= DZ^T (features x samples) . Bbuf (samples x 80 features)
+  auto issue_wgrad = [&](uint32_t dcol, uint32_t bbuf) {
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc)
+      mma_ss(tmem + dcol, make_smem_desc(aDZ + kc * 2 * TT_SG128, TT_SG128, 128),
+             make_smem_desc(bbuf + kc * 2 * TT_SG80, TT_SG80, 128), ID_G80, (tiles_done > 0 || kc > 0) ? 1u : 0u);
+  };
+
+  const unsigned ntiles = (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS);
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tiles_done) {
+    const unsigned n = tile * TT_ROWS + row;
+    const bool live = n < (unsigned)g.N;
+    const unsigned nc = live ? n : (unsigned)g.N - 1;
+    // ------------------------------------------------------------------------------------------ gather + noise -> X~
+    Texel t = texel_of_fast(g, nc, a.origins);
+    AxisCoord ax[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      ax[d] = axis_coord(t.p[d], g.step);
+      ax[d].i0 = clampi(ax[d].i0, 0, g.n0[d] - 2);
+      ax[d].i1 = clampi(ax[d].i1, 0, g.n1[d] - 2);
+    }
+    const int node0 = ax[0].i0 * g.n0[1] + ax[1].i0, node1 = ax[0].i1 * g.n1[1] + ax[1].i1;   // corner (0,0); +1: y, +ny: x
+    {
+      float xv[48];            // this thread's half of the row: wg 0 -> columns [0,48), wg 1 -> columns [48,80)
+      if (wg == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint2* node = a.s0 + 3 * (size_t)(node0 + (j & 1) + (j >> 1) * g.n0[1]);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            uint2 v = __ldg(node + q);
+            float2 lo = unpack2<FMT>(v.x), hi = unpack2<FMT>(v.y);
+            xv[12 * j + 4 * q] = lo.x;
+            xv[12 * j + 4 * q + 1] = lo.y;
+            xv[12 * j + 4 * q + 2] = hi.x;
+            xv[12 * j + 4 * q + 3] = hi.y;
+          }
+        }
+      } else {
+        const float kx = ax[0].k, ky = ax[1].k;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int dy = j & 1, dx = j >> 1;
+          float w = 1.0f;
+          if (g.interp) w = (dx ? kx : 1.0f - kx) * (dy ? ky : 1.0f - ky);
+          const uint2* node = a.s1 + 3 * (size_t)(node1 + dy + dx * g.n1[1]);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            uint2 v = __ldg(node + q);
+            float2 lo = unpack2<FMT>(v.x), hi = unpack2<FMT>(v.y);
+            xv[4 * q] = j == 0 ? w * lo.x : fmaf(w, lo.x, xv[4 * q]);
+            xv[4 * q + 1] = j == 0 ? w * lo.y : fmaf(w, lo.y, xv[4 * q + 1]);
+            xv[4 * q + 2] = j == 0 ? w * hi.x : fmaf(w, hi.x, xv[4 * q + 2]);
+            xv[4 * q + 3] = j == 0 ? w * hi.y : fmaf(w, hi.y, xv[4 * q + 3]);
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+#pragma unroll
+          for (int r = 0; r < 6; ++r) xv[12 + 6 * d + r] = pe_value(g, ax[d].u1, r);
+        xv[24] = g.lod;
+#pragma unroll
+        for (int i = 25; i < 32; ++i) xv[i] = 0.f;
+      }
+      const int col0 = wg == 0 ? 0 : 48, ncols = wg == 0 ? 48 : 25;     // real (noisy) columns of this half
+      if (a.noise) {
+        const float* nz = a.noise + (size_t)nc * TT_CIN + col0;
+#pragma unroll
+        for (int i = 0; i < 48; ++i)
+          if (i < ncols) xv[i] += nz[i];
+      } else if (a.noise_amp > 0.f) {
+#pragma unroll
+        for (int blk = 0; blk < 6; ++blk) {
+          if (8 * blk < ncols) {
+            uint4 r = philox4x32(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(col0 / 8 + blk));
+            const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 z = noise_pair(wds[k], a.noise_amp);
+              if (8 * blk + 2 * k < ncols) xv[8 * blk + 2 * k] += z.x;
+              if (8 * blk + 2 * k + 1 < ncols) xv[8 * blk + 2 * k + 1] += z.y;
+            }
+          }
+        }
+      }
+      if (wg == 1) xv[25] = 1.0f;                    // feature 73: the bias carrier (not an input: no noise)
+      // 16-byte chunks of 8 features -> X~ buffer
+      const int fg0 = wg == 0 ? 0 : 6, nfg = wg == 0 ? 6 : 4;
+#pragma unroll
+      for (int f = 0; f < 6; ++f) {
+        if (f < nfg) {
+          uint4 v;
+          auto p0 = P::pack(xv[8 * f], xv[8 * f + 1]), p1 = P::pack(xv[8 * f + 2], xv[8 * f + 3]);
+          auto p2 = P::pack(xv[8 * f + 4], xv[8 * f + 5]), p3 = P::pack(xv[8 * f + 6], xv[8 * f + 7]);
+          v.x = *reinterpret_cast<uint32_t*>(&p0);
+          v.y = *reinterpret_cast<uint32_t*>(&p1);
+          v.z = *reinterpret_cast<uint32_t*>(&p2);
+          v.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(sX + roff80 + (fg0 + f) * 128) = v;
+        }
+      }
+    }
+    // ------------------------------------------------------------------------------------------ forward
+    // d h'/d z of this thread's 32 hidden columns, layers 1 and 2.  The two layer loops below are FULLY unrolled: with a
+    // rolled loop (layer a run-time value) nvcc 12.9 mis-compiled the conditional writes into these register arrays.
+    uint32_t gd1[16], gd2[16];
+    run_mmas([&] {
+#pragma unroll
+      for (int kc = 0; kc < TT_K1 / 16; ++kc)
+        mma_ss(tmem + TT_COL_D, make_smem_desc(aX + kc * 256, 128, TT_SG80), make_smem_desc(aW1 + kc * 2 * WG64, WG64, 128),
+               ID_F64, kc > 0);
+    });
+#pragma unroll
+    for (int layer = 0; layer < 2; ++layer) {
+      uint32_t acc[32];
+      tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
+      tc_wait_ld();
+      uint8_t* dstb = (layer == 0 ? sH1 : sH2) + roff80 + wg * 4 * 128;
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        uint32_t hp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t gg;
+          gelu2x_pair_grad<FMT>(__uint_as_float(acc[8 * f + 2 * i]), __uint_as_float(acc[8 * f + 2 * i + 1]), hp[i], gg);
+          if (layer == 0) gd1[4 * f + i] = gg;
+          else gd2[4 * f + i] = gg;
+        }
+        *reinterpret_cast<uint4*>(dstb + f * 128) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      }
+      if (layer == 0) {
+        run_mmas([&] {
+#pragma unroll
+          for (int kc = 0; kc < TT_K2 / 16; ++kc)
+            mma_ss(tmem + TT_COL_D, make_smem_desc(aH1 + kc * 256, 128, TT_SG80),
+                   make_smem_desc(aW2 + kc * 2 * WG64, WG64, 128), ID_F64, kc > 0);
+        });
+      } else {
+        run_mmas([&] {
+#pragma unroll
+          for (int kc = 0; kc < TT_K2 / 16; ++kc)
+            mma_ss(tmem + TT_COL_D, make_smem_desc(aH2 + kc * 256, 128, TT_SG80),
+                   make_smem_desc(aW3 + kc * 2 * WG16, WG16, 128), ID_F16, kc > 0);
+        });
+      }
+    }
+    // ------------------------------------------------------------------------------------------ output, loss, dz3
+    if (wg == 0) {
+      uint32_t acc[16];
+      tmem_ld16(tmem + TT_COL_D + lane_base, acc);
+      tc_wait_ld();
+      float dz[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        dz[c] = 0.f;
+        if (c < a.cout && live) {
+          const float o = 1.0f / (1.0f + __expf(-__uint_as_float(acc[c])));
+          const float d = o - a.targets[(size_t)n * a.cout + c];
+          loss_local += d * d;
+          if (a.out_save) a.out_save[(size_t)n * a.cout + c] = o;
+          dz[c] = TT_LOSS_SCALE * d * o * (1.0f - o);
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        auto p0 = P::pack(dz[8 * f], dz[8 * f + 1]), p1 = P::pack(dz[8 * f + 2], dz[8 * f + 3]);
+        auto p2 = P::pack(dz[8 * f + 4], dz[8 * f + 5]), p3 = P::pack(dz[8 * f + 6], dz[8 * f + 7]);
+        *reinterpret_cast<uint4*>(sDZ + roff128 + f * 128) =
+            make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                       *reinterpret_cast<uint32_t*>(&p3));
+      }
+    }
+    // ------------------------------------------------------------------------------------------ backward
+    // dH2 = dZ3 W3' (K = 16 output features) and D3 += DZ^T [H2 | 1].  DZ[16:80) still holds the PREVIOUS tile's dZ1 here:
+    // it lands in rows 16..79 of D3, which are never read.
+    run_mmas([&] {
+      mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ, 128, TT_SG128), make_smem_desc(aW3T, WG64, 128), ID_B64, 0);
+      issue_wgrad(TT_COL_D3, aH2);
+    });
+#pragma unroll
+    for (int layer = 1; layer >= 0; --layer) {
+      uint32_t acc[32];
+      tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
+      tc_wait_ld();
+      uint8_t* dstb = sDZ + roff128 + (2 + wg * 4) * 128;
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        uint32_t dp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 gg = unpack2<FMT>(layer == 1 ? gd2[4 * f + i] : gd1[4 * f + i]);
+          auto v = P::pack(__uint_as_float(acc[8 * f + 2 * i]) * gg.x, __uint_as_float(acc[8 * f + 2 * i + 1]) * gg.y);
+          dp[i] = *reinterpret_cast<uint32_t*>(&v);
+        }
+        *reinterpret_cast<uint4*>(dstb + f * 128) = make_uint4(dp[0], dp[1], dp[2], dp[3]);
+      }
+      if (layer == 1) {
+        run_mmas([&] {      // dH1 = dZ2 W2'  and  D2 += DZ^T [H1 | 1]
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc)
+            mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG128),
+                   make_smem_desc(aW2T + kc * 2 * WG64, WG64, 128), ID_B64, kc > 0);
+          issue_wgrad(TT_COL_D2, aH1);
+        });
+      } else {
+        run_mmas([&] {      // dX = dZ1 W1' (grid columns only)  and  D1 += DZ^T X~
+          if (a.dgs0) {
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc)
+              mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG128),
+                     make_smem_desc(aW1T + kc * 2 * WG64, WG64, 128), ID_B64, kc > 0);
+          }
+          issue_wgrad(TT_COL_D1, aX);
+        });
+      }
+    }
+    // ------------------------------------------------------------------------------------------ grid-gradient scatter
+    if (a.dgs0) {
+      uint32_t acc[32];
+      tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
+      tc_wait_ld();
+      const float kx = ax[0].k, ky = ax[1].k;
+      // v4 group gi of this thread covers dX columns [32 wg + 4 gi, +4)
+#pragma unroll
+      for (int gi = 0; gi < 8; ++gi) {
+        const int gq = 8 * wg + gi;                 // global v4 group: 0..11 G0 (corner gq/3, part gq%3), 12..14 G1, 15 unused
+        float v[4] = {__uint_as_float(acc[4 * gi]), __uint_as_float(acc[4 * gi + 1]), __uint_as_float(acc[4 * gi + 2]),
+                      __uint_as_float(acc[4 * gi + 3])};
+        if (gq < 12) {
+          const int j = gq / 3, q = gq - 3 * j;
+          const int key = node0 + (j & 1) + (j >> 1) * g.n0[1];
+          const bool head = seg_reduce4(key, a.steps0, lane, v);
+          if (live && head) {
+            float* dst = a.dgs0 + (size_t)key * 12 + 4 * q;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+                         : "memory");
+          }
+        } else if (gq < 15) {
+          const int q = gq - 12;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int dy = j & 1, dx = j >> 1;
+            float w = 1.0f;
+            if (g.interp) w = (dx ? kx : 1.0f - kx) * (dy ? ky : 1.0f - ky);
+            float u[4] = {w * v[0], w * v[1], w * v[2], w * v[3]};
+            const int key = node1 + dy + dx * g.n1[1];
+            const bool head = seg_reduce4(key, a.steps1, lane, u);
+            if (live && head) {
+              float* dst = a.dgs1 + (size_t)key * 12 + 4 * q;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(u[0]), "f"(u[1]), "f"(u[2]), "f"(u[3])
+                           : "memory");
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
+  }
+  // -------------------------------------------------------------------------------------------- flush: MLP gradients
+  __syncthreads();
+  tc_fence_after();
+  if (tiles_done > 0) {
+    const float fs = a.flush_scale;
+    // D3: rows 0..cout-1 = output feature c; columns 0..63 = dW3'[c][h] (W3' = W3/2), column 64 = db3[c]
+    // D2 / D1: rows 16..79 = hidden unit j = row - 16; D2 columns 0..63 = dW2'[j][k] (W2' = W2/2), 64 = db2[j];
+    //          D1 columns 0..72 = dW1[j][cin], 73 = db1[j].  Warp-group 0 reads columns [0,48), 1 reads [48,80).
+    const int c0 = wg * 48, cw = wg == 0 ? 48 : 32;
+    for (int which = 0; which < 3; ++which) {
+      const uint32_t dcol = which == 0 ? TT_COL_D3 : (which == 1 ? TT_COL_D2 : TT_COL_D1);
+      uint32_t acc[48];
+      tmem_ld16(tmem + dcol + lane_base + c0, acc);
+      tmem_ld16(tmem + dcol + lane_base + c0 + 16, acc + 16);
+      if (wg == 0) tmem_ld16(tmem + dcol + lane_base + c0 + 32, acc + 32);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 48; ++i) {
+        if (i >= cw) continue;
+        const int col = c0 + i;
+        const float v = __uint_as_float(acc[i]) * fs;
+        if (which == 0) {
+          if (row < a.cout) {
+            if (col < 64) atomicAdd(a.gm.w3 + row * 64 + col, 0.5f * v);
+            else if (col == 64) atomicAdd(a.gm.b3 + row, v);
+          }
+        } else if (row >= 16 && row < 80) {
+          const int j = row - 16;
+          if (which == 1) {
+            if (col < 64) atomicAdd(a.gm.w2 + j * 64 + col, 0.5f * v);
+            else if (col == 64) atomicAdd(a.gm.b2 + j, v);
+          } else {
+            if (col < TT_CIN) atomicAdd(a.gm.w1 + j * TT_CIN + col, v);
+            else if (col == TT_CIN) atomicAdd(a.gm.b1 + j, v);
+          }
+        }
+      }
+    }
+  }
+  if (a.loss_sum) {
+    float v = loss_local;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) sRed[warp] = v;
+    __syncthreads();
+    if (tid == 0) atomicAdd(a.loss_sum, ((sRed[0] + sRed[1]) + (sRed[2] + sRed[3])));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TT_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+template <int FMT>
+static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradDev& gm, const float* g0,
+                             const float* g1, const long long* origins, const float* targets, const float* noise,
+                             int noise_bits, unsigned long long seed, unsigned long long step, float grad_scale, float* dg0,
+                             float* dg1, float* loss_sum, float* out_save, cudaStream_t st) {
+  const long long nodes0 = plane_size_host(g.n0, 2), nodes1 = plane_size_host(g.n1, 2);
+  const size_t b0 = ((size_t)nodes0 * g.C * 2 + 255) & ~(size_t)255, b1 = ((size_t)nodes1 * g.C * 2 + 255) & ~(size_t)255;
+  int rc = ensure_scratch(&h->tc_weights, &h->tc_weights_bytes, 64 * 1024);
+  if (rc) return rc;
+  rc = ensure_scratch(&h->tc_shadow, &h->tc_shadow_bytes, b0 + b1);
+  if (rc) return rc;
+  h->prepared.valid = 0;                       // the decode tables share this scratch
+  uint16_t* s0 = (uint16_t*)h->tc_shadow;
+  uint16_t* s1 = (uint16_t*)((uint8_t*)h->tc_shadow + b0);
+  // channel-last fp32 gradient scratch (zero between steps: grad_relayout_add_kernel re-zeroes what it consumes)
+  const size_t gb0 = (size_t)nodes0 * g.C * 4, gb1 = (size_t)nodes1 * g.C * 4;
+  float *gs0 = nullptr, *gs1 = nullptr;
+  if (dg0) {
+    size_t have = h->tc_gscratch_bytes;
+    rc = ensure_scratch(&h->tc_gscratch, &h->tc_gscratch_bytes, gb0 + gb1 + 256);
+    if (rc) return rc;
+    if (h->tc_gscratch_bytes != have) {
+      cudaError_t e = cudaMemsetAsync(h->tc_gscratch, 0, h->tc_gscratch_bytes, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    gs0 = (float*)h->tc_gscratch;
+    gs1 = (float*)((uint8_t*)h->tc_gscratch + ((gb0 + 255) & ~(size_t)255));
+  }
+  cudaError_t e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
+  if (e != cudaSuccess) return (int)e;
+  e = (cudaError_t)launch_relayout<FMT>(h, g, g1, g.n1, s1, st);
+  if (e != cudaSuccess) return (int)e;
+  pack_train_weights_kernel<FMT><<<16, 256, 0, st>>>(m, (uint16_t*)h->tc_weights);
+  h->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+
+  TrainArgs a;
+  memset(&a, 0, sizeof(a));
+  a.s0 = (const uint2*)s0;
+  a.s1 = (const uint2*)s1;
+  a.origins = origins;
+  a.wimg = (const uint4*)h->tc_weights;
+  a.targets = targets;
+  a.noise = noise;
+  a.dgs0 = gs0;
+  a.dgs1 = gs1;
+  a.loss_sum = loss_sum;
+  a.out_save = out_save;
+  a.gm = gm;
+  a.noise_amp = (!noise && noise_bits > 0) ? ldexpf(1.0f, -noise_bits) : 0.f;
+  a.seed = seed;
+  a.step = step;
+  a.flush_scale = 2.0f * grad_scale / TT_LOSS_SCALE;
+  a.cout = m.cout;
+  int s0n = 0;
+  while (s0n < 5 && ldexpf(1.0f, -s0n) > g.step) ++s0n;       // lanes sharing a G0 node along the fast axis: 1/step
+  a.steps0 = s0n;
+  a.steps1 = s0n + 1 > 5 ? 5 : s0n + 1;
+  auto kern = train_tc_kernel<FMT>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  if (g.N >= (1ll << 27)) return NIC_ERR_UNSUPPORTED;          // Philox counter packs (sample << 4 | block)
+  long long ntiles = (g.N + TT_ROWS - 1) / TT_ROWS;
+  int grid = (int)(ntiles < h->sms ? ntiles : h->sms);
+  {
+    KernelTimer timer(h, st);
+    kern<<<grid, TT_THREADS, TT_SMEM, st>>>(g, a);
+  }
+  h->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (dg0) {
+    const float sc = 2.0f * grad_scale / TT_LOSS_SCALE;
+    size_t smem = (size_t)g.C * 32 * 33 * sizeof(float);
+    e = cudaFuncSetAttribute(grad_relayout_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    grad_relayout_add_kernel<<<dim3((g.n0[0] + 31) / 32, (g.n0[1] + 31) / 32), 256, smem, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sc);
+    grad_relayout_add_kernel<<<dim3((g.n1[0] + 31) / 32, (g.n1[1] + 31) / 32), 256, smem, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sc);
+    h->launches += 2;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return NIC_OK;
+}
+
+int launch_train_tc(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradDev& gm, const float* g0, const float* g1,
+                    const long long* origins, const float* targets, const float* noise, int noise_bits,
+                    unsigned long long seed, unsigned long long step, float grad_scale, float* dg0, float* dg1,
+                    float* loss_sum, float* out_save, int precision, cudaStream_t st) {
+  if (g.N == 0) return NIC_OK;
+  if (g.method != NIC_METHOD_2D || g.C != 12 || g.PE != 6 || m.hidden != 64 || m.cout > 16 || m.cin != TT_CIN || !origins)
+    return NIC_ERR_UNSUPPORTED;
+  if (precision == NIC_PREC_F16)
+    return launch_train_tc_t<0>(h, g, m, gm, g0, g1, origins, targets, noise, noise_bits, seed, step, grad_scale, dg0, dg1,
+                                loss_sum, out_save, st);
+  return launch_train_tc_t<1>(h, g, m, gm, g0, g1, origins, targets, noise, noise_bits, seed, step, grad_scale, dg0, dg1,
+                              loss_sum, out_save, st);
+}
+
+}  // namespace nic

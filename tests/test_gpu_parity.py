@@ -584,3 +584,93 @@ def test_philox_noise_distribution_and_determinism():
     assert abs(da.mean()) < 0.05 * np.abs(da).mean() + 1e-6          # zero-mean perturbation
     assert abs(np.corrcoef(da.reshape(-1), dc.reshape(-1))[0, 1]) < 0.1   # independent streams per seed
     assert abs(la - l0) < 0.05 * l0
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core training step
+def _rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+@pytest.mark.parametrize("case", ["mip2_aligned", "mip0_unaligned", "mip5_small_ragged"])
+def test_train_tc_step_vs_oracle_fp64(prec, case):
+    """The tcgen05 training step against the oracle's fp64 backward.  Tolerances are those of 16-bit operands with fp32
+    accumulation (tanh-form GELU in forward and backward): loss 1e-2 relative; every gradient tensor within a few % in
+    relative L2 norm.  Noise is injected (the same tensor on both sides)."""
+    n = nic()
+    L = n._lib
+    import ctypes as C
+    size = 256
+    grids = I.make_grids(size, 2, seed=60)
+    params = I.make_mlp(73, seed=61, gain=1.5)
+    rng = np.random.default_rng(64)
+    if case == "mip2_aligned":
+        mip, fl, nc, crop = 2, 0, 3, 64
+        coord = np.array([[0, 0], [0, 0], [0, 0]])
+    elif case == "mip0_unaligned":
+        mip, fl, nc, crop = 0, 0, 2, 128            # step 1/4: 4 (G0) and 8 (G1) lanes share a node, origins unaligned
+        coord = rng.integers(0, size - crop + 1, (nc, 2))
+    else:
+        mip, fl, nc, crop = 5, 1, 5, 5              # step 2 (no interpolation), N = 125: one ragged tile
+        coord = rng.integers(0, (size >> mip) - crop + 1, (nc, 2))
+    img = I.box_mips(I.make_image(size, 2, seed=62), 8)[mip]
+    target = np.concatenate([img[:, c[0]:c[0] + crop, c[1]:c[1] + crop].reshape(3, -1).T for c in coord], 0)
+    noise = I.make_noise(nc * crop * crop, 73, 8, 63)
+    loss, out, grads, dg0, dg1 = O.train_forward_backward(grids, params, coord, target, fl, mip, 1, noise, size=crop)
+    fp = [T(a) for a in grids]
+    pt = [T(p) for p in params]
+    m = L.make_mlp(pt)
+    g = [torch.zeros_like(p) for p in pt]
+    gm = L.make_mlp_grad(g)
+    g0t, g1t = fp[2 * fl], fp[2 * fl + 1]
+    d0, d1 = torch.zeros_like(g0t), torch.zeros_like(g1t)
+    ls = torch.zeros(4, device=dev())
+    o = torch.empty((nc * crop * crop, 3), device=dev())
+    geom = L.make_geom(L.METHOD_2D, g0t, g1t, crop, nc, mip - 2 * (fl + 1), mip, 6, L.PE_TRIANGULAR)
+    h = L.handle(dev())
+    coord_t, target_t, noise_t = T(coord, torch.int64), T(target), T(noise)
+    for rep in range(2):            # twice: the second call checks that the private gradient scratch was left zeroed
+        for t in g + [d0, d1, ls]:
+            t.zero_()
+        L.check(h, L.load_library().nic_train_step(h, C.byref(geom), L.ptr(g0t), L.ptr(g1t), L.ptr(coord_t), C.byref(m),
+                                                   L.ptr(target_t), L.ptr(noise_t), 0, 0, 0, 0, C.byref(gm), L.ptr(d0),
+                                                   L.ptr(d1), L.ptr(ls), L.ptr(o), L.PRECISIONS[prec], L.stream_ptr(dev())))
+        n_all = nc * crop * crop * 3
+        tol = 1.0 if prec == "f16" else 4.0
+        assert abs(float(ls[0]) / n_all - loss) <= 1e-2 * tol * loss
+        assert np.abs(o.cpu().numpy() - out).max() <= 4e-3 * tol
+        for t, k in zip(g, ("W1", "b1", "W2", "b2", "W3", "b3")):
+            assert _rel_l2(t.cpu().numpy(), grads[k]) <= 2e-2 * tol, (k, _rel_l2(t.cpu().numpy(), grads[k]))
+        assert _rel_l2(d0.cpu().numpy(), dg0) <= 2e-2 * tol, _rel_l2(d0.cpu().numpy(), dg0)
+        assert _rel_l2(d1.cpu().numpy(), dg1) <= 2e-2 * tol, _rel_l2(d1.cpu().numpy(), dg1)
+        # nodes outside the crop footprints receive exactly nothing
+        assert np.array_equal(d0.cpu().numpy() == 0, dg0 == 0) or np.all((d0.cpu().numpy() != 0) <= (dg0 != 0))
+
+
+def test_train_tc_short_run_tracks_f32_path():
+    """200 fused steps on a 512^2 synthetic image, once on the fp32 path and once on the f16 tensor-core path with the
+    same crops and LODs: the final full-frame PSNR (reference formula) agrees within 0.05 dB (north-star tolerance)."""
+    n = nic()
+    ic = n.image_compression
+    size, steps = 512, 200
+    img = I.make_image(size, 2, seed=80)
+    target8 = torch.tensor(np.floor(img * 255 + 0.5).astype(np.uint8)).permute(1, 2, 0).contiguous().to(dev())
+    rng = np.random.default_rng(81)
+    coords = rng.integers(0, size - 256 + 1, (steps, 8, 2))
+    img_t = T(img)
+    psnr = {}
+    for prec in ("f32", "f16"):
+        configure(IMAGE_SIZE=size)
+        grids = I.make_grids(size, 2, seed=82, no_mip=True)
+        fp = [T(a) for a in grids]
+        dec = make_decoder(I.make_mlp(73, seed=83))
+        tr = ic.FusedTrainer(fp, dec, num_epochs=steps, fp_bits=8, seed=5, precision=prec)
+        for s in range(steps):
+            c = coords[s]
+            tg = torch.stack([img_t[:, a:a + 256, b:b + 256].reshape(3, -1).T for a, b in c])
+            tr.step(torch.tensor(c), tg, 0)
+        out8 = ic.decode(tr.fp, dec, 0, precision="f32", out_dtype=torch.uint8)
+        psnr[prec] = n.utils.calculate_psnr(target8, out8)
+    assert psnr["f32"] > 18.0, psnr
+    assert abs(psnr["f16"] - psnr["f32"]) <= 0.05, psnr
