@@ -120,6 +120,7 @@ def handle(device):
 OPT_DISABLE_FAST2D = 1
 OPT_TIME_KERNELS = 2
 OPT_REUSE_PREPARED = 3
+OPT_LEGACY_FAST2D = 4
 
 
 def kernel_time_ms(device):

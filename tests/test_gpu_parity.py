@@ -351,6 +351,17 @@ def test_fast2d_path_matches_general_kernel():
             assert within1 >= 0.999, (prec, within1, same, worst)
     # an eligible sub-block at a non-zero aligned origin, and a non-eligible (unaligned) one, agree with the full frame
     whole = ic.decode(fp, dec, 0, precision="f16", out_dtype=torch.uint8)
+    # the warp-specialised kernel and the first-generation kernel issue the same MMAs: bit-identical frames
+    L.set_option(dev(), L.OPT_LEGACY_FAST2D, 1)
+    try:
+        legacy = ic.decode(fp, dec, 0, precision="f16", out_dtype=torch.uint8)
+    finally:
+        L.set_option(dev(), L.OPT_LEGACY_FAST2D, 0)
+    assert torch.equal(whole, legacy)
+    # frames with fewer tiles than slots / SMs, and tile counts that are not multiples of the slot count
+    for sx, sy in ((8, 16), (8, 48), (24, 16), (40, 80), (448, 16)):
+        part = ic.decode(fp, dec, 0, size=(sx, sy), origin=(64, 32), precision="f16", out_dtype=torch.uint8)
+        assert torch.equal(part, whole[64:64 + sx, 32:32 + sy]), (sx, sy)
     a = ic.decode(fp, dec, 0, size=(64, 128), origin=(200, 304), precision="f16", out_dtype=torch.uint8)      # fast path
     assert torch.equal(a, whole[200:264, 304:432])
     b = ic.decode(fp, dec, 0, size=(64, 128), origin=(201, 300), precision="f16", out_dtype=torch.uint8)      # general path
