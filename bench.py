@@ -27,8 +27,8 @@ SIZE = 4096                      # BASELINE.json configs[1]
 FLOP_PER_TEXEL = 2 * (73 * 64 + 64 * 64 + 64 * 3)      # 17,920
 METRIC, UNIT = "decoded Gtexel/s (4096x4096 RGB full-frame decode)", "Gtexel/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of decode_tc2d_kernel per launch, from the committed ncu --set full capture
-NCU_TRAFFIC_BYTES = 59308032 + 15698688
-NCU_TRAFFIC_SOURCE = "profiles/r01e_decode_tc2d_pingpong_metrics.txt"
+NCU_TRAFFIC_BYTES = 58965504 + 14352128
+NCU_TRAFFIC_SOURCE = "profiles/r01i_decode_tc2d_ws_metrics.txt"
 
 
 def peaks():
@@ -343,7 +343,7 @@ def run_ours(args):
                        "decoder": "73-64-64-3", "output": "uint8", "l2": "flushed between timed iterations (256 MB write)"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "traffic": NCU_TRAFFIC_BYTES, "peak_source": f"{src} bf16_tflops (burst: kernel timed alone)",
-                         "flop_per_texel": FLOP_PER_TEXEL, "kernel": "decode_tc2d_kernel", "kernel_ms": kms,
+                         "flop_per_texel": FLOP_PER_TEXEL, "kernel": "decode_tc2d_ws_kernel", "kernel_ms": kms,
                          "kernel_share_of_step": kms / ms_per_step,
                          "traffic_source": NCU_TRAFFIC_SOURCE},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -373,7 +373,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--prec", default="f16", choices=["f16", "bf16", "f32"])
-    ap.add_argument("--train-prec", default="f32", choices=["f16", "bf16", "f32"])
+    ap.add_argument("--train-prec", default="f16", choices=["f16", "bf16", "f32"])
     ap.add_argument("--cpu-tiles", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the gather and training side benchmarks")

@@ -124,6 +124,12 @@ int nic_gather(NicHandle* h, const NicGeom* g, const float* g0, const float* g1,
 int nic_scatter(NicHandle* h, const NicGeom* g, const float* dx, const int64_t* origins, float* dg0, float* dg1,
                 void* stream);
 
+/* Target gather of random_crop_dataset (image_compression.py:44-47): image [channels, S0, S1(, S2)] fp32 -> targets
+ * [num_crops, crop0*crop1(*crop2), channels] fp32 for crops whose origins are the DEVICE tensor `origins` [num_crops, dim]
+ * (the reference's `coord`).  size / crop: HOST pointers to dim ints.  Origins are clamped into the image. */
+int nic_sample_crops(NicHandle* h, const float* image, int dim, int channels, const int32_t* size, const int64_t* origins,
+                     int num_crops, const int32_t* crop, float* targets, void* stream);
+
 /* Stand-alone positional encodings, utils.triangular_positional_encoding (utils.py:211-223) and
  * utils.positional_encoding (utils.py:198-208): coord [dim, n] fp32 -> out [pe_channels*dim, n] fp32.
  * pe_div: HOST pointer to pe_channels/2 floats (sinusoidal div_term), ignored for the triangular kind. */

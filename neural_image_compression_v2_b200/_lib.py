@@ -74,6 +74,7 @@ SYMBOLS = {
     "nic_clamp": (_I, [_P, _P, _L, _F, _F, _P]),
     "nic_output_to_u8": (_I, [_P, _P, _P, _L, _I, _P]),
     "nic_sse_u8": (_I, [_P, _P, _P, _L, _P, _P]),
+    "nic_sample_crops": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
     "nic_positional_encoding": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P]),
 }
 

@@ -237,6 +237,18 @@ int nic_scatter(NicHandle* h, const NicGeom* g, const float* dx, const int64_t* 
   return cuda_fail(h, launch_scatter(h, d, dx, (const long long*)origins, dg0, dg1, st), "nic_scatter");
 }
 
+int nic_sample_crops(NicHandle* h, const float* image, int dim, int channels, const int32_t* size, const int64_t* origins,
+                     int num_crops, const int32_t* crop, float* targets, void* stream) {
+  NIC_ENTER(h);
+  if ((dim != 2 && dim != 3) || channels < 1 || num_crops < 0 || !size || !crop)
+    return fail(h, NIC_ERR_ARG, "nic_sample_crops: dim %d channels %d num_crops %d", dim, channels, num_crops);
+  for (int a = 0; a < dim; ++a)
+    if (size[a] < 1 || crop[a] < 0 || crop[a] > size[a]) return fail(h, NIC_ERR_ARG, "nic_sample_crops: axis %d size %d crop %d", a, size[a], crop[a]);
+  if (num_crops > 0 && (!image || !origins || !targets)) return fail(h, NIC_ERR_ARG, "nic_sample_crops: NULL pointer");
+  return cuda_fail(h, launch_sample_crops(h, image, dim, channels, size, (const long long*)origins, num_crops, crop, targets, st),
+                   "nic_sample_crops");
+}
+
 int nic_positional_encoding(NicHandle* h, const float* coord, int dim, int64_t n, int pe_channels, int pe_kind,
                             const float* pe_div, float* out, void* stream) {
   NIC_ENTER(h);

@@ -176,6 +176,8 @@ int launch_gather_tile(Handle* h, const DevGeom& g, const float* g0, const float
                        int x_dtype, cudaStream_t st);
 int launch_scatter(Handle* h, const DevGeom& g, const float* dx, const long long* origins, float* dg0, float* dg1,
                    cudaStream_t st);
+int launch_sample_crops(Handle* h, const float* img, int dim, int ci, const int* size, const long long* origins, int ncrops,
+                        const int* crop, float* out, cudaStream_t st);
 int launch_pe(Handle* h, const float* coord, int dim, long long n, int PE, int kind, const float* div_host, float* out,
               cudaStream_t st);
 int launch_mlp_forward_f32(Handle* h, const DevGeom* g, const MlpDev& m, const float* g0, const float* g1,

@@ -356,8 +356,28 @@ def decode_image(fp, arc_decoder, mip_level, pr=True, div_size=10, precision=Non
 
 
 # ------------------------------------------------------------------------------------------------ crop sampler
+def sample_crops(dataset, coord, crop_size):
+    """Target gather of random_crop_dataset (image_compression.py:44-47) as ONE kernel: `dataset` [Ci, S, S(, S)]
+    float32 on the device, `coord` [NC, D] crop origins -> `[NC, crop^D, Ci]`."""
+    dim = dataset.dim() - 1
+    if not dataset.is_cuda:
+        raise L.NicError(-3, "dataset must be a CUDA tensor (no CPU fallback)")
+    if dataset.dtype != torch.float32 or not dataset.is_contiguous():
+        raise TypeError("dataset must be contiguous float32")
+    coord = L.origins_tensor(coord, dataset.device, dim)
+    nc, ci = coord.shape[0], dataset.shape[0]
+    out = torch.empty((nc, crop_size ** dim, ci), dtype=torch.float32, device=dataset.device)
+    size = (C.c_int32 * 3)(*(list(dataset.shape[1:]) + [1] * (3 - dim)))
+    crop = (C.c_int32 * 3)(*([crop_size] * dim + [1] * (3 - dim)))
+    h = L.handle(dataset.device)
+    L.check(h, L.load_library().nic_sample_crops(h, L.ptr(dataset), dim, ci, C.cast(size, C.c_void_p), L.ptr(coord), nc,
+                                                 C.cast(crop, C.c_void_p), L.ptr(out), L.stream_ptr(dataset.device)))
+    return out
+
+
 def random_crop_dataset(datasets, crop_size, num_crops, uniform_distribution, dim=2):
-    """image_compression.py:26-50 — host RNG LOD draw + integer crop origins; targets `[NC, S^D, C]`."""
+    """image_compression.py:26-50 — host RNG LOD draw + integer crop origins (as in the reference); the target
+    slices `[NC, S^D, C]` are gathered by one kernel instead of NC slice/reshape/transpose chains."""
     if uniform_distribution:
         lod = random.randint(0, var2.MAX_MIP_LEVEL)
     else:
@@ -367,12 +387,8 @@ def random_crop_dataset(datasets, crop_size, num_crops, uniform_distribution, di
     dataset = datasets[lod]
     data_size = dataset.shape[1]
     re_crop_size = max(1, crop_size // pow(2, lod))
-    coord = torch.randint(0, data_size - re_crop_size + 1, (num_crops, dim))
-    crops = []
-    for c in coord.tolist():
-        sl = (slice(None),) + tuple(slice(c[a], c[a] + re_crop_size) for a in range(dim))
-        crops.append(dataset[sl].reshape(dataset.shape[0], -1).T)
-    return torch.stack(crops), coord.to(dataset.device), lod
+    coord = torch.randint(0, data_size - re_crop_size + 1, (num_crops, dim)).to(dataset.device)
+    return sample_crops(dataset, coord, re_crop_size), coord, lod
 
 
 # ------------------------------------------------------------------------------------------------ fused training

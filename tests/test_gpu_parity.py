@@ -685,3 +685,25 @@ def test_train_tc_short_run_tracks_f32_path():
         psnr[prec] = n.utils.calculate_psnr(target8, out8)
     assert psnr["f32"] > 18.0, psnr
     assert abs(psnr["f16"] - psnr["f32"]) <= 0.05, psnr
+
+
+def test_random_crop_dataset_targets():
+    """random_crop_dataset (image_compression.py:26-50): the one-kernel target gather equals the reference's per-crop
+    slice / reshape / transpose, in 2-D and 3-D, and the LOD / origin draws stay inside the image."""
+    import random
+    ic = nic().image_compression
+    configure(IMAGE_SIZE=64, TF_NO_MIP=False, MAX_MIP_LEVEL=6)
+    rng = np.random.default_rng(90)
+    for dim in (2, 3):
+        size = 64 if dim == 2 else 16
+        imgs = [T(rng.random((3,) + (size >> m,) * dim).astype(np.float32)) for m in range(4)]
+        configure(IMAGE_SIZE=size, TF_NO_MIP=False, MAX_MIP_LEVEL=3)
+        random.seed(3)
+        torch.manual_seed(4)
+        for _ in range(6):
+            tg, coord, lod = ic.random_crop_dataset(imgs, 8, 5, False, dim=dim)
+            s = max(1, 8 // 2 ** lod)
+            assert tuple(tg.shape) == (5, s ** dim, 3) and 0 <= lod <= 3
+            for k, c in enumerate(coord.tolist()):
+                sl = (slice(None),) + tuple(slice(c[a], c[a] + s) for a in range(dim))
+                assert torch.equal(tg[k], imgs[lod][sl].reshape(3, -1).T)
