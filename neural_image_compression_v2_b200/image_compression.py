@@ -265,11 +265,12 @@ def decode_points(fp, decoder, coords, mip_level=0, precision=None, out_dtype=to
 
 
 class HostDecodePipeline:
-    """End-to-end decode of one 2-D frame from HOST buffers to a HOST buffer (what `process_images` does with a saved
+    """End-to-end decode of 2-D frames from HOST buffers to a HOST buffer (what `process_images` does with a saved
     model, image_compression.py:393-407): pinned H2D of the uint8 grid codes and the decoder, `fp_load`, fused decode in
     row bands, and the D2H of each 8-bit band on a second stream while the next band decodes.  The preparation tables
     (shadow grids, per-node G1 rows, packed weights) are built by the first band and reused by the others
-    (NIC_OPT_REUSE_PREPARED)."""
+    (NIC_OPT_REUSE_PREPARED).  The device frame is double-buffered: with `wait=False` the D2H of frame i overlaps the
+    H2D and decode of frame i + 1 (PCIe is full duplex); call `finish()` before reading the last host buffer."""
 
     def __init__(self, size, device, precision="f16", bands=4, bits=8):
         self.size, self.device, self.precision, self.bits = size, torch.device(device), precision, bits
@@ -278,25 +279,33 @@ class HostDecodePipeline:
         self.decoder = None
         self.dcodes = None
         self.out = None
+        self.d2h_done = [None, None]
+        self.frame = 0
 
-    def decode_frame(self, codes, host_params, host_out, mip_level=0):
+    def decode_frame(self, codes, host_params, host_out, mip_level=0, wait=True):
         from .fp_def import fp_load
         dev = self.device
         if self.dcodes is None:
             self.dcodes = [torch.empty(c.shape, dtype=torch.uint8, device=dev) for c in codes]
             self.decoder = ColorDecoder(host_params[0].shape[1], host_params[0].shape[0], host_params[4].shape[0]).to(dev)
-            self.out = torch.empty((self.size, self.size, host_params[4].shape[0]), dtype=torch.uint8, device=dev)
+            shape = (self.size, self.size, host_params[4].shape[0])
+            self.out = [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+        main = torch.cuda.current_stream(dev)
+        k = self.frame & 1
+        self.frame += 1
+        if self.d2h_done[k] is not None:
+            main.wait_event(self.d2h_done[k])        # the frame that used this device buffer two frames ago has left
         for d, c in zip(self.dcodes, codes):
             d.copy_(c, non_blocking=True)
         with torch.no_grad():
             for p, hp in zip(self.decoder.parameters_list(), host_params):
                 p.copy_(hp, non_blocking=True)
         fp = fp_load(self.dcodes, self.bits)
-        main = torch.cuda.current_stream(dev)
+        out = self.out[k]
         try:
             for i, (r0, n) in enumerate(self.bands):
                 L.set_option(dev, L.OPT_REUSE_PREPARED, int(i > 0))
-                band = self.out[r0:r0 + n]
+                band = out[r0:r0 + n]
                 decode(fp, self.decoder, mip_level, size=(n, self.size), origin=(r0, 0), precision=self.precision,
                        out_dtype=torch.uint8, out=band)
                 ready = torch.cuda.Event()
@@ -308,8 +317,16 @@ class HostDecodePipeline:
             L.set_option(dev, L.OPT_REUSE_PREPARED, 0)
         done = torch.cuda.Event()
         done.record(self.copy_stream)
-        main.wait_event(done)            # the frame is complete (in host memory) when the caller's stream gets here
+        self.d2h_done[k] = done
+        self._last = done
+        if wait:
+            main.wait_event(done)            # the frame is complete (in host memory) when the caller's stream gets here
         return host_out
+
+    def finish(self):
+        """Makes the caller's stream wait for every outstanding device-to-host copy."""
+        if getattr(self, "_last", None) is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._last)
 
 
 def _band(size, b, bands):
