@@ -183,6 +183,11 @@ typedef struct NicAdamTensor {
 } NicAdamTensor;
 int nic_adam_step(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
                   float grad_scale, int zero_grad, void* stream);
+/* The same, and in the same launch: loss_out[0] = loss_sum[0] * loss_scale, loss_sum[0] = 0 — the `loss.item()`
+ * bookkeeping of image_compression.py:275 without a host sync or extra kernels (the caller reads loss_out when it
+ * wants to). */
+int nic_adam_step_loss(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                       float grad_scale, int zero_grad, float* loss_sum, float* loss_out, float loss_scale, void* stream);
 
 /* ---- quantisers (K6) ------------------------------------------------------------------------------------ */
 /* models.quantize4fp (models.py:55-57): dst = floor(src*(2^b-1)+.5)/(2^b-1), separate fp32 mul and add. */
@@ -192,6 +197,11 @@ int nic_quantize_pack(NicHandle* h, const float* src, uint8_t* codes, int64_t n,
 /* models.load4fp (models.py:68-71) with the intended float result (the reference call site passes uint8 and
  * wraps, image_compression.py:396): dst = (code - 2^(b-1) + 1)/(2^b-1). */
 int nic_unpack(NicHandle* h, const uint8_t* codes, float* dst, int64_t n, int bits, void* stream);
+/* Sub-byte storage of the codes above (an extension: the reference's fp_savable keeps one code per byte even for
+ * FP_BITS 4 / 2, fp_def.py:250-255): 8/bits codes per byte, code i in bits [(i mod 8/bits)*bits, +bits) of byte
+ * i / (8/bits); bits in {1, 2, 4, 8}; `packed` holds ceil(n*bits/8) bytes. */
+int nic_pack_codes(NicHandle* h, const uint8_t* codes, uint8_t* packed, int64_t n, int bits, void* stream);
+int nic_unpack_codes(NicHandle* h, const uint8_t* packed, uint8_t* codes, int64_t n, int bits, void* stream);
 /* fp_quantize_clamp / models.quantize_clamp (fp_def.py:227-232, models.py:48-51): in-place clamp. */
 int nic_clamp(NicHandle* h, float* p, int64_t n, float lo, float hi, void* stream);
 /* models.quantize_to_bit + astype(uint8) (models.py:29-40, image_compression.py:406-407):

@@ -68,9 +68,12 @@ SYMBOLS = {
     "nic_train_step": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, C.POINTER(NicMlp), _P, _P, _I, C.c_uint64, C.c_uint64,
                             _L, C.POINTER(NicMlpGrad), _P, _P, _P, _P, _I, _P]),
     "nic_adam_step": (_I, [_P, C.POINTER(NicAdamTensor), _I, _F, _F, _F, _F, _I, _P]),
+    "nic_adam_step_loss": (_I, [_P, C.POINTER(NicAdamTensor), _I, _F, _F, _F, _F, _I, _P, _P, _F, _P]),
     "nic_quantize4fp": (_I, [_P, _P, _P, _L, _I, _P]),
     "nic_quantize_pack": (_I, [_P, _P, _P, _L, _I, _P]),
     "nic_unpack": (_I, [_P, _P, _P, _L, _I, _P]),
+    "nic_pack_codes": (_I, [_P, _P, _P, _L, _I, _P]),
+    "nic_unpack_codes": (_I, [_P, _P, _P, _L, _I, _P]),
     "nic_clamp": (_I, [_P, _P, _L, _F, _F, _P]),
     "nic_output_to_u8": (_I, [_P, _P, _P, _L, _I, _P]),
     "nic_sse_u8": (_I, [_P, _P, _P, _L, _P, _P]),

@@ -338,16 +338,29 @@ int nic_train_step(NicHandle* h, const NicGeom* g, const float* g0, const float*
                                        grad_scale, dg0, dg1, loss_sum, out, st), "nic_train_step");
 }
 
-int nic_adam_step(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
-                  float grad_scale, int zero_grad, void* stream) {
-  NIC_ENTER(h);
+static int adam_common(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                       float grad_scale, int zero_grad, float* loss_sum, float* loss_out, float loss_scale, cudaStream_t st) {
   if (count < 0 || (count > 0 && !tensors)) return fail(h, NIC_ERR_ARG, "nic_adam_step: count %d", count);
   for (int i = 0; i < count; ++i) {
     const NicAdamTensor& t = tensors[i];
     if (t.numel < 0 || t.t < 1 || (t.numel > 0 && (!t.p || !t.g || !t.m || !t.v)))
       return fail(h, NIC_ERR_ARG, "nic_adam_step: tensor %d invalid (numel %lld, t %d)", i, (long long)t.numel, t.t);
   }
-  return cuda_fail(h, launch_adam(h, tensors, count, beta1, beta2, eps, grad_scale, zero_grad, st), "nic_adam_step");
+  return cuda_fail(h, launch_adam(h, tensors, count, beta1, beta2, eps, grad_scale, zero_grad, loss_sum, loss_out, loss_scale, st),
+                   "nic_adam_step");
+}
+
+int nic_adam_step(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                  float grad_scale, int zero_grad, void* stream) {
+  NIC_ENTER(h);
+  return adam_common(h, tensors, count, beta1, beta2, eps, grad_scale, zero_grad, nullptr, nullptr, 0.f, st);
+}
+
+int nic_adam_step_loss(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                       float grad_scale, int zero_grad, float* loss_sum, float* loss_out, float loss_scale, void* stream) {
+  NIC_ENTER(h);
+  if (count < 1 || !loss_sum || !loss_out) return fail(h, NIC_ERR_ARG, "nic_adam_step_loss: needs tensors and loss buffers");
+  return adam_common(h, tensors, count, beta1, beta2, eps, grad_scale, zero_grad, loss_sum, loss_out, loss_scale, st);
 }
 
 static int check_bits(NicHandle* h, int bits, const char* who) {
@@ -374,6 +387,25 @@ int nic_unpack(NicHandle* h, const uint8_t* codes, float* dst, int64_t n, int bi
   if (int rc = check_bits(h, bits, "nic_unpack")) return rc;
   if (n < 0 || (n > 0 && (!codes || !dst))) return fail(h, NIC_ERR_ARG, "nic_unpack: bad buffer");
   return cuda_fail(h, launch_unpack(h, codes, dst, n, bits, st), "nic_unpack");
+}
+
+static int check_pack_bits(NicHandle* h, int bits, const char* who) {
+  if (bits != 1 && bits != 2 && bits != 4 && bits != 8) return fail(h, NIC_ERR_ARG, "%s: bits %d (1, 2, 4 or 8)", who, bits);
+  return NIC_OK;
+}
+
+int nic_pack_codes(NicHandle* h, const uint8_t* codes, uint8_t* packed, int64_t n, int bits, void* stream) {
+  NIC_ENTER(h);
+  if (int rc = check_pack_bits(h, bits, "nic_pack_codes")) return rc;
+  if (n < 0 || (n > 0 && (!codes || !packed))) return fail(h, NIC_ERR_ARG, "nic_pack_codes: bad buffer");
+  return cuda_fail(h, launch_pack_bits(h, codes, packed, n, bits, 0, st), "nic_pack_codes");
+}
+
+int nic_unpack_codes(NicHandle* h, const uint8_t* packed, uint8_t* codes, int64_t n, int bits, void* stream) {
+  NIC_ENTER(h);
+  if (int rc = check_pack_bits(h, bits, "nic_unpack_codes")) return rc;
+  if (n < 0 || (n > 0 && (!codes || !packed))) return fail(h, NIC_ERR_ARG, "nic_unpack_codes: bad buffer");
+  return cuda_fail(h, launch_pack_bits(h, packed, codes, n, bits, 1, st), "nic_unpack_codes");
 }
 
 int nic_clamp(NicHandle* h, float* p, int64_t n, float lo, float hi, void* stream) {

@@ -197,10 +197,11 @@ int launch_train_tc(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradD
                     unsigned long long seed, unsigned long long step, float grad_scale, float* dg0, float* dg1,
                     float* loss_sum, float* out_save, int precision, cudaStream_t st);
 int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
-                float grad_scale, int zero_grad, cudaStream_t st);
+                float grad_scale, int zero_grad, float* loss_sum, float* loss_out, float loss_scale, cudaStream_t st);
 int launch_quantize4fp(Handle* h, const float* src, float* dst, long long n, int bits, cudaStream_t st);
 int launch_quantize_pack(Handle* h, const float* src, uint8_t* codes, long long n, int bits, cudaStream_t st);
 int launch_unpack(Handle* h, const uint8_t* codes, float* dst, long long n, int bits, cudaStream_t st);
+int launch_pack_bits(Handle* h, const uint8_t* src, uint8_t* dst, long long n, int bits, int unpack, cudaStream_t st);
 int launch_clamp(Handle* h, float* p, long long n, float lo, float hi, cudaStream_t st);
 int launch_output_to_u8(Handle* h, const float* src, uint8_t* dst, long long n, int bits, cudaStream_t st);
 int launch_sse_u8(Handle* h, const uint8_t* a, const uint8_t* b, long long n, double* sse, cudaStream_t st);

@@ -12,6 +12,9 @@ struct AdamBatch {
   int count;
   float beta1, beta2, eps, grad_scale;
   int zero_grad;
+  float* loss_sum;      // optional: loss_out[0] = loss_sum[0] * loss_scale; loss_sum[0] = 0  (done by one thread)
+  float* loss_out;
+  float loss_scale;
 };
 
 __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float beta1, float beta2, float eps,
@@ -26,6 +29,10 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b) {
+  if (b.loss_sum && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    b.loss_out[0] = b.loss_sum[0] * b.loss_scale;
+    b.loss_sum[0] = 0.f;
+  }
   const NicAdamTensor& t = b.t[blockIdx.y];
   // bias corrections in double on every thread is cheap next to the memory traffic and keeps torch's values
   const double bc1 = 1.0 - pow((double)b.beta1, (double)t.t);
@@ -56,9 +63,12 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b) {
 }
 
 int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
-                float grad_scale, int zero_grad, cudaStream_t st) {
+                float grad_scale, int zero_grad, float* loss_sum, float* loss_out, float loss_scale, cudaStream_t st) {
   for (int base = 0; base < count; base += NIC_ADAM_BATCH) {
     AdamBatch b;
+    b.loss_sum = base == 0 ? loss_sum : nullptr;
+    b.loss_out = loss_out;
+    b.loss_scale = loss_scale;
     b.count = count - base < NIC_ADAM_BATCH ? count - base : NIC_ADAM_BATCH;
     b.beta1 = beta1; b.beta2 = beta2; b.eps = eps; b.grad_scale = grad_scale; b.zero_grad = zero_grad;
     long long maxn = 0;
@@ -128,6 +138,40 @@ int launch_clamp(Handle* h, float* p, long long n, float lo, float hi, cudaStrea
 }
 int launch_output_to_u8(Handle* h, const float* src, uint8_t* dst, long long n, int bits, cudaStream_t st) {
   return launch_q<Q_OUT8>(h, src, nullptr, nullptr, dst, n, (float)((1 << bits) - 1), 0.f, 0.f, 0.f, st);
+}
+
+// True sub-byte storage of the grid codes (the reference spends one byte per code even for
+// FP_BITS 4 / 2, models.py:61-64).  bits in {1, 2, 4, 8}: 8/bits codes per byte, code i in bits [(i % per) * bits, ...).
+__global__ void __launch_bounds__(256) pack_bits_kernel(const uint8_t* __restrict__ codes, uint8_t* __restrict__ packed,
+                                                        long long n, int bits) {
+  const int per = 8 / bits;
+  const long long nbytes = (n + per - 1) / per, stride = (long long)gridDim.x * blockDim.x;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nbytes; b += stride) {
+    unsigned v = 0;
+    for (int k = 0; k < per; ++k) {
+      const long long i = b * per + k;
+      if (i < n) v |= (unsigned)(codes[i] & ((1u << bits) - 1u)) << (k * bits);
+    }
+    packed[b] = (uint8_t)v;
+  }
+}
+__global__ void __launch_bounds__(256) unpack_bits_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ codes,
+                                                          long long n, int bits) {
+  const int per = 8 / bits;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    codes[i] = (uint8_t)((packed[i / per] >> ((int)(i % per) * bits)) & ((1u << bits) - 1u));
+}
+
+int launch_pack_bits(Handle* h, const uint8_t* codes, uint8_t* packed, long long n, int bits, int unpack, cudaStream_t st) {
+  if (n == 0) return NIC_OK;
+  long long work = unpack ? n : (n + 8 / bits - 1) / (8 / bits);
+  long long blocks = (work + 255) / 256, cap = (long long)h->sms * 16;
+  unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
+  if (unpack) unpack_bits_kernel<<<grid, 256, 0, st>>>(codes, packed, n, bits);      // (packed, codes) swapped by the caller
+  else pack_bits_kernel<<<grid, 256, 0, st>>>(codes, packed, n, bits);
+  h->launches++;
+  return (int)cudaGetLastError();
 }
 
 // sum of squared differences of two 8-bit images (integer-exact per thread, double at the end)

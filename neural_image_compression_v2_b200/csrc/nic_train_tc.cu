@@ -109,6 +109,32 @@ __global__ void __launch_bounds__(256) grad_relayout_add_kernel(float* __restric
   }
 }
 
+// Small-grid variants (one thread per element): the tiled kernels above are bandwidth-shaped and take tens of
+// microseconds of pure latency on a [12, 129, 129] grid, which is a third of a 0.36 ms training step.
+__global__ void __launch_bounds__(256) grad_add_small_kernel(float* __restrict__ s, float* __restrict__ dg, int C, int nx, int ny,
+                                                             float scale) {
+  const int total = C * nx * ny;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, node = i / C;                 // s is [x][y][C]: i walks it linearly (coalesced read + zero)
+    const int y = node % ny, x = node / ny;
+    const float v = s[i];
+    if (v != 0.f) {
+      dg[((size_t)c * ny + y) * nx + x] += scale * v;
+      s[i] = 0.f;
+    }
+  }
+}
+template <int FMT>
+__global__ void __launch_bounds__(256) relayout_small_kernel(const float* __restrict__ g, uint16_t* __restrict__ sh, int C, int nx,
+                                                             int ny) {
+  const int total = C * nx * ny;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % C, node = i / C;
+    const int y = node % ny, x = node / ny;
+    sh[i] = to16<FMT>(__ldg(g + ((size_t)c * ny + y) * nx + x));
+  }
+}
+
 // (h', g') for a pair: h' = 2 gelu_tanh(x) = x + x t,  g' = d h'/dx = (1 + t) + x (1 - t^2)(c1 + 3 c2 x^2),
 // t = tanh(x (c1 + c2 x^2)).  Packed 16-bit math; the activation feeds the next MMA, the derivative stays in registers.
 template <int FMT>
@@ -584,10 +610,18 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
     gs0 = (float*)h->tc_gscratch;
     gs1 = (float*)((uint8_t*)h->tc_gscratch + ((gb0 + 255) & ~(size_t)255));
   }
-  cudaError_t e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
-  if (e != cudaSuccess) return (int)e;
-  e = (cudaError_t)launch_relayout<FMT>(h, g, g1, g.n1, s1, st);
-  if (e != cudaSuccess) return (int)e;
+  cudaError_t e = cudaSuccess;
+  const bool small = nodes0 <= (1 << 20);
+  if (small) {
+    relayout_small_kernel<FMT><<<(int)((nodes0 * g.C + 255) / 256), 256, 0, st>>>(g0, s0, g.C, g.n0[0], g.n0[1]);
+    relayout_small_kernel<FMT><<<(int)((nodes1 * g.C + 255) / 256), 256, 0, st>>>(g1, s1, g.C, g.n1[0], g.n1[1]);
+    h->launches += 2;
+  } else {
+    e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
+    if (e != cudaSuccess) return (int)e;
+    e = (cudaError_t)launch_relayout<FMT>(h, g, g1, g.n1, s1, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   pack_train_weights_kernel<FMT><<<16, 256, 0, st>>>(m, (uint16_t*)h->tc_weights);
   h->launches++;
   e = cudaGetLastError();
@@ -630,11 +664,16 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   if (e != cudaSuccess) return (int)e;
   if (dg0) {
     const float sc = 2.0f * grad_scale / TT_LOSS_SCALE;
-    size_t smem = (size_t)g.C * 32 * 33 * sizeof(float);
-    e = cudaFuncSetAttribute(grad_relayout_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    grad_relayout_add_kernel<<<dim3((g.n0[0] + 31) / 32, (g.n0[1] + 31) / 32), 256, smem, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sc);
-    grad_relayout_add_kernel<<<dim3((g.n1[0] + 31) / 32, (g.n1[1] + 31) / 32), 256, smem, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sc);
+    if (small) {
+      grad_add_small_kernel<<<(int)((nodes0 * g.C + 255) / 256), 256, 0, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sc);
+      grad_add_small_kernel<<<(int)((nodes1 * g.C + 255) / 256), 256, 0, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sc);
+    } else {
+      size_t smem = (size_t)g.C * 32 * 33 * sizeof(float);
+      e = cudaFuncSetAttribute(grad_relayout_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      grad_relayout_add_kernel<<<dim3((g.n0[0] + 31) / 32, (g.n0[1] + 31) / 32), 256, smem, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sc);
+      grad_relayout_add_kernel<<<dim3((g.n1[0] + 31) / 32, (g.n1[1] + 31) / 32), 256, smem, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sc);
+    }
     h->launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

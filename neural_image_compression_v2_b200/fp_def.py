@@ -92,6 +92,36 @@ def fp_load(compressed_fp, num_bits, dtype=torch.float32):
     return [load4fp(g, num_bits, dtype) for g in compressed_fp]
 
 
+def fp_savable_packed(fp, num_bits):
+    """Extension of fp_savable: the same bit-exact codes, stored 8/num_bits per byte.
+    Returns a list of (packed uint8 tensor [ceil(n*bits/8)], shape) pairs; num_bits in {1, 2, 4, 8}."""
+    lib = L.load_library()
+    out = []
+    for g in fp:
+        codes = save4fp(g, num_bits).reshape(-1)
+        n = codes.numel()
+        packed = torch.empty(((n * num_bits + 7) // 8,), dtype=torch.uint8, device=codes.device)
+        h = L.handle(codes.device)
+        L.check(h, lib.nic_pack_codes(h, L.ptr(codes), L.ptr(packed), n, num_bits, L.stream_ptr(codes.device)))
+        out.append((packed, tuple(g.shape)))
+    return out
+
+
+def fp_load_packed(packed_fp, num_bits, dtype=torch.float32):
+    """Inverse of fp_savable_packed: float32 grids `(code - 2^(b-1) + 1) / (2^b - 1)` (models.load4fp)."""
+    lib = L.load_library()
+    out = []
+    for packed, shape in packed_fp:
+        n = 1
+        for d in shape:
+            n *= d
+        codes = torch.empty((n,), dtype=torch.uint8, device=packed.device)
+        h = L.handle(packed.device)
+        L.check(h, lib.nic_unpack_codes(h, L.ptr(packed.contiguous()), L.ptr(codes), n, num_bits, L.stream_ptr(packed.device)))
+        out.append(load4fp(codes.reshape(shape), num_bits, dtype))
+    return out
+
+
 def fp_freeze(fp):
     """fp_def.py:266-268."""
     for g in fp:

@@ -604,7 +604,7 @@ def _rel_l2(a, b):
 
 
 @pytest.mark.parametrize("prec", ["f16", "bf16"])
-@pytest.mark.parametrize("case", ["mip2_aligned", "mip0_unaligned", "mip5_small_ragged"])
+@pytest.mark.parametrize("case", ["mip2_aligned", "mip0_unaligned", "mip5_small_ragged", "large_grid"])
 def test_train_tc_step_vs_oracle_fp64(prec, case):
     """The tcgen05 training step against the oracle's fp64 backward.  Tolerances are those of 16-bit operands with fp32
     accumulation (tanh-form GELU in forward and backward): loss 1e-2 relative; every gradient tensor within a few % in
@@ -612,11 +612,14 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
     n = nic()
     L = n._lib
     import ctypes as C
-    size = 256
-    grids = I.make_grids(size, 2, seed=60)
+    size = 4096 if case == "large_grid" else 256       # 1025^2 nodes: the tiled (bandwidth-shaped) relayout kernels
+    grids = I.make_grids(size, 2, seed=60, no_mip=case == "large_grid")
     params = I.make_mlp(73, seed=61, gain=1.5)
     rng = np.random.default_rng(64)
-    if case == "mip2_aligned":
+    if case == "large_grid":
+        mip, fl, nc, crop = 0, 0, 2, 128
+        coord = rng.integers(0, size - crop + 1, (nc, 2))
+    elif case == "mip2_aligned":
         mip, fl, nc, crop = 2, 0, 3, 64
         coord = np.array([[0, 0], [0, 0], [0, 0]])
     elif case == "mip0_unaligned":
@@ -625,10 +628,11 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
     else:
         mip, fl, nc, crop = 5, 1, 5, 5              # step 2 (no interpolation), N = 125: one ragged tile
         coord = rng.integers(0, (size >> mip) - crop + 1, (nc, 2))
-    img = I.box_mips(I.make_image(size, 2, seed=62), 8)[mip]
-    target = np.concatenate([img[:, c[0]:c[0] + crop, c[1]:c[1] + crop].reshape(3, -1).T for c in coord], 0)
+    img = I.box_mips(I.make_image(512 if case == "large_grid" else size, 2, seed=62), 8)[mip]
+    target = np.concatenate([img[:, c[0] % 256:c[0] % 256 + crop, c[1] % 256:c[1] % 256 + crop].reshape(3, -1).T for c in coord], 0)
     noise = I.make_noise(nc * crop * crop, 73, 8, 63)
-    loss, out, grads, dg0, dg1 = O.train_forward_backward(grids, params, coord, target, fl, mip, 1, noise, size=crop)
+    loss, out, grads, dg0, dg1 = O.train_forward_backward(grids, params, coord, target, fl, mip, 1, noise, size=crop,
+                                                          dtype=np.float32 if case == "large_grid" else np.float64)
     fp = [T(a) for a in grids]
     pt = [T(p) for p in params]
     m = L.make_mlp(pt)
@@ -707,3 +711,24 @@ def test_random_crop_dataset_targets():
             for k, c in enumerate(coord.tolist()):
                 sl = (slice(None),) + tuple(slice(c[a], c[a] + s) for a in range(dim))
                 assert torch.equal(tg[k], imgs[lod][sl].reshape(3, -1).T)
+
+
+@pytest.mark.parametrize("bits", [8, 4, 2])
+def test_sub_byte_code_packing_round_trip(bits):
+    """fp_savable_packed / fp_load_packed: 8/bits codes per byte, lossless w.r.t. the reference's one-code-per-byte
+    fp_savable (bit-exact codes), ragged sizes included; the reloaded grids equal quantize4fp of the originals."""
+    fpd, models = nic().fp_def, nic().models
+    rng = np.random.default_rng(91)
+    lo, hi = I.q_range(bits)
+    grids = [T(rng.uniform(lo, hi, shape).astype(np.float32)) for shape in ((12, 33, 33), (12, 17, 17), (3, 5, 7), (1, 1, 3))]
+    packed = fpd.fp_savable_packed(grids, bits)
+    ref_codes = fpd.fp_savable(grids, bits)
+    for (p, shape), g, c in zip(packed, grids, ref_codes):
+        assert p.numel() == (g.numel() * bits + 7) // 8 and shape == tuple(g.shape)
+        per = 8 // bits
+        want = np.zeros(p.numel() * per, np.uint8)
+        want[:g.numel()] = c.cpu().numpy().reshape(-1)
+        want = (want.reshape(-1, per).astype(np.uint32) << (np.arange(per) * bits)).sum(1).astype(np.uint8)
+        assert np.array_equal(p.cpu().numpy(), want)
+    for g, r in zip(grids, fpd.fp_load_packed(packed, bits)):
+        assert torch.equal(r, models.quantize4fp(g, bits))

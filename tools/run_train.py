@@ -1,0 +1,44 @@
+"""Small driver for profiling the fused training step: python tools/run_train.py [f16|bf16|f32] [steps]"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import inputs as I  # noqa: E402
+from neural_image_compression_v2_b200 import _lib as L  # noqa: E402
+from neural_image_compression_v2_b200 import image_compression as ic, var2  # noqa: E402
+
+prec = sys.argv[1] if len(sys.argv) > 1 else "f16"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+dev = torch.device("cuda:0")
+size, nc, crop = 512, 8, 256
+var2.update(IMAGE_SIZE=size)
+fp = [torch.tensor(g, device=dev) for g in I.make_grids(size, 2, seed=3, no_mip=True)]
+dec = ic.ColorDecoder(73, 64, 3).to(dev)
+with torch.no_grad():
+    for p, v in zip(dec.parameters_list(), I.make_mlp(73, seed=4)):
+        p.copy_(torch.tensor(v))
+tr = ic.FusedTrainer(fp, dec, num_epochs=100000, fp_bits=8, seed=1, precision=prec)
+img = torch.tensor(I.make_image(size, 2, seed=5), device=dev)
+g = torch.Generator().manual_seed(100)
+coord = torch.randint(0, size - crop + 1, (nc, 2), generator=g).to(dev)
+tg = ic.sample_crops(img, coord, crop)
+for _ in range(3):
+    tr.step(coord, tg, 0)
+torch.cuda.synchronize()
+L.set_option(dev, L.OPT_TIME_KERNELS, 1)
+t0 = time.perf_counter()
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+for _ in range(steps):
+    loss = tr.step(coord, tg, 0)
+e.record()
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+ms, n = L.kernel_time_ms(dev)
+print(f"{prec}: step {s.elapsed_time(e) / steps:.4f} ms (GPU events), host issue {1e3 * (t1 - t0) / steps:.4f} ms/step, "
+      f"train kernel {ms / n:.4f} ms, {nc * crop * crop / (s.elapsed_time(e) / steps * 1e-3) / 1e6:.0f} Msamples/s, loss {float(loss):.6f}")
