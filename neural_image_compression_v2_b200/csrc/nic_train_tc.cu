@@ -3,17 +3,17 @@
 // Reference behaviour: the body of train_models up to loss.backward() (Projects/image_compression.py:239-265) on the
 // 2-D path (create_decoder_input_2d :71-100, fp_def.create_g0_g1 fp_def.py:115-145, ColorDecoder :54-68).
 //
-// Per CTA (persistent, 256 threads = 2 warpgroups, one CTA per SM), per tile of 128 samples (= MMA M = TMEM lanes):
+// Per CTA (persistent, 256 threads = 2 warpgroups, TWO CTAs per SM: 106 KB smem, 256 TMEM columns, <= 128 registers), per tile of 128 samples (= MMA M = TMEM lanes):
 //   activations live in shared memory as [sample-group of 8][feature-group of 8][8 samples][8 features] 16-bit core
 //   matrices.  ONE copy serves three operand views (no transposes are ever materialised):
 //     * K-major A  (M = samples,  K = features)  for the forward GEMMs and the delta-propagation GEMMs,
 //     * MN-major A (M = features, K = samples)   for the weight-gradient GEMMs (the reduction runs over the samples),
 //     * MN-major B (N = features, K = samples)   likewise;
-//   the delta-propagation GEMMs take small transposed weight images (K-major B) packed next to the forward ones.
+//   and the forward weight images W' (K-major B) double as MN-major B for the delta-propagation GEMMs (W'^T).
 //   forward : Z1 = X~ W1'^T           (5 MMAs K=16)  -> h1' = 2 gelu(z1), g1' = d h1'/d z1 (registers)   -> H1
 //             Z2 = [H1|1] W2'^T       (5)            -> h2', g2'                                        -> H2
 //             Z3 = [H2|1] W3'^T       (5, N=16)      -> out = sigmoid, loss, dz3 = S (out - t) out (1 - out) -> DZ[0:16)
-//   backward: dH2 = dZ3 W3'           (1)   and  D3 += DZ^T [H2|1]   (8 MMAs, M=128 N=80 K=128: dW3', db3 in rows 0..2)
+//   backward: dH2 = dZ3 W3'           (1)   and  D3^T += [H2|1]^T dZ3 (8 MMAs, M=128 N=16 K=128: dW3'^T, db3 in row 64)
 //             dZ2 = dH2 * g2' -> DZ[16:80)
 //             dH1 = dZ2 W2'           (4)   and  D2 += DZ^T [H1|1]   (8: dW2', db2 in rows 16..79)
 //             dZ1 = dH1 * g1' -> DZ[16:80)
@@ -32,20 +32,20 @@ namespace nic {
 
 constexpr int TT_ROWS = 128, TT_THREADS = 256;
 constexpr int TT_CIN = 73, TT_K1 = 80, TT_H = 64, TT_K2 = 80;
-constexpr int TT_SG80 = 10 * 128;          // sample-group stride of an 80-feature activation buffer (bytes)
-constexpr int TT_SG128 = 16 * 128;         // ... of the 128-feature delta buffer
+constexpr int TT_SG80 = 10 * 128;          // sample-group stride of an 80-feature activation / delta buffer (bytes)
 constexpr int TT_W1 = 64 * 80 * 2, TT_W2 = 64 * 80 * 2, TT_W3 = 16 * 80 * 2;
+constexpr int TT_WIMG = TT_W1 + TT_W2 + TT_W3;
 constexpr int TT_ACT = 16 * TT_SG80;       // 20480
-constexpr int TT_DZ = 16 * TT_SG128;       // 32768
-constexpr int TT_W1T = 64 * 64 * 2, TT_W2T = 64 * 64 * 2, TT_W3T = 64 * 16 * 2;   // transposed images for the delta GEMMs
-constexpr int TT_WIMG = TT_W1 + TT_W2 + TT_W3 + TT_W1T + TT_W2T + TT_W3T;
 constexpr int TT_OFF_W1 = 0, TT_OFF_W2 = TT_OFF_W1 + TT_W1, TT_OFF_W3 = TT_OFF_W2 + TT_W2;
-constexpr int TT_OFF_W1T = TT_OFF_W3 + TT_W3, TT_OFF_W2T = TT_OFF_W1T + TT_W1T, TT_OFF_W3T = TT_OFF_W2T + TT_W2T;
-constexpr int TT_OFF_X = TT_OFF_W3T + TT_W3T, TT_OFF_H1 = TT_OFF_X + TT_ACT, TT_OFF_H2 = TT_OFF_H1 + TT_ACT;
-constexpr int TT_OFF_DZ = TT_OFF_H2 + TT_ACT, TT_OFF_MISC = TT_OFF_DZ + TT_DZ;
-constexpr int TT_SMEM = TT_OFF_MISC + 256;
-constexpr int TT_TMEM_COLS = 512;
-constexpr int TT_COL_D = 0, TT_COL_D1 = 64, TT_COL_D2 = 144, TT_COL_D3 = 224;
+constexpr int TT_OFF_X = TT_OFF_W3 + TT_W3, TT_OFF_H1 = TT_OFF_X + TT_ACT, TT_OFF_H2 = TT_OFF_H1 + TT_ACT;
+constexpr int TT_OFF_DZ = TT_OFF_H2 + TT_ACT;
+// MN-major A operands with M = 128 read 16 feature groups per sample group from buffers that hold 10: groups 10..15
+// alias the start of the next sample group (finite garbage -> accumulator rows 80..127, never read); for the last
+// sample group that is 768 bytes past the buffer, hence the zeroed pad after DZ (H2's overrun lands in DZ).
+constexpr int TT_OFF_PAD = TT_OFF_DZ + TT_ACT, TT_OFF_MISC = TT_OFF_PAD + 1024;
+constexpr int TT_SMEM = TT_OFF_MISC + 256;                 // 106,240 B: two CTAs per SM
+constexpr int TT_TMEM_COLS = 256;                          // two CTAs per SM share the 512 columns
+constexpr int TT_COL_D = 0, TT_COL_D1 = 64, TT_COL_D2 = 144, TT_COL_D3 = 224;       // D3 is 16 columns wide (transposed)
 constexpr float TT_LOSS_SCALE = 64.0f;
 
 // Instruction descriptor with explicit operand majors (bit 15: A is MN-major, bit 16: B is MN-major).
@@ -60,26 +60,17 @@ __host__ __device__ constexpr uint32_t tt_idesc(int fmt, int M, int N, int a_mn,
 //   W3' [16 x 80]: n < cout: k < 64: W3[n][k]/2; k = 64: b3[n]
 template <int FMT>
 __global__ void pack_train_weights_kernel(MlpDev m, uint16_t* __restrict__ img) {
-  // forward images, then the transposed ones used as K-major B of the delta-propagation GEMMs:
-  //   W1T' [64 x 64]: (n = input column < 64, k = hidden j) = W1[j][n]        (dX = dZ1 W1; only grid columns are needed)
-  //   W2T' [64 x 64]: (n = k_in, k = j) = W2[j][k_in] / 2                     (dH1' = dZ2 W2')
-  //   W3T' [64 x 16]: (n = h, k = c)    = W3[c][h] / 2 for c < cout           (dH2' = dZ3 W3')
-  const int n1 = 64 * 80, n2 = 64 * 80, n3 = 16 * 80, n4 = 64 * 64, n5 = 64 * 64, n6 = 64 * 16;
-  const int off[7] = {0, n1, n1 + n2, n1 + n2 + n3, n1 + n2 + n3 + n4, n1 + n2 + n3 + n4 + n5, n1 + n2 + n3 + n4 + n5 + n6};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < off[6]; i += gridDim.x * blockDim.x) {
-    int which = 0;
-    while (i >= off[which + 1]) ++which;
-    const int local = i - off[which];
-    const int nrows = which == 2 ? 16 : 64;
-    const int kc = local / (nrows * 8), rem = local - kc * nrows * 8;
-    const int n = rem / 8, k = kc * 8 + (rem - n * 8);
+  const int n1 = 64 * 80, n2 = 64 * 80, n3 = 16 * 80;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += gridDim.x * blockDim.x) {
+    int which = i < n1 ? 0 : (i < n1 + n2 ? 1 : 2);
+    int local = which == 0 ? i : (which == 1 ? i - n1 : i - n1 - n2);
+    int nrows = which == 2 ? 16 : 64;
+    int kc = local / (nrows * 8), rem = local - kc * nrows * 8;
+    int n = rem / 8, k = kc * 8 + (rem - n * 8);
     float v = 0.f;
     if (which == 0) v = k < m.cin ? m.w1[n * m.cin + k] : (k == m.cin ? m.b1[n] : 0.f);
     else if (which == 1) v = k < 64 ? 0.5f * m.w2[n * 64 + k] : (k == 64 ? m.b2[n] : 0.f);
-    else if (which == 2) { if (n < m.cout) v = k < 64 ? 0.5f * m.w3[n * 64 + k] : (k == 64 ? m.b3[n] : 0.f); }
-    else if (which == 3) v = m.w1[k * m.cin + n];
-    else if (which == 4) v = 0.5f * m.w2[k * 64 + n];
-    else if (k < m.cout) v = 0.5f * m.w3[k * 64 + n];
+    else if (n < m.cout) v = k < 64 ? 0.5f * m.w3[n * 64 + k] : (k == 64 ? m.b3[n] : 0.f);
     img[i] = to16<FMT>(v);
   }
 }
@@ -206,7 +197,7 @@ struct TrainArgs {
 };
 
 template <int FMT>
-__global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, TrainArgs a) {
+__global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, TrainArgs a) {
   using P = Pair<FMT>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sX = smem + TT_OFF_X;
@@ -222,7 +213,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
   const int row = tid & (TT_ROWS - 1);            // sample of the tile = TMEM lane
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   // byte offset of this sample's 16-byte chunk inside a feature group, for the two buffer widths
-  const int roff80 = (row >> 3) * TT_SG80 + (row & 7) * 16, roff128 = (row >> 3) * TT_SG128 + (row & 7) * 16;
+  const int roff80 = (row >> 3) * TT_SG80 + (row & 7) * 16;
 
   if (warp == 0) tmem_alloc(tmem_slot, TT_TMEM_COLS);
   if (tid == 0) mbar_init(mbar, 1);
@@ -231,7 +222,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
     for (int i = tid; i < TT_WIMG / 16; i += TT_THREADS) dst[i] = __ldg(a.wimg + i);
     // zero the activation / delta buffers once (padding features must be finite), then the constant-1 bias features
     uint4* act = reinterpret_cast<uint4*>(smem + TT_OFF_X);
-    for (int i = tid; i < (3 * TT_ACT + TT_DZ) / 16; i += TT_THREADS) act[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (4 * TT_ACT + 1024) / 16; i += TT_THREADS) act[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   if (wg == 0) {
@@ -246,10 +237,10 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t aW1 = smem_u32(smem + TT_OFF_W1), aW2 = smem_u32(smem + TT_OFF_W2), aW3 = smem_u32(smem + TT_OFF_W3);
-  const uint32_t aW1T = smem_u32(smem + TT_OFF_W1T), aW2T = smem_u32(smem + TT_OFF_W2T), aW3T = smem_u32(smem + TT_OFF_W3T);
   const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aDZ = smem_u32(sDZ);
   constexpr uint32_t ID_F64 = tt_idesc(FMT, 128, 64, 0, 0), ID_F16 = tt_idesc(FMT, 128, 16, 0, 0);
-  constexpr uint32_t ID_B64 = tt_idesc(FMT, 128, 64, 0, 0);        // delta propagation: A K-major, B = transposed image
+  constexpr uint32_t ID_B64 = tt_idesc(FMT, 128, 64, 0, 1);        // delta propagation: A K-major, B = W'^T (MN-major view)
+  constexpr uint32_t ID_G16 = tt_idesc(FMT, 128, 16, 1, 1);        // D3^T = [H2|1]^T dZ3
   constexpr uint32_t ID_G80 = tt_idesc(FMT, 128, 80, 1, 1);        // weight gradients: both operands MN-major
   constexpr uint32_t WG64 = 8 * 128, WG16 = 2 * 128;               // k-group strides of the 64-row / 16-row weight images
   uint32_t phase = 0;
@@ -274,7 +265,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
   auto issue_wgrad = [&](uint32_t dcol, uint32_t bbuf) {
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc)
-      mma_ss(tmem + dcol, make_smem_desc(aDZ + kc * 2 * TT_SG128, TT_SG128, 128),
+      mma_ss(tmem + dcol, make_smem_desc(aDZ + kc * 2 * TT_SG80, TT_SG80, 128),
              make_smem_desc(bbuf + kc * 2 * TT_SG80, TT_SG80, 128), ID_G80, (tiles_done > 0 || kc > 0) ? 1u : 0u);
   };
 
@@ -438,24 +429,27 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
       for (int f = 0; f < 2; ++f) {
         auto p0 = P::pack(dz[8 * f], dz[8 * f + 1]), p1 = P::pack(dz[8 * f + 2], dz[8 * f + 3]);
         auto p2 = P::pack(dz[8 * f + 4], dz[8 * f + 5]), p3 = P::pack(dz[8 * f + 6], dz[8 * f + 7]);
-        *reinterpret_cast<uint4*>(sDZ + roff128 + f * 128) =
+        *reinterpret_cast<uint4*>(sDZ + roff80 + f * 128) =
             make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
                        *reinterpret_cast<uint32_t*>(&p3));
       }
     }
     // ------------------------------------------------------------------------------------------ backward
-    // dH2 = dZ3 W3' (K = 16 output features) and D3 += DZ^T [H2 | 1].  DZ[16:80) still holds the PREVIOUS tile's dZ1 here:
-    // it lands in rows 16..79 of D3, which are never read.
+    // dH2 = dZ3 W3' (K = 16 output features) and D3^T += [H2 | 1]^T dZ3.
     run_mmas([&] {
-      mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ, 128, TT_SG128), make_smem_desc(aW3T, WG64, 128), ID_B64, 0);
-      issue_wgrad(TT_COL_D3, aH2);
+      mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ, 128, TT_SG80), make_smem_desc(aW3, 128, WG16), ID_B64, 0);
+      // D3^T [H2 feature x output c] += [H2|1]^T (MN-major A, M = 128 aliased) . dZ3 (MN-major B, N = 16)
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc)
+        mma_ss(tmem + TT_COL_D3, make_smem_desc(aH2 + kc * 2 * TT_SG80, TT_SG80, 128),
+               make_smem_desc(aDZ + kc * 2 * TT_SG80, TT_SG80, 128), ID_G16, (tiles_done > 0 || kc > 0) ? 1u : 0u);
     });
 #pragma unroll
     for (int layer = 1; layer >= 0; --layer) {
       uint32_t acc[32];
       tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
       tc_wait_ld();
-      uint8_t* dstb = sDZ + roff128 + (2 + wg * 4) * 128;
+      uint8_t* dstb = sDZ + roff80 + (2 + wg * 4) * 128;
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
         uint32_t dp[4];
@@ -471,8 +465,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
         run_mmas([&] {      // dH1 = dZ2 W2'  and  D2 += DZ^T [H1 | 1]
 #pragma unroll
           for (int kc = 0; kc < 4; ++kc)
-            mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG128),
-                   make_smem_desc(aW2T + kc * 2 * WG64, WG64, 128), ID_B64, kc > 0);
+            mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
+                   make_smem_desc(aW2 + kc * 256, 128, WG64), ID_B64, kc > 0);
           issue_wgrad(TT_COL_D2, aH1);
         });
       } else {
@@ -480,8 +474,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
           if (a.dgs0) {
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc)
-              mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG128),
-                     make_smem_desc(aW1T + kc * 2 * WG64, WG64, 128), ID_B64, kc > 0);
+              mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
+                     make_smem_desc(aW1 + kc * 256, 128, WG64), ID_B64, kc > 0);
           }
           issue_wgrad(TT_COL_D1, aX);
         });
@@ -534,12 +528,24 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
   tc_fence_after();
   if (tiles_done > 0) {
     const float fs = a.flush_scale;
-    // D3: rows 0..cout-1 = output feature c; columns 0..63 = dW3'[c][h] (W3' = W3/2), column 64 = db3[c]
+    // D3^T: rows 0..63 = hidden unit h, row 64 = the bias feature; columns c < cout: dW3'[c][h] (W3' = W3/2) / db3[c]
     // D2 / D1: rows 16..79 = hidden unit j = row - 16; D2 columns 0..63 = dW2'[j][k] (W2' = W2/2), 64 = db2[j];
     //          D1 columns 0..72 = dW1[j][cin], 73 = db1[j].  Warp-group 0 reads columns [0,48), 1 reads [48,80).
+    if (wg == 0) {
+      uint32_t acc[16];
+      tmem_ld16(tmem + TT_COL_D3 + lane_base, acc);
+      tc_wait_ld();
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < a.cout) {
+          const float v = __uint_as_float(acc[c]) * fs;
+          if (row < 64) atomicAdd(a.gm.w3 + c * 64 + row, 0.5f * v);
+          else if (row == 64) atomicAdd(a.gm.b3 + c, v);
+        }
+    }
     const int c0 = wg * 48, cw = wg == 0 ? 48 : 32;
-    for (int which = 0; which < 3; ++which) {
-      const uint32_t dcol = which == 0 ? TT_COL_D3 : (which == 1 ? TT_COL_D2 : TT_COL_D1);
+    for (int which = 1; which < 3; ++which) {
+      const uint32_t dcol = which == 1 ? TT_COL_D2 : TT_COL_D1;
       uint32_t acc[48];
       tmem_ld16(tmem + dcol + lane_base + c0, acc);
       tmem_ld16(tmem + dcol + lane_base + c0 + 16, acc + 16);
@@ -550,12 +556,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) train_tc_kernel(DevGeom g, Trai
         if (i >= cw) continue;
         const int col = c0 + i;
         const float v = __uint_as_float(acc[i]) * fs;
-        if (which == 0) {
-          if (row < a.cout) {
-            if (col < 64) atomicAdd(a.gm.w3 + row * 64 + col, 0.5f * v);
-            else if (col == 64) atomicAdd(a.gm.b3 + row, v);
-          }
-        } else if (row >= 16 && row < 80) {
+        if (row >= 16 && row < 80) {
           const int j = row - 16;
           if (which == 1) {
             if (col < 64) atomicAdd(a.gm.w2 + j * 64 + col, 0.5f * v);
@@ -654,7 +655,7 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   if (e != cudaSuccess) return (int)e;
   if (g.N >= (1ll << 27)) return NIC_ERR_UNSUPPORTED;          // Philox counter packs (sample << 4 | block)
   long long ntiles = (g.N + TT_ROWS - 1) / TT_ROWS;
-  int grid = (int)(ntiles < h->sms ? ntiles : h->sms);
+  int grid = (int)(ntiles < 2 * h->sms ? ntiles : 2 * h->sms);          // two resident CTAs per SM
   {
     KernelTimer timer(h, st);
     kern<<<grid, TT_THREADS, TT_SMEM, st>>>(g, a);
