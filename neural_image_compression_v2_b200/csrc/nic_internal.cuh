@@ -31,6 +31,7 @@ struct Handle {
   size_t tc_gscratch_bytes;
   int disable_fast2d;        // testing knob: force the general tensor-core kernel
   int reuse_prepared;        // NIC_OPT_REUSE_PREPARED
+  int debug_flags;           // knock-out experiments (option 100), never set in production
   int legacy_fast2d;         // NIC_OPT_LEGACY_FAST2D: the first-generation (non warp-specialised) fast-path kernel
   struct PreparedKey {       // what the tables in tc_weights / tc_shadow were last built from
     const void *g0, *g1, *w1, *b1, *w2, *b2, *w3, *b3;

@@ -645,24 +645,31 @@ __global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, co
 }
 
 // ================================================================================================ 2-D fast path, v2
-// Warp-specialised persistent form of the kernel above: ONE CTA per SM, 17 warps.
-//   warps 0..15  four warp-groups; group s owns tile slot s (TMEM: D 64 columns + A 40 columns), does the WHOLE
-//                64-column epilogue of its tile (tcgen05.ld -> packed 2*gelu -> tcgen05.st) and, after a 128-thread named
-//                barrier, its elected lane issues the slot's next tcgen05.mma batch (layer 1: 3 aliased-cell MMAs +
-//                selector x [G1 rows | LUTx] + selector x LUTy; layers 2, 3: 5 MMAs each).  The four slots run
-//                independently and never meet at a CTA-wide barrier: one slot's MMAs run under the others' epilogues;
-//   warp 16      producer: stages each tile's G0 cell rows and per-node G1 rows (2 KB) into a double-buffered slot area.
-//   Hand-offs: full[s] (tensor core -> group s, by tcgen05.commit), stage_full[s][b] (producer -> group s, 32 arrivals),
-//   stage_empty[s][b] (tensor core -> producer, by tcgen05.commit).
-//   TMEM (512 columns): slot s at [104 s, 104 s + 104): D then A;  selector matrix at [416, 432).
-constexpr int WS_SLOTS = 4, WS_EPI_WARPS = 16, WS_THREADS = 32 * (WS_EPI_WARPS + 1);
-constexpr int WS_TMEM_COLS = 512, WS_SLOT_COLS = 104, WS_COL_SEL = 416;
+// Warp-specialised persistent form of the kernel above.  Knock-out experiments (NIC option 100, tools/run_decode.py)
+// showed the first versions were bound by the LATENCY of the per-tile chain (epilogue -> barrier -> MMA issue ->
+// ~95 cycles per tcgen05.mma -> commit -> wake-up -> tcgen05.ld), i.e. by how many tiles are in flight, not by any pipe.
+// TMEM caps that number: with the next layer's A operand in TMEM a tile needs 104 columns (4 tiles).  Here the
+// activations go to SHARED memory instead (st.shared in the UMMA K-major core-matrix layout, SS-form MMAs), a tile
+// needs only its 64 accumulator columns, and EIGHT tiles are in flight per SM:
+//   * ONE CTA of 1024 threads per SM = eight independent warp-groups of 4 warps; group s owns TMEM columns [64 s, +64),
+//     a 16 KB activation buffer and a double-buffered 2 KB operand staging area;
+//   * a group runs its tiles as a private pipeline: tcgen05.ld 16 columns -> packed 2*gelu -> one 16-byte st.shared per
+//     8 columns; after a 128-thread named barrier its elected lane issues the next tcgen05.mma batch (layer 1: 3
+//     aliased-cell MMAs + selector x [G1 rows | LUTx] + selector x LUTy; layers 2, 3: 4 MMAs + 1 bias MMA against a
+//     shared constant ones block) and the group waits on its own mbarrier (tcgen05.commit).  Groups never meet at a
+//     CTA-wide barrier, so one group's MMAs and hand-offs run under the other groups' epilogues;
+//   * the group stages its own operands: its threads fetch the pieces (8 B of a G0 cell row / 16 B of a G1 node row)
+//     of the tile after next into registers while the current tile is processed.
+constexpr int WS_SLOTS = 8, WS_GROUP = 128, WS_THREADS = WS_SLOTS * WS_GROUP;
+constexpr int WS_TMEM_COLS = 512;
 constexpr int WS_STAGE = WS_SLOTS * 2 * 2048;       // [slot][buffer][Ag0 1 KB | G1 rows 1 KB]
-constexpr int WS_SMEM = WS_STAGE + F_IMG + 512;
+constexpr int WS_KG = 16 * 128;                     // bytes of one k-group (8 columns) of a 128-row K-major A operand
+constexpr int WS_OFF_SEL = WS_STAGE + F_IMG;        // selector matrix, 128 x 32 (4 k-groups)
+constexpr int WS_OFF_ONE = WS_OFF_SEL + 4 * WS_KG;  // ones block, 128 x 16: column 0 = 1
+constexpr int WS_OFF_ACT = WS_OFF_ONE + 2 * WS_KG;  // [slot] 128 x 64 activations (8 k-groups)
+constexpr int WS_OFF_BAR = WS_OFF_ACT + WS_SLOTS * 8 * WS_KG;
+constexpr int WS_SMEM = WS_OFF_BAR + 256;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -675,7 +682,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
                                                                        const uint4* __restrict__ R,
                                                                        const uint4* __restrict__ wimg, int cout,
                                                                        unsigned tiles_y, unsigned fd_mul, unsigned fd_shift,
-                                                                       OutT* __restrict__ out) {
+                                                                       OutT* __restrict__ out, int dbg) {
   using P = Pair<FMT>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sW = smem_raw + WS_STAGE;                // weight images + LUTs sit ABOVE the staging buffers (LBO = distance)
@@ -684,28 +691,57 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
   uint8_t* sW3 = sW2 + b_image_bytes(64, TC_K2);
   uint8_t* sLx = sW3 + b_image_bytes(16, TC_K2);
   uint8_t* sLy = sLx + F_LUT;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sLy + F_LUT);     // [4]
-  uint64_t* bar_ready = bar_full + WS_SLOTS;                         // [4]
-  uint64_t* bar_sfull = bar_ready + WS_SLOTS;                        // [4][2]
-  uint64_t* bar_sempty = bar_sfull + 2 * WS_SLOTS;                   // [4][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sempty + 2 * WS_SLOTS);
+  uint8_t* sSel = smem_raw + WS_OFF_SEL;
+  uint8_t* sOne = smem_raw + WS_OFF_ONE;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + WS_OFF_BAR);     // [8]: tensor core -> group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + WS_SLOTS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slot = warp >> 2;                        // warp-group = tile slot
+  const int row = 32 * (warp & 3) + lane;            // texel row of the tile = TMEM lane
+  const int cell = row & 7, within = row >> 3;
+  const int lx = 4 * (cell >> 2) + (within >> 2), ly = 4 * (cell & 3) + (within & 3);
+  const int roff = (row >> 3) * 128 + (row & 7) * 16;      // this row's 16-byte chunk inside a k-group block
   if (warp == 0) tmem_alloc(tmem_slot, WS_TMEM_COLS);
-  if (tid == 0) {
-    for (int s = 0; s < WS_SLOTS; ++s) {
-      mbar_init(bar_full + s, 1);
-      mbar_init(bar_ready + s, 128);
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(bar_sfull + 2 * s + b, 32);
-        mbar_init(bar_sempty + 2 * s + b, 1);
-      }
-    }
-  }
+  if (tid == 0)
+    for (int s = 0; s < WS_SLOTS; ++s) mbar_init(bar_full + s, 1);
   {
     uint4* dst = reinterpret_cast<uint4*>(sW);
     for (int i = tid; i < F_IMG / 16; i += WS_THREADS) dst[i] = __ldg(wimg + i);
     for (int i = tid; i < WS_STAGE / 16; i += WS_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (slot == 0) {
+    // selector row of this texel: [6 tent weights of the 2 x 3 G1 nodes, 0, 0 | one-hot x (8) | one-hot y (16)]
+    float kx = (float)lx * 0.125f, ky = (float)(ly & 7) * 0.125f;
+    int cy1 = ly >> 3;
+    float sel[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sel[i] = 0.f;
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix)
+#pragma unroll
+      for (int iy = 0; iy < 3; ++iy) {
+        float wx = ix ? kx : 1.0f - kx;
+        float wy = iy == cy1 ? 1.0f - ky : (iy == cy1 + 1 ? ky : 0.f);
+        sel[ix * 3 + iy] = wx * wy;
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sel[8 + j] = j == lx ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sel[16 + j] = j == ly ? 1.f : 0.f;
+#pragma unroll
+    for (int kg = 0; kg < 4; ++kg) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        auto v = P::pack(sel[8 * kg + 2 * i], sel[8 * kg + 2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&v);
+      }
+      *reinterpret_cast<uint4*>(sSel + kg * WS_KG + roff) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    auto one = P::pack(1.0f, 0.0f);
+    *reinterpret_cast<uint4*>(sOne + roff) = make_uint4(*reinterpret_cast<uint32_t*>(&one), 0, 0, 0);
+    *reinterpret_cast<uint4*>(sOne + WS_KG + roff) = make_uint4(0, 0, 0, 0);
   }
   fence_async_smem();
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -724,189 +760,151 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
     py0 = g.origin0[1] + by0;
   };
 
-  if (warp < WS_EPI_WARPS) {
-    // ============================================================== epilogue warp-groups
-    const int slot = warp >> 2;
-    const int row = 32 * (warp & 3) + lane;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tD = tmem + slot * WS_SLOT_COLS + lane_base, tA = tD + 64;
-    const int cell = row & 7, within = row >> 3;
-    const int lx = 4 * (cell >> 2) + (within >> 2), ly = 4 * (cell & 3) + (within & 3);
-    // ---- constants in TMEM: the selector rows (group 0 writes them), the bias block of this slot's A area
-    if (slot == 0) {
-      float kx = (float)lx * 0.125f, ky = (float)(ly & 7) * 0.125f;
-      int cy1 = ly >> 3;
-      float sel[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) sel[i] = 0.f;
-#pragma unroll
-      for (int ix = 0; ix < 2; ++ix)
-#pragma unroll
-        for (int iy = 0; iy < 3; ++iy) {
-          float wx = ix ? kx : 1.0f - kx;
-          float wy = iy == cy1 ? 1.0f - ky : (iy == cy1 + 1 ? ky : 0.f);
-          sel[ix * 3 + iy] = wx * wy;
-        }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sel[8 + j] = j == lx ? 1.f : 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) sel[16 + j] = j == ly ? 1.f : 0.f;
-      uint32_t sp[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        auto v = P::pack(sel[2 * i], sel[2 * i + 1]);
-        sp[i] = *reinterpret_cast<uint32_t*>(&v);
-      }
-      tmem_st16(tmem + WS_COL_SEL + lane_base, sp);
+  const int gt = tid & (WS_GROUP - 1);               // thread index inside the group
+  const uint32_t tDs = tmem + slot * 64;             // this slot's accumulator columns
+  const uint32_t tD = tDs + ((uint32_t)((warp & 3) * 32) << 16);
+  uint8_t* sAct = smem_raw + WS_OFF_ACT + slot * 8 * WS_KG;
+  const bool elected = (warp & 3) == 0 && lane == 0;
+  constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
+  constexpr uint32_t IDESC_64_BMN = make_idesc(FMT, 128, 64, 1);
+  constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
+  const uint32_t aStage = smem_u32(smem_raw), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+  const uint32_t aLx = smem_u32(sLx), aLy = smem_u32(sLy), aSel = smem_u32(sSel), aOne = smem_u32(sOne), aAct = smem_u32(sAct);
+  const int ny0 = g.n0[1], ny1 = g.n1[1];
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(WS_GROUP) : "memory"); };
+  // ---- operand staging: 144 pieces per tile over 128 threads (threads 0..15 take a second piece)
+  uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = make_uint4(0, 0, 0, 0);
+  auto fetch_piece = [&](int p, int px0, int py0) -> uint4 {
+    if (p < 96) {
+      int c8 = p / 12, piece = p - c8 * 12;
+      int seg = piece >= 6, off = piece - seg * 6;
+      int nx_ = (px0 >> 2) + (c8 >> 2) + seg, ny_ = (py0 >> 2) + (c8 & 3);
+      uint2 v = __ldg(shadow0 + ((size_t)nx_ * ny0 + ny_) * 3 + off);      // nodes (x, y) and (x, y + 1) are contiguous
+      return make_uint4(v.x, v.y, 0, 0);
     }
-    {
-      uint32_t ones[8];
-      auto one = P::pack(1.0f, 0.0f);
-      ones[0] = *reinterpret_cast<uint32_t*>(&one);
-#pragma unroll
-      for (int i = 1; i < 8; ++i) ones[i] = 0u;
-      tmem_st8(tA + 32, ones);
+    int t2 = p - 96, r6 = t2 >> 3, piece = t2 & 7;
+    int nx_ = (px0 >> 3) + r6 / 3, ny_ = (py0 >> 3) + r6 % 3;
+    return __ldg(R + ((size_t)nx_ * ny1 + ny_) * 8 + piece);
+  };
+  auto store_piece = [&](uint8_t* base, int p, const uint4& v) {
+    if (p < 96) {
+      int c8 = p / 12, piece = p - c8 * 12;
+      int seg = piece >= 6, off = piece - seg * 6;
+      int k = seg * 24 + off * 4;
+      *reinterpret_cast<uint2*>(base + (k >> 3) * 128 + c8 * 16 + (k & 7) * 2) = make_uint2(v.x, v.y);
+    } else {
+      int t2 = p - 96, r6 = t2 >> 3, piece = t2 & 7;
+      *reinterpret_cast<uint4*>(base + 1024 + piece * 128 + r6 * 16) = v;
     }
-    tc_wait_st();
-  }
-  tc_fence_before();
-  __syncthreads();                 // the TMEM constants are in place before the first MMA
-  tc_fence_after();
-
-  if (warp < WS_EPI_WARPS) {
-    const int slot = warp >> 2;
-    const int row = 32 * (warp & 3) + lane;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tD = tmem + slot * WS_SLOT_COLS + lane_base;
-    const int cell = row & 7, within = row >> 3;
-    const int lx = 4 * (cell >> 2) + (within >> 2), ly = 4 * (cell & 3) + (within & 3);
-    const uint32_t tA = tD + 64;
-    // ---- this group's elected lane issues the group's MMAs (no separate issuer warp: a 128-thread named barrier, then
-    //      ~30 instructions on one lane, is a much shorter hand-off than an mbarrier round trip through a polling warp)
-    const bool elected = (warp & 3) == 0 && lane == 0;
-    constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
-    constexpr uint32_t IDESC_64_BMN = make_idesc(FMT, 128, 64, 1);
-    constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
-    const uint32_t aStage = smem_u32(smem_raw), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-    const uint32_t aLx = smem_u32(sLx), aLy = smem_u32(sLy);
-    const uint32_t tDs = tmem + slot * WS_SLOT_COLS, tAs = tDs + 64;       // slot base without the lane offset
-    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory"); };
-    auto issue_layer1 = [&](unsigned i) {          // elected lane only
-      const unsigned j = i / WS_SLOTS, bsel = j & 1;
-      mbar_wait(bar_sfull + 2 * slot + bsel, (j >> 1) & 1);
-      tc_fence_after();
-      int px0, py0, bx0, by0;
-      tile_origin(blockIdx.x + i * gridDim.x, px0, py0, bx0, by0);
-      const uint32_t aAg0 = aStage + (slot * 2 + bsel) * 2048, aG1 = aAg0 + 1024;
+  };
+  auto fetch = [&](unsigned i) {
+    if (i >= my_tiles) return;
+    int px0, py0, bx0, by0;
+    tile_origin(blockIdx.x + i * gridDim.x, px0, py0, bx0, by0);
+    pre0 = fetch_piece(gt, px0, py0);
+    if (gt < 16) pre1 = fetch_piece(128 + gt, px0, py0);
+  };
+  auto stage = [&](unsigned i) {          // store the fetched pieces of tile i into its staging buffer
+    if (i >= my_tiles) return;
+    uint8_t* base = smem_raw + (slot * 2 + ((i / WS_SLOTS) & 1)) * 2048;
+    store_piece(base, gt, pre0);
+    if (gt < 16) store_piece(base, 128 + gt, pre1);
+    fence_async_smem();
+  };
+  auto issue_layer1 = [&](unsigned i) {          // elected lane only; tile i's operands are staged
+    int px0, py0, bx0, by0;
+    tile_origin(blockIdx.x + i * gridDim.x, px0, py0, bx0, by0);
+    const uint32_t aAg0 = aStage + (slot * 2 + ((i / WS_SLOTS) & 1)) * 2048, aG1 = aAg0 + 1024;
 #pragma unroll
-      for (int kc = 0; kc < 3; ++kc)
+    for (int kc = 0; kc < 3; ++kc)
+      if (!((dbg & 4) && kc > 0))
         mma_ss(tDs, make_smem_desc(aAg0 + kc * 256, 128, 0), make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
-      const uint32_t lx_grp = aLx + ((px0 & 63) >> 3) * 1024;
-      mma_ts(tDs, tmem + WS_COL_SEL, make_smem_desc(aG1, lx_grp - aG1, SBO), IDESC_64_BMN, 1);
-      mma_ts(tDs, tmem + WS_COL_SEL + 8, make_smem_desc(aLy + ((py0 & 63) >> 3) * 1024, 1024, SBO), IDESC_64_BMN, 1);
-      tc_commit(bar_sempty + 2 * slot + bsel);
-      tc_commit(bar_full + slot);
-    };
-    uint32_t ph = 0;
-    if (elected && (unsigned)slot < my_tiles) issue_layer1(slot);
-    for (unsigned i = slot; i < my_tiles; i += WS_SLOTS) {
-      const unsigned tile = blockIdx.x + i * gridDim.x;
+    const uint32_t lx_grp = aLx + ((px0 & 63) >> 3) * 1024;
+    if (!(dbg & 4)) {
+      mma_ss(tDs, make_smem_desc(aSel, WS_KG, SBO), make_smem_desc(aG1, lx_grp - aG1, SBO), IDESC_64_BMN, 1);
+      mma_ss(tDs, make_smem_desc(aSel + 2 * WS_KG, WS_KG, SBO), make_smem_desc(aLy + ((py0 & 63) >> 3) * 1024, 1024, SBO),
+             IDESC_64_BMN, 1);
+    }
+    tc_commit(bar_full + slot);
+  };
+  auto issue_layer23 = [&](int layer) {          // elected lane only: A = this slot's activations (+ the ones block: bias)
+    const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
+    const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc)
+      if (!((dbg & 4) && kc > 0)) mma_ss(tDs, make_smem_desc(aAct + kc * 2 * WS_KG, WS_KG, SBO), make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
+    if (!(dbg & 4)) mma_ss(tDs, make_smem_desc(aOne, WS_KG, SBO), make_smem_desc(aW + 4 * 2 * lbo, lbo, SBO), idesc, 1);
+    tc_commit(bar_full + slot);
+  };
+
+  // ---- prologue: first tile of this slot
+  fetch(slot);
+  stage(slot);
+  tc_fence_before();
+  group_sync();
+  if (elected && (unsigned)slot < my_tiles) {
+    tc_fence_after();
+    issue_layer1(slot);
+  }
+  fetch(slot + WS_SLOTS);
+  uint32_t ph = 0;
+  for (unsigned i = slot; i < my_tiles; i += WS_SLOTS) {
+    const unsigned tile = blockIdx.x + i * gridDim.x;
 #pragma unroll 1
-      for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(bar_full + slot, ph);
-        ph ^= 1;
-        __syncwarp();
-        tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t acc[32];
-          tmem_ld32(tD + 32 * half, acc);
-          tc_wait_ld();
-          uint32_t hp[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) hp[k] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]));
-          tmem_st16(tA + 16 * half, hp);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        group_sync();
-        if (elected) {
-          tc_fence_after();
-          const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
-          const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
-#pragma unroll
-          for (int kc = 0; kc < TC_K2 / 16; ++kc)
-            mma_ts(tDs, tAs + kc * 8, make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
-          tc_commit(bar_full + slot);
-        }
-      }
+    for (int layer = 0; layer < 2; ++layer) {
       mbar_wait(bar_full + slot, ph);
       ph ^= 1;
       __syncwarp();
       tc_fence_after();
-      {
-        int px0, py0, bx0, by0;
-        tile_origin(tile, px0, py0, bx0, by0);
-        uint32_t acc[4];
-        tmem_ld4(tD, acc);
-        tc_wait_ld();
-        tc_fence_before();
-        group_sync();                                 // every thread has read D: the next tile's layer 1 may overwrite it
-        if (elected && i + WS_SLOTS < my_tiles) issue_layer1(i + WS_SLOTS);
-        const size_t n = (size_t)(bx0 + lx) * g.B[1] + (by0 + ly);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < cout) store_out(out + n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+      for (int q = 0; q < 4; ++q) {
+        uint32_t acc[16];
+        tmem_ld16(tD + 16 * q, acc);
+        tc_wait_ld();
+        uint32_t hp[8];
+        if (dbg & 2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            auto v = P::pack(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]));
+            hp[k] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) hp[k] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]));
+        }
+        *reinterpret_cast<uint4*>(sAct + (2 * q) * WS_KG + roff) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(sAct + (2 * q + 1) * WS_KG + roff) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+      }
+      fence_async_smem();                           // the activations (generic-proxy stores) -> visible to the tensor core
+      tc_fence_before();
+      group_sync();
+      if (elected) {
+        tc_fence_after();
+        issue_layer23(layer);
       }
     }
-  } else {
-    // ============================================================== producer: tile operands -> staging buffers
-    const int ny0 = g.n0[1], ny1 = g.n1[1];
-    uint4 cur[5], nxt[5];
-    auto load_tile = [&](unsigned i, uint4* v) {
+    mbar_wait(bar_full + slot, ph);
+    ph ^= 1;
+    __syncwarp();
+    tc_fence_after();
+    uint32_t acc[4];
+    tmem_ld4(tD, acc);
+    tc_wait_ld();
+    stage(i + WS_SLOTS);                          // operands of this slot's next tile (fetched one tile ago)
+    tc_fence_before();
+    group_sync();                                 // D has been read and the next operands are staged
+    if (elected && i + WS_SLOTS < my_tiles) {
+      tc_fence_after();
+      issue_layer1(i + WS_SLOTS);
+    }
+    fetch(i + 2 * WS_SLOTS);
+    {
       int px0, py0, bx0, by0;
-      tile_origin(blockIdx.x + i * gridDim.x, px0, py0, bx0, by0);
+      tile_origin(tile, px0, py0, bx0, by0);
+      const size_t n = (size_t)(bx0 + lx) * g.B[1] + (by0 + ly);
 #pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        const int p = lane + 32 * r;
-        v[r] = make_uint4(0, 0, 0, 0);
-        if (p < 96) {
-          int c8 = p / 12, piece = p - c8 * 12;
-          int seg = piece >= 6, off = piece - seg * 6;
-          int nx_ = (px0 >> 2) + (c8 >> 2) + seg, ny_ = (py0 >> 2) + (c8 & 3);
-          uint2 w = __ldg(shadow0 + ((size_t)nx_ * ny0 + ny_) * 3 + off);      // nodes (x, y) and (x, y + 1) are contiguous
-          v[r].x = w.x;
-          v[r].y = w.y;
-        } else if (p < 144) {
-          int t2 = p - 96, r6 = t2 >> 3, piece = t2 & 7;
-          int nx_ = (px0 >> 3) + r6 / 3, ny_ = (py0 >> 3) + r6 % 3;
-          v[r] = __ldg(R + ((size_t)nx_ * ny1 + ny_) * 8 + piece);
-        }
-      }
-    };
-    if (my_tiles > 0) load_tile(0, cur);
-    for (unsigned i = 0; i < my_tiles; ++i) {
-      const unsigned s = i & 3, j = i >> 2, b = j & 1;
-      if (i + 1 < my_tiles) load_tile(i + 1, nxt);
-      if (j >= 2) mbar_wait(bar_sempty + 2 * s + b, ((j >> 1) - 1) & 1);
-      uint8_t* base = smem_raw + (s * 2 + b) * 2048;
-#pragma unroll
-      for (int r = 0; r < 5; ++r) {
-        const int p = lane + 32 * r;
-        if (p < 96) {
-          int c8 = p / 12, piece = p - c8 * 12;
-          int seg = piece >= 6, off = piece - seg * 6;
-          int k = seg * 24 + off * 4;
-          *reinterpret_cast<uint2*>(base + (k >> 3) * 128 + c8 * 16 + (k & 7) * 2) = make_uint2(cur[r].x, cur[r].y);
-        } else if (p < 144) {
-          int t2 = p - 96, r6 = t2 >> 3, piece = t2 & 7;
-          *reinterpret_cast<uint4*>(base + 1024 + piece * 128 + r6 * 16) = cur[r];
-        }
-      }
-      fence_async_smem();
-      mbar_arrive(bar_sfull + 2 * s + b);
-#pragma unroll
-      for (int r = 0; r < 5; ++r) cur[r] = nxt[r];
+      for (int c = 0; c < 4; ++c)
+        if (c < cout && !(dbg & 1)) store_out(out + n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
     }
   }
   tc_fence_before();
@@ -969,7 +967,7 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
   unsigned mul = (unsigned)(((1ull << (31 + sh)) + tiles_y - 1) / tiles_y);
   if (!h->legacy_fast2d) {
     // warp-specialised persistent kernel: one CTA per SM (all 512 TMEM columns)
-    static_assert(WS_SMEM <= 200 * 1024, "shared memory budget");
+    static_assert(WS_SMEM <= 227 * 1024, "shared memory budget");
     auto kern = decode_tc2d_ws_kernel<FMT, OutT>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
     if (e != cudaSuccess) return (int)e;
@@ -977,7 +975,7 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
     {
       KernelTimer timer(h, st);
       kern<<<grid, WS_THREADS, WS_SMEM, st>>>(g, (const uint2*)s0, (const uint4*)R, (const uint4*)h->tc_weights, m.cout,
-                                               tiles_y, mul, sh, out);
+                                               tiles_y, mul, sh, out, h->debug_flags);
     }
     h->launches++;
     return (int)cudaGetLastError();

@@ -22,6 +22,9 @@ with torch.no_grad():
     for p, v in zip(dec.parameters_list(), I.make_mlp(73, seed=1, gain=2.0)):
         p.copy_(torch.tensor(v))
 out = torch.empty((size, size, 3), dtype=torch.uint8, device=dev)
+for a in sys.argv:
+    if a.startswith("dbg="):
+        L.set_option(dev, 100, int(a[4:]))
 if "legacy" in sys.argv:
     L.set_option(dev, L.OPT_LEGACY_FAST2D, 1)
 L.set_option(dev, L.OPT_TIME_KERNELS, 1)
