@@ -27,8 +27,8 @@ SIZE = 4096                      # BASELINE.json configs[1]
 FLOP_PER_TEXEL = 2 * (73 * 64 + 64 * 64 + 64 * 3)      # 17,920
 METRIC, UNIT = "decoded Gtexel/s (4096x4096 RGB full-frame decode)", "Gtexel/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of decode_tc2d_kernel per launch, from the committed ncu --set full capture
-NCU_TRAFFIC_BYTES = 58965504 + 14352128
-NCU_TRAFFIC_SOURCE = "profiles/r01i_decode_tc2d_ws_metrics.txt"
+NCU_TRAFFIC_BYTES = 58980096 + 12962048
+NCU_TRAFFIC_SOURCE = "profiles/r01k_decode_tc2d_ws8_metrics.txt"
 
 
 def peaks():
