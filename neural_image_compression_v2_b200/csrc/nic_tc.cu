@@ -887,8 +887,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
     ph ^= 1;
     __syncwarp();
     tc_fence_after();
-    uint32_t acc[4];
-    tmem_ld4(tD, acc);
+    uint32_t acc[16];
+    if (cout > 4) tmem_ld16(tD, acc);               // multi-channel outputs (material stacks): up to 16 channels
+    else tmem_ld4(tD, acc);
     tc_wait_ld();
     stage(i + WS_SLOTS);                          // operands of this slot's next tile (fetched one tile ago)
     tc_fence_before();
@@ -905,6 +906,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < cout && !(dbg & 1)) store_out(out + n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+      if (cout > 4) {
+#pragma unroll
+        for (int c = 4; c < 16; ++c)
+          if (c < cout) store_out(out + n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+      }
     }
   }
   tc_fence_before();

@@ -604,7 +604,7 @@ def _rel_l2(a, b):
 
 
 @pytest.mark.parametrize("prec", ["f16", "bf16"])
-@pytest.mark.parametrize("case", ["mip2_aligned", "mip0_unaligned", "mip5_small_ragged", "large_grid"])
+@pytest.mark.parametrize("case", ["mip2_aligned", "mip0_unaligned", "mip5_small_ragged", "large_grid", "mip2_cout5"])
 def test_train_tc_step_vs_oracle_fp64(prec, case):
     """The tcgen05 training step against the oracle's fp64 backward.  Tolerances are those of 16-bit operands with fp32
     accumulation (tanh-form GELU in forward and backward): loss 1e-2 relative; every gradient tensor within a few % in
@@ -614,12 +614,13 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
     import ctypes as C
     size = 4096 if case == "large_grid" else 256       # 1025^2 nodes: the tiled (bandwidth-shaped) relayout kernels
     grids = I.make_grids(size, 2, seed=60, no_mip=case == "large_grid")
-    params = I.make_mlp(73, seed=61, gain=1.5)
+    cout = 5 if case == "mip2_cout5" else 3
+    params = I.make_mlp(73, cout=cout, seed=61, gain=1.5)
     rng = np.random.default_rng(64)
     if case == "large_grid":
         mip, fl, nc, crop = 0, 0, 2, 128
         coord = rng.integers(0, size - crop + 1, (nc, 2))
-    elif case == "mip2_aligned":
+    elif case in ("mip2_aligned", "mip2_cout5"):
         mip, fl, nc, crop = 2, 0, 3, 64
         coord = np.array([[0, 0], [0, 0], [0, 0]])
     elif case == "mip0_unaligned":
@@ -630,6 +631,8 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
         coord = rng.integers(0, (size >> mip) - crop + 1, (nc, 2))
     img = I.box_mips(I.make_image(512 if case == "large_grid" else size, 2, seed=62), 8)[mip]
     target = np.concatenate([img[:, c[0] % 256:c[0] % 256 + crop, c[1] % 256:c[1] % 256 + crop].reshape(3, -1).T for c in coord], 0)
+    if cout != 3:       # multi-channel material stack: extra target channels
+        target = np.concatenate([target, 1.0 - target], 1)[:, :cout].astype(np.float32)
     noise = I.make_noise(nc * crop * crop, 73, 8, 63)
     loss, out, grads, dg0, dg1 = O.train_forward_backward(grids, params, coord, target, fl, mip, 1, noise, size=crop,
                                                           dtype=np.float32 if case == "large_grid" else np.float64)
@@ -641,7 +644,7 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
     g0t, g1t = fp[2 * fl], fp[2 * fl + 1]
     d0, d1 = torch.zeros_like(g0t), torch.zeros_like(g1t)
     ls = torch.zeros(4, device=dev())
-    o = torch.empty((nc * crop * crop, 3), device=dev())
+    o = torch.empty((nc * crop * crop, cout), device=dev())
     geom = L.make_geom(L.METHOD_2D, g0t, g1t, crop, nc, mip - 2 * (fl + 1), mip, 6, L.PE_TRIANGULAR)
     h = L.handle(dev())
     coord_t, target_t, noise_t = T(coord, torch.int64), T(target), T(noise)
@@ -651,7 +654,7 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
         L.check(h, L.load_library().nic_train_step(h, C.byref(geom), L.ptr(g0t), L.ptr(g1t), L.ptr(coord_t), C.byref(m),
                                                    L.ptr(target_t), L.ptr(noise_t), 0, 0, 0, 0, C.byref(gm), L.ptr(d0),
                                                    L.ptr(d1), L.ptr(ls), L.ptr(o), L.PRECISIONS[prec], L.stream_ptr(dev())))
-        n_all = nc * crop * crop * 3
+        n_all = nc * crop * crop * cout
         tol = 1.0 if prec == "f16" else 4.0
         assert abs(float(ls[0]) / n_all - loss) <= 1e-2 * tol * loss
         assert np.abs(o.cpu().numpy() - out).max() <= 4e-3 * tol
@@ -732,3 +735,26 @@ def test_sub_byte_code_packing_round_trip(bits):
         assert np.array_equal(p.cpu().numpy(), want)
     for g, r in zip(grids, fpd.fp_load_packed(packed, bits)):
         assert torch.equal(r, models.quantize4fp(g, bits))
+
+
+@pytest.mark.parametrize("cout", [1, 5, 9, 16])
+def test_decode_multi_channel_outputs(cout):
+    """BASELINE config 3 shape (multi-channel material stack): decoders with Cout != 3 on every decode path (fast 2-D
+    tensor-core kernel, general tensor-core kernel, fp32 kernel) against the oracle."""
+    ic = nic().image_compression
+    size = 128
+    configure(IMAGE_SIZE=size, OUTPUT_CHANNELS=cout)
+    grids = I.make_grids(size, 2, seed=96, no_mip=True, quantized=True)
+    params = I.make_mlp(73, cout=cout, seed=97, gain=2.0)
+    fp, dec = [T(a) for a in grids], make_decoder(params)
+    table = O.create_pyramid_mip_levels(size, size // 4)
+    ref = O.decode_block(grids, params, size, 0, table, 1)
+    assert ref.shape == (size, size, cout)
+    f32 = ic.decode(fp, dec, 0, precision="f32").cpu().numpy()
+    np.testing.assert_allclose(f32, ref, rtol=1e-5, atol=1e-6)
+    ref8 = O.quantize_to_bit(ref, 8).astype(np.uint8)
+    fast = ic.decode(fp, dec, 0, precision="f16", out_dtype=torch.uint8).cpu().numpy()                       # fast path
+    gen = ic.decode(fp, dec, 0, size=(120, 120), origin=(3, 5), precision="f16", out_dtype=torch.uint8).cpu().numpy()
+    for got, want in ((fast, ref8), (gen, ref8[3:123, 5:125])):
+        within1, same, worst = lsb_stats(got, want)
+        assert got.shape == want.shape and within1 >= 0.999, (cout, within1, same, worst)
