@@ -176,22 +176,36 @@ template <int FMT>
 __global__ void __launch_bounds__(256) relayout_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C,
                                                        int nx, int nf, int no, long long sf, long long so,
                                                        long long plane) {
-  // tile: 32 nodes along x  x  32 nodes along the output-fast axis f, all channels; blockIdx.z = the other axis
-  extern __shared__ uint16_t tile[];           // [C][32][33]
+  // tile: 32 nodes along x  x  32 nodes along the output-fast axis f, all channels; blockIdx.z = the other axis.
+  // tile[e * 33 + xi] with e = fi * C + c = the element's position in output row xi: conflict-free both ways.
+  extern __shared__ uint16_t tile[];           // [32 * C][33]
   const int x0 = blockIdx.x * 32, f0 = blockIdx.y * 32, o = blockIdx.z;
   for (int i = threadIdx.x; i < C * 1024; i += blockDim.x) {
     int c = i >> 10, r = i & 1023, fi = r >> 5, xi = r & 31;
     int x = x0 + xi, f = f0 + fi;
     float v = (x < nx && f < nf) ? __ldg(src + (long long)c * plane + (long long)f * sf + (long long)o * so + x) : 0.f;
-    tile[(c * 32 + fi) * 33 + xi] = to16<FMT>(v);
+    tile[(fi * C + c) * 33 + xi] = to16<FMT>(v);
   }
   __syncthreads();
   const int fw = nf - f0 < 32 ? nf - f0 : 32;   // valid nodes along f in this tile
-  for (int xi = 0; xi < 32 && x0 + xi < nx; ++xi) {
-    uint16_t* row = dst + (((long long)(x0 + xi) * no + o) * nf + f0) * C;
-    for (int i = threadIdx.x; i < fw * C; i += blockDim.x) {
-      int fi = i / C, c = i - fi * C;
-      row[i] = tile[(c * 32 + fi) * 33 + xi];
+  const int xw = nx - x0 < 32 ? nx - x0 : 32;   // valid output rows
+  const int row_elems = fw * C;
+  if ((C & 3) == 0) {
+    // 8-byte stores (rows start 8-byte aligned when C % 4 == 0), all rows of the tile in parallel
+    const int per_row = row_elems >> 2;
+    for (int j = threadIdx.x; j < xw * per_row; j += blockDim.x) {
+      const int xi = j / per_row, q = j - xi * per_row;
+      const uint16_t* t = tile + (4 * q) * 33 + xi;
+      uint2 v;
+      v.x = (uint32_t)t[0] | ((uint32_t)t[33] << 16);
+      v.y = (uint32_t)t[66] | ((uint32_t)t[99] << 16);
+      uint16_t* row = dst + (((long long)(x0 + xi) * no + o) * nf + f0) * C;
+      *reinterpret_cast<uint2*>(row + 4 * q) = v;
+    }
+  } else {
+    for (int j = threadIdx.x; j < xw * row_elems; j += blockDim.x) {
+      const int xi = j / row_elems, e = j - xi * row_elems;
+      dst[(((long long)(x0 + xi) * no + o) * nf + f0) * C + e] = tile[e * 33 + xi];
     }
   }
 }

@@ -758,3 +758,39 @@ def test_decode_multi_channel_outputs(cout):
     for got, want in ((fast, ref8), (gen, ref8[3:123, 5:125])):
         within1, same, worst = lsb_stats(got, want)
         assert got.shape == want.shape and within1 >= 0.999, (cout, within1, same, worst)
+
+
+def test_train_tc_multi_lod_trajectory_tracks_f32():
+    """FusedTrainer with mips on (alternating LODs, per-tensor Adam step counts, freeze + quantise at 95 %): the f16
+    tensor-core trainer follows the fp32 trainer step for step — same crops, same injected noise, losses within 2 %,
+    and identical Adam step counters (tensors of inactive levels are never touched)."""
+    n = nic()
+    ic = n.image_compression
+    size, steps = 256, 24
+    configure(IMAGE_SIZE=size, TF_NO_MIP=False, MAX_MIP_LEVEL=8)
+    mips = [T(m) for m in I.box_mips(I.make_image(size, 2, seed=84), 8)]
+    lods = [0, 1, 2, 4, 0, 3, 5, 1, 6, 0, 2, 7, 0, 1, 4, 0, 2, 0, 1, 0, 3, 0, 1, 0]
+    rng = np.random.default_rng(85)
+    runs = {}
+    for prec in ("f32", "f16"):
+        fp = [T(a) for a in I.make_grids(size, 2, seed=86)]
+        dec = make_decoder(I.make_mlp(73, seed=87))
+        tr = ic.FusedTrainer(fp, dec, num_epochs=steps, fp_bits=8, seed=9, precision=prec)
+        r2 = np.random.default_rng(88)
+        losses = []
+        for s, lod in enumerate(lods):
+            crop = 2 ** (8 - lod)
+            dsize = size >> lod
+            coord = r2.integers(0, dsize - crop + 1, (4, 2))
+            tg = ic.sample_crops(mips[lod], torch.tensor(coord), crop)
+            noise = T(I.make_noise(4 * crop * crop, 73, 8, 4000 + s)) if s < steps * 0.95 else None
+            losses.append(float(tr.step(torch.tensor(coord), tg, lod, noise=noise)))
+        runs[prec] = (losses, {k: v[2] for k, v in tr.state.items()}, [g.clone() for g in tr.fp], tr.frozen)
+    l32, l16 = np.array(runs["f32"][0]), np.array(runs["f16"][0])
+    assert np.all(np.abs(l16 - l32) <= 0.02 * l32 + 1e-5), (l32, l16)
+    assert runs["f32"][1] == runs["f16"][1]                        # per-tensor Adam step counts
+    assert runs["f32"][3] and runs["f16"][3]                        # both froze + quantised the grids at 95 %
+    for a, b in zip(runs["f32"][2], runs["f16"][2]):
+        # quantised grids: codes may differ by one level where the two trajectories straddle a rounding boundary
+        assert float((a - b).abs().max()) <= 1.0 / 255 + 1e-6
+        assert float(((a - b).abs() > 1e-6).float().mean()) < 0.05
