@@ -64,6 +64,21 @@ def decode_band(fp, decoder, mip_level=0, size=None, rank=None, world=None, grou
     return row0, ic.decode(fp, decoder, mip_level, size=(rows, size), origin=(row0, 0), **kw)
 
 
+def decode_slab(fp, decoder, volume, mip_level=0, rank=None, world=None, group=None, **kw):
+    """This rank's slab of a 3-D volume of `volume` = (S0, S1, S2) texels: frames [f0, f0 + n) along the FIRST axis
+    (BASELINE config 5: frame-sharded video decode).  A rank only touches the grid nodes under its slab, but the grids
+    are small enough to replicate.  Returns (f0, slab) with slab `[n, S1, S2, Cout]`."""
+    from . import image_compression as ic
+    r, w = world_info(group)
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    f0, f1 = shard_range(volume[0], rank, world)
+    if f1 == f0:
+        cout = decoder.parameters_list()[4].shape[0]
+        return f0, torch.empty((0, volume[1], volume[2], cout), dtype=kw.get("out_dtype", torch.float32), device=fp[0].device)
+    return f0, ic.decode(fp, decoder, mip_level, size=(f1 - f0, volume[1], volume[2]), origin=(f0, 0, 0), **kw)
+
+
 def gather_bands(band, size, group=None):
     """Assembles the full frame on every rank from the per-rank bands (all_gather of padded bands).  Convenience
     for callers that need it; decode itself never communicates."""

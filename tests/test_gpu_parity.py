@@ -794,3 +794,60 @@ def test_train_tc_multi_lod_trajectory_tracks_f32():
         # quantised grids: codes may differ by one level where the two trajectories straddle a rounding boundary
         assert float((a - b).abs().max()) <= 1.0 / 255 + 1e-6
         assert float(((a - b).abs() > 1e-6).float().mean()) < 0.05
+
+
+def test_non_cubic_volume_and_slab_sharding():
+    """BASELINE config 5 shape in miniature: a non-cubic volume (x, y, t) = (24, 16, 40) on non-cubic grids, decoded
+    whole and as per-rank frame slabs (parallel.decode_slab, no collective); every 8^3 sub-cube equals the oracle's
+    cube decode at that origin (the reference itself only decodes cubes), slabs are bit-equal to the whole volume."""
+    n = nic()
+    ic, par = n.image_compression, n.parallel
+    configure(IMAGE_SIZE=64, IMAGE_DIMENSION=3, COMPRESSION_METHOD=3, CROP_MIP_LEVEL=3)
+    vol = (24, 16, 40)
+    rng = np.random.default_rng(92)
+    lo, hi = I.q_range(8)
+    # grids [C, z, y, x] with nodes = texels/4 + 1 (G0) and texels/8 + 1 (G1) per axis; x is the FIRST image axis
+    g0 = rng.uniform(lo, hi, (12, vol[2] // 4 + 1, vol[1] // 4 + 1, vol[0] // 4 + 1)).astype(np.float32)
+    g1 = rng.uniform(lo, hi, (12, vol[2] // 8 + 1, vol[1] // 8 + 1, vol[0] // 8 + 1)).astype(np.float32)
+    grids = [g0, g1]
+    params = I.make_mlp(127, seed=93, gain=2.0)
+    fp, dec = [T(a) for a in grids], make_decoder(params)
+    table = {0: 0}
+    for prec, tol in (("f32", 2e-6), ("f16", 4e-3)):
+        whole = ic.decode(fp, dec, 0, size=vol, precision=prec, level_table=table)
+        assert tuple(whole.shape) == vol + (3,)
+        for origin in ((0, 0, 0), (16, 8, 32), (8, 0, 16)):
+            ref = O.decode_block(grids, params, 8, 0, table, 3, origin=origin)
+            got = whole[origin[0]:origin[0] + 8, origin[1]:origin[1] + 8, origin[2]:origin[2] + 8].cpu().numpy()
+            assert np.abs(got - ref).max() <= tol, (prec, origin, np.abs(got - ref).max())
+        for world in (1, 3, 8):
+            seen = 0
+            for rank in range(world):
+                f0, slab = par.decode_slab(fp, dec, vol, 0, rank=rank, world=world, precision=prec, level_table=table)
+                assert torch.equal(slab, whole[f0:f0 + slab.shape[0]])
+                seen += slab.shape[0]
+            assert seen == vol[0]
+
+
+def test_lut_65_cubed_extension():
+    """BASELINE config 4 shape: a 65^3 LUT.  The reference cannot hold it (FEATURE_PYRAMID_SIZE = 65 // 4 = 16 gives 17
+    nodes, texel 64 needs node 17: SURVEY 8(d)); with ONE more node per grid axis the same arithmetic covers it.  Dense
+    decode of all 65^3 texels and random-access queries agree with the oracle evaluated on the same 18-/10-node grids."""
+    n = nic()
+    ic = n.image_compression
+    configure(IMAGE_SIZE=64, IMAGE_DIMENSION=3, COMPRESSION_METHOD=3, CROP_MIP_LEVEL=3)
+    rng = np.random.default_rng(94)
+    lo, hi = I.q_range(8)
+    grids = [rng.uniform(lo, hi, (12, 18, 18, 18)).astype(np.float32), rng.uniform(lo, hi, (12, 10, 10, 10)).astype(np.float32)]
+    params = I.make_mlp(127, seed=95, gain=2.0)
+    fp, dec = [T(a) for a in grids], make_decoder(params)
+    table = {0: 0}
+    ref = O.decode_block(grids, params, 65, 0, table, 3)
+    dense = ic.decode(fp, dec, 0, size=65, precision="f32", level_table=table).cpu().numpy()
+    np.testing.assert_allclose(dense, ref, rtol=1e-5, atol=1e-6)
+    q = rng.integers(0, 65, (4099, 3))
+    q[:3] = [[64, 64, 64], [0, 0, 64], [64, 0, 0]]
+    pts = ic.decode_points(fp, dec, torch.tensor(q), 0, precision="f16", out_dtype=torch.uint8, level_table=table).cpu().numpy()
+    want = O.quantize_to_bit(ref, 8).astype(np.uint8)[q[:, 0], q[:, 1], q[:, 2]]
+    within1, same, worst = lsb_stats(pts, want)
+    assert within1 >= 0.999, (within1, same, worst)
