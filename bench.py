@@ -238,6 +238,38 @@ def bench_gather(args, nic, ic, var2, dev, fp):
             "bytes_per_texel": bytes_per_texel, "workload": "gather_4096x4096_f16_X", "gtexel_s": n * kn / (kms * 1e-3) / 1e9}
 
 
+def bench_3d(args, nic, ic, var2, dev):
+    """General tensor-core decode kernel on the 3-D shapes of BASELINE configs 4 / 5 (side metrics, kernel-only):
+    dense 256^3 volume (method 3) and 16.7 M random-access LUT queries."""
+    import torch
+    import inputs as I
+    from neural_image_compression_v2_b200 import _lib as L
+    size = 256
+    var2.update(IMAGE_SIZE=size, IMAGE_DIMENSION=3, COMPRESSION_METHOD=3, CROP_MIP_LEVEL=5)
+    fp = [torch.tensor(g, device=dev) for g in I.make_grids(size, 3, seed=2, no_mip=True, quantized=True)]
+    dec = ic.ColorDecoder(127, 64, 3).to(dev)
+    with torch.no_grad():
+        for p, v in zip(dec.parameters_list(), I.make_mlp(127, seed=3, gain=2.0)):
+            p.copy_(torch.tensor(v))
+    out = torch.empty((size, size, size, 3), dtype=torch.uint8, device=dev)
+    q = torch.randint(0, size, (1 << 24, 3), device=dev)
+    res = {}
+    for name, fn, units in (("dense_256^3_method3", lambda: ic.decode(fp, dec, 0, precision=args.prec, out_dtype=torch.uint8, out=out), size ** 3),
+                            ("random_access_16.7M_queries", lambda: ic.decode_points(fp, dec, q, 0, precision=args.prec, out_dtype=torch.uint8), q.shape[0])):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        L.set_option(dev, L.OPT_TIME_KERNELS, 1)
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        kms, kn = L.kernel_time_ms(dev)
+        L.set_option(dev, L.OPT_TIME_KERNELS, 0)
+        res[name] = {"value": units * kn / (kms * 1e-3) / 1e9, "unit": "Gtexel/s", "kernel_ms": kms / max(kn, 1)}
+    var2.update(IMAGE_SIZE=SIZE, IMAGE_DIMENSION=2, COMPRESSION_METHOD=1)
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -331,6 +363,7 @@ def run_ours(args):
     if not args.no_extras:
         extras["gather"] = bench_gather(args, nic, ic, var2, dev, fp)
         del fp, out, flush
+        extras["decode_3d"] = bench_3d(args, nic, ic, var2, dev)
         extras["train"] = bench_train(args, nic, ic, var2, dev, world, rank, dist, barrier)
 
     if rank == 0:

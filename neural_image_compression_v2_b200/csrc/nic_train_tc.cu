@@ -1,7 +1,8 @@
 // nic_train_tc.cu — K3 + K4 on tensor cores: one fused training step (gather, quantisation noise, decoder forward, MSE,
 // full backward, weight-gradient sums, grid-gradient scatter) with EVERY GEMM on tcgen05.mma (sm_100a).
 // Reference behaviour: the body of train_models up to loss.backward() (Projects/image_compression.py:239-265) on the
-// 2-D path (create_decoder_input_2d :71-100, fp_def.create_g0_g1 fp_def.py:115-145, ColorDecoder :54-68).
+// 2-D path (create_decoder_input_2d :71-100, fp_def.create_g0_g1 fp_def.py:115-145) and the 3-D "v2" path (method 4:
+// create_decoder_input_3d_v2 :137-167, fp_def.create_g0_g1_3d_v2 fp_def.py:187-223), ColorDecoder :54-68.
 //
 // Per CTA (persistent, 256 threads = 2 warpgroups, TWO CTAs per SM: 106 KB smem, 256 TMEM columns, <= 128 registers), per tile of 128 samples (= MMA M = TMEM lanes):
 //   activations live in shared memory as [sample-group of 8][feature-group of 8][8 samples][8 features] 16-bit core
@@ -31,7 +32,13 @@
 namespace nic {
 
 constexpr int TT_ROWS = 128, TT_THREADS = 256;
-constexpr int TT_CIN = 73, TT_K1 = 80, TT_H = 64, TT_K2 = 80;
+constexpr int TT_K1 = 80, TT_H = 64, TT_K2 = 80;
+// decoder-input width: 2-D 5C + 2 PE + 1 = 73; 3-D "v2" (method 4) 5C + 3 PE + 1 = 79; both + the bias carrier <= 80 = K1
+template <int METHOD> struct TrainShape {
+  static constexpr int DIM = METHOD == NIC_METHOD_2D ? 2 : 3;
+  static constexpr int CIN = 5 * 12 + 6 * DIM + 1;
+  static constexpr int NC1 = DIM == 2 ? 4 : 8;           // G1 corners
+};
 constexpr int TT_SG80 = 10 * 128;          // sample-group stride of an 80-feature activation / delta buffer (bytes)
 constexpr int TT_W1 = 64 * 80 * 2, TT_W2 = 64 * 80 * 2, TT_W3 = 16 * 80 * 2;
 constexpr int TT_WIMG = TT_W1 + TT_W2 + TT_W3;
@@ -103,26 +110,32 @@ __global__ void __launch_bounds__(256) grad_relayout_add_kernel(float* __restric
 // Small-grid variants (one thread per element): the tiled kernels above are bandwidth-shaped and take tens of
 // microseconds of pure latency on a [12, 129, 129] grid, which is a third of a 0.36 ms training step.
 __global__ void __launch_bounds__(256) grad_add_small_kernel(float* __restrict__ s, float* __restrict__ dg, int C, int nx, int ny,
-                                                             float scale) {
-  const int total = C * nx * ny;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i % C, node = i / C;                 // s is [x][y][C]: i walks it linearly (coalesced read + zero)
-    const int y = node % ny, x = node / ny;
+                                                             int nz, float scale) {
+  const long long total = (long long)C * nx * ny * nz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);                        // s is [x][y][z][C]: i walks it linearly (coalesced read + zero)
+    long long node = i / C;
+    const int z = (int)(node % nz);
+    node /= nz;
+    const int y = (int)(node % ny), x = (int)(node / ny);
     const float v = s[i];
     if (v != 0.f) {
-      dg[((size_t)c * ny + y) * nx + x] += scale * v;
+      dg[(((size_t)c * nz + z) * ny + y) * nx + x] += scale * v;      // dg is [C][z][y][x]
       s[i] = 0.f;
     }
   }
 }
 template <int FMT>
 __global__ void __launch_bounds__(256) relayout_small_kernel(const float* __restrict__ g, uint16_t* __restrict__ sh, int C, int nx,
-                                                             int ny) {
-  const int total = C * nx * ny;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i % C, node = i / C;
-    const int y = node % ny, x = node / ny;
-    sh[i] = to16<FMT>(__ldg(g + ((size_t)c * ny + y) * nx + x));
+                                                             int ny, int nz) {
+  const long long total = (long long)C * nx * ny * nz;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long node = i / C;
+    const int z = (int)(node % nz);
+    node /= nz;
+    const int y = (int)(node % ny), x = (int)(node / ny);
+    sh[i] = to16<FMT>(__ldg(g + (((size_t)c * nz + z) * ny + y) * nx + x));
   }
 }
 
@@ -196,9 +209,11 @@ struct TrainArgs {
   int steps0, steps1;         // segmented-reduction depths of the scatter (lanes sharing a G0 / G1 node)
 };
 
-template <int FMT>
+template <int FMT, int METHOD>
 __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, TrainArgs a) {
   using P = Pair<FMT>;
+  using TS = TrainShape<METHOD>;
+  constexpr int DIM = TS::DIM, CIN = TS::CIN, NC1 = TS::NC1;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sX = smem + TT_OFF_X;
   uint8_t* sH1 = smem + TT_OFF_H1;
@@ -276,20 +291,38 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
     const unsigned nc = live ? n : (unsigned)g.N - 1;
     // ------------------------------------------------------------------------------------------ gather + noise -> X~
     Texel t = texel_of_fast(g, nc, a.origins);
-    AxisCoord ax[2];
+    AxisCoord ax[3];
 #pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      ax[d] = axis_coord(t.p[d], g.step);
-      ax[d].i0 = clampi(ax[d].i0, 0, g.n0[d] - 2);
-      ax[d].i1 = clampi(ax[d].i1, 0, g.n1[d] - 2);
+    for (int d = 0; d < 3; ++d) {
+      ax[d] = axis_coord(d < DIM ? t.p[d] : 0, g.step);
+      ax[d].i0 = clampi(ax[d].i0, 0, g.n0[d] - 2 < 0 ? 0 : g.n0[d] - 2);
+      ax[d].i1 = clampi(ax[d].i1, 0, g.n1[d] - 2 < 0 ? 0 : g.n1[d] - 2);
     }
-    const int node0 = ax[0].i0 * g.n0[1] + ax[1].i0, node1 = ax[0].i1 * g.n1[1] + ax[1].i1;   // corner (0,0); +1: y, +ny: x
+    // shadow node order: x slowest, then y, then z (2-D: x, y).  Linear index of corner (0,0,0) and the axis strides.
+    const int sy0 = DIM == 2 ? 1 : g.n0[2], sx0 = g.n0[1] * sy0, sy1 = DIM == 2 ? 1 : g.n1[2], sx1 = g.n1[1] * sy1;
+    const int node0 = ax[0].i0 * sx0 + ax[1].i0 * sy0 + (DIM == 3 ? ax[2].i0 : 0);
+    const int node1 = ax[0].i1 * sx1 + ax[1].i1 * sy1 + (DIM == 3 ? ax[2].i1 : 0);
+    // corner tables are (dz, dy, dx): offset of G0 corner j / G1 corner j from corner 0
+    auto off0 = [&](int j) {
+      const int8_t* d = DIM == 2 ? kCorner2D[j] : kCorner3Dv2[j];
+      return d[2] * sx0 + d[1] * sy0 + (DIM == 3 ? d[0] : 0);
+    };
+    auto off1 = [&](int j) {
+      const int8_t* d = DIM == 2 ? kCorner2D[j] : kCorner3D[j];
+      return d[2] * sx1 + d[1] * sy1 + (DIM == 3 ? d[0] : 0);
+    };
+    auto w1 = [&](int j) {          // interpolation weight of G1 corner j (2-D bilinear; 3-D: the AS-CODED table)
+      if (!g.interp) return 1.0f;
+      float f[3];
+      g1_factors(g, j, ax, f);
+      return DIM == 2 ? f[0] * f[1] : f[0] * f[1] * f[2];
+    };
     {
       float xv[48];            // this thread's half of the row: wg 0 -> columns [0,48), wg 1 -> columns [48,80)
       if (wg == 0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint2* node = a.s0 + 3 * (size_t)(node0 + (j & 1) + (j >> 1) * g.n0[1]);
+          const uint2* node = a.s0 + 3 * (size_t)(node0 + off0(j));
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             uint2 v = __ldg(node + q);
@@ -301,13 +334,10 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
           }
         }
       } else {
-        const float kx = ax[0].k, ky = ax[1].k;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int dy = j & 1, dx = j >> 1;
-          float w = 1.0f;
-          if (g.interp) w = (dx ? kx : 1.0f - kx) * (dy ? ky : 1.0f - ky);
-          const uint2* node = a.s1 + 3 * (size_t)(node1 + dy + dx * g.n1[1]);
+        for (int j = 0; j < NC1; ++j) {
+          const float w = w1(j);
+          const uint2* node = a.s1 + 3 * (size_t)(node1 + off1(j));
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             uint2 v = __ldg(node + q);
@@ -319,16 +349,16 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
           }
         }
 #pragma unroll
-        for (int d = 0; d < 2; ++d)
+        for (int d = 0; d < DIM; ++d)
 #pragma unroll
           for (int r = 0; r < 6; ++r) xv[12 + 6 * d + r] = pe_value(g, ax[d].u1, r);
-        xv[24] = g.lod;
+        xv[12 + 6 * DIM] = g.lod;
 #pragma unroll
-        for (int i = 25; i < 32; ++i) xv[i] = 0.f;
+        for (int i = 13 + 6 * DIM; i < 32; ++i) xv[i] = 0.f;
       }
-      const int col0 = wg == 0 ? 0 : 48, ncols = wg == 0 ? 48 : 25;     // real (noisy) columns of this half
+      const int col0 = wg == 0 ? 0 : 48, ncols = wg == 0 ? 48 : CIN - 48;     // real (noisy) columns of this half
       if (a.noise) {
-        const float* nz = a.noise + (size_t)nc * TT_CIN + col0;
+        const float* nz = a.noise + (size_t)nc * CIN + col0;
 #pragma unroll
         for (int i = 0; i < 48; ++i)
           if (i < ncols) xv[i] += nz[i];
@@ -347,7 +377,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
           }
         }
       }
-      if (wg == 1) xv[25] = 1.0f;                    // feature 73: the bias carrier (not an input: no noise)
+      if (wg == 1) xv[CIN - 48] = 1.0f;              // feature CIN: the bias carrier (not an input: no noise)
       // 16-byte chunks of 8 features -> X~ buffer
       const int fg0 = wg == 0 ? 0 : 6, nfg = wg == 0 ? 6 : 4;
 #pragma unroll
@@ -486,7 +516,6 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
       uint32_t acc[32];
       tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
       tc_wait_ld();
-      const float kx = ax[0].k, ky = ax[1].k;
       // v4 group gi of this thread covers dX columns [32 wg + 4 gi, +4)
 #pragma unroll
       for (int gi = 0; gi < 8; ++gi) {
@@ -495,7 +524,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
                       __uint_as_float(acc[4 * gi + 3])};
         if (gq < 12) {
           const int j = gq / 3, q = gq - 3 * j;
-          const int key = node0 + (j & 1) + (j >> 1) * g.n0[1];
+          const int key = node0 + off0(j);
           const bool head = seg_reduce4(key, a.steps0, lane, v);
           if (live && head) {
             float* dst = a.dgs0 + (size_t)key * 12 + 4 * q;
@@ -505,12 +534,10 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
         } else if (gq < 15) {
           const int q = gq - 12;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int dy = j & 1, dx = j >> 1;
-            float w = 1.0f;
-            if (g.interp) w = (dx ? kx : 1.0f - kx) * (dy ? ky : 1.0f - ky);
+          for (int j = 0; j < NC1; ++j) {
+            const float w = w1(j);
             float u[4] = {w * v[0], w * v[1], w * v[2], w * v[3]};
-            const int key = node1 + dy + dx * g.n1[1];
+            const int key = node1 + off1(j);
             const bool head = seg_reduce4(key, a.steps1, lane, u);
             if (live && head) {
               float* dst = a.dgs1 + (size_t)key * 12 + 4 * q;
@@ -562,8 +589,8 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
             if (col < 64) atomicAdd(a.gm.w2 + j * 64 + col, 0.5f * v);
             else if (col == 64) atomicAdd(a.gm.b2 + j, v);
           } else {
-            if (col < TT_CIN) atomicAdd(a.gm.w1 + j * TT_CIN + col, v);
-            else if (col == TT_CIN) atomicAdd(a.gm.b1 + j, v);
+            if (col < CIN) atomicAdd(a.gm.w1 + j * CIN + col, v);
+            else if (col == CIN) atomicAdd(a.gm.b1 + j, v);
           }
         }
       }
@@ -583,12 +610,12 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
-template <int FMT>
+template <int FMT, int METHOD>
 static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradDev& gm, const float* g0,
                              const float* g1, const long long* origins, const float* targets, const float* noise,
                              int noise_bits, unsigned long long seed, unsigned long long step, float grad_scale, float* dg0,
                              float* dg1, float* loss_sum, float* out_save, cudaStream_t st) {
-  const long long nodes0 = plane_size_host(g.n0, 2), nodes1 = plane_size_host(g.n1, 2);
+  const long long nodes0 = plane_size_host(g.n0, g.dim), nodes1 = plane_size_host(g.n1, g.dim);
   const size_t b0 = ((size_t)nodes0 * g.C * 2 + 255) & ~(size_t)255, b1 = ((size_t)nodes1 * g.C * 2 + 255) & ~(size_t)255;
   int rc = ensure_scratch(&h->tc_weights, &h->tc_weights_bytes, 64 * 1024);
   if (rc) return rc;
@@ -612,10 +639,11 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
     gs1 = (float*)((uint8_t*)h->tc_gscratch + ((gb0 + 255) & ~(size_t)255));
   }
   cudaError_t e = cudaSuccess;
-  const bool small = nodes0 <= (1 << 20);
+  const bool small = nodes0 <= (1 << 20) || g.dim == 3;        // the tiled relayout-add kernel is 2-D only
+  const int nz0 = g.dim == 3 ? g.n0[2] : 1, nz1 = g.dim == 3 ? g.n1[2] : 1;
   if (small) {
-    relayout_small_kernel<FMT><<<(int)((nodes0 * g.C + 255) / 256), 256, 0, st>>>(g0, s0, g.C, g.n0[0], g.n0[1]);
-    relayout_small_kernel<FMT><<<(int)((nodes1 * g.C + 255) / 256), 256, 0, st>>>(g1, s1, g.C, g.n1[0], g.n1[1]);
+    relayout_small_kernel<FMT><<<(int)((nodes0 * g.C + 255) / 256), 256, 0, st>>>(g0, s0, g.C, g.n0[0], g.n0[1], nz0);
+    relayout_small_kernel<FMT><<<(int)((nodes1 * g.C + 255) / 256), 256, 0, st>>>(g1, s1, g.C, g.n1[0], g.n1[1], nz1);
     h->launches += 2;
   } else {
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
@@ -650,7 +678,7 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   while (s0n < 5 && ldexpf(1.0f, -s0n) > g.step) ++s0n;       // lanes sharing a G0 node along the fast axis: 1/step
   a.steps0 = s0n;
   a.steps1 = s0n + 1 > 5 ? 5 : s0n + 1;
-  auto kern = train_tc_kernel<FMT>;
+  auto kern = train_tc_kernel<FMT, METHOD>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM);
   if (e != cudaSuccess) return (int)e;
   if (g.N >= (1ll << 27)) return NIC_ERR_UNSUPPORTED;          // Philox counter packs (sample << 4 | block)
@@ -666,8 +694,8 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   if (dg0) {
     const float sc = 2.0f * grad_scale / TT_LOSS_SCALE;
     if (small) {
-      grad_add_small_kernel<<<(int)((nodes0 * g.C + 255) / 256), 256, 0, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sc);
-      grad_add_small_kernel<<<(int)((nodes1 * g.C + 255) / 256), 256, 0, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sc);
+      grad_add_small_kernel<<<(int)((nodes0 * g.C + 255) / 256), 256, 0, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], nz0, sc);
+      grad_add_small_kernel<<<(int)((nodes1 * g.C + 255) / 256), 256, 0, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], nz1, sc);
     } else {
       size_t smem = (size_t)g.C * 32 * 33 * sizeof(float);
       e = cudaFuncSetAttribute(grad_relayout_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -687,13 +715,16 @@ int launch_train_tc(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradD
                     unsigned long long seed, unsigned long long step, float grad_scale, float* dg0, float* dg1,
                     float* loss_sum, float* out_save, int precision, cudaStream_t st) {
   if (g.N == 0) return NIC_OK;
-  if (g.method != NIC_METHOD_2D || g.C != 12 || g.PE != 6 || m.hidden != 64 || m.cout > 16 || m.cin != TT_CIN || !origins)
+  const bool m2d = g.method == NIC_METHOD_2D, m3v2 = g.method == NIC_METHOD_3D_V2;
+  const int cin = m2d ? TrainShape<NIC_METHOD_2D>::CIN : TrainShape<NIC_METHOD_3D_V2>::CIN;
+  if ((!m2d && !m3v2) || g.C != 12 || g.PE != 6 || m.hidden != 64 || m.cout > 16 || m.cin != cin || !origins)
     return NIC_ERR_UNSUPPORTED;
-  if (precision == NIC_PREC_F16)
-    return launch_train_tc_t<0>(h, g, m, gm, g0, g1, origins, targets, noise, noise_bits, seed, step, grad_scale, dg0, dg1,
-                                loss_sum, out_save, st);
-  return launch_train_tc_t<1>(h, g, m, gm, g0, g1, origins, targets, noise, noise_bits, seed, step, grad_scale, dg0, dg1,
-                              loss_sum, out_save, st);
+#define NIC_TT_CALL(F, M)                                                                                               \
+  launch_train_tc_t<F, M>(h, g, m, gm, g0, g1, origins, targets, noise, noise_bits, seed, step, grad_scale, dg0, dg1, \
+                          loss_sum, out_save, st)
+  if (precision == NIC_PREC_F16) return m2d ? NIC_TT_CALL(0, NIC_METHOD_2D) : NIC_TT_CALL(0, NIC_METHOD_3D_V2);
+  return m2d ? NIC_TT_CALL(1, NIC_METHOD_2D) : NIC_TT_CALL(1, NIC_METHOD_3D_V2);
+#undef NIC_TT_CALL
 }
 
 }  // namespace nic

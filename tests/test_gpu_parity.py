@@ -851,3 +851,48 @@ def test_lut_65_cubed_extension():
     want = O.quantize_to_bit(ref, 8).astype(np.uint8)[q[:, 0], q[:, 1], q[:, 2]]
     within1, same, worst = lsb_stats(pts, want)
     assert within1 >= 0.999, (within1, same, worst)
+
+
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+@pytest.mark.parametrize("mip", [0, 2])
+def test_train_tc_step_3d_v2_vs_oracle_fp64(prec, mip):
+    """The tcgen05 training step on the 3-D "proposed" method (COMPRESSION_METHOD 4: tetrahedral G0 corners, 8-corner
+    AS-CODED G1 weights, sinusoidal PE) against the oracle's fp64 backward: step 1/4 (mip 0) and step 1 (mip 2)."""
+    n = nic()
+    L = n._lib
+    import ctypes as C
+    size = 64
+    grids = I.make_grids(size, 3, seed=50)
+    cin = 79
+    params = I.make_mlp(cin, seed=51, gain=1.5)
+    rng = np.random.default_rng(65)
+    fl, nc, crop = 0, 3, 8
+    coord = rng.integers(0, (size >> mip) - crop + 1, (nc, 3))
+    target = rng.random((nc * crop ** 3, 3)).astype(np.float32)
+    noise = I.make_noise(nc * crop ** 3, cin, 8, 66)
+    loss, out, grads, dg0, dg1 = O.train_forward_backward(grids, params, coord, target, fl, mip, 4, noise, size=crop)
+    fp = [T(a) for a in grids]
+    pt = [T(p) for p in params]
+    m = L.make_mlp(pt)
+    g = [torch.zeros_like(p) for p in pt]
+    gm = L.make_mlp_grad(g)
+    g0t, g1t = fp[0], fp[1]
+    d0, d1 = torch.zeros_like(g0t), torch.zeros_like(g1t)
+    ls = torch.zeros(4, device=dev())
+    o = torch.empty((nc * crop ** 3, 3), device=dev())
+    geom = L.make_geom(L.METHOD_3D_V2, g0t, g1t, crop, nc, mip - 2, mip, 6, L.PE_SINUSOIDAL)
+    h = L.handle(dev())
+    coord_t, target_t, noise_t = T(coord, torch.int64), T(target), T(noise)
+    for rep in range(2):
+        for t in g + [d0, d1, ls]:
+            t.zero_()
+        L.check(h, L.load_library().nic_train_step(h, C.byref(geom), L.ptr(g0t), L.ptr(g1t), L.ptr(coord_t), C.byref(m),
+                                                   L.ptr(target_t), L.ptr(noise_t), 0, 0, 0, 0, C.byref(gm), L.ptr(d0),
+                                                   L.ptr(d1), L.ptr(ls), L.ptr(o), L.PRECISIONS[prec], L.stream_ptr(dev())))
+        tol = 1.0 if prec == "f16" else 4.0
+        assert abs(float(ls[0]) / (nc * crop ** 3 * 3) - loss) <= 1e-2 * tol * loss
+        assert np.abs(o.cpu().numpy() - out).max() <= 4e-3 * tol
+        for t, k in zip(g, ("W1", "b1", "W2", "b2", "W3", "b3")):
+            assert _rel_l2(t.cpu().numpy(), grads[k]) <= 2e-2 * tol, (k, _rel_l2(t.cpu().numpy(), grads[k]))
+        assert _rel_l2(d0.cpu().numpy(), dg0) <= 2e-2 * tol, _rel_l2(d0.cpu().numpy(), dg0)
+        assert _rel_l2(d1.cpu().numpy(), dg1) <= 2e-2 * tol, _rel_l2(d1.cpu().numpy(), dg1)
