@@ -154,6 +154,12 @@ int nic_mlp_backward(NicHandle* h, const NicMlp* m, const float* x, int64_t ldx,
 int nic_decode(NicHandle* h, const NicGeom* g, const float* g0, const float* g1, const int64_t* origins,
                const NicMlp* m, void* out, int out_dtype, int precision, void* stream);
 
+/* The same from the SAVED model: codes0 / codes1 are the uint8 grid codes of models.save4fp (one code per byte, `bits`
+ * wide, same [C, (z,) y, x] layout); they are de-quantised exactly as models.load4fp does inside the grid read, so the
+ * float32 grids of fp_load are never materialised (image_compression.py:393-400).  Tensor-core precisions only. */
+int nic_decode_codes(NicHandle* h, const NicGeom* g, const uint8_t* codes0, const uint8_t* codes1, int bits,
+                     const int64_t* origins, const NicMlp* m, void* out, int out_dtype, int precision, void* stream);
+
 /* ---- fused training forward+backward (K3+K4) ----------------------------------------------------------- */
 /* One step of train_models up to loss.backward() (image_compression.py:239-265).
  *   targets [N, cout] fp32; noise: NULL (no noise), or [N, Cin] fp32 injected tensor (parity tests), or use

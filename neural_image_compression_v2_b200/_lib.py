@@ -65,6 +65,7 @@ SYMBOLS = {
     "nic_mlp_forward": (_I, [_P, C.POINTER(NicMlp), _P, _L, _L, _P, _P, _P, _P]),
     "nic_mlp_backward": (_I, [_P, C.POINTER(NicMlp), _P, _L, _L, _P, _P, _P, _P, C.POINTER(NicMlpGrad), _P, _P]),
     "nic_decode": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, C.POINTER(NicMlp), _P, _I, _I, _P]),
+    "nic_decode_codes": (_I, [_P, C.POINTER(NicGeom), _P, _P, _I, _P, C.POINTER(NicMlp), _P, _I, _I, _P]),
     "nic_train_step": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, C.POINTER(NicMlp), _P, _P, _I, C.c_uint64, C.c_uint64,
                             _L, C.POINTER(NicMlpGrad), _P, _P, _P, _P, _I, _P]),
     "nic_adam_step": (_I, [_P, C.POINTER(NicAdamTensor), _I, _F, _F, _F, _F, _I, _P]),

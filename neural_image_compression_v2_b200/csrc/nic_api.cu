@@ -307,6 +307,27 @@ int nic_decode(NicHandle* h, const NicGeom* g, const float* g0, const float* g1,
   return fail(h, NIC_ERR_ARG, "nic_decode: precision %d", precision);
 }
 
+int nic_decode_codes(NicHandle* h, const NicGeom* g, const uint8_t* codes0, const uint8_t* codes1, int bits,
+                     const int64_t* origins, const NicMlp* m, void* out, int out_dtype, int precision, void* stream) {
+  NIC_ENTER(h);
+  DevGeom d;
+  int rc = flatten_geom(h, g, origins != nullptr, &d);
+  if (rc) return rc;
+  MlpDev md;
+  rc = flatten_mlp(h, m, &md, d.cin);
+  if (rc) return rc;
+  if (bits < 1 || bits > 8) return fail(h, NIC_ERR_ARG, "nic_decode_codes: bits %d (1..8)", bits);
+  if (!codes0 || !codes1 || (!out && d.N > 0)) return fail(h, NIC_ERR_ARG, "nic_decode_codes: NULL pointer");
+  if (out_dtype != NIC_DT_F32 && out_dtype != NIC_DT_U8) return fail(h, NIC_ERR_ARG, "nic_decode_codes: out_dtype %d", out_dtype);
+  if (precision != NIC_PREC_F16 && precision != NIC_PREC_BF16)
+    return fail(h, NIC_ERR_UNSUPPORTED, "nic_decode_codes: tensor-core precisions only (f16 / bf16); unpack the codes for NIC_PREC_F32");
+  h->src_code_bits = bits;
+  rc = launch_decode_tc(h, d, md, reinterpret_cast<const float*>(codes0), reinterpret_cast<const float*>(codes1),
+                        (const long long*)origins, out, out_dtype, precision, st);
+  h->src_code_bits = 0;
+  return cuda_fail(h, rc, "nic_decode_codes");
+}
+
 int nic_train_step(NicHandle* h, const NicGeom* g, const float* g0, const float* g1, const int64_t* origins,
                    const NicMlp* m, const float* targets, const float* noise, int noise_bits, uint64_t seed,
                    uint64_t step, int64_t global_n, const NicMlpGrad* gm, float* dg0, float* dg1, float* loss_sum,

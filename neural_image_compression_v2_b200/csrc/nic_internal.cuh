@@ -30,12 +30,13 @@ struct Handle {
   void* tc_gscratch;         // channel-last fp32 grid-gradient scratch of the tensor-core training step (kept zero)
   size_t tc_gscratch_bytes;
   int disable_fast2d;        // testing knob: force the general tensor-core kernel
+  int src_code_bits;         // > 0 while a nic_decode_codes call is in flight: grid pointers are uint8 codes of that width
   int reuse_prepared;        // NIC_OPT_REUSE_PREPARED
   int debug_flags;           // knock-out experiments (option 100), never set in production
   int legacy_fast2d;         // NIC_OPT_LEGACY_FAST2D: the first-generation (non warp-specialised) fast-path kernel
   struct PreparedKey {       // what the tables in tc_weights / tc_shadow were last built from
     const void *g0, *g1, *w1, *b1, *w2, *b2, *w3, *b3;
-    int n0[3], n1[3], method, pe_kind, mip, fmt, fast, valid;
+    int n0[3], n1[3], method, pe_kind, mip, fmt, fast, valid, code_bits;
     float step;
   } prepared;
   void* adam_desc;           // device copy of NicAdamTensor descriptors

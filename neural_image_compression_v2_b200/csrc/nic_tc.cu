@@ -337,7 +337,7 @@ constexpr int F_IMG = F_W1G0 + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K
 // 12 coalesced loads, 64 x 12 fma against weights broadcast from shared memory, one 128-byte row out.
 template <int FMT>
 __global__ void __launch_bounds__(128) g1_rows_kernel(MlpDev m, const float* __restrict__ g1, int nx, int ny,
-                                                      uint16_t* __restrict__ R) {
+                                                      uint16_t* __restrict__ R, int code_bits) {
   constexpr int C = 12;
   __shared__ float w[C * 64];                 // [c][n]
   for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) w[(i % C) * 64 + i / C] = m.w1[(i / C) * m.cin + 4 * C + (i % C)];
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(128) g1_rows_kernel(MlpDev m, const float* __r
   for (int n = 0; n < 64; ++n) acc[n] = 0.f;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    float g = __ldg(g1 + c * nodes + node);
+    float g = grid_value(g1, (long long)(c * nodes + node), code_bits);
     const float4* wr = reinterpret_cast<const float4*>(w + c * 64);
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -920,12 +920,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
 
 // ------------------------------------------------------------------------------------------------ launcher
 // NIC_OPT_REUSE_PREPARED: do the private tables already describe these inputs?
-static Handle::PreparedKey make_key(const DevGeom& g, const MlpDev& m, const float* g0, const float* g1, int fmt, int fast) {
+static Handle::PreparedKey make_key(const DevGeom& g, const MlpDev& m, const float* g0, const float* g1, int fmt, int fast,
+                                    int code_bits = 0) {
   Handle::PreparedKey k;
   memset(&k, 0, sizeof(k));
   k.g0 = g0; k.g1 = g1; k.w1 = m.w1; k.b1 = m.b1; k.w2 = m.w2; k.b2 = m.b2; k.w3 = m.w3; k.b3 = m.b3;
   for (int a = 0; a < 3; ++a) { k.n0[a] = g.n0[a]; k.n1[a] = g.n1[a]; }
   k.method = g.method; k.pe_kind = g.pe_kind; k.mip = g.mip; k.fmt = fmt; k.fast = fast; k.valid = 1;
+  k.code_bits = code_bits;
   k.step = g.step;
   return k;
 }
@@ -951,13 +953,13 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
   uint16_t* s0 = (uint16_t*)h->tc_shadow;
   uint16_t* R = (uint16_t*)((uint8_t*)h->tc_shadow + b0);
   cudaError_t e = cudaSuccess;
-  const Handle::PreparedKey key = make_key(g, m, g0, g1, FMT, 1);
+  const Handle::PreparedKey key = make_key(g, m, g0, g1, FMT, 1, h->src_code_bits);
   if (!prepared_matches(h, key)) {
     h->prepared.valid = 0;
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
     if (e != cudaSuccess) return (int)e;
     dim3 grid_r((g.n1[0] + 127) / 128, g.n1[1]);
-    g1_rows_kernel<FMT><<<grid_r, 128, 0, st>>>(m, g1, g.n1[0], g.n1[1], R);
+    g1_rows_kernel<FMT><<<grid_r, 128, 0, st>>>(m, g1, g.n1[0], g.n1[1], R, h->src_code_bits);
     h->launches++;
     pack_fast_kernel<FMT><<<32, 256, 0, st>>>(m, g.lod, g.step, (uint16_t*)h->tc_weights);
     h->launches++;
@@ -1021,7 +1023,7 @@ static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float
   uint16_t* s0 = (uint16_t*)h->tc_shadow;
   uint16_t* s1 = (uint16_t*)((uint8_t*)h->tc_shadow + b0);
   cudaError_t e = cudaSuccess;
-  const Handle::PreparedKey key = make_key(g, m, g0, g1, FMT, 0);
+  const Handle::PreparedKey key = make_key(g, m, g0, g1, FMT, 0, h->src_code_bits);
   if (!prepared_matches(h, key)) {
     h->prepared.valid = 0;
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);

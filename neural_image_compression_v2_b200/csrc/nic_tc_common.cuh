@@ -172,10 +172,19 @@ __host__ __device__ constexpr int b_image_bytes(int nrows, int k) { return nrows
 // axis is contiguous: shadow[((x*Ny + y)*Nz + z)*C + c] = grid[c][z][y][x]  (2-D: Nz = 1, shadow[(x*Ny + y)*C + c]).
 // One node = C*2 bytes (24 B at C = 12) -> a corner is three 8-byte loads that land in the operand registers as is.
 // Written once per decode call by relayout_kernel (coalesced both ways through shared memory).
+// A grid element from the caller's tensor: float32 as is, or (code_bits > 0) a uint8 code of models.save4fp de-quantised
+// exactly as models.load4fp does, (code - 2^(b-1) + 1) / (2^b - 1) — the quantiser fused into the grid read.
+__device__ __forceinline__ float grid_value(const float* __restrict__ src, long long idx, int code_bits) {
+  if (code_bits == 0) return __ldg(src + idx);
+  const float c = (float)__ldg(reinterpret_cast<const uint8_t*>(src) + idx);
+  const float z = __fadd_rn(__fsub_rn(c, (float)(1 << (code_bits - 1))), 1.0f);
+  return __fdiv_rn(z, (float)((1 << code_bits) - 1));
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(256) relayout_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C,
                                                        int nx, int nf, int no, long long sf, long long so,
-                                                       long long plane) {
+                                                       long long plane, int code_bits) {
   // tile: 32 nodes along x  x  32 nodes along the output-fast axis f, all channels; blockIdx.z = the other axis.
   // tile[e * 33 + xi] with e = fi * C + c = the element's position in output row xi: conflict-free both ways.
   extern __shared__ uint16_t tile[];           // [32 * C][33]
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(256) relayout_kernel(const float* __restrict__
   for (int i = threadIdx.x; i < C * 1024; i += blockDim.x) {
     int c = i >> 10, r = i & 1023, fi = r >> 5, xi = r & 31;
     int x = x0 + xi, f = f0 + fi;
-    float v = (x < nx && f < nf) ? __ldg(src + (long long)c * plane + (long long)f * sf + (long long)o * so + x) : 0.f;
+    float v = (x < nx && f < nf) ? grid_value(src, (long long)c * plane + (long long)f * sf + (long long)o * so + x, code_bits) : 0.f;
     tile[(fi * C + c) * 33 + xi] = to16<FMT>(v);
   }
   __syncthreads();
@@ -255,7 +264,7 @@ static inline int launch_relayout(Handle* h, const DevGeom& g, const float* src,
   const long long plane = (long long)nx * nodes[1] * (dim == 2 ? 1 : nodes[2]);
   dim3 grid((nx + 31) / 32, (nf + 31) / 32, no);
   size_t smem = (size_t)g.C * 32 * 33 * sizeof(uint16_t);
-  relayout_kernel<FMT><<<grid, 256, smem, st>>>(src, dst, g.C, nx, nf, no, sf, so, plane);
+  relayout_kernel<FMT><<<grid, 256, smem, st>>>(src, dst, g.C, nx, nf, no, sf, so, plane, h->src_code_bits);
   h->launches++;
   return (int)cudaGetLastError();
 }

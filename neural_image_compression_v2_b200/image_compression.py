@@ -238,6 +238,37 @@ def decode(fp, decoder, mip_level=0, size=None, origin=None, precision=None, out
     return out
 
 
+def decode_codes(codes, decoder, num_bits, mip_level=0, size=None, origin=None, precision="f16", out_dtype=torch.uint8,
+                 out=None, method=None, level_table=None):
+    """`decode` straight from the saved model: `codes` is the list fp_savable / torch.load returns (uint8, one code per
+    byte).  The de-quantisation of models.load4fp is fused into the grid read (no float32 grids are materialised)."""
+    method = _method() if method is None else method
+    dim = 2 if method == L.METHOD_2D else 3
+    table = feature_pyramid_mip_levels() if level_table is None else level_table
+    fl = table[mip_level]
+    c0, c1 = codes[fl * 2], codes[fl * 2 + 1]
+    for c in (c0, c1):
+        if not c.is_cuda or c.dtype != torch.uint8 or not c.is_contiguous():
+            raise TypeError("codes must be contiguous uint8 CUDA tensors")
+    if size is None:
+        size = var2.IMAGE_SIZE // pow(2, mip_level)
+    block = (size,) * dim if isinstance(size, int) else tuple(size)
+    params = [p.detach().contiguous() for p in decoder.parameters_list()]
+    m = L.make_mlp(params)
+    geom = L.make_geom(method, c0, c1, block, 1, _step_log2(mip_level, fl), mip_level, var2.PE_CHANNELS, _pe_kind(method),
+                       origin0=origin)
+    shape = block + (m.cout,)
+    if out is None:
+        out = torch.empty(shape, dtype=out_dtype, device=c0.device)
+    elif tuple(out.shape) != shape or out.dtype != out_dtype or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous {out_dtype} tensor of shape {shape}")
+    h = L.handle(c0.device)
+    L.check(h, L.load_library().nic_decode_codes(h, C.byref(geom), L.ptr(c0), L.ptr(c1), num_bits, None, C.byref(m), L.ptr(out),
+                                                 L.DT_U8 if out_dtype == torch.uint8 else L.DT_F32,
+                                                 L.PRECISIONS[precision.lower()], L.stream_ptr(c0.device)))
+    return out
+
+
 def decode_points(fp, decoder, coords, mip_level=0, precision=None, out_dtype=torch.float32, method=None,
                   level_table=None):
     """Random-access decode: coords `[Q, D]` integer texel coordinates of mip `mip_level` -> `[Q, Cout]`.
@@ -266,7 +297,7 @@ def decode_points(fp, decoder, coords, mip_level=0, precision=None, out_dtype=to
 
 class HostDecodePipeline:
     """End-to-end decode of 2-D frames from HOST buffers to a HOST buffer (what `process_images` does with a saved
-    model, image_compression.py:393-407): pinned H2D of the uint8 grid codes and the decoder, `fp_load`, fused decode in
+    model, image_compression.py:393-407): pinned H2D of the uint8 grid codes and the decoder, fused decode-from-codes in
     row bands, and the D2H of each 8-bit band on a second stream while the next band decodes.  The preparation tables
     (shadow grids, per-node G1 rows, packed weights) are built by the first band and reused by the others
     (NIC_OPT_REUSE_PREPARED).  The device frame is double-buffered: with `wait=False` the D2H of frame i overlaps the
@@ -283,7 +314,6 @@ class HostDecodePipeline:
         self.frame = 0
 
     def decode_frame(self, codes, host_params, host_out, mip_level=0, wait=True):
-        from .fp_def import fp_load
         dev = self.device
         if self.dcodes is None:
             self.dcodes = [torch.empty(c.shape, dtype=torch.uint8, device=dev) for c in codes]
@@ -300,14 +330,13 @@ class HostDecodePipeline:
         with torch.no_grad():
             for p, hp in zip(self.decoder.parameters_list(), host_params):
                 p.copy_(hp, non_blocking=True)
-        fp = fp_load(self.dcodes, self.bits)
         out = self.out[k]
         try:
             for i, (r0, n) in enumerate(self.bands):
                 L.set_option(dev, L.OPT_REUSE_PREPARED, int(i > 0))
                 band = out[r0:r0 + n]
-                decode(fp, self.decoder, mip_level, size=(n, self.size), origin=(r0, 0), precision=self.precision,
-                       out_dtype=torch.uint8, out=band)
+                decode_codes(self.dcodes, self.decoder, self.bits, mip_level, size=(n, self.size), origin=(r0, 0),
+                             precision=self.precision, out_dtype=torch.uint8, out=band)
                 ready = torch.cuda.Event()
                 ready.record(main)
                 self.copy_stream.wait_event(ready)

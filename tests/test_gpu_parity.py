@@ -896,3 +896,29 @@ def test_train_tc_step_3d_v2_vs_oracle_fp64(prec, mip):
             assert _rel_l2(t.cpu().numpy(), grads[k]) <= 2e-2 * tol, (k, _rel_l2(t.cpu().numpy(), grads[k]))
         assert _rel_l2(d0.cpu().numpy(), dg0) <= 2e-2 * tol, _rel_l2(d0.cpu().numpy(), dg0)
         assert _rel_l2(d1.cpu().numpy(), dg1) <= 2e-2 * tol, _rel_l2(d1.cpu().numpy(), dg1)
+
+
+@pytest.mark.parametrize("bits", [8, 4])
+def test_decode_from_codes_equals_decode_of_loaded_grids(bits):
+    """nic_decode_codes (the quantiser fused into the grid read) is bit-identical to fp_load + decode, on the fast 2-D
+    path, the general path (unaligned block) and a 3-D volume."""
+    n = nic()
+    ic, fpd = n.image_compression, n.fp_def
+    size = 256
+    configure(IMAGE_SIZE=size)
+    grids = I.make_grids(size, 2, bits=bits, seed=98, no_mip=True)
+    fp, dec = [T(a) for a in grids], make_decoder(I.make_mlp(73, seed=99, gain=2.0))
+    codes = fpd.fp_savable(fp, bits)
+    loaded = fpd.fp_load(codes, bits)
+    for prec in ("f16", "bf16"):
+        a = ic.decode_codes(codes, dec, bits, 0, precision=prec)
+        b = ic.decode(loaded, dec, 0, precision=prec, out_dtype=torch.uint8)
+        assert torch.equal(a, b)
+        a = ic.decode_codes(codes, dec, bits, 0, size=(37, 50), origin=(5, 9), precision=prec)
+        b = ic.decode(loaded, dec, 0, size=(37, 50), origin=(5, 9), precision=prec, out_dtype=torch.uint8)
+        assert torch.equal(a, b)
+    configure(IMAGE_SIZE=32, IMAGE_DIMENSION=3, COMPRESSION_METHOD=3, CROP_MIP_LEVEL=3)
+    g3 = [T(a) for a in I.make_grids(32, 3, bits=bits, seed=100, no_mip=True)]
+    d3 = make_decoder(I.make_mlp(127, seed=101, gain=2.0))
+    c3 = fpd.fp_savable(g3, bits)
+    assert torch.equal(ic.decode_codes(c3, d3, bits, 0), ic.decode(fpd.fp_load(c3, bits), d3, 0, precision="f16", out_dtype=torch.uint8))
