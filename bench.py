@@ -380,7 +380,11 @@ def run_ours(args):
                          "traffic": NCU_TRAFFIC_BYTES, "peak_source": f"{src} bf16_tflops (burst: kernel timed alone)",
                          "flop_per_texel": FLOP_PER_TEXEL, "kernel": "decode_tc2d_ws_kernel", "kernel_ms": kms,
                          "kernel_share_of_step": kms / ms_per_step,
-                         "traffic_source": NCU_TRAFFIC_SOURCE},
+                         "traffic_source": NCU_TRAFFIC_SOURCE,
+                         # measured with tools/ubench/mma_rate.cu: a K=16 tcgen05.mma occupies the tensor pipe >= 95.4
+                         # cycles for any N <= 128, of which an M128 x N64 instruction (hidden width 64) does 32 cycles
+                         # of math: 33.5 % is the ceiling of the tensor pipe's math utilisation for this decoder
+                         "attainable_frac_for_hidden_64": 32.0 / 95.4},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "matches_resident_output": e2e_ok},
             "gpu_launches": int(launches), "clocks": clocks,
