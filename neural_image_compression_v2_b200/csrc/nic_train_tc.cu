@@ -172,22 +172,39 @@ __device__ __forceinline__ float2 noise_pair(uint32_t w, float amp) {
 
 // Segmented warp reduction for the scatter: lanes whose `key` (grid node) is equal and contiguous are summed into the
 // first lane of the run; runs are also cut every 2^steps lanes so that `steps` shuffle rounds always suffice.
-// Returns true on the lanes that must issue the atomic.
-__device__ __forceinline__ bool seg_reduce4(int key, int steps, int lane, float* v) {
+// The run structure depends only on the corner, so it is computed once per corner (SegInfo) and reused by the three
+// 4-channel parts; the values travel as two f16x2 words (they carry the loss scale, so they are well inside f16 range,
+// and dX itself comes from 16-bit MMA operands).
+struct SegInfo {
+  unsigned same;     // bit s: lane + 2^s belongs to the same run
+  bool head;         // this lane issues the atomic
+};
+__device__ __forceinline__ SegInfo seg_info(int key, int steps, int lane) {
   const int prev = __shfl_up_sync(0xffffffffu, key, 1);
   const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
   const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
   const int L = 1 << steps, sub = (lane - start) & (L - 1);
-  for (int d = 1; d < L; d <<= 1) {
+  SegInfo si;
+  si.same = 0u;
+  si.head = sub == 0;
+  for (int s = 0, d = 1; s < steps; ++s, d <<= 1) {
     const int kd = __shfl_down_sync(0xffffffffu, key, d);
-    const bool same = lane + d < 32 && kd == key && sub + d < L;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float o = __shfl_down_sync(0xffffffffu, v[e], d);
-      if (same) v[e] += o;
+    if (lane + d < 32 && kd == key && sub + d < L) si.same |= 1u << s;
+  }
+  return si;
+}
+__device__ __forceinline__ void seg_reduce4(const SegInfo& si, int steps, float* v) {
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  for (int s = 0, d = 1; s < steps; ++s, d <<= 1) {
+    const uint32_t oa = __shfl_down_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&a), d);
+    const uint32_t ob = __shfl_down_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&b), d);
+    if (si.same & (1u << s)) {
+      a = __hadd2(a, *reinterpret_cast<const __half2*>(&oa));
+      b = __hadd2(b, *reinterpret_cast<const __half2*>(&ob));
     }
   }
-  return sub == 0;
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
 }
 
 struct TrainArgs {
@@ -515,35 +532,44 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
     if (a.dgs0) {
       uint32_t acc[32];
       tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
+      uint32_t accg1[16];                             // dX columns [48, 64): the G1 block, read by BOTH warp-groups
+      tmem_ld16(tmem + TT_COL_D + lane_base + 48, accg1);
       tc_wait_ld();
-      // v4 group gi of this thread covers dX columns [32 wg + 4 gi, +4)
+      // ---- G0: v4 group gi of this thread covers dX columns [32 wg + 4 gi, +4); groups 0..11 = (corner gq/3, part gq%3)
+      SegInfo si0[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) si0[j] = seg_info(node0 + off0(j), a.steps0, lane);
 #pragma unroll
       for (int gi = 0; gi < 8; ++gi) {
-        const int gq = 8 * wg + gi;                 // global v4 group: 0..11 G0 (corner gq/3, part gq%3), 12..14 G1, 15 unused
-        float v[4] = {__uint_as_float(acc[4 * gi]), __uint_as_float(acc[4 * gi + 1]), __uint_as_float(acc[4 * gi + 2]),
-                      __uint_as_float(acc[4 * gi + 3])};
+        const int gq = 8 * wg + gi;
         if (gq < 12) {
           const int j = gq / 3, q = gq - 3 * j;
-          const int key = node0 + off0(j);
-          const bool head = seg_reduce4(key, a.steps0, lane, v);
-          if (live && head) {
-            float* dst = a.dgs0 + (size_t)key * 12 + 4 * q;
+          float v[4] = {__uint_as_float(acc[4 * gi]), __uint_as_float(acc[4 * gi + 1]), __uint_as_float(acc[4 * gi + 2]),
+                        __uint_as_float(acc[4 * gi + 3])};
+          seg_reduce4(si0[j], a.steps0, v);
+          if (live && si0[j].head) {
+            float* dst = a.dgs0 + (size_t)(node0 + off0(j)) * 12 + 4 * q;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
                          : "memory");
           }
-        } else if (gq < 15) {
-          const int q = gq - 12;
+        }
+      }
+      // ---- G1: the NC1 corners are split between the warp-groups (balance: G0 gives wg 0 eight groups and wg 1 four)
 #pragma unroll
-          for (int j = 0; j < NC1; ++j) {
-            const float w = w1(j);
-            float u[4] = {w * v[0], w * v[1], w * v[2], w * v[3]};
-            const int key = node1 + off1(j);
-            const bool head = seg_reduce4(key, a.steps1, lane, u);
-            if (live && head) {
-              float* dst = a.dgs1 + (size_t)key * 12 + 4 * q;
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(u[0]), "f"(u[1]), "f"(u[2]), "f"(u[3])
-                           : "memory");
-            }
+      for (int jj = 0; jj < NC1 / 2; ++jj) {
+        const int j = wg * (NC1 / 2) + jj;
+        const float w = w1(j);
+        const int key = node1 + off1(j);
+        const SegInfo si = seg_info(key, a.steps1, lane);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          float u[4] = {w * __uint_as_float(accg1[4 * q]), w * __uint_as_float(accg1[4 * q + 1]),
+                        w * __uint_as_float(accg1[4 * q + 2]), w * __uint_as_float(accg1[4 * q + 3])};
+          seg_reduce4(si, a.steps1, u);
+          if (live && si.head) {
+            float* dst = a.dgs1 + (size_t)key * 12 + 4 * q;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(u[0]), "f"(u[1]), "f"(u[2]), "f"(u[3])
+                         : "memory");
           }
         }
       }

@@ -27,15 +27,18 @@ img = torch.tensor(I.make_image(size, 2, seed=5), device=dev)
 g = torch.Generator().manual_seed(100)
 coord = torch.randint(0, size - crop + 1, (nc, 2), generator=g).to(dev)
 tg = ic.sample_crops(img, coord, crop)
+noise_arg = False if "nonoise" in sys.argv else None
+if "frozen" in sys.argv:
+    tr.frozen = True
 for _ in range(3):
-    tr.step(coord, tg, 0)
+    tr.step(coord, tg, 0, noise=noise_arg)
 torch.cuda.synchronize()
 L.set_option(dev, L.OPT_TIME_KERNELS, 1)
 t0 = time.perf_counter()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(steps):
-    loss = tr.step(coord, tg, 0)
+    loss = tr.step(coord, tg, 0, noise=noise_arg)
 e.record()
 t1 = time.perf_counter()
 torch.cuda.synchronize()
