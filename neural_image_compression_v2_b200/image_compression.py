@@ -295,6 +295,31 @@ def decode_points(fp, decoder, coords, mip_level=0, precision=None, out_dtype=to
     return out
 
 
+class DecodeSession:
+    """A model that is decoded many times (regions, mips, repeated frames): the private tensor-core tables (16-bit
+    channel-last shadow grids, per-node G1 rows, packed weight images) are built by the first `decode` and REUSED by the
+    following ones (NIC_OPT_REUSE_PREPARED) — the grids and the decoder are the model's weights, and this is their
+    load-time re-packing.  The caller promises not to modify `fp` / `decoder` between calls; call `refresh()` after a
+    change (or simply use `decode(...)`, which always rebuilds)."""
+
+    def __init__(self, fp, decoder, precision="f16"):
+        self.fp, self.decoder, self.precision = fp, decoder, precision
+        self._fresh = False
+
+    def refresh(self):
+        self._fresh = False
+
+    def decode(self, mip_level=0, size=None, origin=None, out_dtype=torch.uint8, out=None, **kw):
+        dev = self.fp[0].device
+        L.set_option(dev, L.OPT_REUSE_PREPARED, int(self._fresh))
+        try:
+            res = decode(self.fp, self.decoder, mip_level, size, origin, self.precision, out_dtype, out, **kw)
+        finally:
+            L.set_option(dev, L.OPT_REUSE_PREPARED, 0)
+        self._fresh = True          # (a different mip level / path re-keys the tables inside the library and rebuilds)
+        return res
+
+
 class HostDecodePipeline:
     """End-to-end decode of 2-D frames from HOST buffers to a HOST buffer (what `process_images` does with a saved
     model, image_compression.py:393-407): pinned H2D of the uint8 grid codes and the decoder, fused decode-from-codes in

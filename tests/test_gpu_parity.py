@@ -922,3 +922,30 @@ def test_decode_from_codes_equals_decode_of_loaded_grids(bits):
     d3 = make_decoder(I.make_mlp(127, seed=101, gain=2.0))
     c3 = fpd.fp_savable(g3, bits)
     assert torch.equal(ic.decode_codes(c3, d3, bits, 0), ic.decode(fpd.fp_load(c3, bits), d3, 0, precision="f16", out_dtype=torch.uint8))
+
+
+def test_decode_session_reuses_tables_and_refreshes():
+    """DecodeSession: repeated decodes reuse the prepared tables and equal plain decode; after the grids change,
+    refresh() (or a different mip level) rebuilds them."""
+    n = nic()
+    ic = n.image_compression
+    size = 256
+    configure(IMAGE_SIZE=size, TF_NO_MIP=False, MAX_MIP_LEVEL=8)
+    fp = [T(a) for a in I.make_grids(size, 2, seed=102, quantized=True)]
+    dec = make_decoder(I.make_mlp(73, seed=103, gain=2.0))
+    ses = ic.DecodeSession(fp, dec, precision="f16")
+    l0 = n.launch_count(dev())
+    a = ses.decode(0)
+    l1 = n.launch_count(dev())
+    b = ses.decode(0)
+    c = ses.decode(0, size=(64, 128), origin=(64, 32))
+    l2 = n.launch_count(dev())
+    assert torch.equal(a, b) and torch.equal(c, a[64:128, 32:160])
+    assert torch.equal(a, ic.decode(fp, dec, 0, precision="f16", out_dtype=torch.uint8))
+    assert (l2 - l1) == 2 and (l1 - l0) > 1                    # one kernel per reused call, several for the first
+    m1 = ses.decode(1)                                          # another mip level re-keys and rebuilds
+    assert torch.equal(m1, ic.decode(fp, dec, 1, precision="f16", out_dtype=torch.uint8))
+    with torch.no_grad():
+        fp[0].mul_(0.5)
+    ses.refresh()
+    assert torch.equal(ses.decode(0), ic.decode(fp, dec, 0, precision="f16", out_dtype=torch.uint8))
