@@ -322,45 +322,57 @@ class DecodeSession:
 
 class HostDecodePipeline:
     """End-to-end decode of 2-D frames from HOST buffers to a HOST buffer (what `process_images` does with a saved
-    model, image_compression.py:393-407): pinned H2D of the uint8 grid codes and the decoder, fused decode-from-codes in
-    row bands, and the D2H of each 8-bit band on a second stream while the next band decodes.  The preparation tables
-    (shadow grids, per-node G1 rows, packed weights) are built by the first band and reused by the others
-    (NIC_OPT_REUSE_PREPARED).  The device frame is double-buffered: with `wait=False` the D2H of frame i overlaps the
-    H2D and decode of frame i + 1 (PCIe is full duplex); call `finish()` before reading the last host buffer."""
+    model, image_compression.py:393-407), as a three-stream pipeline:
+      upload stream : pinned H2D of the uint8 grid codes and the decoder parameters (double-buffered on the device);
+      caller stream : decode-from-codes in row bands (the tables are built by the first band and reused by the others);
+      copy stream   : D2H of each 8-bit band while the next band decodes (the device frame is double-buffered too).
+    With `wait=False` the H2D of frame i + 1 and the D2H of frame i overlap the decode of frame i (PCIe is full
+    duplex); call `finish()` before reading the last host buffer."""
 
     def __init__(self, size, device, precision="f16", bands=4, bits=8):
         self.size, self.device, self.precision, self.bits = size, torch.device(device), precision, bits
         self.bands = [(r0, n) for r0, n in (_band(size, b, bands) for b in range(bands)) if n > 0]
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.decoder = None
+        self.up_stream = torch.cuda.Stream(device=self.device)
+        self.decoders = None
         self.dcodes = None
         self.out = None
         self.d2h_done = [None, None]
+        self.dec_done = [None, None]
         self.frame = 0
+        self._last = None
 
     def decode_frame(self, codes, host_params, host_out, mip_level=0, wait=True):
         dev = self.device
         if self.dcodes is None:
-            self.dcodes = [torch.empty(c.shape, dtype=torch.uint8, device=dev) for c in codes]
-            self.decoder = ColorDecoder(host_params[0].shape[1], host_params[0].shape[0], host_params[4].shape[0]).to(dev)
+            self.dcodes = [[torch.empty(c.shape, dtype=torch.uint8, device=dev) for c in codes] for _ in range(2)]
+            self.decoders = [ColorDecoder(host_params[0].shape[1], host_params[0].shape[0], host_params[4].shape[0]).to(dev)
+                             for _ in range(2)]
             shape = (self.size, self.size, host_params[4].shape[0])
             self.out = [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(2)]
         main = torch.cuda.current_stream(dev)
         k = self.frame & 1
         self.frame += 1
+        # ---- upload (buffer k was last read by the decode of frame - 2)
+        if self.dec_done[k] is not None:
+            self.up_stream.wait_event(self.dec_done[k])
+        with torch.cuda.stream(self.up_stream):
+            for d, c in zip(self.dcodes[k], codes):
+                d.copy_(c, non_blocking=True)
+            with torch.no_grad():
+                for p, hp in zip(self.decoders[k].parameters_list(), host_params):
+                    p.copy_(hp, non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(self.up_stream)
+        main.wait_event(uploaded)
         if self.d2h_done[k] is not None:
             main.wait_event(self.d2h_done[k])        # the frame that used this device buffer two frames ago has left
-        for d, c in zip(self.dcodes, codes):
-            d.copy_(c, non_blocking=True)
-        with torch.no_grad():
-            for p, hp in zip(self.decoder.parameters_list(), host_params):
-                p.copy_(hp, non_blocking=True)
         out = self.out[k]
         try:
             for i, (r0, n) in enumerate(self.bands):
                 L.set_option(dev, L.OPT_REUSE_PREPARED, int(i > 0))
                 band = out[r0:r0 + n]
-                decode_codes(self.dcodes, self.decoder, self.bits, mip_level, size=(n, self.size), origin=(r0, 0),
+                decode_codes(self.dcodes[k], self.decoders[k], self.bits, mip_level, size=(n, self.size), origin=(r0, 0),
                              precision=self.precision, out_dtype=torch.uint8, out=band)
                 ready = torch.cuda.Event()
                 ready.record(main)
@@ -369,6 +381,8 @@ class HostDecodePipeline:
                     host_out[r0:r0 + n].copy_(band, non_blocking=True)
         finally:
             L.set_option(dev, L.OPT_REUSE_PREPARED, 0)
+        self.dec_done[k] = torch.cuda.Event()
+        self.dec_done[k].record(main)
         done = torch.cuda.Event()
         done.record(self.copy_stream)
         self.d2h_done[k] = done
@@ -379,7 +393,7 @@ class HostDecodePipeline:
 
     def finish(self):
         """Makes the caller's stream wait for every outstanding device-to-host copy."""
-        if getattr(self, "_last", None) is not None:
+        if self._last is not None:
             torch.cuda.current_stream(self.device).wait_event(self._last)
 
 
