@@ -102,7 +102,10 @@ int64_t nic_launch_count(const NicHandle* h);
  * packed weights) for the same pointers, node counts, step, mip level and precision, they are reused instead of being
  * rebuilt (decoding one frame as several row bands).  Off by default: every call rebuilds from the caller's tensors. */
 /* NIC_OPT_LEGACY_FAST2D = 1 selects the first-generation fast-path decode kernel (A/B comparisons in tests). */
-enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3, NIC_OPT_LEGACY_FAST2D = 4 };
+/* NIC_OPT_DEBUG_KNOCKOUT: profiling only (tools/run_decode.py) — bit 0 skips the output stores, bit 1 replaces GELU by a
+ * plain pack, bit 2 issues one MMA per layer; results are then WRONG on purpose.  Never set in production. */
+enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3, NIC_OPT_LEGACY_FAST2D = 4,
+       NIC_OPT_DEBUG_KNOCKOUT = 100 };
 int nic_set_option(NicHandle* h, int option, int value);
 /* With NIC_OPT_TIME_KERNELS = 1 every nic_decode / nic_train_step / nic_gather call brackets its DOMINANT kernel
  * (not the small preparation kernels) with CUDA events on the call's stream.  This call synchronises on the recorded

@@ -100,7 +100,7 @@ int64_t nic_launch_count(const NicHandle* h) { return h ? h->launches : 0; }
 int nic_set_option(NicHandle* h, int option, int value) {
   if (!h) return fail(nullptr, NIC_ERR_ARG, "handle is NULL");
   if (option == NIC_OPT_DISABLE_FAST2D) { h->disable_fast2d = value != 0; return NIC_OK; }
-  if (option == 100) { h->debug_flags = value; return NIC_OK; }
+  if (option == NIC_OPT_DEBUG_KNOCKOUT) { h->debug_flags = value; return NIC_OK; }
   if (option == NIC_OPT_LEGACY_FAST2D) { h->legacy_fast2d = value != 0; return NIC_OK; }
   if (option == NIC_OPT_REUSE_PREPARED) { h->reuse_prepared = value != 0; return NIC_OK; }
   if (option == NIC_OPT_TIME_KERNELS) { h->time_kernels = value != 0; h->timed_count = 0; return NIC_OK; }
