@@ -918,6 +918,229 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
   if (warp == 0) tmem_dealloc(tmem, WS_TMEM_COLS);
 }
 
+// ================================================================================================ general kernel, v2
+// The general decode (any mip / origin / block shape, 2-D and both 3-D methods, random-access queries) in the same
+// warp-specialised form as decode_tc2d_ws_kernel: ONE persistent CTA per SM made of NG independent groups of 4 warps
+// (NG = 8 for a decoder input of <= 80 columns, 5 for method 3's 128), group s owning TMEM columns [64 s, +64) and one
+// [128 x KX] operand buffer in shared memory.  A group's thread = one texel of its tile:
+//   gather : the texel's decoder-input row goes STRAIGHT from the 16-bit channel-last shadow grids to the operand
+//            buffer — a G0 corner is three 8-byte loads and three 8-byte shared stores, G1 is interpolated in packed
+//            16-bit math (6 registers), the triangular PE comes from a shared LUT — so no thread ever holds the row;
+//   layers : SS-form tcgen05.mma issued by the group's elected lane after a 128-thread named barrier (layer 1: KX/16
+//            MMAs; layers 2, 3: 4 MMAs + 1 bias MMA against a shared constant ones block), the epilogue overwrites the
+//            operand buffer with the next layer's activations;  the groups never meet at a CTA-wide barrier.
+constexpr int GW_GROUP = 128;
+
+template <int METHOD, int FMT, typename OutT>
+__global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 * GW_GROUP, 1)
+    decode_tc_gws_kernel(DevGeom g, ShadowGeom sg, const long long* __restrict__ origins, const uint4* __restrict__ wimg,
+                         int cout, int lut_n, OutT* __restrict__ out) {
+  using S = RowShape<METHOD>;
+  using P = Pair<FMT>;
+  constexpr int KX = S::KX, NG = KX > 80 ? 5 : 8, THREADS = NG * GW_GROUP;
+  constexpr int W1_BYTES = b_image_bytes(64, KX), W2_BYTES = b_image_bytes(64, TC_K2), W3_BYTES = b_image_bytes(16, TC_K2);
+  constexpr int KG = 16 * 128;                       // bytes of one k-group (8 columns) of a 128-row K-major operand
+  constexpr int OFF_LUT = W1_BYTES + W2_BYTES + W3_BYTES, OFF_ONE = OFF_LUT + TC_LUT_MAX * 16, OFF_ACT = OFF_ONE + 2 * KG;
+  constexpr int ACT_BYTES = (KX / 8) * KG, OFF_BAR = OFF_ACT + NG * ACT_BYTES;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* sW1 = smem_raw;
+  uint8_t* sW2 = sW1 + W1_BYTES;
+  uint8_t* sW3 = sW2 + W2_BYTES;
+  uint4* sLut = reinterpret_cast<uint4*>(smem_raw + OFF_LUT);
+  uint8_t* sOne = smem_raw + OFF_ONE;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + NG);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slot = warp >> 2;
+  const int row = 32 * (warp & 3) + lane;
+  const int roff = (row >> 3) * 128 + (row & 7) * 16;
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 0)
+    for (int s = 0; s < NG; ++s) mbar_init(bar_full + s, 1);
+  {
+    uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+    for (int i = tid; i < OFF_LUT / 16; i += THREADS) dst[i] = __ldg(wimg + i);
+    for (int i = tid; i < lut_n; i += THREADS) {
+      float u1 = __fmul_rn(__fmul_rn((float)i, g.step), 0.5f);
+      uint4 e;
+      auto v0 = P::pack(pe_triangular(u1, 0, 6), pe_triangular(u1, 1, 6));
+      auto v1 = P::pack(pe_triangular(u1, 2, 6), pe_triangular(u1, 3, 6));
+      auto v2 = P::pack(pe_triangular(u1, 4, 6), pe_triangular(u1, 5, 6));
+      e.x = *reinterpret_cast<uint32_t*>(&v0);
+      e.y = *reinterpret_cast<uint32_t*>(&v1);
+      e.z = *reinterpret_cast<uint32_t*>(&v2);
+      e.w = 0u;
+      sLut[i] = e;
+    }
+    if (slot == 0) {
+      auto one = P::pack(1.0f, 0.0f);
+      *reinterpret_cast<uint4*>(sOne + roff) = make_uint4(*reinterpret_cast<uint32_t*>(&one), 0, 0, 0);
+      *reinterpret_cast<uint4*>(sOne + KG + roff) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  fence_async_smem();
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tDs = tmem + slot * 64;
+  const uint32_t tD = tDs + ((uint32_t)((warp & 3) * 32) << 16);
+  uint8_t* sAct = smem_raw + OFF_ACT + slot * ACT_BYTES;
+  const bool elected = (warp & 3) == 0 && lane == 0;
+  constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
+  constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
+  const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3), aOne = smem_u32(sOne), aAct = smem_u32(sAct);
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(GW_GROUP) : "memory"); };
+  // this thread's 8-byte piece holding features [f, f + 4) of its row (f a multiple of 4)
+  auto piece = [&](int f) -> uint2* { return reinterpret_cast<uint2*>(sAct + (f >> 3) * KG + roff + (f & 7) * 2); };
+
+  const unsigned ntiles = (unsigned)((g.N + TC_ROWS - 1) / TC_ROWS);
+  const int lut_mask = lut_n - 1;
+  uint32_t ph = 0;
+  for (unsigned tile = blockIdx.x + gridDim.x * slot; tile < ntiles; tile += gridDim.x * NG) {
+    const unsigned n = tile * TC_ROWS + row;
+    const bool live = n < (unsigned)g.N;
+    // ------------------------------------------------------------------------------------ gather -> operand buffer
+    {
+      Texel t = texel_of_fast(g, live ? n : (unsigned)g.N - 1, origins);
+      AxisCoord ax[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ax[a] = axis_coord(t.p[a], g.step);
+        ax[a].i0 = clampi(ax[a].i0, 0, g.n0[a] - 2 < 0 ? 0 : g.n0[a] - 2);
+        ax[a].i1 = clampi(ax[a].i1, 0, g.n1[a] - 2 < 0 ? 0 : g.n1[a] - 2);
+      }
+#pragma unroll
+      for (int j = 0; j < S::NC0; ++j) {             // G0 corners: raw copies
+        const int8_t* d = S::DIM == 2 ? kCorner2D[j] : (METHOD == NIC_METHOD_3D ? kCorner3D[j] : kCorner3Dv2[j]);
+        const int dz = S::DIM == 3 ? d[0] : 0;
+        const uint2* node = sg.s0 + 3 * node_lin(g.n0, S::DIM, ax[0].i0 + d[2], ax[1].i0 + d[1], ax[2].i0 + dz);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) *piece(12 * j + 4 * q) = __ldg(node + q);
+      }
+      typename P::T2 acc[6];                          // G1: weighted sum of corners
+#pragma unroll
+      for (int j = 0; j < S::NC1; ++j) {
+        const int8_t* d = S::DIM == 2 ? kCorner2D[j] : kCorner3D[j];
+        const int dz = S::DIM == 3 ? d[0] : 0;
+        const uint2* node = sg.s1 + 3 * node_lin(g.n1, S::DIM, ax[0].i1 + d[2], ax[1].i1 + d[1], ax[2].i1 + dz);
+        float f[3];
+        g1_factors(g, j, ax, f);
+        float w = f[0] * f[1];
+        if (S::DIM == 3) w *= f[2];
+        typename P::T2 w2 = P::cst(w);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          uint2 v = __ldg(node + q);
+          typename P::T2 va = *reinterpret_cast<typename P::T2*>(&v.x), vb = *reinterpret_cast<typename P::T2*>(&v.y);
+          acc[2 * q] = j == 0 ? __hmul2(va, w2) : __hfma2(va, w2, acc[2 * q]);
+          acc[2 * q + 1] = j == 0 ? __hmul2(vb, w2) : __hfma2(vb, w2, acc[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        *piece(12 * S::NC0 + 4 * q) = make_uint2(*reinterpret_cast<uint32_t*>(&acc[2 * q]), *reinterpret_cast<uint32_t*>(&acc[2 * q + 1]));
+      // positional encoding (3 pairs per axis), the bias carrier (feature CIN - 1 = 1) and zero padding up to KX: the
+      // tail of the row, [12 (NC0 + 1), KX), is assembled as packed pairs and stored in 8-byte pieces
+      constexpr int T0 = 12 * (S::NC0 + 1), NTAIL = (KX - T0) / 2;      // pairs in the tail
+      uint32_t tail[NTAIL];
+#pragma unroll
+      for (int i = 0; i < NTAIL; ++i) tail[i] = 0u;
+#pragma unroll
+      for (int a = 0; a < S::DIM; ++a) {
+        if (g.pe_kind == NIC_PE_TRIANGULAR) {
+          uint4 e = sLut[t.p[a] & lut_mask];
+          tail[3 * a] = e.x;
+          tail[3 * a + 1] = e.y;
+          tail[3 * a + 2] = e.z;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            float arg = __fmul_rn(ax[a].u1, g.pe_div[q]);
+            auto v = P::pack(sinf(arg), cosf(arg));
+            tail[3 * a + q] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        }
+      }
+      {
+        auto one = P::pack(1.0f, 0.0f);
+        tail[(S::CIN - 1 - T0) / 2] = *reinterpret_cast<uint32_t*>(&one);
+      }
+#pragma unroll
+      for (int i = 0; i < NTAIL / 2; ++i) *piece(T0 + 4 * i) = make_uint2(tail[2 * i], tail[2 * i + 1]);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    group_sync();
+    if (elected) {
+      tc_fence_after();
+#pragma unroll
+      for (int kc = 0; kc < KX / 16; ++kc)
+        mma_ss(tDs, make_smem_desc(aAct + kc * 2 * KG, KG, SBO), make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
+      tc_commit(bar_full + slot);
+    }
+    // ------------------------------------------------------------------------------------ layers 1, 2: epilogues
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+      mbar_wait(bar_full + slot, ph);
+      ph ^= 1;
+      __syncwarp();
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t acc[16];
+        tmem_ld16(tD + 16 * q, acc);
+        tc_wait_ld();
+        uint32_t hp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hp[k] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]));
+        *reinterpret_cast<uint4*>(sAct + (2 * q) * KG + roff) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(sAct + (2 * q + 1) * KG + roff) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      group_sync();
+      if (elected) {
+        tc_fence_after();
+        const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
+        const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc)
+          mma_ss(tDs, make_smem_desc(aAct + kc * 2 * KG, KG, SBO), make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
+        mma_ss(tDs, make_smem_desc(aOne, KG, SBO), make_smem_desc(aW + 4 * 2 * lbo, lbo, SBO), idesc, 1);
+        tc_commit(bar_full + slot);
+      }
+    }
+    // ------------------------------------------------------------------------------------ output
+    mbar_wait(bar_full + slot, ph);
+    ph ^= 1;
+    __syncwarp();
+    tc_fence_after();
+    uint32_t acc[16];
+    if (cout > 4) tmem_ld16(tD, acc);
+    else tmem_ld4(tD, acc);
+    tc_wait_ld();
+    tc_fence_before();
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < cout) store_out(out + (size_t)n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+      if (cout > 4) {
+#pragma unroll
+        for (int c = 4; c < 16; ++c)
+          if (c < cout) store_out(out + (size_t)n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+      }
+    }
+    // (every thread passes its own tcgen05.wait::ld above before it reaches the next tile's pre-MMA barrier, so the next
+    //  layer-1 MMAs cannot overwrite D early)
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ launcher
 // NIC_OPT_REUSE_PREPARED: do the private tables already describe these inputs?
 static Handle::PreparedKey make_key(const DevGeom& g, const MlpDev& m, const float* g0, const float* g1, int fmt, int fast,
@@ -1043,17 +1266,34 @@ static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float
     while (lut_n < period && lut_n < TC_LUT_MAX) lut_n <<= 1;
     if (g.pe_kind == NIC_PE_TRIANGULAR && (float)lut_n < period) return NIC_ERR_UNSUPPORTED;
   }
-  // 56 KB of dynamic shared memory per CTA caps residency at 4 CTAs/SM = 4 x 128 TMEM columns = all 512.
+  if (g.N >= (1ll << 31) - TC_ROWS) return NIC_ERR_UNSUPPORTED;     // 32-bit sample index in the kernel
+  long long ntiles = (g.N + TC_ROWS - 1) / TC_ROWS;
+  ShadowGeom sg = {(const uint2*)s0, (const uint2*)s1};
+  if (!h->legacy_fast2d) {
+    // warp-specialised persistent kernel: one CTA per SM, NG groups of 4 warps
+    constexpr int NG = S::KX > 80 ? 5 : 8;
+    constexpr int GSMEM = IMG + TC_LUT_MAX * 16 + 2 * 2048 + NG * (S::KX / 8) * 2048 + 256;
+    static_assert(GSMEM <= 227 * 1024, "shared memory budget");
+    auto kern = decode_tc_gws_kernel<METHOD, FMT, OutT>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM);
+    if (e != cudaSuccess) return (int)e;
+    long long groups = (ntiles + NG - 1) / NG;
+    int grid = (int)(groups < h->sms ? groups : h->sms);
+    {
+      KernelTimer timer(h, st);
+      kern<<<grid, NG * GW_GROUP, GSMEM, st>>>(g, sg, origins, (const uint4*)h->tc_weights, m.cout, lut_n, out);
+    }
+    h->launches++;
+    return (int)cudaGetLastError();
+  }
+  // first-generation kernel: 56 KB of dynamic shared memory per CTA caps residency at 4 CTAs/SM = 4 x 128 TMEM columns.
   size_t smem = 56 * 1024;
   static_assert(IMG + TC_LUT_MAX * 16 + 64 <= 56 * 1024, "shared memory budget");
   auto kern = decode_tc_kernel<METHOD, FMT, OutT>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  if (g.N >= (1ll << 31) - TC_ROWS) return NIC_ERR_UNSUPPORTED;     // 32-bit sample index in the kernel
-  long long ntiles = (g.N + TC_ROWS - 1) / TC_ROWS;
   long long cap = (long long)h->sms * 4;
   int grid = (int)(ntiles < cap ? ntiles : cap);
-  ShadowGeom sg = {(const uint2*)s0, (const uint2*)s1};
   {
     KernelTimer timer(h, st);
     kern<<<grid, TC_THREADS, smem, st>>>(g, sg, origins, (const uint4*)h->tc_weights, m.cout, lut_n, out);

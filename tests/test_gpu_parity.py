@@ -949,3 +949,36 @@ def test_decode_session_reuses_tables_and_refreshes():
         fp[0].mul_(0.5)
     ses.refresh()
     assert torch.equal(ses.decode(0), ic.decode(fp, dec, 0, precision="f16", out_dtype=torch.uint8))
+
+
+def test_general_kernel_generations_agree():
+    """The warp-specialised general decode kernel and the first-generation one build the same operand rows and issue
+    the same MMAs: bit-identical outputs for 2-D (unaligned, several mips), both 3-D methods and random-access queries."""
+    n = nic()
+    ic, L = n.image_compression, n._lib
+
+    def both(fn):
+        a = fn()
+        L.set_option(dev(), L.OPT_LEGACY_FAST2D, 1)
+        try:
+            b = fn()
+        finally:
+            L.set_option(dev(), L.OPT_LEGACY_FAST2D, 0)
+        assert torch.equal(a, b)
+        return a
+
+    size = 256
+    configure(IMAGE_SIZE=size, TF_NO_MIP=False, MAX_MIP_LEVEL=8)
+    fp = [T(a) for a in I.make_grids(size, 2, seed=104, quantized=True)]
+    dec = make_decoder(I.make_mlp(73, seed=105, gain=2.0))
+    for prec in ("f16", "bf16"):
+        for mip, sz, org in ((0, (37, 50), (5, 9)), (0, (250, 3), (1, 200)), (1, (128, 128), (0, 0)), (3, (32, 32), (0, 0)), (5, (8, 8), (0, 0))):
+            both(lambda: ic.decode(fp, dec, mip, size=sz, origin=org, precision=prec, out_dtype=torch.uint8))
+    for method, cin in ((3, 127), (4, 79)):
+        configure(IMAGE_SIZE=32, IMAGE_DIMENSION=3, COMPRESSION_METHOD=method, CROP_MIP_LEVEL=3)
+        g3 = [T(a) for a in I.make_grids(32, 3, seed=106, no_mip=True, quantized=True)]
+        d3 = make_decoder(I.make_mlp(cin, seed=107, gain=2.0))
+        both(lambda: ic.decode(g3, d3, 0, precision="f16"))
+        both(lambda: ic.decode(g3, d3, 0, size=(5, 7, 3), origin=(9, 2, 20), precision="bf16", out_dtype=torch.uint8))
+        q = torch.tensor(np.random.default_rng(108).integers(0, 32, (1003, 3)))
+        both(lambda: ic.decode_points(g3, d3, q, 0, precision="f16"))
