@@ -32,27 +32,33 @@
 namespace nic {
 
 constexpr int TT_ROWS = 128, TT_THREADS = 256;
-constexpr int TT_K1 = 80, TT_H = 64, TT_K2 = 80;
-// decoder-input width: 2-D 5C + 2 PE + 1 = 73; 3-D "v2" (method 4) 5C + 3 PE + 1 = 79; both + the bias carrier <= 80 = K1
+constexpr int TT_H = 64, TT_K2 = 80;
+constexpr int TT_SG80 = 10 * 128;          // sample-group stride of an 80-feature activation / delta buffer (bytes)
+constexpr int TT_W2 = 64 * 80 * 2, TT_W3 = 16 * 80 * 2;
+constexpr int TT_ACT = 16 * TT_SG80;       // 20480
+// Everything that depends on the decoder-input width.  2-D: Cin = 5C + 2 PE + 1 = 73 and 3-D "v2" (method 4): 79 both
+// fit K1 = 80 (with the bias carrier) -> 106 KB smem, 240 TMEM columns, two CTAs per SM;  3-D method 3: Cin = 9C + 3 PE
+// + 1 = 127 -> K1 = 128, dX is 108 columns wide (N = 128), 122 KB smem, 352 TMEM columns, one CTA per SM.
 template <int METHOD> struct TrainShape {
   static constexpr int DIM = METHOD == NIC_METHOD_2D ? 2 : 3;
-  static constexpr int CIN = 5 * 12 + 6 * DIM + 1;
-  static constexpr int NC1 = DIM == 2 ? 4 : 8;           // G1 corners
+  static constexpr int NC0 = METHOD == NIC_METHOD_3D ? 8 : 4;      // G0 corners
+  static constexpr int NC1 = DIM == 2 ? 4 : 8;                     // G1 corners
+  static constexpr int CIN = 12 * (NC0 + 1) + 6 * DIM + 1;
+  static constexpr int K1 = (CIN + 1 + 15) / 16 * 16;              // 80 / 128
+  static constexpr int KG1 = K1 / 8, SGX = KG1 * 128, XBYTES = 16 * SGX, W1BYTES = 64 * K1 * 2;
+  static constexpr int NDX = 12 * (NC0 + 1) <= 64 ? 64 : 128;      // N of the dX GEMM = width of the D accumulator
+  static constexpr int C0 = METHOD == NIC_METHOD_3D ? 9 : 6;       // feature groups (of 8) gathered by warp-group 0
+  static constexpr int XV = 8 * C0 > K1 - 8 * C0 ? 8 * C0 : K1 - 8 * C0;
+  static constexpr int COL_D = 0, COL_D1 = NDX, COL_D2 = COL_D1 + K1, COL_D3 = COL_D2 + 80;       // D3 (transposed): 16 columns
+  static constexpr int TMEM = COL_D3 + 16 <= 256 ? 256 : 512, CTAS = TMEM == 256 ? 2 : 1;
+  static constexpr int WIMG = W1BYTES + TT_W2 + TT_W3;
+  static constexpr int OFF_W1 = 0, OFF_W2 = W1BYTES, OFF_W3 = OFF_W2 + TT_W2, OFF_X = OFF_W3 + TT_W3;
+  static constexpr int OFF_H1 = OFF_X + XBYTES, OFF_H2 = OFF_H1 + TT_ACT, OFF_DZ = OFF_H2 + TT_ACT;
+  // MN-major A operands with M = 128 read 16 feature groups per sample group from buffers that hold 10: groups 10..15
+  // alias the start of the next sample group (finite garbage -> accumulator rows 80..127, never read); for the last
+  // sample group that is 768 bytes past the buffer, hence the zeroed pad after DZ (H2's overrun lands in DZ).
+  static constexpr int OFF_PAD = OFF_DZ + TT_ACT, OFF_MISC = OFF_PAD + 1024, SMEM = OFF_MISC + 256;
 };
-constexpr int TT_SG80 = 10 * 128;          // sample-group stride of an 80-feature activation / delta buffer (bytes)
-constexpr int TT_W1 = 64 * 80 * 2, TT_W2 = 64 * 80 * 2, TT_W3 = 16 * 80 * 2;
-constexpr int TT_WIMG = TT_W1 + TT_W2 + TT_W3;
-constexpr int TT_ACT = 16 * TT_SG80;       // 20480
-constexpr int TT_OFF_W1 = 0, TT_OFF_W2 = TT_OFF_W1 + TT_W1, TT_OFF_W3 = TT_OFF_W2 + TT_W2;
-constexpr int TT_OFF_X = TT_OFF_W3 + TT_W3, TT_OFF_H1 = TT_OFF_X + TT_ACT, TT_OFF_H2 = TT_OFF_H1 + TT_ACT;
-constexpr int TT_OFF_DZ = TT_OFF_H2 + TT_ACT;
-// MN-major A operands with M = 128 read 16 feature groups per sample group from buffers that hold 10: groups 10..15
-// alias the start of the next sample group (finite garbage -> accumulator rows 80..127, never read); for the last
-// sample group that is 768 bytes past the buffer, hence the zeroed pad after DZ (H2's overrun lands in DZ).
-constexpr int TT_OFF_PAD = TT_OFF_DZ + TT_ACT, TT_OFF_MISC = TT_OFF_PAD + 1024;
-constexpr int TT_SMEM = TT_OFF_MISC + 256;                 // 106,240 B: two CTAs per SM
-constexpr int TT_TMEM_COLS = 256;                          // two CTAs per SM share the 512 columns
-constexpr int TT_COL_D = 0, TT_COL_D1 = 64, TT_COL_D2 = 144, TT_COL_D3 = 224;       // D3 is 16 columns wide (transposed)
 constexpr float TT_LOSS_SCALE = 64.0f;
 
 // Instruction descriptor with explicit operand majors (bit 15: A is MN-major, bit 16: B is MN-major).
@@ -62,12 +68,12 @@ __host__ __device__ constexpr uint32_t tt_idesc(int fmt, int M, int N, int a_mn,
 }
 
 // Training weight images (K-major B, no swizzle): element (n, k) at (k/8)*(NR/8)*128 + (n/8)*128 + (n%8)*16 + (k%8)*2.
-//   W1' [64 x 80]: k < 73: W1[n][k]; k = 73: b1[n]; rest 0      (the LOD column is a real, noisy input in training)
+//   W1' [64 x K1]: k < Cin: W1[n][k]; k = Cin: b1[n]; rest 0     (the LOD column is a real, noisy input in training)
 //   W2' [64 x 80]: k < 64: W2[n][k]/2; k = 64: b2[n]
 //   W3' [16 x 80]: n < cout: k < 64: W3[n][k]/2; k = 64: b3[n]
 template <int FMT>
-__global__ void pack_train_weights_kernel(MlpDev m, uint16_t* __restrict__ img) {
-  const int n1 = 64 * 80, n2 = 64 * 80, n3 = 16 * 80;
+__global__ void pack_train_weights_kernel(MlpDev m, int K1, uint16_t* __restrict__ img) {
+  const int n1 = 64 * K1, n2 = 64 * 80, n3 = 16 * 80;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += gridDim.x * blockDim.x) {
     int which = i < n1 ? 0 : (i < n1 + n2 ? 1 : 2);
     int local = which == 0 ? i : (which == 1 ? i - n1 : i - n1 - n2);
@@ -227,34 +233,35 @@ struct TrainArgs {
 };
 
 template <int FMT, int METHOD>
-__global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, TrainArgs a) {
+__global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc_kernel(DevGeom g, TrainArgs a) {
   using P = Pair<FMT>;
   using TS = TrainShape<METHOD>;
-  constexpr int DIM = TS::DIM, CIN = TS::CIN, NC1 = TS::NC1;
+  constexpr int DIM = TS::DIM, CIN = TS::CIN, NC0 = TS::NC0, NC1 = TS::NC1, K1 = TS::K1, SGX = TS::SGX, NDX = TS::NDX, C0 = TS::C0;
+  constexpr int TT_COL_D = TS::COL_D, TT_COL_D1 = TS::COL_D1, TT_COL_D2 = TS::COL_D2, TT_COL_D3 = TS::COL_D3;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sX = smem + TT_OFF_X;
-  uint8_t* sH1 = smem + TT_OFF_H1;
-  uint8_t* sH2 = smem + TT_OFF_H2;
-  uint8_t* sDZ = smem + TT_OFF_DZ;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TT_OFF_MISC);
+  uint8_t* sX = smem + TS::OFF_X;
+  uint8_t* sH1 = smem + TS::OFF_H1;
+  uint8_t* sH2 = smem + TS::OFF_H2;
+  uint8_t* sDZ = smem + TS::OFF_DZ;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TS::OFF_MISC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-  float* sRed = reinterpret_cast<float*>(smem + TT_OFF_MISC + 32);      // [8] loss partials
+  float* sRed = reinterpret_cast<float*>(smem + TS::OFF_MISC + 32);      // [8] loss partials
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2;                       // column half of the epilogues / row half of the gather
   const int row = tid & (TT_ROWS - 1);            // sample of the tile = TMEM lane
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   // byte offset of this sample's 16-byte chunk inside a feature group, for the two buffer widths
-  const int roff80 = (row >> 3) * TT_SG80 + (row & 7) * 16;
+  const int roff80 = (row >> 3) * TT_SG80 + (row & 7) * 16, roffx = (row >> 3) * SGX + (row & 7) * 16;
 
-  if (warp == 0) tmem_alloc(tmem_slot, TT_TMEM_COLS);
+  if (warp == 0) tmem_alloc(tmem_slot, TS::TMEM);
   if (tid == 0) mbar_init(mbar, 1);
   {
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < TT_WIMG / 16; i += TT_THREADS) dst[i] = __ldg(a.wimg + i);
+    for (int i = tid; i < TS::WIMG / 16; i += TT_THREADS) dst[i] = __ldg(a.wimg + i);
     // zero the activation / delta buffers once (padding features must be finite), then the constant-1 bias features
-    uint4* act = reinterpret_cast<uint4*>(smem + TT_OFF_X);
-    for (int i = tid; i < (4 * TT_ACT + 1024) / 16; i += TT_THREADS) act[i] = make_uint4(0, 0, 0, 0);
+    uint4* act = reinterpret_cast<uint4*>(smem + TS::OFF_X);
+    for (int i = tid; i < (TS::XBYTES + 3 * TT_ACT + 1024) / 16; i += TT_THREADS) act[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   if (wg == 0) {
@@ -268,12 +275,14 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t aW1 = smem_u32(smem + TT_OFF_W1), aW2 = smem_u32(smem + TT_OFF_W2), aW3 = smem_u32(smem + TT_OFF_W3);
+  const uint32_t aW1 = smem_u32(smem + TS::OFF_W1), aW2 = smem_u32(smem + TS::OFF_W2), aW3 = smem_u32(smem + TS::OFF_W3);
   const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aDZ = smem_u32(sDZ);
   constexpr uint32_t ID_F64 = tt_idesc(FMT, 128, 64, 0, 0), ID_F16 = tt_idesc(FMT, 128, 16, 0, 0);
   constexpr uint32_t ID_B64 = tt_idesc(FMT, 128, 64, 0, 1);        // delta propagation: A K-major, B = W'^T (MN-major view)
   constexpr uint32_t ID_G16 = tt_idesc(FMT, 128, 16, 1, 1);        // D3^T = [H2|1]^T dZ3
   constexpr uint32_t ID_G80 = tt_idesc(FMT, 128, 80, 1, 1);        // weight gradients: both operands MN-major
+  constexpr uint32_t ID_GX = tt_idesc(FMT, 128, K1, 1, 1);         // ... against the K1-wide input buffer
+  constexpr uint32_t ID_BDX = tt_idesc(FMT, 128, NDX, 0, 1);       // dX = dZ1 W1' (N = NDX input columns)
   constexpr uint32_t WG64 = 8 * 128, WG16 = 2 * 128;               // k-group strides of the 64-row / 16-row weight images
   uint32_t phase = 0;
   float loss_local = 0.f;
@@ -294,11 +303,11 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
     tc_fence_after();
   };
   // weight-gradient GEMM: Dacc[128 x 80] (+)= DZ^T (features x samples) . Bbuf (samples x 80 features)
-  auto issue_wgrad = [&](uint32_t dcol, uint32_t bbuf) {
+  auto issue_wgrad = [&](uint32_t dcol, uint32_t bbuf, uint32_t sgb, uint32_t idesc) {
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc)
       mma_ss(tmem + dcol, make_smem_desc(aDZ + kc * 2 * TT_SG80, TT_SG80, 128),
-             make_smem_desc(bbuf + kc * 2 * TT_SG80, TT_SG80, 128), ID_G80, (tiles_done > 0 || kc > 0) ? 1u : 0u);
+             make_smem_desc(bbuf + kc * 2 * sgb, sgb, 128), idesc, (tiles_done > 0 || kc > 0) ? 1u : 0u);
   };
 
   const unsigned ntiles = (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS);
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
     const int node1 = ax[0].i1 * sx1 + ax[1].i1 * sy1 + (DIM == 3 ? ax[2].i1 : 0);
     // corner tables are (dz, dy, dx): offset of G0 corner j / G1 corner j from corner 0
     auto off0 = [&](int j) {
-      const int8_t* d = DIM == 2 ? kCorner2D[j] : kCorner3Dv2[j];
+      const int8_t* d = DIM == 2 ? kCorner2D[j] : (METHOD == NIC_METHOD_3D ? kCorner3D[j] : kCorner3Dv2[j]);
       return d[2] * sx0 + d[1] * sy0 + (DIM == 3 ? d[0] : 0);
     };
     auto off1 = [&](int j) {
@@ -334,23 +343,28 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
       g1_factors(g, j, ax, f);
       return DIM == 2 ? f[0] * f[1] : f[0] * f[1] * f[2];
     };
+    constexpr int NCW0 = 8 * C0 / 12;          // G0 corners gathered by warp-group 0 (4 / 6); the rest go to warp-group 1
+    constexpr int R0 = 12 * (NC0 - NCW0);      // ... which therefore starts with R0 raw G0 features (0 / 24)
     {
-      float xv[48];            // this thread's half of the row: wg 0 -> columns [0,48), wg 1 -> columns [48,80)
+      float xv[TS::XV];        // this thread's part of the row: wg 0 -> features [0, 8 C0), wg 1 -> features [8 C0, K1)
+      auto load_corner = [&](int j, float* dst) {
+        const uint2* node = a.s0 + 3 * (size_t)(node0 + off0(j));
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          uint2 v = __ldg(node + q);
+          float2 lo = unpack2<FMT>(v.x), hi = unpack2<FMT>(v.y);
+          dst[4 * q] = lo.x;
+          dst[4 * q + 1] = lo.y;
+          dst[4 * q + 2] = hi.x;
+          dst[4 * q + 3] = hi.y;
+        }
+      };
       if (wg == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint2* node = a.s0 + 3 * (size_t)(node0 + off0(j));
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            uint2 v = __ldg(node + q);
-            float2 lo = unpack2<FMT>(v.x), hi = unpack2<FMT>(v.y);
-            xv[12 * j + 4 * q] = lo.x;
-            xv[12 * j + 4 * q + 1] = lo.y;
-            xv[12 * j + 4 * q + 2] = hi.x;
-            xv[12 * j + 4 * q + 3] = hi.y;
-          }
-        }
+        for (int j = 0; j < NCW0; ++j) load_corner(j, xv + 12 * j);
       } else {
+#pragma unroll
+        for (int j = NCW0; j < NC0; ++j) load_corner(j, xv + 12 * (j - NCW0));
 #pragma unroll
         for (int j = 0; j < NC1; ++j) {
           const float w = w1(j);
@@ -359,29 +373,29 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
           for (int q = 0; q < 3; ++q) {
             uint2 v = __ldg(node + q);
             float2 lo = unpack2<FMT>(v.x), hi = unpack2<FMT>(v.y);
-            xv[4 * q] = j == 0 ? w * lo.x : fmaf(w, lo.x, xv[4 * q]);
-            xv[4 * q + 1] = j == 0 ? w * lo.y : fmaf(w, lo.y, xv[4 * q + 1]);
-            xv[4 * q + 2] = j == 0 ? w * hi.x : fmaf(w, hi.x, xv[4 * q + 2]);
-            xv[4 * q + 3] = j == 0 ? w * hi.y : fmaf(w, hi.y, xv[4 * q + 3]);
+            xv[R0 + 4 * q] = j == 0 ? w * lo.x : fmaf(w, lo.x, xv[R0 + 4 * q]);
+            xv[R0 + 4 * q + 1] = j == 0 ? w * lo.y : fmaf(w, lo.y, xv[R0 + 4 * q + 1]);
+            xv[R0 + 4 * q + 2] = j == 0 ? w * hi.x : fmaf(w, hi.x, xv[R0 + 4 * q + 2]);
+            xv[R0 + 4 * q + 3] = j == 0 ? w * hi.y : fmaf(w, hi.y, xv[R0 + 4 * q + 3]);
           }
         }
 #pragma unroll
         for (int d = 0; d < DIM; ++d)
 #pragma unroll
-          for (int r = 0; r < 6; ++r) xv[12 + 6 * d + r] = pe_value(g, ax[d].u1, r);
-        xv[12 + 6 * DIM] = g.lod;
+          for (int r = 0; r < 6; ++r) xv[R0 + 12 + 6 * d + r] = pe_value(g, ax[d].u1, r);
+        xv[R0 + 12 + 6 * DIM] = g.lod;
 #pragma unroll
-        for (int i = 13 + 6 * DIM; i < 32; ++i) xv[i] = 0.f;
+        for (int i = R0 + 13 + 6 * DIM; i < K1 - 8 * C0; ++i) xv[i] = 0.f;
       }
-      const int col0 = wg == 0 ? 0 : 48, ncols = wg == 0 ? 48 : CIN - 48;     // real (noisy) columns of this half
+      const int col0 = wg == 0 ? 0 : 8 * C0, ncols = wg == 0 ? 8 * C0 : CIN - 8 * C0;     // real (noisy) columns of this part
       if (a.noise) {
         const float* nz = a.noise + (size_t)nc * CIN + col0;
 #pragma unroll
-        for (int i = 0; i < 48; ++i)
+        for (int i = 0; i < TS::XV; ++i)
           if (i < ncols) xv[i] += nz[i];
       } else if (a.noise_amp > 0.f) {
 #pragma unroll
-        for (int blk = 0; blk < 6; ++blk) {
+        for (int blk = 0; blk < TS::XV / 8; ++blk) {
           if (8 * blk < ncols) {
             uint4 r = philox4x32(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(col0 / 8 + blk));
             const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
@@ -394,11 +408,11 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
           }
         }
       }
-      if (wg == 1) xv[CIN - 48] = 1.0f;              // feature CIN: the bias carrier (not an input: no noise)
+      if (wg == 1) xv[CIN - 8 * C0] = 1.0f;          // feature CIN: the bias carrier (not an input: no noise)
       // 16-byte chunks of 8 features -> X~ buffer
-      const int fg0 = wg == 0 ? 0 : 6, nfg = wg == 0 ? 6 : 4;
+      const int fg0 = wg == 0 ? 0 : C0, nfg = wg == 0 ? C0 : TS::KG1 - C0;
 #pragma unroll
-      for (int f = 0; f < 6; ++f) {
+      for (int f = 0; f < TS::XV / 8; ++f) {
         if (f < nfg) {
           uint4 v;
           auto p0 = P::pack(xv[8 * f], xv[8 * f + 1]), p1 = P::pack(xv[8 * f + 2], xv[8 * f + 3]);
@@ -407,7 +421,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
           v.y = *reinterpret_cast<uint32_t*>(&p1);
           v.z = *reinterpret_cast<uint32_t*>(&p2);
           v.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(sX + roff80 + (fg0 + f) * 128) = v;
+          *reinterpret_cast<uint4*>(sX + roffx + (fg0 + f) * 128) = v;
         }
       }
     }
@@ -417,8 +431,8 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
     uint32_t gd1[16], gd2[16];
     run_mmas([&] {
 #pragma unroll
-      for (int kc = 0; kc < TT_K1 / 16; ++kc)
-        mma_ss(tmem + TT_COL_D, make_smem_desc(aX + kc * 256, 128, TT_SG80), make_smem_desc(aW1 + kc * 2 * WG64, WG64, 128),
+      for (int kc = 0; kc < K1 / 16; ++kc)
+        mma_ss(tmem + TT_COL_D, make_smem_desc(aX + kc * 256, 128, SGX), make_smem_desc(aW1 + kc * 2 * WG64, WG64, 128),
                ID_F64, kc > 0);
     });
 #pragma unroll
@@ -514,7 +528,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
           for (int kc = 0; kc < 4; ++kc)
             mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
                    make_smem_desc(aW2 + kc * 256, 128, WG64), ID_B64, kc > 0);
-          issue_wgrad(TT_COL_D2, aH1);
+          issue_wgrad(TT_COL_D2, aH1, TT_SG80, ID_G80);
         });
       } else {
         run_mmas([&] {      // dX = dZ1 W1' (grid columns only)  and  D1 += DZ^T X~
@@ -522,27 +536,29 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc)
               mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
-                     make_smem_desc(aW1 + kc * 256, 128, WG64), ID_B64, kc > 0);
+                     make_smem_desc(aW1 + kc * 256, 128, WG64), ID_BDX, kc > 0);
           }
-          issue_wgrad(TT_COL_D1, aX);
+          issue_wgrad(TT_COL_D1, aX, SGX, ID_GX);
         });
       }
     }
     // ------------------------------------------------------------------------------------------ grid-gradient scatter
     if (a.dgs0) {
-      uint32_t acc[32];
-      tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
-      uint32_t accg1[16];                             // dX columns [48, 64): the G1 block, read by BOTH warp-groups
-      tmem_ld16(tmem + TT_COL_D + lane_base + 48, accg1);
+      constexpr int HW = NDX / 2;                     // dX columns read by each warp-group: [HW wg, HW wg + HW)
+      uint32_t acc[HW];
+#pragma unroll
+      for (int c = 0; c < HW; c += 32) tmem_ld32(tmem + TT_COL_D + lane_base + wg * HW + c, acc + c);
+      uint32_t accg1[16];                             // dX columns [12 NC0, +12): the G1 block, read by BOTH warp-groups
+      tmem_ld16(tmem + TT_COL_D + lane_base + 12 * NC0, accg1);
       tc_wait_ld();
-      // ---- G0: v4 group gi of this thread covers dX columns [32 wg + 4 gi, +4); groups 0..11 = (corner gq/3, part gq%3)
-      SegInfo si0[4];
+      // ---- G0: v4 group gi of this thread covers dX columns [HW wg + 4 gi, +4); groups 0..3 NC0-1 = (corner gq/3, part gq%3)
+      SegInfo si0[NC0];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) si0[j] = seg_info(node0 + off0(j), a.steps0, lane);
+      for (int j = 0; j < NC0; ++j) si0[j] = seg_info(node0 + off0(j), a.steps0, lane);
 #pragma unroll
-      for (int gi = 0; gi < 8; ++gi) {
-        const int gq = 8 * wg + gi;
-        if (gq < 12) {
+      for (int gi = 0; gi < HW / 4; ++gi) {
+        const int gq = (HW / 4) * wg + gi;
+        if (gq < 3 * NC0) {
           const int j = gq / 3, q = gq - 3 * j;
           float v[4] = {__uint_as_float(acc[4 * gi]), __uint_as_float(acc[4 * gi + 1]), __uint_as_float(acc[4 * gi + 2]),
                         __uint_as_float(acc[4 * gi + 3])};
@@ -596,16 +612,17 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
           else if (row == 64) atomicAdd(a.gm.b3 + c, v);
         }
     }
-    const int c0 = wg * 48, cw = wg == 0 ? 48 : 32;
     for (int which = 1; which < 3; ++which) {
       const uint32_t dcol = which == 1 ? TT_COL_D2 : TT_COL_D1;
-      uint32_t acc[48];
-      tmem_ld16(tmem + dcol + lane_base + c0, acc);
-      tmem_ld16(tmem + dcol + lane_base + c0 + 16, acc + 16);
-      if (wg == 0) tmem_ld16(tmem + dcol + lane_base + c0 + 32, acc + 32);
+      const int width = which == 1 ? 80 : K1;                            // 80-wide: wg 0 reads [0,48), wg 1 [48,80); 128: halves
+      const int c0 = width == 80 ? wg * 48 : wg * 64, cw = width == 80 ? (wg == 0 ? 48 : 32) : 64;
+      uint32_t acc[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 16)
+        if (c < cw) tmem_ld16(tmem + dcol + lane_base + c0 + c, acc + c);
       tc_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 48; ++i) {
+      for (int i = 0; i < 64; ++i) {
         if (i >= cw) continue;
         const int col = c0 + i;
         const float v = __uint_as_float(acc[i]) * fs;
@@ -632,7 +649,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) train_tc_kernel(DevGeom g, Trai
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TT_TMEM_COLS);
+  if (warp == 0) tmem_dealloc(tmem, TS::TMEM);
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
@@ -677,7 +694,7 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
     e = (cudaError_t)launch_relayout<FMT>(h, g, g1, g.n1, s1, st);
     if (e != cudaSuccess) return (int)e;
   }
-  pack_train_weights_kernel<FMT><<<16, 256, 0, st>>>(m, (uint16_t*)h->tc_weights);
+  pack_train_weights_kernel<FMT><<<16, 256, 0, st>>>(m, TrainShape<METHOD>::K1, (uint16_t*)h->tc_weights);
   h->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
@@ -705,14 +722,15 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   a.steps0 = s0n;
   a.steps1 = s0n + 1 > 5 ? 5 : s0n + 1;
   auto kern = train_tc_kernel<FMT, METHOD>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TrainShape<METHOD>::SMEM);
   if (e != cudaSuccess) return (int)e;
   if (g.N >= (1ll << 27)) return NIC_ERR_UNSUPPORTED;          // Philox counter packs (sample << 4 | block)
   long long ntiles = (g.N + TT_ROWS - 1) / TT_ROWS;
-  int grid = (int)(ntiles < 2 * h->sms ? ntiles : 2 * h->sms);          // two resident CTAs per SM
+  const long long cap = (long long)TrainShape<METHOD>::CTAS * h->sms;        // resident CTAs (two per SM when K1 = 80)
+  int grid = (int)(ntiles < cap ? ntiles : cap);
   {
     KernelTimer timer(h, st);
-    kern<<<grid, TT_THREADS, TT_SMEM, st>>>(g, a);
+    kern<<<grid, TT_THREADS, TrainShape<METHOD>::SMEM, st>>>(g, a);
   }
   h->launches++;
   e = cudaGetLastError();
@@ -741,15 +759,16 @@ int launch_train_tc(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradD
                     unsigned long long seed, unsigned long long step, float grad_scale, float* dg0, float* dg1,
                     float* loss_sum, float* out_save, int precision, cudaStream_t st) {
   if (g.N == 0) return NIC_OK;
-  const bool m2d = g.method == NIC_METHOD_2D, m3v2 = g.method == NIC_METHOD_3D_V2;
-  const int cin = m2d ? TrainShape<NIC_METHOD_2D>::CIN : TrainShape<NIC_METHOD_3D_V2>::CIN;
-  if ((!m2d && !m3v2) || g.C != 12 || g.PE != 6 || m.hidden != 64 || m.cout > 16 || m.cin != cin || !origins)
+  const bool m2d = g.method == NIC_METHOD_2D, m3 = g.method == NIC_METHOD_3D, m3v2 = g.method == NIC_METHOD_3D_V2;
+  const int cin = m2d ? TrainShape<NIC_METHOD_2D>::CIN : (m3 ? TrainShape<NIC_METHOD_3D>::CIN : TrainShape<NIC_METHOD_3D_V2>::CIN);
+  if ((!m2d && !m3 && !m3v2) || g.C != 12 || g.PE != 6 || m.hidden != 64 || m.cout > 16 || m.cin != cin || !origins)
     return NIC_ERR_UNSUPPORTED;
 #define NIC_TT_CALL(F, M)                                                                                               \
   launch_train_tc_t<F, M>(h, g, m, gm, g0, g1, origins, targets, noise, noise_bits, seed, step, grad_scale, dg0, dg1, \
                           loss_sum, out_save, st)
-  if (precision == NIC_PREC_F16) return m2d ? NIC_TT_CALL(0, NIC_METHOD_2D) : NIC_TT_CALL(0, NIC_METHOD_3D_V2);
-  return m2d ? NIC_TT_CALL(1, NIC_METHOD_2D) : NIC_TT_CALL(1, NIC_METHOD_3D_V2);
+  if (precision == NIC_PREC_F16)
+    return m2d ? NIC_TT_CALL(0, NIC_METHOD_2D) : (m3 ? NIC_TT_CALL(0, NIC_METHOD_3D) : NIC_TT_CALL(0, NIC_METHOD_3D_V2));
+  return m2d ? NIC_TT_CALL(1, NIC_METHOD_2D) : (m3 ? NIC_TT_CALL(1, NIC_METHOD_3D) : NIC_TT_CALL(1, NIC_METHOD_3D_V2));
 #undef NIC_TT_CALL
 }
 

@@ -855,22 +855,24 @@ def test_lut_65_cubed_extension():
 
 @pytest.mark.parametrize("prec", ["f16", "bf16"])
 @pytest.mark.parametrize("mip", [0, 2])
-def test_train_tc_step_3d_v2_vs_oracle_fp64(prec, mip):
-    """The tcgen05 training step on the 3-D "proposed" method (COMPRESSION_METHOD 4: tetrahedral G0 corners, 8-corner
-    AS-CODED G1 weights, sinusoidal PE) against the oracle's fp64 backward: step 1/4 (mip 0) and step 1 (mip 2)."""
+@pytest.mark.parametrize("method", [3, 4])
+def test_train_tc_step_3d_vs_oracle_fp64(prec, mip, method):
+    """The tcgen05 training step on the 3-D methods against the oracle's fp64 backward, at step 1/4 (mip 0) and step 1
+    (mip 2): method 3 (8 raw G0 corners, Cin 127 -> K = 128, one CTA per SM, triangular PE) and the "proposed" method 4
+    (tetrahedral G0 corners, sinusoidal PE, Cin 79); both use the 8-corner AS-CODED G1 weights."""
     n = nic()
     L = n._lib
     import ctypes as C
     size = 64
     grids = I.make_grids(size, 3, seed=50)
-    cin = 79
+    cin = 127 if method == 3 else 79
     params = I.make_mlp(cin, seed=51, gain=1.5)
     rng = np.random.default_rng(65)
     fl, nc, crop = 0, 3, 8
     coord = rng.integers(0, (size >> mip) - crop + 1, (nc, 3))
     target = rng.random((nc * crop ** 3, 3)).astype(np.float32)
     noise = I.make_noise(nc * crop ** 3, cin, 8, 66)
-    loss, out, grads, dg0, dg1 = O.train_forward_backward(grids, params, coord, target, fl, mip, 4, noise, size=crop)
+    loss, out, grads, dg0, dg1 = O.train_forward_backward(grids, params, coord, target, fl, mip, method, noise, size=crop)
     fp = [T(a) for a in grids]
     pt = [T(p) for p in params]
     m = L.make_mlp(pt)
@@ -880,7 +882,8 @@ def test_train_tc_step_3d_v2_vs_oracle_fp64(prec, mip):
     d0, d1 = torch.zeros_like(g0t), torch.zeros_like(g1t)
     ls = torch.zeros(4, device=dev())
     o = torch.empty((nc * crop ** 3, 3), device=dev())
-    geom = L.make_geom(L.METHOD_3D_V2, g0t, g1t, crop, nc, mip - 2, mip, 6, L.PE_SINUSOIDAL)
+    geom = L.make_geom(L.METHOD_3D if method == 3 else L.METHOD_3D_V2, g0t, g1t, crop, nc, mip - 2, mip, 6,
+                       L.PE_TRIANGULAR if method == 3 else L.PE_SINUSOIDAL)
     h = L.handle(dev())
     coord_t, target_t, noise_t = T(coord, torch.int64), T(target), T(noise)
     for rep in range(2):
