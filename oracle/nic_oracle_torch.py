@@ -193,4 +193,4 @@ class Trainer:
             self.fp[2 * fl].clamp_(q_min, 0.5)
             self.fp[2 * fl + 1].clamp_(q_min, 0.5)
         self.epoch += 1
-        return float(loss)
+        return float(loss.detach())
