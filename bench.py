@@ -270,6 +270,31 @@ def bench_3d(args, nic, ic, var2, dev):
     return res
 
 
+def bind_to_gpu_numa_node(local):
+    """Pins this rank (and therefore its first-touch pinned host buffers) to the CPUs of the NUMA node its GPU hangs
+    off, so the e2e host<->device copies of different ranks do not all cross the socket interconnect."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                 capture_output=True, text=True).stdout.strip()
+            bus = out[-12:] if out else None              # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus.lower()}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -283,6 +308,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries the ONE JSON line and nothing else: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     var2.update(IMAGE_SIZE=SIZE)
@@ -408,7 +437,7 @@ def run_ours(args):
                          "attainable_frac_for_hidden_64": 32.0 / 95.4},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "matches_resident_output": e2e_ok},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "numa_node_rank0": numa,
         }
         line.update(extras)
         if world == 1 and not args.no_cpu:
@@ -421,7 +450,10 @@ def run_ours(args):
                                               "port of the reference op sequence (oracle/nic_oracle_torch.py)"}
             if "train" in line:
                 line["train"]["cpu_value"] = cpu_train_rate(threads)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
