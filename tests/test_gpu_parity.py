@@ -1032,3 +1032,44 @@ def test_end_to_end_training_psnr_vs_reference_port():
     assert psnr_ref > 18.0, psnr_ref
     assert abs(psnr["f32"] - psnr_ref) <= 0.3 and abs(psnr["f16"] - psnr_ref) <= 0.3, (psnr_ref, psnr)
     assert abs(psnr["f16"] - psnr["f32"]) <= 0.1, psnr
+
+
+def test_edge_cases_empty_and_oversized():
+    """Empty inputs are no-ops on every fused entry point; sample counts beyond the kernels' 32-bit index are refused
+    with NIC_ERR_UNSUPPORTED (never a silent wrap), checked before anything is launched or dereferenced."""
+    import ctypes as C
+    n = nic()
+    ic, L = n.image_compression, n._lib
+    size = 64
+    configure(IMAGE_SIZE=size)
+    fp = [T(a) for a in I.make_grids(size, 2, seed=113, no_mip=True, quantized=True)]
+    pt = [T(p) for p in I.make_mlp(73, seed=114)]
+    dec = make_decoder([p.cpu().numpy() for p in pt])
+    h, lib = L.handle(dev()), L.load_library()
+    # empty decode / empty query batch / empty crop batch
+    for prec in ("f32", "f16"):
+        assert ic.decode(fp, dec, 0, size=(0, 16), precision=prec).shape == (0, 16, 3)
+        assert ic.decode_points(fp, dec, torch.zeros((0, 2), dtype=torch.int64), 0, precision=prec).shape == (0, 3)
+    m = L.make_mlp(pt)
+    g = [torch.zeros_like(p) for p in pt]
+    gm = L.make_mlp_grad(g)
+    d0, d1, ls = torch.zeros_like(fp[0]), torch.zeros_like(fp[1]), torch.zeros(4, device=dev())
+    dummy = torch.zeros((1, 2), dtype=torch.int64, device=dev())
+    for prec in (L.PREC_F32, L.PREC_F16):
+        geom = L.make_geom(L.METHOD_2D, fp[0], fp[1], 16, 0, -2, 0, 6, L.PE_TRIANGULAR)
+        L.check(h, lib.nic_train_step(h, C.byref(geom), L.ptr(fp[0]), L.ptr(fp[1]), L.ptr(dummy), C.byref(m), None, None, 0, 0, 0, 0,
+                                      C.byref(gm), L.ptr(d0), L.ptr(d1), L.ptr(ls), None, prec, L.stream_ptr(dev())))
+    torch.cuda.synchronize()
+    assert float(ls[0]) == 0 and all(float(t.abs().max()) == 0 for t in g + [d0, d1])
+    # 2^32 samples: refused
+    geom = L.make_geom(L.METHOD_2D, fp[0], fp[1], (1024, 1024), 4096, -2, 0, 6, L.PE_TRIANGULAR)
+    out = torch.zeros(16, dtype=torch.uint8, device=dev())
+    for prec in (L.PREC_F16, L.PREC_BF16):
+        rc = lib.nic_decode(h, C.byref(geom), L.ptr(fp[0]), L.ptr(fp[1]), L.ptr(dummy), C.byref(m), L.ptr(out), L.DT_U8, prec,
+                            L.stream_ptr(dev()))
+        assert rc == -2, rc
+    tg = torch.zeros(16, device=dev())
+    rc = lib.nic_train_step(h, C.byref(geom), L.ptr(fp[0]), L.ptr(fp[1]), L.ptr(dummy), C.byref(m), L.ptr(tg), None, 0, 0, 0, 0,
+                            C.byref(gm), L.ptr(d0), L.ptr(d1), L.ptr(ls), None, L.PREC_F16, L.stream_ptr(dev()))
+    assert rc == -2, rc
+    torch.cuda.synchronize()
