@@ -112,6 +112,11 @@ int nic_set_option(NicHandle* h, int option, int value);
  * events, adds up their durations, returns the sum (milliseconds) and the number of bracketed launches, and clears
  * the list.  bench.py uses it for the roofline fraction of the dominant kernel. */
 int nic_kernel_time_ms(NicHandle* h, double* total_ms, int64_t* launches);
+/* Profiling aid (tools/run_train.py phases): with bit 3 of NIC_OPT_DEBUG_KNOCKOUT set, thread 0 of every CTA of the
+ * tensor-core training kernel adds the SM cycles it spends in each of its 13 per-tile phases (gather, 3 forward MMA
+ * waits, 2 GELU epilogues, loss, 3 backward MMA waits, 2 delta epilogues, scatter) to device counters; counter 15 counts
+ * tiles.  This call synchronises the device, copies counters[0, n) (n <= 16) to `out` and clears them. */
+int nic_debug_counters(NicHandle* h, int64_t* out, int n);
 
 /* ---- decoder input (K1) ------------------------------------------------------------------------------- */
 /* Width of the decoder input for a geometry: C*(corners+1) + PE*D + 1 (Projects/var2.py:114-118). */

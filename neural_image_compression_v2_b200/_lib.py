@@ -59,6 +59,7 @@ SYMBOLS = {
     "nic_launch_count": (_L, [_P]),
     "nic_set_option": (_I, [_P, _I, _I]),
     "nic_kernel_time_ms": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "nic_debug_counters": (_I, [_P, C.POINTER(C.c_int64), _I]),
     "nic_cin": (_I, [C.POINTER(NicGeom)]),
     "nic_gather": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, _P, _I, _P]),
     "nic_scatter": (_I, [_P, C.POINTER(NicGeom), _P, _P, _P, _P, _P]),
@@ -126,6 +127,7 @@ OPT_DISABLE_FAST2D = 1
 OPT_TIME_KERNELS = 2
 OPT_REUSE_PREPARED = 3
 OPT_LEGACY_FAST2D = 4
+OPT_DEBUG_KNOCKOUT = 100     # profiling only (nic.h); bit 3 = training phase counters
 
 
 def kernel_time_ms(device):
@@ -134,6 +136,14 @@ def kernel_time_ms(device):
     ms, n = C.c_double(0.0), C.c_int64(0)
     check(h, load_library().nic_kernel_time_ms(h, C.byref(ms), C.byref(n)))
     return float(ms.value), int(n.value)
+
+
+def debug_counters(device, n=16):
+    """The 16 device debug counters (nic_debug_counters): read and cleared; see nic.h."""
+    h = handle(device)
+    out = (C.c_int64 * 16)()
+    check(h, load_library().nic_debug_counters(h, out, int(n)))
+    return [int(v) for v in out[:n]]
 
 
 def set_option(device, option, value):

@@ -87,6 +87,7 @@ int nic_destroy(NicHandle* h) {
   if (h->tc_weights) cudaFree(h->tc_weights);
   if (h->tc_shadow) cudaFree(h->tc_shadow);
   if (h->tc_gscratch) cudaFree(h->tc_gscratch);
+  if (h->dbg_counters) cudaFree(h->dbg_counters);
   if (h->adam_desc) cudaFree(h->adam_desc);
   for (int i = 0; i < 2 * NIC_MAX_TIMED; ++i)
     if (h->timed_ev[i]) cudaEventDestroy(h->timed_ev[i]);
@@ -120,6 +121,21 @@ int nic_kernel_time_ms(NicHandle* h, double* total_ms, int64_t* launches) {
   *total_ms = sum;
   *launches = h->timed_count;
   h->timed_count = 0;
+  return NIC_OK;
+}
+
+int nic_debug_counters(NicHandle* h, int64_t* out, int n) {
+  if (!h || !out || n < 0 || n > 16) return fail(h, NIC_ERR_ARG, "nic_debug_counters: bad argument");
+  for (int i = 0; i < n; ++i) out[i] = 0;
+  if (!h->dbg_counters) return NIC_OK;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(h->device);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out, h->dbg_counters, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(h->dbg_counters, 0, 16 * 8);
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) return fail(h, (int)e, "nic_debug_counters: %s", cudaGetErrorString(e));
   return NIC_OK;
 }
 

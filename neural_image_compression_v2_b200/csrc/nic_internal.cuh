@@ -33,6 +33,7 @@ struct Handle {
   int src_code_bits;         // > 0 while a nic_decode_codes call is in flight: grid pointers are uint8 codes of that width
   int reuse_prepared;        // NIC_OPT_REUSE_PREPARED
   int debug_flags;           // knock-out experiments (option 100), never set in production
+  unsigned long long* dbg_counters;   // 16 device counters (nic_debug_counters), allocated on first use
   int legacy_fast2d;         // NIC_OPT_LEGACY_FAST2D: the first-generation (non warp-specialised) fast-path kernel
   struct PreparedKey {       // what the tables in tc_weights / tc_shadow were last built from
     const void *g0, *g1, *w1, *b1, *w2, *b2, *w3, *b3;

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sLut + TC_LUT_MAX);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = uniform_warp_index();
   const int grp = warp >> 2;                 // 0: columns [0, 32) of D / first half of the row; 1: the rest
   const int row = tid & (TC_ROWS - 1);       // texel row of the tile = TMEM lane
   // ---- one-time setup: TMEM allocation, barrier, weight images and PE LUT -> shared memory
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
     __syncthreads();
     // ---- layer 1
     if (warp == 0) {               // one warp issues and waits for the MMAs; the others sleep at the barrier below
-      if (tid == 0) {
+      if (elect_one()) {
         tc_fence_after();
 #pragma unroll
         for (int kc = 0; kc < KX / 16; ++kc)
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
       tc_fence_before();
       __syncthreads();
       if (warp == 0) {
-        if (tid == 0) {
+        if (elect_one()) {
           tc_fence_after();
           const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
           const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, co
   uint64_t* mbar = reinterpret_cast<uint64_t*>(sLy + F_LUT);       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = uniform_warp_index();
   const int cs = warp >> 2;                          // which 16 accumulator columns this thread owns
   const int row = tid & (TC_ROWS - 1);
   if (warp == 0) tmem_alloc(tmem_slot, F_TMEM_COLS);
@@ -600,10 +600,13 @@ __global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, co
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer1(0, tA_);
-      if (hasB) issue_layer1(1, tB_);
+    if (warp == 0) {
+      if (elect_one()) {
+        tc_fence_after();
+        issue_layer1(0, tA_);
+        if (hasB) issue_layer1(1, tB_);
+      }
+      __syncwarp();
     }
     prefetch(pair + gridDim.x);                 // next pair's operands: in flight during this pair's epilogues
 #pragma unroll 1
@@ -613,9 +616,12 @@ __global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, co
       tc_fence_after();
       epilogue(0);
       __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        issue_layer23(0, layer);
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          issue_layer23(0, layer);
+        }
+        __syncwarp();
       }
       if (hasB) {
         mbar_wait_sleep(mbar + 1, ph1);
@@ -624,9 +630,12 @@ __global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, co
         epilogue(1);
       }
       __syncthreads();
-      if (hasB && tid == 0) {
-        tc_fence_after();
-        issue_layer23(1, layer);
+      if (hasB && warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
+          issue_layer23(1, layer);
+        }
+        __syncwarp();
       }
     }
     mbar_wait_sleep(mbar, ph0);
@@ -696,7 +705,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + WS_OFF_BAR);     // [8]: tensor core -> group
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + WS_SLOTS);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_index(), lane = tid & 31;     // warp: provably uniform (MMA operands)
   const int slot = warp >> 2;                        // warp-group = tile slot
   const int row = 32 * (warp & 3) + lane;            // texel row of the tile = TMEM lane
   const int cell = row & 7, within = row >> 3;
@@ -764,7 +773,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
   const uint32_t tDs = tmem + slot * 64;             // this slot's accumulator columns
   const uint32_t tD = tDs + ((uint32_t)((warp & 3) * 32) << 16);
   uint8_t* sAct = smem_raw + WS_OFF_ACT + slot * 8 * WS_KG;
-  const bool elected = (warp & 3) == 0 && lane == 0;
+  const bool issuer_warp = (warp & 3) == 0;          // its elected lane issues the group's MMAs (uniform control flow)
   constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
   constexpr uint32_t IDESC_64_BMN = make_idesc(FMT, 128, 64, 1);
   constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
@@ -842,9 +851,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
   stage(slot);
   tc_fence_before();
   group_sync();
-  if (elected && (unsigned)slot < my_tiles) {
-    tc_fence_after();
-    issue_layer1(slot);
+  if (issuer_warp && (unsigned)slot < my_tiles) {
+    if (elect_one()) {
+      tc_fence_after();
+      issue_layer1(slot);
+    }
+    __syncwarp();
   }
   fetch(slot + WS_SLOTS);
   uint32_t ph = 0;
@@ -878,9 +890,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
       fence_async_smem();                           // the activations (generic-proxy stores) -> visible to the tensor core
       tc_fence_before();
       group_sync();
-      if (elected) {
-        tc_fence_after();
-        issue_layer23(layer);
+      if (issuer_warp) {
+        if (elect_one()) {
+          tc_fence_after();
+          issue_layer23(layer);
+        }
+        __syncwarp();
       }
     }
     mbar_wait(bar_full + slot, ph);
@@ -894,9 +909,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
     stage(i + WS_SLOTS);                          // operands of this slot's next tile (fetched one tile ago)
     tc_fence_before();
     group_sync();                                 // D has been read and the next operands are staged
-    if (elected && i + WS_SLOTS < my_tiles) {
-      tc_fence_after();
-      issue_layer1(i + WS_SLOTS);
+    if (issuer_warp && i + WS_SLOTS < my_tiles) {
+      if (elect_one()) {
+        tc_fence_after();
+        issue_layer1(i + WS_SLOTS);
+      }
+      __syncwarp();
     }
     fetch(i + 2 * WS_SLOTS);
     {
@@ -951,7 +969,7 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + NG);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_index(), lane = tid & 31;     // warp: provably uniform (MMA operands)
   const int slot = warp >> 2;
   const int row = 32 * (warp & 3) + lane;
   const int roff = (row >> 3) * 128 + (row & 7) * 16;
@@ -988,7 +1006,7 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
   const uint32_t tDs = tmem + slot * 64;
   const uint32_t tD = tDs + ((uint32_t)((warp & 3) * 32) << 16);
   uint8_t* sAct = smem_raw + OFF_ACT + slot * ACT_BYTES;
-  const bool elected = (warp & 3) == 0 && lane == 0;
+  const bool issuer_warp = (warp & 3) == 0;          // its elected lane issues the group's MMAs (uniform control flow)
   constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
   constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
   const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3), aOne = smem_u32(sOne), aAct = smem_u32(sAct);
@@ -1074,12 +1092,15 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
     fence_async_smem();
     tc_fence_before();
     group_sync();
-    if (elected) {
-      tc_fence_after();
+    if (issuer_warp) {
+      if (elect_one()) {
+        tc_fence_after();
 #pragma unroll
-      for (int kc = 0; kc < KX / 16; ++kc)
-        mma_ss(tDs, make_smem_desc(aAct + kc * 2 * KG, KG, SBO), make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
-      tc_commit(bar_full + slot);
+        for (int kc = 0; kc < KX / 16; ++kc)
+          mma_ss(tDs, make_smem_desc(aAct + kc * 2 * KG, KG, SBO), make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
+        tc_commit(bar_full + slot);
+      }
+      __syncwarp();
     }
     // ------------------------------------------------------------------------------------ layers 1, 2: epilogues
 #pragma unroll 1
@@ -1102,15 +1123,18 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
       fence_async_smem();
       tc_fence_before();
       group_sync();
-      if (elected) {
-        tc_fence_after();
-        const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
-        const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
+      if (issuer_warp) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
+          const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc)
-          mma_ss(tDs, make_smem_desc(aAct + kc * 2 * KG, KG, SBO), make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
-        mma_ss(tDs, make_smem_desc(aOne, KG, SBO), make_smem_desc(aW + 4 * 2 * lbo, lbo, SBO), idesc, 1);
-        tc_commit(bar_full + slot);
+          for (int kc = 0; kc < 4; ++kc)
+            mma_ss(tDs, make_smem_desc(aAct + kc * 2 * KG, KG, SBO), make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
+          mma_ss(tDs, make_smem_desc(aOne, KG, SBO), make_smem_desc(aW + 4 * 2 * lbo, lbo, SBO), idesc, 1);
+          tc_commit(bar_full + slot);
+        }
+        __syncwarp();
       }
     }
     // ------------------------------------------------------------------------------------ output

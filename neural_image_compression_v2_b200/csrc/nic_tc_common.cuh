@@ -69,6 +69,18 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
       : "memory");
 }
 
+// One elected lane of a CONVERGED warp.  tcgen05.mma must be issued from warp-uniform control flow with warp-uniform
+// operands: `if (warp_u == X) if (elect_one()) mma(...)` with warp_u = uniform_warp_index() keeps descriptors in uniform
+// registers and the UTCHMMAs back to back (48 cycles each for M128 N64 SS, 32 for TS; tools/ubench/mma_rate2.cu).
+// `if (lane == 0)` instead makes the compiler wrap EVERY mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop
+// (operands are then per-thread values): 95..120 cycles per mma from one issuing thread.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): in 16-byte units the
 // canonical layout is ((8,n),2):((1,SBO),LBO) — 8 rows x 16 B form a 128-byte core matrix, SBO steps to the next
 // 8-row group, LBO to the next 8-element K chunk.

@@ -25,7 +25,7 @@
 //   power-of-two loss scale S so that f16 deltas stay normal; S and the 2/(N*Cout) of the MSE mean are applied at the flush.
 //   GELU is the tanh form in forward AND backward (the gradient of the function actually evaluated).
 //   Noise: X~ = x + (U - 1/2) / 2^bits on all Cin columns (image_compression.py:248-251), Philox4x32-10 keyed by
-//   (seed), counter (sample, block, step); 16-bit uniforms, two per word.
+//   (seed), counter (sample, block of 16 features, step); 8-bit uniforms, sixteen per Philox call.
 // Algorithmic work: 3 * 2 * (Cin*64 + 64*64 + 64*Cout) = 53,760 FLOP/sample; tensor-bound roofline.
 #include "nic_tc_common.cuh"
 
@@ -168,19 +168,20 @@ __device__ __forceinline__ float2 unpack2(uint32_t v) {
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
 }
 
-// (U - 1/2) * amp for the two 16-bit halves of a Philox word; U = (u16 + 1/2) / 65536.
-__device__ __forceinline__ float2 noise_pair(uint32_t w, float amp) {
-  float lo = ((float)(w & 0xFFFFu) - 32767.5f) * (1.0f / 65536.0f);
-  float hi = ((float)(w >> 16) - 32767.5f) * (1.0f / 65536.0f);
-  return make_float2(lo * amp, hi * amp);
+// hw = two f16 values 1024 + b (b = a uniform byte)  ->  ((b + 1/2) / 256 - 1/2) * amp for both, exactly, in packed f16:
+// sc = amp / 256, hs = sc / 2.
+__device__ __forceinline__ uint32_t noise_h2(uint32_t hw, __half2 sc, __half2 hs) {
+  __half2 v = __hadd2(*reinterpret_cast<const __half2*>(&hw), __float2half2_rn(-1152.0f));
+  v = __hfma2(v, sc, hs);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 
 // Segmented warp reduction for the scatter: lanes whose `key` (grid node) is equal and contiguous are summed into the
 // first lane of the run; runs are also cut every 2^steps lanes so that `steps` shuffle rounds always suffice.
-// The run structure depends only on the corner, so it is computed once per corner (SegInfo) and reused by the three
-// 4-channel parts; the values travel as two f16x2 words (they carry the loss scale, so they are well inside f16 range,
-// and dX itself comes from 16-bit MMA operands).
+// The run structure depends only on the grid (corner keys differ by lane-independent offsets), so it is computed once
+// per grid (SegInfo) and reused by every corner and 4-channel part; the values travel as two f16x2 words (they carry
+// the loss scale, so they are well inside f16 range, and dX itself comes from 16-bit MMA operands).
 struct SegInfo {
   unsigned same;     // bit s: lane + 2^s belongs to the same run
   bool head;         // this lane issues the atomic
@@ -199,20 +200,6 @@ __device__ __forceinline__ SegInfo seg_info(int key, int steps, int lane) {
   }
   return si;
 }
-__device__ __forceinline__ void seg_reduce4(const SegInfo& si, int steps, float* v) {
-  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
-  for (int s = 0, d = 1; s < steps; ++s, d <<= 1) {
-    const uint32_t oa = __shfl_down_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&a), d);
-    const uint32_t ob = __shfl_down_sync(0xffffffffu, *reinterpret_cast<uint32_t*>(&b), d);
-    if (si.same & (1u << s)) {
-      a = __hadd2(a, *reinterpret_cast<const __half2*>(&oa));
-      b = __hadd2(b, *reinterpret_cast<const __half2*>(&ob));
-    }
-  }
-  const float2 fa = __half22float2(a), fb = __half22float2(b);
-  v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
-}
-
 struct TrainArgs {
   const uint2* s0;            // 16-bit channel-last shadow of G0: [x][y][12]
   const uint2* s1;            // ... of G1
@@ -230,6 +217,7 @@ struct TrainArgs {
   float flush_scale;          // 2 / (N_global * cout) / S
   int cout;
   int steps0, steps1;         // segmented-reduction depths of the scatter (lanes sharing a G0 / G1 node)
+  unsigned long long* prof;   // NULL, or 16 device counters: cycles per phase seen by thread 0 (nic_debug_counters)
 };
 
 template <int FMT, int METHOD>
@@ -247,7 +235,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   float* sRed = reinterpret_cast<float*>(smem + TS::OFF_MISC + 32);      // [8] loss partials
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_index(), lane = tid & 31;     // warp: provably uniform (MMA issue)
   const int wg = warp >> 2;                       // column half of the epilogues / row half of the gather
   const int row = tid & (TT_ROWS - 1);            // sample of the tile = TMEM lane
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -288,15 +276,27 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   float loss_local = 0.f;
   unsigned tiles_done = 0;
 
+  // phase profile (debug): thread 0 adds the cycles since its previous mark to counter `i`
+  long long prof_t = a.prof ? clock64() : 0;
+  auto mark = [&](int i) {
+    if (a.prof && tid == 0) {
+      const long long t = clock64();
+      atomicAdd(a.prof + i, (unsigned long long)(t - prof_t));
+      prof_t = t;
+    }
+  };
   // hand the tensor core a batch of MMAs and wait for them
   auto run_mmas = [&](auto&& issue) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue();
-      tc_commit(mbar);
+    if (warp == 0) {               // uniform branch + elected lane: operands stay in uniform registers (nic_tc_common.cuh)
+      if (elect_one()) {
+        tc_fence_after();
+        issue();
+        tc_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait_sleep(mbar, phase);
     phase ^= 1;
@@ -315,6 +315,14 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     const unsigned n = tile * TT_ROWS + row;
     const bool live = n < (unsigned)g.N;
     const unsigned nc = live ? n : (unsigned)g.N - 1;
+    float tgt[4] = {0.f, 0.f, 0.f, 0.f};           // targets of the first 4 outputs: loaded now, used after the forward pass
+    if (wg == 0 && live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < a.cout)       // volatile: keep the load HERE (the compiler would sink it to its use, 2,000 cycles later)
+          asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(tgt[c]) : "l"(a.targets + (size_t)n * a.cout + c));
+    }
+    if (a.prof && (tid == 0 || tid == 128)) prof_t = clock64();
     // ------------------------------------------------------------------------------------------ gather + noise -> X~
     Texel t = texel_of_fast(g, nc, a.origins);
     AxisCoord ax[3];
@@ -347,12 +355,17 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     constexpr int R0 = 12 * (NC0 - NCW0);      // ... which therefore starts with R0 raw G0 features (0 / 24)
     {
       float xv[TS::XV];        // this thread's part of the row: wg 0 -> features [0, 8 C0), wg 1 -> features [8 C0, K1)
-      auto load_corner = [&](int j, float* dst) {
-        const uint2* node = a.s0 + 3 * (size_t)(node0 + off0(j));
+      // All grid loads of this thread are issued FIRST (volatile: the compiler keeps them here instead of sinking each
+      // next to its use, which serialised four ~800-cycle L2 round trips per tile); the arithmetic follows.
+      auto ldg2 = [](const uint2* p) {
+        uint2 v;
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+        return v;
+      };
+      auto unpack_corner = [&](const uint2* raw, float* dst) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          uint2 v = __ldg(node + q);
-          float2 lo = unpack2<FMT>(v.x), hi = unpack2<FMT>(v.y);
+          float2 lo = unpack2<FMT>(raw[q].x), hi = unpack2<FMT>(raw[q].y);
           dst[4 * q] = lo.x;
           dst[4 * q + 1] = lo.y;
           dst[4 * q + 2] = hi.x;
@@ -360,29 +373,62 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         }
       };
       if (wg == 0) {
+        uint2 raw[3 * NCW0];
 #pragma unroll
-        for (int j = 0; j < NCW0; ++j) load_corner(j, xv + 12 * j);
+        for (int j = 0; j < NCW0; ++j)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) raw[3 * j + q] = ldg2(a.s0 + 3 * (size_t)(node0 + off0(j)) + q);
+#pragma unroll
+        for (int j = 0; j < NCW0; ++j) unpack_corner(raw + 3 * j, xv + 12 * j);
       } else {
+        uint2 raw0[3 * (NC0 - NCW0) + 1], raw1[3 * NC1];
 #pragma unroll
-        for (int j = NCW0; j < NC0; ++j) load_corner(j, xv + 12 * (j - NCW0));
+        for (int j = NCW0; j < NC0; ++j)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) raw0[3 * (j - NCW0) + q] = ldg2(a.s0 + 3 * (size_t)(node0 + off0(j)) + q);
+#pragma unroll
+        for (int j = 0; j < NC1; ++j)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) raw1[3 * j + q] = ldg2(a.s1 + 3 * (size_t)(node1 + off1(j)) + q);
+#pragma unroll
+        for (int j = NCW0; j < NC0; ++j) unpack_corner(raw0 + 3 * (j - NCW0), xv + 12 * (j - NCW0));
 #pragma unroll
         for (int j = 0; j < NC1; ++j) {
           const float w = w1(j);
-          const uint2* node = a.s1 + 3 * (size_t)(node1 + off1(j));
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
-            uint2 v = __ldg(node + q);
-            float2 lo = unpack2<FMT>(v.x), hi = unpack2<FMT>(v.y);
+            float2 lo = unpack2<FMT>(raw1[3 * j + q].x), hi = unpack2<FMT>(raw1[3 * j + q].y);
             xv[R0 + 4 * q] = j == 0 ? w * lo.x : fmaf(w, lo.x, xv[R0 + 4 * q]);
             xv[R0 + 4 * q + 1] = j == 0 ? w * lo.y : fmaf(w, lo.y, xv[R0 + 4 * q + 1]);
             xv[R0 + 4 * q + 2] = j == 0 ? w * hi.x : fmaf(w, hi.x, xv[R0 + 4 * q + 2]);
             xv[R0 + 4 * q + 3] = j == 0 ? w * hi.y : fmaf(w, hi.y, xv[R0 + 4 * q + 3]);
           }
         }
+        // ONE branch on the encoding kind (pe_value per element interleaves twelve copies of the sin/cos slow path with
+        // the code that actually runs: 112 KB of SASS and instruction-cache misses every tile)
+        if (g.pe_kind == NIC_PE_TRIANGULAR) {
 #pragma unroll
-        for (int d = 0; d < DIM; ++d)
+          for (int d = 0; d < DIM; ++d)
 #pragma unroll
-          for (int r = 0; r < 6; ++r) xv[R0 + 12 + 6 * d + r] = pe_value(g, ax[d].u1, r);
+            for (int r = 0; r < 6; ++r) xv[R0 + 12 + 6 * d + r] = pe_triangular(ax[d].u1, r, 6);
+        } else {
+#pragma unroll 1
+          for (int d = 0; d < DIM; ++d) {
+#pragma unroll 1
+            for (int h = 0; h < 3; ++h) {
+              float sv, cv;
+              sincosf(__fmul_rn(ax[d].u1, g.pe_div[h]), &sv, &cv);
+#pragma unroll
+              for (int dd = 0; dd < DIM; ++dd)
+#pragma unroll
+                for (int hh = 0; hh < 3; ++hh)
+                  if (dd == d && hh == h) {
+                    xv[R0 + 12 + 6 * dd + 2 * hh] = sv;
+                    xv[R0 + 12 + 6 * dd + 2 * hh + 1] = cv;
+                  }
+            }
+          }
+        }
         xv[R0 + 12 + 6 * DIM] = g.lod;
 #pragma unroll
         for (int i = R0 + 13 + 6 * DIM; i < K1 - 8 * C0; ++i) xv[i] = 0.f;
@@ -393,38 +439,57 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
 #pragma unroll
         for (int i = 0; i < TS::XV; ++i)
           if (i < ncols) xv[i] += nz[i];
-      } else if (a.noise_amp > 0.f) {
+      }
+      if (wg == 1) xv[CIN - 8 * C0] = 1.0f;          // feature CIN: the bias carrier (not an input: no noise)
+      // Pack to 16-byte chunks of 8 features -> X~ buffer, adding the in-kernel noise on the way: one Philox call
+      // yields 16 bytes = the 8-bit uniforms of 16 features (two chunks).  (b - 127.5) * amp / 256 is built in packed
+      // f16 (0x6400 | b = 1024 + b exactly) — 8 bits are far below what a 16-bit X~ resolves.
+      const bool gen = !a.noise && a.noise_amp > 0.f;
+      const __half2 nsc = __float2half2_rn(a.noise_amp * (1.0f / 256.0f)), nhs = __float2half2_rn(a.noise_amp * (0.5f / 256.0f));
+      const int fg0 = wg == 0 ? 0 : C0, nfg = wg == 0 ? C0 : TS::KG1 - C0;
 #pragma unroll
-        for (int blk = 0; blk < TS::XV / 8; ++blk) {
-          if (8 * blk < ncols) {
-            uint4 r = philox4x32(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(col0 / 8 + blk));
-            const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
+      for (int b16 = 0; b16 < (TS::XV + 15) / 16; ++b16) {
+        uint32_t nzw[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float2 z = noise_pair(wds[k], a.noise_amp);
-              if (8 * blk + 2 * k < ncols) xv[8 * blk + 2 * k] += z.x;
-              if (8 * blk + 2 * k + 1 < ncols) xv[8 * blk + 2 * k + 1] += z.y;
+        for (int i = 0; i < 8; ++i) nzw[i] = 0u;
+        if (gen && 16 * b16 < ncols) {
+          const uint4 r = philox4x32(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(8 * wg + b16));
+          const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            nzw[2 * k] = noise_h2(__byte_perm(wds[k], 0x64646464u, 0x5140), nsc, nhs);
+            nzw[2 * k + 1] = noise_h2(__byte_perm(wds[k], 0x64646464u, 0x5342), nsc, nhs);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {          // no noise beyond the real input columns
+            if (16 * b16 + 2 * i >= ncols) nzw[i] = 0u;
+            else if (16 * b16 + 2 * i + 1 >= ncols) nzw[i] &= 0x0000FFFFu;
+          }
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int f = 2 * b16 + hh;
+          if (f < TS::XV / 8 && f < nfg) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (FMT == 0) {
+                __half2 v = __hadd2(__floats2half2_rn(xv[8 * f + 2 * i], xv[8 * f + 2 * i + 1]),
+                                    *reinterpret_cast<const __half2*>(&nzw[4 * hh + i]));
+                w[i] = *reinterpret_cast<uint32_t*>(&v);
+              } else {
+                const float2 z = __half22float2(*reinterpret_cast<const __half2*>(&nzw[4 * hh + i]));
+                auto v = P::pack(xv[8 * f + 2 * i] + z.x, xv[8 * f + 2 * i + 1] + z.y);
+                w[i] = *reinterpret_cast<uint32_t*>(&v);
+              }
             }
+            *reinterpret_cast<uint4*>(sX + roffx + (fg0 + f) * 128) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
-      if (wg == 1) xv[CIN - 8 * C0] = 1.0f;          // feature CIN: the bias carrier (not an input: no noise)
-      // 16-byte chunks of 8 features -> X~ buffer
-      const int fg0 = wg == 0 ? 0 : C0, nfg = wg == 0 ? C0 : TS::KG1 - C0;
-#pragma unroll
-      for (int f = 0; f < TS::XV / 8; ++f) {
-        if (f < nfg) {
-          uint4 v;
-          auto p0 = P::pack(xv[8 * f], xv[8 * f + 1]), p1 = P::pack(xv[8 * f + 2], xv[8 * f + 3]);
-          auto p2 = P::pack(xv[8 * f + 4], xv[8 * f + 5]), p3 = P::pack(xv[8 * f + 6], xv[8 * f + 7]);
-          v.x = *reinterpret_cast<uint32_t*>(&p0);
-          v.y = *reinterpret_cast<uint32_t*>(&p1);
-          v.z = *reinterpret_cast<uint32_t*>(&p2);
-          v.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(sX + roffx + (fg0 + f) * 128) = v;
-        }
-      }
     }
+    mark(0);
+    if (a.prof && tid == 128) atomicAdd(a.prof + 13, (unsigned long long)(clock64() - prof_t));     // warp-group 1's gather
     // ------------------------------------------------------------------------------------------ forward
     // d h'/d z of this thread's 32 hidden columns, layers 1 and 2.  The two layer loops below are FULLY unrolled: with a
     // rolled loop (layer a run-time value) nvcc 12.9 mis-compiled the conditional writes into these register arrays.
@@ -435,6 +500,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         mma_ss(tmem + TT_COL_D, make_smem_desc(aX + kc * 256, 128, SGX), make_smem_desc(aW1 + kc * 2 * WG64, WG64, 128),
                ID_F64, kc > 0);
     });
+    mark(1);
 #pragma unroll
     for (int layer = 0; layer < 2; ++layer) {
       uint32_t acc[32];
@@ -453,6 +519,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         }
         *reinterpret_cast<uint4*>(dstb + f * 128) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
       }
+      mark(layer == 0 ? 2 : 4);
       if (layer == 0) {
         run_mmas([&] {
 #pragma unroll
@@ -468,6 +535,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
                    make_smem_desc(aW3 + kc * 2 * WG16, WG16, 128), ID_F16, kc > 0);
         });
       }
+      mark(layer == 0 ? 3 : 5);
     }
     // ------------------------------------------------------------------------------------------ output, loss, dz3
     if (wg == 0) {
@@ -475,15 +543,28 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       tmem_ld16(tmem + TT_COL_D + lane_base, acc);
       tc_wait_ld();
       float dz[16];
+      const bool save = a.out_save != nullptr;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        dz[c] = 0.f;
-        if (c < a.cout && live) {
-          const float o = 1.0f / (1.0f + __expf(-__uint_as_float(acc[c])));
-          const float d = o - a.targets[(size_t)n * a.cout + c];
-          loss_local += d * d;
-          if (a.out_save) a.out_save[(size_t)n * a.cout + c] = o;
-          dz[c] = TT_LOSS_SCALE * d * o * (1.0f - o);
+      for (int c = 0; c < 4; ++c) {                  // branch-free for the usual 3 outputs (targets were prefetched)
+        const bool on = live && c < a.cout;
+        const float o = __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c])));
+        const float d = o - tgt[c];
+        loss_local += on ? d * d : 0.f;
+        if (on && save) a.out_save[(size_t)n * a.cout + c] = o;
+        dz[c] = on ? TT_LOSS_SCALE * d * o * (1.0f - o) : 0.f;
+      }
+#pragma unroll
+      for (int c = 4; c < 16; ++c) dz[c] = 0.f;
+      if (a.cout > 4 && live) {
+#pragma unroll
+        for (int c = 4; c < 16; ++c) {
+          if (c < a.cout) {
+            const float o = __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c])));
+            const float d = o - a.targets[(size_t)n * a.cout + c];
+            loss_local += d * d;
+            if (save) a.out_save[(size_t)n * a.cout + c] = o;
+            dz[c] = TT_LOSS_SCALE * d * o * (1.0f - o);
+          }
         }
       }
 #pragma unroll
@@ -495,6 +576,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
                        *reinterpret_cast<uint32_t*>(&p3));
       }
     }
+    mark(6);
     // ------------------------------------------------------------------------------------------ backward
     // dH2 = dZ3 W3' (K = 16 output features) and D3^T += [H2 | 1]^T dZ3.
     run_mmas([&] {
@@ -505,6 +587,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         mma_ss(tmem + TT_COL_D3, make_smem_desc(aH2 + kc * 2 * TT_SG80, TT_SG80, 128),
                make_smem_desc(aDZ + kc * 2 * TT_SG80, TT_SG80, 128), ID_G16, (tiles_done > 0 || kc > 0) ? 1u : 0u);
     });
+    mark(7);
 #pragma unroll
     for (int layer = 1; layer >= 0; --layer) {
       uint32_t acc[32];
@@ -522,6 +605,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         }
         *reinterpret_cast<uint4*>(dstb + f * 128) = make_uint4(dp[0], dp[1], dp[2], dp[3]);
       }
+      mark(layer == 1 ? 8 : 10);
       if (layer == 1) {
         run_mmas([&] {      // dH1 = dZ2 W2'  and  D2 += DZ^T [H1 | 1]
 #pragma unroll
@@ -541,6 +625,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
           issue_wgrad(TT_COL_D1, aX, SGX, ID_GX);
         });
       }
+      mark(layer == 1 ? 9 : 11);
     }
     // ------------------------------------------------------------------------------------------ grid-gradient scatter
     if (a.dgs0) {
@@ -551,45 +636,96 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       uint32_t accg1[16];                             // dX columns [12 NC0, +12): the G1 block, read by BOTH warp-groups
       tmem_ld16(tmem + TT_COL_D + lane_base + 12 * NC0, accg1);
       tc_wait_ld();
-      // ---- G0: v4 group gi of this thread covers dX columns [HW wg + 4 gi, +4); groups 0..3 NC0-1 = (corner gq/3, part gq%3)
-      SegInfo si0[NC0];
+      // The run structure (which lanes share a node) is the same for every corner of a grid: corner keys differ from
+      // node0 / node1 by a lane-independent offset.  All groups of a grid are reduced TOGETHER, one shuffle round at a
+      // time, so that the 2 x groups independent shuffles of a round are in flight at once (reducing group after group
+      // serialises ~30-cycle shuffle latencies: 9,200 of the 25,000 cycles of a tile in the first version).
+      const SegInfo si0 = seg_info(node0, a.steps0, lane), si1 = seg_info(node1, a.steps1, lane);
+      auto pack_h2 = [](uint32_t x, uint32_t y) {
+        __half2 h = __floats2half2_rn(__uint_as_float(x), __uint_as_float(y));
+        return *reinterpret_cast<uint32_t*>(&h);
+      };
+      auto red4 = [](float* dst, uint32_t lo, uint32_t hi) {
+        const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&lo)), fb = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(fa.x), "f"(fa.y), "f"(fb.x), "f"(fb.y) : "memory");
+      };
+      // ---- G0: v4 group gi of this thread covers dX columns [HW wg + 4 gi, +4); group gq = (corner gq / 3, part gq % 3)
+      constexpr int NG0 = HW / 4;
+      const int ng0 = 3 * NC0 - NG0 * wg < NG0 ? 3 * NC0 - NG0 * wg : NG0;      // groups of this warp-group that exist
+      uint32_t pk[2 * NG0];
 #pragma unroll
-      for (int j = 0; j < NC0; ++j) si0[j] = seg_info(node0 + off0(j), a.steps0, lane);
+      for (int gi = 0; gi < NG0; ++gi) {
+        pk[2 * gi] = pack_h2(acc[4 * gi], acc[4 * gi + 1]);
+        pk[2 * gi + 1] = pack_h2(acc[4 * gi + 2], acc[4 * gi + 3]);
+      }
 #pragma unroll
-      for (int gi = 0; gi < HW / 4; ++gi) {
-        const int gq = (HW / 4) * wg + gi;
-        if (gq < 3 * NC0) {
-          const int j = gq / 3, q = gq - 3 * j;
-          float v[4] = {__uint_as_float(acc[4 * gi]), __uint_as_float(acc[4 * gi + 1]), __uint_as_float(acc[4 * gi + 2]),
-                        __uint_as_float(acc[4 * gi + 3])};
-          seg_reduce4(si0[j], a.steps0, v);
-          if (live && si0[j].head) {
-            float* dst = a.dgs0 + (size_t)(node0 + off0(j)) * 12 + 4 * q;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
-                         : "memory");
+      for (int s = 0; s < 5; ++s) {
+        if (s < a.steps0) {
+          uint32_t o[2 * NG0];
+#pragma unroll
+          for (int i = 0; i < 2 * NG0; ++i)
+            if (i < 2 * ng0) o[i] = __shfl_down_sync(0xffffffffu, pk[i], 1 << s);
+          if (si0.same & (1u << s)) {
+#pragma unroll
+            for (int i = 0; i < 2 * NG0; ++i)
+              if (i < 2 * ng0) {
+                __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&pk[i]), *reinterpret_cast<const __half2*>(&o[i]));
+                pk[i] = *reinterpret_cast<uint32_t*>(&r);
+              }
+          }
+        }
+      }
+      mark(14);
+      if (live && si0.head) {
+#pragma unroll
+        for (int gi = 0; gi < NG0; ++gi) {
+          const int gq = NG0 * wg + gi;
+          if (gi < ng0) {
+            const int j = gq / 3, q = gq - 3 * j;
+            red4(a.dgs0 + (size_t)(node0 + off0(j)) * 12 + 4 * q, pk[2 * gi], pk[2 * gi + 1]);
           }
         }
       }
       // ---- G1: the NC1 corners are split between the warp-groups (balance: G0 gives wg 0 eight groups and wg 1 four)
+      constexpr int NG1 = 3 * (NC1 / 2);
+      uint32_t pk1[2 * NG1];
 #pragma unroll
       for (int jj = 0; jj < NC1 / 2; ++jj) {
-        const int j = wg * (NC1 / 2) + jj;
-        const float w = w1(j);
-        const int key = node1 + off1(j);
-        const SegInfo si = seg_info(key, a.steps1, lane);
+        const float w = w1(wg * (NC1 / 2) + jj);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          float u[4] = {w * __uint_as_float(accg1[4 * q]), w * __uint_as_float(accg1[4 * q + 1]),
-                        w * __uint_as_float(accg1[4 * q + 2]), w * __uint_as_float(accg1[4 * q + 3])};
-          seg_reduce4(si, a.steps1, u);
-          if (live && si.head) {
-            float* dst = a.dgs1 + (size_t)key * 12 + 4 * q;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(u[0]), "f"(u[1]), "f"(u[2]), "f"(u[3])
-                         : "memory");
+          __half2 lo = __floats2half2_rn(w * __uint_as_float(accg1[4 * q]), w * __uint_as_float(accg1[4 * q + 1]));
+          __half2 hi = __floats2half2_rn(w * __uint_as_float(accg1[4 * q + 2]), w * __uint_as_float(accg1[4 * q + 3]));
+          pk1[2 * (3 * jj + q)] = *reinterpret_cast<uint32_t*>(&lo);
+          pk1[2 * (3 * jj + q) + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        if (s < a.steps1) {
+          uint32_t o[2 * NG1];
+#pragma unroll
+          for (int i = 0; i < 2 * NG1; ++i) o[i] = __shfl_down_sync(0xffffffffu, pk1[i], 1 << s);
+          if (si1.same & (1u << s)) {
+#pragma unroll
+            for (int i = 0; i < 2 * NG1; ++i) {
+              __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&pk1[i]), *reinterpret_cast<const __half2*>(&o[i]));
+              pk1[i] = *reinterpret_cast<uint32_t*>(&r);
+            }
           }
         }
       }
+      if (live && si1.head) {
+#pragma unroll
+        for (int jj = 0; jj < NC1 / 2; ++jj) {
+          const int key = node1 + off1(wg * (NC1 / 2) + jj);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) red4(a.dgs1 + (size_t)key * 12 + 4 * q, pk1[2 * (3 * jj + q)], pk1[2 * (3 * jj + q) + 1]);
+        }
+      }
     }
+    mark(12);
+    if (a.prof && tid == 0) atomicAdd(a.prof + 15, 1ull);
     tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
   }
   // -------------------------------------------------------------------------------------------- flush: MLP gradients
@@ -721,6 +857,14 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   while (s0n < 5 && ldexpf(1.0f, -s0n) > g.step) ++s0n;       // lanes sharing a G0 node along the fast axis: 1/step
   a.steps0 = s0n;
   a.steps1 = s0n + 1 > 5 ? 5 : s0n + 1;
+  if (h->debug_flags & 8) {
+    if (!h->dbg_counters) {
+      e = cudaMalloc(&h->dbg_counters, 16 * 8);
+      if (e == cudaSuccess) e = cudaMemsetAsync(h->dbg_counters, 0, 16 * 8, st);
+      if (e != cudaSuccess) return (int)e;
+    }
+    a.prof = h->dbg_counters;
+  }
   auto kern = train_tc_kernel<FMT, METHOD>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TrainShape<METHOD>::SMEM);
   if (e != cudaSuccess) return (int)e;

@@ -45,3 +45,20 @@ torch.cuda.synchronize()
 ms, n = L.kernel_time_ms(dev)
 print(f"{prec}: step {s.elapsed_time(e) / steps:.4f} ms (GPU events), host issue {1e3 * (t1 - t0) / steps:.4f} ms/step, "
       f"train kernel {ms / n:.4f} ms, {nc * crop * crop / (s.elapsed_time(e) / steps * 1e-3) / 1e6:.0f} Msamples/s, loss {float(loss):.6f}")
+
+if "phases" in sys.argv:
+    # per-tile phase profile of the tensor-core training kernel as seen by thread 0 of every CTA (nic_debug_counters)
+    L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, 8)
+    tr.step(coord, tg, 0, noise=noise_arg)
+    L.debug_counters(dev)
+    for _ in range(5):
+        tr.step(coord, tg, 0, noise=noise_arg)
+    c = L.debug_counters(dev)
+    L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, 0)
+    names = ["gather", "mma L1", "gelu 1", "mma L2", "gelu 2", "mma L3", "loss/dz3", "mma dH2+D3", "dz2", "mma dH1+D2", "dz1",
+             "mma dX+D1", "scatter G1 (+rest)", "(wg1 gather)", "scatter G0"]
+    tiles = max(c[15], 1)
+    tot = sum(c[:13]) + c[14]
+    print(f"phase profile: {tiles} tiles, {tot / tiles:.0f} cycles per tile per CTA")
+    for i, nme in enumerate(names):
+        print(f"  {nme:12s} {c[i] / tiles:8.0f} cycles  {100.0 * c[i] / tot:5.1f} %")
