@@ -17,9 +17,11 @@
 //   backward: dH2 = dZ3 W3'           (1)   and  D3^T += [H2|1]^T dZ3 (8 MMAs, M=128 N=16 K=128: dW3'^T, db3 in row 64)
 //             dZ2 = dH2 * g2' -> DZ[16:80)
 //             dH1 = dZ2 W2'           (4)   and  D2 += DZ^T [H1|1]   (8: dW2', db2 in rows 16..79)
-//             dZ1 = dH1 * g1' -> DZ[16:80)
-//             dX  = dZ1 W1'           (4)   and  D1 += DZ^T X~       (8: dW1', db1 in rows 16..79)
+//             dZ1 = dH1 * g1' -> the H2 buffer, features [0:64) (H2 is dead by then; DZ is still read by the D2 batch)
+//             dX  = dZ1 W1'           (4)   and  D1 += dZ1^T X~      (8: dW1', db1 in rows 0..63)
 //             dX -> warp-aggregated red.global.add.v4.f32 into channel-last fp32 scratch grids (K4)
+//   The three weight-gradient batches are DEFERRED: issued behind the delta-propagation MMAs of their stage but not waited
+//   for — they run under the next epilogue / the scatter; the last one is awaited before the next tile overwrites X~.
 //   D1, D2, D3 (fp32, TMEM) accumulate over ALL tiles of the CTA and are flushed once per launch with atomics.
 //   Biases ride in K (a constant-1 feature); the 1/2 of GELU is folded into the next layer's weights; dz3 carries a
 //   power-of-two loss scale S so that f16 deltas stay normal; S and the 2/(N*Cout) of the MSE mean are applied at the flush.
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   uint8_t* sDZ = smem + TS::OFF_DZ;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TS::OFF_MISC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  uint64_t* mbar2 = mbar + 2;                     // completion of the LAST deferred batch of a tile (D1 += dZ1^T X~)
   float* sRed = reinterpret_cast<float*>(smem + TS::OFF_MISC + 32);      // [8] loss partials
 
   const int tid = threadIdx.x, warp = uniform_warp_index(), lane = tid & 31;     // warp: provably uniform (MMA issue)
@@ -243,7 +246,10 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   const int roff80 = (row >> 3) * TT_SG80 + (row & 7) * 16, roffx = (row >> 3) * SGX + (row & 7) * 16;
 
   if (warp == 0) tmem_alloc(tmem_slot, TS::TMEM);
-  if (tid == 0) mbar_init(mbar, 1);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar2, 1);
+  }
   {
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = tid; i < TS::WIMG / 16; i += TT_THREADS) dst[i] = __ldg(a.wimg + i);
@@ -286,7 +292,10 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     }
   };
   // hand the tensor core a batch of MMAs and wait for them
-  auto run_mmas = [&](auto&& issue) {
+  // `issue` is waited for; `deferred` (the weight-gradient MMAs, which nothing in the next stage reads) is issued behind
+  // it and runs under the next epilogue.  tcgen05.commit tracks ALL earlier MMAs of the issuing thread, so the next
+  // stage's wait also covers this stage's deferred batch; the last one of a tile commits to mbar2 (`last`).
+  auto run_mmas2 = [&](auto&& issue, auto&& deferred, bool last) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -295,20 +304,24 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         tc_fence_after();
         issue();
         tc_commit(mbar);
+        deferred();
+        if (last) tc_commit(mbar2);
       }
       __syncwarp();
     }
-    mbar_wait_sleep(mbar, phase);
+    mbar_wait(mbar, phase);
     phase ^= 1;
     tc_fence_after();
   };
-  // weight-gradient GEMM: Dacc[128 x 80] (+)= DZ^T (features x samples) . Bbuf (samples x 80 features)
-  auto issue_wgrad = [&](uint32_t dcol, uint32_t bbuf, uint32_t sgb, uint32_t idesc) {
+  auto run_mmas = [&](auto&& issue) { run_mmas2(issue, [] {}, false); };
+  // weight-gradient GEMM: Dacc[128 x 80] (+)= Abuf^T (features x samples) . Bbuf (samples x 80 features)
+  auto issue_wgrad = [&](uint32_t dcol, uint32_t abuf, uint32_t bbuf, uint32_t sgb, uint32_t idesc) {
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc)
-      mma_ss(tmem + dcol, make_smem_desc(aDZ + kc * 2 * TT_SG80, TT_SG80, 128),
+      mma_ss(tmem + dcol, make_smem_desc(abuf + kc * 2 * TT_SG80, TT_SG80, 128),
              make_smem_desc(bbuf + kc * 2 * sgb, sgb, 128), idesc, (tiles_done > 0 || kc > 0) ? 1u : 0u);
   };
+  uint32_t phase2 = 0;
 
   const unsigned ntiles = (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS);
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tiles_done) {
@@ -444,6 +457,10 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       // Pack to 16-byte chunks of 8 features -> X~ buffer, adding the in-kernel noise on the way: one Philox call
       // yields 16 bytes = the 8-bit uniforms of 16 features (two chunks).  (b - 127.5) * amp / 256 is built in packed
       // f16 (0x6400 | b = 1024 + b exactly) — 8 bits are far below what a 16-bit X~ resolves.
+      if (tiles_done > 0) {          // the previous tile's deferred D1 += dZ1^T X~ still reads X~ (and the H2 buffer)
+        mbar_wait_sleep(mbar2, phase2);
+        phase2 ^= 1;
+      }
       const bool gen = !a.noise && a.noise_amp > 0.f;
       const __half2 nsc = __float2half2_rn(a.noise_amp * (1.0f / 256.0f)), nhs = __float2half2_rn(a.noise_amp * (0.5f / 256.0f));
       const int fg0 = wg == 0 ? 0 : C0, nfg = wg == 0 ? C0 : TS::KG1 - C0;
@@ -579,21 +596,24 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     mark(6);
     // ------------------------------------------------------------------------------------------ backward
     // dH2 = dZ3 W3' (K = 16 output features) and D3^T += [H2 | 1]^T dZ3.
-    run_mmas([&] {
-      mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ, 128, TT_SG80), make_smem_desc(aW3, 128, WG16), ID_B64, 0);
-      // D3^T [H2 feature x output c] += [H2|1]^T (MN-major A, M = 128 aliased) . dZ3 (MN-major B, N = 16)
+    run_mmas2([&] { mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ, 128, TT_SG80), make_smem_desc(aW3, 128, WG16), ID_B64, 0); },
+              [&] {
+                // D3^T [H2 feature x output c] += [H2|1]^T (MN-major A, M = 128 aliased) . dZ3 (MN-major B, N = 16)
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc)
-        mma_ss(tmem + TT_COL_D3, make_smem_desc(aH2 + kc * 2 * TT_SG80, TT_SG80, 128),
-               make_smem_desc(aDZ + kc * 2 * TT_SG80, TT_SG80, 128), ID_G16, (tiles_done > 0 || kc > 0) ? 1u : 0u);
-    });
+                for (int kc = 0; kc < 8; ++kc)
+                  mma_ss(tmem + TT_COL_D3, make_smem_desc(aH2 + kc * 2 * TT_SG80, TT_SG80, 128),
+                         make_smem_desc(aDZ + kc * 2 * TT_SG80, TT_SG80, 128), ID_G16, (tiles_done > 0 || kc > 0) ? 1u : 0u);
+              },
+              false);
     mark(7);
 #pragma unroll
     for (int layer = 1; layer >= 0; --layer) {
       uint32_t acc[32];
       tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
       tc_wait_ld();
-      uint8_t* dstb = sDZ + roff80 + (2 + wg * 4) * 128;
+      // dZ2 -> DZ features [16, 80);  dZ1 -> the H2 buffer, features [0, 64) (H2 is dead once D3 has been accumulated, and
+      // DZ is still being read by the deferred D2 += dZ2^T [H1|1]).  H2's constant-1 feature 64 is left alone.
+      uint8_t* dstb = layer == 1 ? sDZ + roff80 + (2 + wg * 4) * 128 : sH2 + roff80 + (wg * 4) * 128;
 #pragma unroll
       for (int f = 0; f < 4; ++f) {
         uint32_t dp[4];
@@ -607,23 +627,25 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       }
       mark(layer == 1 ? 8 : 10);
       if (layer == 1) {
-        run_mmas([&] {      // dH1 = dZ2 W2'  and  D2 += DZ^T [H1 | 1]
+        run_mmas2(      // dH1 = dZ2 W2'  and (deferred)  D2 += DZ^T [H1 | 1]   (rows 16..79 = hidden units)
+            [&] {
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc)
-            mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
-                   make_smem_desc(aW2 + kc * 256, 128, WG64), ID_B64, kc > 0);
-          issue_wgrad(TT_COL_D2, aH1, TT_SG80, ID_G80);
-        });
+              for (int kc = 0; kc < 4; ++kc)
+                mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
+                       make_smem_desc(aW2 + kc * 256, 128, WG64), ID_B64, kc > 0);
+            },
+            [&] { issue_wgrad(TT_COL_D2, aDZ, aH1, TT_SG80, ID_G80); }, false);
       } else {
-        run_mmas([&] {      // dX = dZ1 W1' (grid columns only)  and  D1 += DZ^T X~
-          if (a.dgs0) {
+        run_mmas2(      // dX = dZ1 W1' (grid columns only)  and (deferred)  D1 += dZ1^T X~   (rows 0..63 = hidden units)
+            [&] {
+              if (a.dgs0) {
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc)
-              mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
-                     make_smem_desc(aW1 + kc * 256, 128, WG64), ID_BDX, kc > 0);
-          }
-          issue_wgrad(TT_COL_D1, aX, SGX, ID_GX);
-        });
+                for (int kc = 0; kc < 4; ++kc)
+                  mma_ss(tmem + TT_COL_D, make_smem_desc(aH2 + 2 * kc * 128, 128, TT_SG80),
+                         make_smem_desc(aW1 + kc * 256, 128, WG64), ID_BDX, kc > 0);
+              }
+            },
+            [&] { issue_wgrad(TT_COL_D1, aH2, aX, SGX, ID_GX); }, true);
       }
       mark(layer == 1 ? 9 : 11);
     }
@@ -665,14 +687,14 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
 #pragma unroll
           for (int i = 0; i < 2 * NG0; ++i)
             if (i < 2 * ng0) o[i] = __shfl_down_sync(0xffffffffu, pk[i], 1 << s);
-          if (si0.same & (1u << s)) {
+          const uint32_t m = (si0.same >> s) & 1u ? 0xffffffffu : 0u;      // + 0 where the partner is another node
 #pragma unroll
-            for (int i = 0; i < 2 * NG0; ++i)
-              if (i < 2 * ng0) {
-                __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&pk[i]), *reinterpret_cast<const __half2*>(&o[i]));
-                pk[i] = *reinterpret_cast<uint32_t*>(&r);
-              }
-          }
+          for (int i = 0; i < 2 * NG0; ++i)
+            if (i < 2 * ng0) {
+              const uint32_t om = o[i] & m;
+              __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&pk[i]), *reinterpret_cast<const __half2*>(&om));
+              pk[i] = *reinterpret_cast<uint32_t*>(&r);
+            }
         }
       }
       mark(14);
@@ -706,12 +728,12 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
           uint32_t o[2 * NG1];
 #pragma unroll
           for (int i = 0; i < 2 * NG1; ++i) o[i] = __shfl_down_sync(0xffffffffu, pk1[i], 1 << s);
-          if (si1.same & (1u << s)) {
+          const uint32_t m = (si1.same >> s) & 1u ? 0xffffffffu : 0u;
 #pragma unroll
-            for (int i = 0; i < 2 * NG1; ++i) {
-              __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&pk1[i]), *reinterpret_cast<const __half2*>(&o[i]));
-              pk1[i] = *reinterpret_cast<uint32_t*>(&r);
-            }
+          for (int i = 0; i < 2 * NG1; ++i) {
+            const uint32_t om = o[i] & m;
+            __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&pk1[i]), *reinterpret_cast<const __half2*>(&om));
+            pk1[i] = *reinterpret_cast<uint32_t*>(&r);
           }
         }
       }
@@ -729,13 +751,15 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
   }
   // -------------------------------------------------------------------------------------------- flush: MLP gradients
+  if (tiles_done > 0) mbar_wait_sleep(mbar2, phase2);       // the last tile's deferred D1 batch (and everything before it)
   __syncthreads();
   tc_fence_after();
   if (tiles_done > 0) {
     const float fs = a.flush_scale;
     // D3^T: rows 0..63 = hidden unit h, row 64 = the bias feature; columns c < cout: dW3'[c][h] (W3' = W3/2) / db3[c]
-    // D2 / D1: rows 16..79 = hidden unit j = row - 16; D2 columns 0..63 = dW2'[j][k] (W2' = W2/2), 64 = db2[j];
-    //          D1 columns 0..72 = dW1[j][cin], 73 = db1[j].  Warp-group 0 reads columns [0,48), 1 reads [48,80).
+    // D2: rows 16..79 = hidden unit j = row - 16; columns 0..63 = dW2'[j][k] (W2' = W2/2), 64 = db2[j];
+    // D1: rows 0..63 = hidden unit j (dZ1 lives in the H2 buffer's features 0..63); columns 0..72 = dW1[j][cin], 73 = db1[j].
+    // Warp-group 0 reads columns [0,48), 1 reads [48,80).
     if (wg == 0) {
       uint32_t acc[16];
       tmem_ld16(tmem + TT_COL_D3 + lane_base, acc);
@@ -762,15 +786,15 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         if (i >= cw) continue;
         const int col = c0 + i;
         const float v = __uint_as_float(acc[i]) * fs;
-        if (row >= 16 && row < 80) {
-          const int j = row - 16;
-          if (which == 1) {
+        if (which == 1) {
+          if (row >= 16 && row < 80) {
+            const int j = row - 16;
             if (col < 64) atomicAdd(a.gm.w2 + j * 64 + col, 0.5f * v);
             else if (col == 64) atomicAdd(a.gm.b2 + j, v);
-          } else {
-            if (col < CIN) atomicAdd(a.gm.w1 + j * CIN + col, v);
-            else if (col == CIN) atomicAdd(a.gm.b1 + j, v);
           }
+        } else if (row < 64) {
+          if (col < CIN) atomicAdd(a.gm.w1 + row * CIN + col, v);
+          else if (col == CIN) atomicAdd(a.gm.b1 + row, v);
         }
       }
     }
