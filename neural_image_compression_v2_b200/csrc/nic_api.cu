@@ -87,6 +87,7 @@ int nic_destroy(NicHandle* h) {
   if (h->tc_weights) cudaFree(h->tc_weights);
   if (h->tc_shadow) cudaFree(h->tc_shadow);
   if (h->tc_gscratch) cudaFree(h->tc_gscratch);
+  if (h->tc_partials) cudaFree(h->tc_partials);
   if (h->dbg_counters) cudaFree(h->dbg_counters);
   if (h->adam_desc) cudaFree(h->adam_desc);
   for (int i = 0; i < 2 * NIC_MAX_TIMED; ++i)

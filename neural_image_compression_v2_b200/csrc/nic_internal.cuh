@@ -29,6 +29,8 @@ struct Handle {
   size_t tc_shadow_bytes;
   void* tc_gscratch;         // channel-last fp32 grid-gradient scratch of the tensor-core training step (kept zero)
   size_t tc_gscratch_bytes;
+  void* tc_partials;         // per-CTA MLP-gradient partial sums of the tensor-core training step
+  size_t tc_partials_bytes;
   int disable_fast2d;        // testing knob: force the general tensor-core kernel
   int src_code_bits;         // > 0 while a nic_decode_codes call is in flight: grid pointers are uint8 codes of that width
   int reuse_prepared;        // NIC_OPT_REUSE_PREPARED

@@ -74,9 +74,9 @@ __host__ __device__ constexpr uint32_t tt_idesc(int fmt, int M, int N, int a_mn,
 //   W2' [64 x 80]: k < 64: W2[n][k]/2; k = 64: b2[n]
 //   W3' [16 x 80]: n < cout: k < 64: W3[n][k]/2; k = 64: b3[n]
 template <int FMT>
-__global__ void pack_train_weights_kernel(MlpDev m, int K1, uint16_t* __restrict__ img) {
-  const int n1 = 64 * K1, n2 = 64 * 80, n3 = 16 * 80;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void pack_train_weights_item(int i, const MlpDev& m, int K1, uint16_t* __restrict__ img) {
+  const int n1 = 64 * K1, n2 = 64 * 80;
+  {
     int which = i < n1 ? 0 : (i < n1 + n2 ? 1 : 2);
     int local = which == 0 ? i : (which == 1 ? i - n1 : i - n1 - n2);
     int nrows = which == 2 ? 16 : 64;
@@ -117,34 +117,28 @@ __global__ void __launch_bounds__(256) grad_relayout_add_kernel(float* __restric
 
 // Small-grid variants (one thread per element): the tiled kernels above are bandwidth-shaped and take tens of
 // microseconds of pure latency on a [12, 129, 129] grid, which is a third of a 0.36 ms training step.
-__global__ void __launch_bounds__(256) grad_add_small_kernel(float* __restrict__ s, float* __restrict__ dg, int C, int nx, int ny,
-                                                             int nz, float scale) {
-  const long long total = (long long)C * nx * ny * nz;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);                        // s is [x][y][z][C]: i walks it linearly (coalesced read + zero)
-    long long node = i / C;
-    const int z = (int)(node % nz);
-    node /= nz;
-    const int y = (int)(node % ny), x = (int)(node / ny);
-    const float v = s[i];
-    if (v != 0.f) {
-      dg[(((size_t)c * nz + z) * ny + y) * nx + x] += scale * v;      // dg is [C][z][y][x]
-      s[i] = 0.f;
-    }
+__device__ __forceinline__ void grad_add_small_item(long long i, float* __restrict__ s, float* __restrict__ dg, int C, int nx, int ny,
+                                                    int nz, float scale) {
+  const int c = (int)(i % C);                        // s is [x][y][z][C]: i walks it linearly (coalesced read + zero)
+  long long node = i / C;
+  const int z = (int)(node % nz);
+  node /= nz;
+  const int y = (int)(node % ny), x = (int)(node / ny);
+  const float v = s[i];
+  if (v != 0.f) {
+    dg[(((size_t)c * nz + z) * ny + y) * nx + x] += scale * v;      // dg is [C][z][y][x]
+    s[i] = 0.f;
   }
 }
 template <int FMT>
-__global__ void __launch_bounds__(256) relayout_small_kernel(const float* __restrict__ g, uint16_t* __restrict__ sh, int C, int nx,
-                                                             int ny, int nz) {
-  const long long total = (long long)C * nx * ny * nz;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long node = i / C;
-    const int z = (int)(node % nz);
-    node /= nz;
-    const int y = (int)(node % ny), x = (int)(node / ny);
-    sh[i] = to16<FMT>(__ldg(g + (((size_t)c * nz + z) * ny + y) * nx + x));
-  }
+__device__ __forceinline__ void relayout_small_item(long long i, const float* __restrict__ g, uint16_t* __restrict__ sh, int C, int nx,
+                                                    int ny, int nz) {
+  const int c = (int)(i % C);
+  long long node = i / C;
+  const int z = (int)(node % nz);
+  node /= nz;
+  const int y = (int)(node % ny), x = (int)(node / ny);
+  sh[i] = to16<FMT>(__ldg(g + (((size_t)c * nz + z) * ny + y) * nx + x));
 }
 
 // (h', g') for a pair: h' = 2 gelu_tanh(x) = x + x t,  g' = d h'/dx = (1 + t) + x (1 - t^2)(c1 + 3 c2 x^2),
@@ -219,6 +213,8 @@ struct TrainArgs {
   float flush_scale;          // 2 / (N_global * cout) / S
   int cout;
   int steps0, steps1;         // segmented-reduction depths of the scatter (lanes sharing a G0 / G1 node)
+  float* partials;            // [gridDim.x][pstride]: this CTA's MLP-gradient sums (w1 | b1 | w2 | b2 | w3 | b3), plain stores
+  int pstride;
   unsigned long long* prof;   // NULL, or 16 device counters: cycles per phase seen by thread 0 (nic_debug_counters)
 };
 
@@ -284,6 +280,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
 
   // phase profile (debug): thread 0 adds the cycles since its previous mark to counter `i`
   long long prof_t = a.prof ? clock64() : 0;
+  const long long prof_start = prof_t;
   auto mark = [&](int i) {
     if (a.prof && tid == 0) {
       const long long t = clock64();
@@ -335,7 +332,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         if (c < a.cout)       // volatile: keep the load HERE (the compiler would sink it to its use, 2,000 cycles later)
           asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(tgt[c]) : "l"(a.targets + (size_t)n * a.cout + c));
     }
-    if (a.prof && (tid == 0 || tid == 128)) prof_t = clock64();
+    if (a.prof && tid == 0) prof_t = clock64();
     // ------------------------------------------------------------------------------------------ gather + noise -> X~
     Texel t = texel_of_fast(g, nc, a.origins);
     AxisCoord ax[3];
@@ -506,7 +503,6 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       }
     }
     mark(0);
-    if (a.prof && tid == 128) atomicAdd(a.prof + 13, (unsigned long long)(clock64() - prof_t));     // warp-group 1's gather
     // ------------------------------------------------------------------------------------------ forward
     // d h'/d z of this thread's 32 hidden columns, layers 1 and 2.  The two layer loops below are FULLY unrolled: with a
     // rolled loop (layer a run-time value) nvcc 12.9 mis-compiled the conditional writes into these register arrays.
@@ -697,7 +693,6 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
             }
         }
       }
-      mark(14);
       if (live && si0.head) {
 #pragma unroll
         for (int gi = 0; gi < NG0; ++gi) {
@@ -751,11 +746,22 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
   }
   // -------------------------------------------------------------------------------------------- flush: MLP gradients
+  if (a.prof && tid == 0) prof_t = clock64();
   if (tiles_done > 0) mbar_wait_sleep(mbar2, phase2);       // the last tile's deferred D1 batch (and everything before it)
   __syncthreads();
   tc_fence_after();
   if (tiles_done > 0) {
+    // Every CTA writes its sums to its OWN slice with plain stores (each element exactly once); mlp_grad_reduce_kernel
+    // adds the slices up in a fixed order.  (296 CTAs x 9,091 atomicAdds onto the same 9,091 addresses took a fifth of
+    // the kernel, and made the MLP gradients depend on the order of arrival.)
     const float fs = a.flush_scale;
+    float* part = a.partials + (size_t)blockIdx.x * a.pstride;
+    float* p_w1 = part;
+    float* p_b1 = p_w1 + 64 * CIN;
+    float* p_w2 = p_b1 + 64;
+    float* p_b2 = p_w2 + 64 * 64;
+    float* p_w3 = p_b2 + 64;
+    float* p_b3 = p_w3 + 64 * a.cout;
     // D3^T: rows 0..63 = hidden unit h, row 64 = the bias feature; columns c < cout: dW3'[c][h] (W3' = W3/2) / db3[c]
     // D2: rows 16..79 = hidden unit j = row - 16; columns 0..63 = dW2'[j][k] (W2' = W2/2), 64 = db2[j];
     // D1: rows 0..63 = hidden unit j (dZ1 lives in the H2 buffer's features 0..63); columns 0..72 = dW1[j][cin], 73 = db1[j].
@@ -768,8 +774,8 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       for (int c = 0; c < 16; ++c)
         if (c < a.cout) {
           const float v = __uint_as_float(acc[c]) * fs;
-          if (row < 64) atomicAdd(a.gm.w3 + c * 64 + row, 0.5f * v);
-          else if (row == 64) atomicAdd(a.gm.b3 + c, v);
+          if (row < 64) p_w3[c * 64 + row] = 0.5f * v;
+          else if (row == 64) p_b3[c] = v;
         }
     }
     for (int which = 1; which < 3; ++which) {
@@ -789,12 +795,12 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         if (which == 1) {
           if (row >= 16 && row < 80) {
             const int j = row - 16;
-            if (col < 64) atomicAdd(a.gm.w2 + j * 64 + col, 0.5f * v);
-            else if (col == 64) atomicAdd(a.gm.b2 + j, v);
+            if (col < 64) p_w2[j * 64 + col] = 0.5f * v;
+            else if (col == 64) p_b2[j] = v;
           }
         } else if (row < 64) {
-          if (col < CIN) atomicAdd(a.gm.w1 + row * CIN + col, v);
-          else if (col == CIN) atomicAdd(a.gm.b1 + row, v);
+          if (col < CIN) p_w1[row * CIN + col] = v;
+          else if (col == CIN) p_b1[row] = v;
         }
       }
     }
@@ -809,7 +815,86 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   }
   tc_fence_before();
   __syncthreads();
+  mark(13);                    // the flush, once per CTA
+  if (a.prof && tid == 0) atomicAdd(a.prof + 14, (unsigned long long)(clock64() - prof_start));      // CTA lifetime
   if (warp == 0) tmem_dealloc(tmem, TS::TMEM);
+}
+
+// gm.* += sum over the CTAs' slices, in slice order (deterministic).  One block = 32 elements x 8 slice lanes.
+__device__ __forceinline__ void mlp_grad_reduce_block(int block, const float* __restrict__ part, int nparts, int pstride,
+                                                      const MlpGradDev& gm, int cin, int cout) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = block * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < pstride) {
+    int c = ty;
+    for (; c + 24 < nparts; c += 32) {
+      s0 += part[(size_t)c * pstride + i];
+      s1 += part[(size_t)(c + 8) * pstride + i];
+      s2 += part[(size_t)(c + 16) * pstride + i];
+      s3 += part[(size_t)(c + 24) * pstride + i];
+    }
+    for (; c < nparts; c += 8) s0 += part[(size_t)c * pstride + i];
+  }
+  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && i < pstride) {
+    float s = red[0][tx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][tx];
+    const int n_w1 = 64 * cin, o_b1 = n_w1, o_w2 = o_b1 + 64, o_b2 = o_w2 + 4096, o_w3 = o_b2 + 64, o_b3 = o_w3 + 64 * cout;
+    float* dst = i < o_b1 ? gm.w1 + i : (i < o_w2 ? gm.b1 + (i - o_b1) : (i < o_b2 ? gm.w2 + (i - o_w2) : (i < o_w3 ? gm.b2 + (i - o_b2)
+                 : (i < o_b3 ? gm.w3 + (i - o_w3) : gm.b3 + (i - o_b3)))));
+    *dst += s;
+  }
+}
+
+// The small kernels around train_tc_kernel, fused: a training step at config 1 is 0.16 ms of train_tc_kernel, and every
+// extra launch costs 5-8 us of latency on a [12, 129, 129] grid.
+//   prep   : 16-bit channel-last shadows of both grids + the packed weight images         (before train_tc_kernel)
+//   finish : grid-gradient scratch -> the caller's channel-major gradients (+ re-zero), MLP partial sums -> gm  (after)
+struct TrainSideArgs {
+  const float* g0;            // prep: source grids [C][z][y][x]
+  const float* g1;
+  uint16_t* s0;               // prep: shadows [x][y][z][C]
+  uint16_t* s1;
+  uint16_t* img;              // prep: weight images
+  MlpDev m;
+  int K1;
+  float* gs0;                 // finish: channel-last fp32 scratch (NULL: grids frozen)
+  float* gs1;
+  float* dg0;
+  float* dg1;
+  float scale;
+  const float* part;          // finish: per-CTA MLP partial sums
+  int nparts, pstride;
+  MlpGradDev gm;
+  int C, n0[3], n1[3];        // nodes per axis (x, y, z), z = 1 in 2-D
+  long long t0, t1;           // elements of G0 / G1 handled here (0: the tiled kernels do the grids)
+  int nb_items;               // finish: blocks [0, nb_items) walk the grid elements, the rest reduce the partial sums
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(256) train_prep_kernel(TrainSideArgs p) {
+  const long long nw = 64 * p.K1 + 64 * 80 + 16 * 80, total = p.t0 + p.t1 + nw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < p.t0) relayout_small_item<FMT>(i, p.g0, p.s0, p.C, p.n0[0], p.n0[1], p.n0[2]);
+    else if (i < p.t0 + p.t1) relayout_small_item<FMT>(i - p.t0, p.g1, p.s1, p.C, p.n1[0], p.n1[1], p.n1[2]);
+    else pack_train_weights_item<FMT>((int)(i - p.t0 - p.t1), p.m, p.K1, p.img);
+  }
+}
+
+__global__ void __launch_bounds__(256) train_finish_kernel(TrainSideArgs p) {
+  if ((int)blockIdx.x < p.nb_items) {
+    const long long total = p.t0 + p.t1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)p.nb_items * blockDim.x) {
+      if (i < p.t0) grad_add_small_item(i, p.gs0, p.dg0, p.C, p.n0[0], p.n0[1], p.n0[2], p.scale);
+      else grad_add_small_item(i - p.t0, p.gs1, p.dg1, p.C, p.n1[0], p.n1[1], p.n1[2], p.scale);
+    }
+  } else {
+    mlp_grad_reduce_block((int)blockIdx.x - p.nb_items, p.part, p.nparts, p.pstride, p.gm, p.m.cin, p.m.cout);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
@@ -842,19 +927,34 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
     gs1 = (float*)((uint8_t*)h->tc_gscratch + ((gb0 + 255) & ~(size_t)255));
   }
   cudaError_t e = cudaSuccess;
-  const bool small = nodes0 <= (1 << 20) || g.dim == 3;        // the tiled relayout-add kernel is 2-D only
-  const int nz0 = g.dim == 3 ? g.n0[2] : 1, nz1 = g.dim == 3 ? g.n1[2] : 1;
-  if (small) {
-    relayout_small_kernel<FMT><<<(int)((nodes0 * g.C + 255) / 256), 256, 0, st>>>(g0, s0, g.C, g.n0[0], g.n0[1], nz0);
-    relayout_small_kernel<FMT><<<(int)((nodes1 * g.C + 255) / 256), 256, 0, st>>>(g1, s1, g.C, g.n1[0], g.n1[1], nz1);
-    h->launches += 2;
-  } else {
+  const bool small = nodes0 <= (1 << 20) || g.dim == 3;        // the tiled relayout / relayout-add kernels are 2-D only
+  TrainSideArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.g0 = g0;
+  sa.g1 = g1;
+  sa.s0 = s0;
+  sa.s1 = s1;
+  sa.img = (uint16_t*)h->tc_weights;
+  sa.m = m;
+  sa.K1 = TrainShape<METHOD>::K1;
+  sa.C = g.C;
+  for (int d = 0; d < 3; ++d) {
+    sa.n0[d] = d < g.dim ? g.n0[d] : 1;
+    sa.n1[d] = d < g.dim ? g.n1[d] : 1;
+  }
+  sa.t0 = small ? nodes0 * g.C : 0;
+  sa.t1 = small ? nodes1 * g.C : 0;
+  if (!small) {
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
     if (e != cudaSuccess) return (int)e;
     e = (cudaError_t)launch_relayout<FMT>(h, g, g1, g.n1, s1, st);
     if (e != cudaSuccess) return (int)e;
   }
-  pack_train_weights_kernel<FMT><<<16, 256, 0, st>>>(m, TrainShape<METHOD>::K1, (uint16_t*)h->tc_weights);
+  {
+    const long long items = sa.t0 + sa.t1 + 64 * sa.K1 + 64 * 80 + 16 * 80;
+    const long long nb = (items + 255) / 256, cap = 8ll * h->sms;
+    train_prep_kernel<FMT><<<(int)(nb < cap ? nb : cap), 256, 0, st>>>(sa);
+  }
   h->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
@@ -896,6 +996,10 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   long long ntiles = (g.N + TT_ROWS - 1) / TT_ROWS;
   const long long cap = (long long)TrainShape<METHOD>::CTAS * h->sms;        // resident CTAs (two per SM when K1 = 80)
   int grid = (int)(ntiles < cap ? ntiles : cap);
+  a.pstride = 64 * m.cin + 64 + 64 * 64 + 64 + 64 * m.cout + m.cout;
+  rc = ensure_scratch(&h->tc_partials, &h->tc_partials_bytes, (size_t)grid * a.pstride * sizeof(float));
+  if (rc) return rc;
+  a.partials = (float*)h->tc_partials;
   {
     KernelTimer timer(h, st);
     kern<<<grid, TT_THREADS, TrainShape<METHOD>::SMEM, st>>>(g, a);
@@ -903,18 +1007,30 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   h->launches++;
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  if (dg0) {
-    const float sc = 2.0f * grad_scale / TT_LOSS_SCALE;
-    if (small) {
-      grad_add_small_kernel<<<(int)((nodes0 * g.C + 255) / 256), 256, 0, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], nz0, sc);
-      grad_add_small_kernel<<<(int)((nodes1 * g.C + 255) / 256), 256, 0, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], nz1, sc);
-    } else {
-      size_t smem = (size_t)g.C * 32 * 33 * sizeof(float);
-      e = cudaFuncSetAttribute(grad_relayout_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      grad_relayout_add_kernel<<<dim3((g.n0[0] + 31) / 32, (g.n0[1] + 31) / 32), 256, smem, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sc);
-      grad_relayout_add_kernel<<<dim3((g.n1[0] + 31) / 32, (g.n1[1] + 31) / 32), 256, smem, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sc);
-    }
+  sa.gs0 = gs0;
+  sa.gs1 = gs1;
+  sa.dg0 = dg0;
+  sa.dg1 = dg1;
+  sa.scale = 2.0f * grad_scale / TT_LOSS_SCALE;
+  sa.part = a.partials;
+  sa.nparts = grid;
+  sa.pstride = a.pstride;
+  sa.gm = gm;
+  if (!(dg0 && small)) sa.t0 = sa.t1 = 0;                       // frozen grids, or the tiled kernels below do them
+  {
+    const long long nb = (sa.t0 + sa.t1 + 255) / 256, cap = 8ll * h->sms;
+    sa.nb_items = (int)(nb < cap ? nb : cap);
+    train_finish_kernel<<<sa.nb_items + (a.pstride + 31) / 32, 256, 0, st>>>(sa);
+  }
+  h->launches++;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (dg0 && !small) {
+    size_t smem = (size_t)g.C * 32 * 33 * sizeof(float);
+    e = cudaFuncSetAttribute(grad_relayout_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    grad_relayout_add_kernel<<<dim3((g.n0[0] + 31) / 32, (g.n0[1] + 31) / 32), 256, smem, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sa.scale);
+    grad_relayout_add_kernel<<<dim3((g.n1[0] + 31) / 32, (g.n1[1] + 31) / 32), 256, smem, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sa.scale);
     h->launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

@@ -56,9 +56,9 @@ if "phases" in sys.argv:
     c = L.debug_counters(dev)
     L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, 0)
     names = ["gather", "mma L1", "gelu 1", "mma L2", "gelu 2", "mma L3", "loss/dz3", "mma dH2+D3", "dz2", "mma dH1+D2", "dz1",
-             "mma dX+D1", "scatter G1 (+rest)", "(wg1 gather)", "scatter G0"]
+             "mma dX+D1", "scatter", "flush (x tiles/CTA)", "CTA lifetime (x tiles/CTA)"]
     tiles = max(c[15], 1)
-    tot = sum(c[:13]) + c[14]
+    tot = sum(c[:13])
     print(f"phase profile: {tiles} tiles, {tot / tiles:.0f} cycles per tile per CTA")
     for i, nme in enumerate(names):
         print(f"  {nme:12s} {c[i] / tiles:8.0f} cycles  {100.0 * c[i] / tot:5.1f} %")
