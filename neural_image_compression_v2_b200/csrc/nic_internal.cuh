@@ -52,6 +52,28 @@ struct Handle {
 #define NIC_MAX_TIMED 256
 
 // Brackets the dominant kernel of a call with events when NIC_OPT_TIME_KERNELS is on (no-op otherwise).
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still running (after every CTA of the predecessor has called pdl_launch_dependents() or exited); it must call
+// pdl_wait() before touching anything the predecessor writes.  Hides the launch latency between the small dependent
+// kernels of a training step.  Both calls are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 struct KernelTimer {
   Handle* h;
   cudaStream_t st;

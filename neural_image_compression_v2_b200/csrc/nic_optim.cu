@@ -2,6 +2,8 @@
 // Reference: torch.optim.Adam as configured at Projects/image_compression.py:361-365, fp_quantize_clamp
 // (Projects/fp_def.py:227-232) and the quantiser family of Projects/models.py:29-71.
 // HBM-bound elementwise work: 28 B/param for Adam (read p,g,m,v; write p,m,v), vectorised 16-byte accesses.
+#include <cmath>
+
 #include "nic_internal.cuh"
 
 namespace nic {
@@ -9,6 +11,8 @@ namespace nic {
 #define NIC_ADAM_BATCH 24
 struct AdamBatch {
   NicAdamTensor t[NIC_ADAM_BATCH];
+  float step_size[NIC_ADAM_BATCH];     // lr / (1 - beta1^t) and sqrt(1 - beta2^t): evaluated in double ON THE HOST, as torch does
+  float bc2_sqrt[NIC_ADAM_BATCH];      // (a double pow() per thread made this kernel 11 us for 260 k parameters)
   int count;
   float beta1, beta2, eps, grad_scale;
   int zero_grad;
@@ -29,16 +33,13 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b) {
+  pdl_wait();                    // launched programmatically behind the kernel that produced the gradients
   if (b.loss_sum && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     b.loss_out[0] = b.loss_sum[0] * b.loss_scale;
     b.loss_sum[0] = 0.f;
   }
   const NicAdamTensor& t = b.t[blockIdx.y];
-  // bias corrections in double on every thread is cheap next to the memory traffic and keeps torch's values
-  const double bc1 = 1.0 - pow((double)b.beta1, (double)t.t);
-  const double bc2 = 1.0 - pow((double)b.beta2, (double)t.t);
-  const float step_size = (float)((double)t.lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  const float step_size = b.step_size[blockIdx.y], bc2_sqrt = b.bc2_sqrt[blockIdx.y];
   const long long n4 = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0) ? t.numel / 4 : 0;
   float4* p4 = reinterpret_cast<float4*>(t.p);
   float4* g4 = reinterpret_cast<float4*>(t.g);
@@ -74,15 +75,18 @@ int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1,
     long long maxn = 0;
     for (int i = 0; i < b.count; ++i) {
       b.t[i] = tensors[base + i];
+      const double bc1 = 1.0 - pow((double)beta1, (double)b.t[i].t), bc2 = 1.0 - pow((double)beta2, (double)b.t[i].t);
+      b.step_size[i] = (float)((double)b.t[i].lr / bc1);
+      b.bc2_sqrt[i] = (float)sqrt(bc2);
       if (b.t[i].numel > maxn) maxn = b.t[i].numel;
     }
     if (maxn == 0) continue;
     long long blocks = (maxn / 4 + 255) / 256 + 1;
     long long cap = (long long)h->sms * 8;
     dim3 grid((unsigned)(blocks > cap ? cap : blocks), (unsigned)b.count);
-    adam_kernel<<<grid, 256, 0, st>>>(b);
+    cudaError_t e = launch_pdl(adam_kernel, grid, dim3(256), 0, st, b);
     h->launches++;
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
   }
   return NIC_OK;

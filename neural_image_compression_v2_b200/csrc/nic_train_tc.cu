@@ -119,12 +119,11 @@ __global__ void __launch_bounds__(256) grad_relayout_add_kernel(float* __restric
 // microseconds of pure latency on a [12, 129, 129] grid, which is a third of a 0.36 ms training step.
 __device__ __forceinline__ void grad_add_small_item(long long i, float* __restrict__ s, float* __restrict__ dg, int C, int nx, int ny,
                                                     int nz, float scale) {
-  const int c = (int)(i % C);                        // s is [x][y][z][C]: i walks it linearly (coalesced read + zero)
-  long long node = i / C;
-  const int z = (int)(node % nz);
-  node /= nz;
-  const int y = (int)(node % ny), x = (int)(node / ny);
-  const float v = s[i];
+  const float v = s[i];                              // s is [x][y][z][C]: i walks it linearly (coalesced read + zero)
+  if (v == 0.f) return;
+  const unsigned u = (unsigned)i, node = u / 12u, c = u - node * 12u;      // C == 12 on this path; < 2^32 elements (launcher)
+  const unsigned nyz = node / (unsigned)nz, z = node - nyz * (unsigned)nz;
+  const unsigned x = nyz / (unsigned)ny, y = nyz - x * (unsigned)ny;
   if (v != 0.f) {
     dg[(((size_t)c * nz + z) * ny + y) * nx + x] += scale * v;      // dg is [C][z][y][x]
     s[i] = 0.f;
@@ -133,11 +132,9 @@ __device__ __forceinline__ void grad_add_small_item(long long i, float* __restri
 template <int FMT>
 __device__ __forceinline__ void relayout_small_item(long long i, const float* __restrict__ g, uint16_t* __restrict__ sh, int C, int nx,
                                                     int ny, int nz) {
-  const int c = (int)(i % C);
-  long long node = i / C;
-  const int z = (int)(node % nz);
-  node /= nz;
-  const int y = (int)(node % ny), x = (int)(node / ny);
+  const unsigned u = (unsigned)i, node = u / 12u, c = u - node * 12u;      // C == 12 on this path; < 2^32 elements (launcher)
+  const unsigned nyz = node / (unsigned)nz, z = node - nyz * (unsigned)nz;
+  const unsigned x = nyz / (unsigned)ny, y = nyz - x * (unsigned)ny;
   sh[i] = to16<FMT>(__ldg(g + (((size_t)c * nz + z) * ny + y) * nx + x));
 }
 
@@ -247,11 +244,12 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     mbar_init(mbar2, 1);
   }
   {
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < TS::WIMG / 16; i += TT_THREADS) dst[i] = __ldg(a.wimg + i);
     // zero the activation / delta buffers once (padding features must be finite), then the constant-1 bias features
     uint4* act = reinterpret_cast<uint4*>(smem + TS::OFF_X);
     for (int i = tid; i < (TS::XBYTES + 3 * TT_ACT + 1024) / 16; i += TT_THREADS) act[i] = make_uint4(0, 0, 0, 0);
+    pdl_wait();                  // everything above overlaps the tail of train_prep_kernel; its outputs are read from here on
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < TS::WIMG / 16; i += TT_THREADS) dst[i] = __ldg(a.wimg + i);
   }
   __syncthreads();
   if (wg == 0) {
@@ -746,6 +744,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
   }
   // -------------------------------------------------------------------------------------------- flush: MLP gradients
+  pdl_launch_dependents();       // train_finish_kernel may be scheduled now; it waits for this grid to complete
   if (a.prof && tid == 0) prof_t = clock64();
   if (tiles_done > 0) mbar_wait_sleep(mbar2, phase2);       // the last tile's deferred D1 batch (and everything before it)
   __syncthreads();
@@ -820,33 +819,33 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   if (warp == 0) tmem_dealloc(tmem, TS::TMEM);
 }
 
-// gm.* += sum over the CTAs' slices, in slice order (deterministic).  One block = 32 elements x 8 slice lanes.
+// gm.* += sum over the CTAs' slices, in a fixed order (deterministic).  One block of 256 threads = 32 elements x 8 slice
+// lanes, eight independent loads in flight per thread (the slices are L2-resident: just written).
+constexpr int TF_THREADS = 256, TF_LANES = TF_THREADS / 32;
 __device__ __forceinline__ void mlp_grad_reduce_block(int block, const float* __restrict__ part, int nparts, int pstride,
                                                       const MlpGradDev& gm, int cin, int cout) {
-  __shared__ float red[8][33];
+  __shared__ float red[TF_LANES][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i = block * 32 + tx;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float s = 0.f;
   if (i < pstride) {
-    int c = ty;
-    for (; c + 24 < nparts; c += 32) {
-      s0 += part[(size_t)c * pstride + i];
-      s1 += part[(size_t)(c + 8) * pstride + i];
-      s2 += part[(size_t)(c + 16) * pstride + i];
-      s3 += part[(size_t)(c + 24) * pstride + i];
+    for (int c0 = ty; c0 < nparts; c0 += 8 * TF_LANES) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = c0 + k * TF_LANES < nparts ? part[(size_t)(c0 + k * TF_LANES) * pstride + i] : 0.f;
+      s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
-    for (; c < nparts; c += 8) s0 += part[(size_t)c * pstride + i];
   }
-  red[ty][tx] = (s0 + s1) + (s2 + s3);
+  red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && i < pstride) {
-    float s = red[0][tx];
+    float t = 0.f;
 #pragma unroll
-    for (int k = 1; k < 8; ++k) s += red[k][tx];
+    for (int k = 0; k < TF_LANES; ++k) t += red[k][tx];
     const int n_w1 = 64 * cin, o_b1 = n_w1, o_w2 = o_b1 + 64, o_b2 = o_w2 + 4096, o_w3 = o_b2 + 64, o_b3 = o_w3 + 64 * cout;
     float* dst = i < o_b1 ? gm.w1 + i : (i < o_w2 ? gm.b1 + (i - o_b1) : (i < o_b2 ? gm.w2 + (i - o_w2) : (i < o_w3 ? gm.b2 + (i - o_b2)
                  : (i < o_b3 ? gm.w3 + (i - o_w3) : gm.b3 + (i - o_b3)))));
-    *dst += s;
+    *dst += t;
   }
 }
 
@@ -877,6 +876,7 @@ struct TrainSideArgs {
 
 template <int FMT>
 __global__ void __launch_bounds__(256) train_prep_kernel(TrainSideArgs p) {
+  pdl_launch_dependents();       // train_tc_kernel's prologue (TMEM allocation, shared-memory clear) may start
   const long long nw = 64 * p.K1 + 64 * 80 + 16 * 80, total = p.t0 + p.t1 + nw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     if (i < p.t0) relayout_small_item<FMT>(i, p.g0, p.s0, p.C, p.n0[0], p.n0[1], p.n0[2]);
@@ -885,7 +885,9 @@ __global__ void __launch_bounds__(256) train_prep_kernel(TrainSideArgs p) {
   }
 }
 
-__global__ void __launch_bounds__(256) train_finish_kernel(TrainSideArgs p) {
+__global__ void __launch_bounds__(TF_THREADS) train_finish_kernel(TrainSideArgs p) {
+  pdl_wait();                    // launched programmatically behind train_tc_kernel
+  pdl_launch_dependents();       // ... and the Adam kernel behind this one
   if ((int)blockIdx.x < p.nb_items) {
     const long long total = p.t0 + p.t1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)p.nb_items * blockDim.x) {
@@ -944,6 +946,7 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   }
   sa.t0 = small ? nodes0 * g.C : 0;
   sa.t1 = small ? nodes1 * g.C : 0;
+  if (sa.t0 >= (1ll << 32) || sa.t1 >= (1ll << 32)) return NIC_ERR_UNSUPPORTED;        // 32-bit index math in the side kernels
   if (!small) {
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
     if (e != cudaSuccess) return (int)e;
@@ -1000,9 +1003,12 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   rc = ensure_scratch(&h->tc_partials, &h->tc_partials_bytes, (size_t)grid * a.pstride * sizeof(float));
   if (rc) return rc;
   a.partials = (float*)h->tc_partials;
-  {
+  if (h->time_kernels) {          // the event records between the kernels rule out a programmatic launch
     KernelTimer timer(h, st);
     kern<<<grid, TT_THREADS, TrainShape<METHOD>::SMEM, st>>>(g, a);
+  } else {
+    e = launch_pdl(kern, dim3(grid), dim3(TT_THREADS), TrainShape<METHOD>::SMEM, st, g, a);
+    if (e != cudaSuccess) return (int)e;
   }
   h->launches++;
   e = cudaGetLastError();
@@ -1018,9 +1024,10 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   sa.gm = gm;
   if (!(dg0 && small)) sa.t0 = sa.t1 = 0;                       // frozen grids, or the tiled kernels below do them
   {
-    const long long nb = (sa.t0 + sa.t1 + 255) / 256, cap = 8ll * h->sms;
+    const long long nb = (sa.t0 + sa.t1 + TF_THREADS - 1) / TF_THREADS, cap = 16ll * h->sms;
     sa.nb_items = (int)(nb < cap ? nb : cap);
-    train_finish_kernel<<<sa.nb_items + (a.pstride + 31) / 32, 256, 0, st>>>(sa);
+    e = launch_pdl(train_finish_kernel, dim3(sa.nb_items + (a.pstride + 31) / 32), dim3(TF_THREADS), 0, st, sa);
+    if (e != cudaSuccess) return (int)e;
   }
   h->launches++;
   e = cudaGetLastError();
