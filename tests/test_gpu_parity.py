@@ -666,6 +666,51 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
         assert np.array_equal(d0.cpu().numpy() == 0, dg0 == 0) or np.all((d0.cpu().numpy() != 0) <= (dg0 != 0))
 
 
+def test_train_tc_mlp_gradients_deterministic_and_phase_counters():
+    """The tensor-core step sums the decoder gradients in a fixed order (per-CTA partial sums + an ordered reduction):
+    two runs on the same inputs give bit-identical MLP gradients, outputs and per-sample results.  (The grid gradients
+    are scattered with float atomics and are only reproducible to rounding.)  Also exercises nic_debug_counters: the
+    phase profile counts every tile exactly once."""
+    n = nic()
+    L = n._lib
+    import ctypes as C
+    size, mip, fl, nc, crop = 256, 0, 0, 6, 128
+    grids = I.make_grids(size, 2, seed=90)
+    pt = [T(p) for p in I.make_mlp(73, seed=91, gain=1.5)]
+    fp = [T(a) for a in grids]
+    rng = np.random.default_rng(92)
+    coord_t = T(rng.integers(0, size - crop + 1, (nc, 2)), torch.int64)
+    target_t = T(rng.random((nc * crop * crop, 3), dtype=np.float32))
+    noise_t = T(I.make_noise(nc * crop * crop, 73, 8, 93))
+    g0t, g1t = fp[0], fp[1]
+    geom = L.make_geom(L.METHOD_2D, g0t, g1t, crop, nc, mip - 2 * (fl + 1), mip, 6, L.PE_TRIANGULAR)
+    m = L.make_mlp(pt)
+    h = L.handle(dev())
+    runs = []
+    L.set_option(dev(), L.OPT_DEBUG_KNOCKOUT, 8)
+    L.debug_counters(dev())
+    try:
+        for rep in range(2):
+            g = [torch.zeros_like(p) for p in pt]
+            gm = L.make_mlp_grad(g)
+            d0, d1 = torch.zeros_like(g0t), torch.zeros_like(g1t)
+            ls = torch.zeros(4, device=dev())
+            o = torch.empty((nc * crop * crop, 3), device=dev())
+            L.check(h, L.load_library().nic_train_step(h, C.byref(geom), L.ptr(g0t), L.ptr(g1t), L.ptr(coord_t), C.byref(m),
+                                                       L.ptr(target_t), L.ptr(noise_t), 0, 0, 0, 0, C.byref(gm), L.ptr(d0),
+                                                       L.ptr(d1), L.ptr(ls), L.ptr(o), L.PREC_F16, L.stream_ptr(dev())))
+            counters = L.debug_counters(dev())
+            assert counters[15] == nc * crop * crop // 128               # every tile of 128 samples, once
+            assert all(c > 0 for c in counters[:13])
+            runs.append(([t.cpu().numpy() for t in g], o.cpu().numpy(), d0.cpu().numpy(), d1.cpu().numpy()))
+    finally:
+        L.set_option(dev(), L.OPT_DEBUG_KNOCKOUT, 0)
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(runs[0][1], runs[1][1])
+    assert _rel_l2(runs[0][2], runs[1][2]) < 1e-5 and _rel_l2(runs[0][3], runs[1][3]) < 1e-5
+
+
 def test_train_tc_short_run_tracks_f32_path():
     """200 fused steps on a 512^2 synthetic image, once on the fp32 path and once on the f16 tensor-core path with the
     same crops and LODs: the final full-frame PSNR (reference formula) agrees within 0.05 dB (north-star tolerance)."""
