@@ -102,8 +102,10 @@ int64_t nic_launch_count(const NicHandle* h);
  * packed weights) for the same pointers, node counts, step, mip level and precision, they are reused instead of being
  * rebuilt (decoding one frame as several row bands).  Off by default: every call rebuilds from the caller's tensors. */
 /* NIC_OPT_LEGACY_FAST2D = 1 selects the first-generation fast-path decode kernel (A/B comparisons in tests). */
-/* NIC_OPT_DEBUG_KNOCKOUT: profiling only (tools/run_decode.py) — bit 0 skips the output stores, bit 1 replaces GELU by a
- * plain pack, bit 2 issues one MMA per layer; results are then WRONG on purpose.  Never set in production. */
+/* NIC_OPT_DEBUG_KNOCKOUT: profiling only (tools/run_decode.py, tools/run_train.py) — decode: bit 0 skips the output
+ * stores, bit 1 replaces GELU by a plain pack, bit 2 issues one MMA per layer; training: bit 4 skips the grid-gradient
+ * atomics; results are then WRONG on purpose.  Bit 3 only enables the training phase counters (nic_debug_counters) and
+ * leaves the results unchanged.  Never set in production. */
 enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3, NIC_OPT_LEGACY_FAST2D = 4,
        NIC_OPT_DEBUG_KNOCKOUT = 100 };
 int nic_set_option(NicHandle* h, int option, int value);

@@ -212,6 +212,7 @@ struct TrainArgs {
   int steps0, steps1;         // segmented-reduction depths of the scatter (lanes sharing a G0 / G1 node)
   float* partials;            // [gridDim.x][pstride]: this CTA's MLP-gradient sums (w1 | b1 | w2 | b2 | w3 | b3), plain stores
   int pstride;
+  int dbg;                    // knock-out experiments (NIC_OPT_DEBUG_KNOCKOUT): bit 4 skips the grid-gradient REDs
   unsigned long long* prof;   // NULL, or 16 device counters: cycles per phase seen by thread 0 (nic_debug_counters)
 };
 
@@ -691,7 +692,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
             }
         }
       }
-      if (live && si0.head) {
+      if (live && si0.head && !(a.dbg & 16)) {
 #pragma unroll
         for (int gi = 0; gi < NG0; ++gi) {
           const int gq = NG0 * wg + gi;
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
           }
         }
       }
-      if (live && si1.head) {
+      if (live && si1.head && !(a.dbg & 16)) {
 #pragma unroll
         for (int jj = 0; jj < NC1 / 2; ++jj) {
           const int key = node1 + off1(wg * (NC1 / 2) + jj);
@@ -984,6 +985,7 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   while (s0n < 5 && ldexpf(1.0f, -s0n) > g.step) ++s0n;       // lanes sharing a G0 node along the fast axis: 1/step
   a.steps0 = s0n;
   a.steps1 = s0n + 1 > 5 ? 5 : s0n + 1;
+  a.dbg = h->debug_flags;
   if (h->debug_flags & 8) {
     if (!h->dbg_counters) {
       e = cudaMalloc(&h->dbg_counters, 16 * 8);

@@ -49,7 +49,8 @@ print(f"{prec}: step {s.elapsed_time(e) / steps:.4f} ms (GPU events), host issue
 
 if "phases" in sys.argv:
     # per-tile phase profile of the tensor-core training kernel as seen by thread 0 of every CTA (nic_debug_counters)
-    L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, 8)
+    extra = sum(int(a[4:]) for a in sys.argv if a.startswith("dbg="))
+    L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, 8 | extra)
     tr.step(coord, tg, 0, noise=noise_arg)
     L.debug_counters(dev)
     for _ in range(5):
