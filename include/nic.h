@@ -174,7 +174,10 @@ int nic_decode_codes(NicHandle* h, const NicGeom* g, const uint8_t* codes0, cons
 /* One step of train_models up to loss.backward() (image_compression.py:239-265).
  *   targets [N, cout] fp32; noise: NULL (no noise), or [N, Cin] fp32 injected tensor (parity tests), or use
  *   in-kernel Philox when noise == NULL and noise_bits > 0: X += (U[0,1) - .5) / 2^noise_bits with
- *   (seed, step) as the Philox key/offset.
+ *   (seed, step) as the Philox key/offset (U has 24 bits on the fp32 path and 8 bits on the tensor-core paths, whose
+ *   16-bit X~ cannot resolve more; the two paths draw different streams).
+ *   On the tensor-core precisions the decoder gradients are summed in a fixed order (bit-reproducible); the grid
+ *   gradients are scattered with float atomics (reproducible to rounding).
  *   Writes: loss_sum[0] += sum((out-target)^2) (caller divides by N*cout), gradients ACCUMULATED into
  *   gm / dg0 / dg1 (caller zeroes them), already scaled by 2/(N*cout*loss_scale_den) where loss_scale_den
  *   lets data-parallel callers pass the GLOBAL sample count (0 = use local N).
