@@ -1,4 +1,8 @@
 // Microbenchmark: cycles per tcgen05.mma for the shapes the decode / training kernels use (one CTA per SM).
+// NOTE: this first version issues the MMAs under `if (threadIdx.x == 0)`, which makes the compiler wrap every mma in a
+// waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY): the ~95 cycles per MMA it reports for every N <= 128 are an ISSUE
+// cost of that code shape, not a tensor-pipe floor.  mma_rate2.cu measures both shapes side by side (48 cycles SS /
+// 32 cycles TS for M128 N64 K16 when issued from uniform control flow).  Kept for the record.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../neural_image_compression_v2_b200/csrc -o mma_rate mma_rate.cu
 #include <cstdio>
 #include "nic_tc_common.cuh"
