@@ -208,6 +208,40 @@ int nic_adam_step(NicHandle* h, const NicAdamTensor* tensors, int count, float b
 int nic_adam_step_loss(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
                        float grad_scale, int zero_grad, float* loss_sum, float* loss_out, float loss_scale, void* stream);
 
+/* ---- the exchange step of data-parallel training, fused into the optimiser (NVLink peer memory) ------------------- */
+/* Replaces `all_reduce(flat gradient buffer); Adam` (the one collective of the path; reference: single-GPU, so this is
+ * the drop-in for what a DistributedDataParallel wrapper would add around image_compression.py:265-269) by ONE kernel:
+ * every rank keeps its flat gradient buffer in IPC-shared ("symmetric") device memory, and the Adam kernel itself waits
+ * until all ranks have published this step's token, reads the `world` peer buffers over NVLink in rank order (every
+ * rank forms bit-identical sums, so the replicas never drift) and updates its parameters.
+ *   nic_sym_alloc: cudaMalloc'ed, zero-filled memory + its 64-byte IPC handle (send it to the other ranks out of band).
+ *   nic_sym_open / nic_sym_close: map / unmap another rank's allocation.  nic_sym_free: release one's own.
+ * Protocol (FusedTrainer implements it): gradient buffers are double-buffered by use parity; tensors[i].g points into
+ * THIS rank's current buffer `peer_flat[rank]`; peer_flat[r] / peer_flag[r] are the same buffer / the 32-bit flag word of
+ * rank r; `token` increases by one per use; `zero_buf` (the OTHER parity buffer of this rank, `zero_numel` floats) is
+ * cleared in the same launch — no peer can still be reading it once every flag shows `token`.  A rank that waits more
+ * than ~2 s for a flag records a timeout (nic_exchange_status) and continues, so a lost peer cannot hang the GPU. */
+#define NIC_MAX_PEERS 16
+typedef struct NicExchange {
+  int32_t world, rank;
+  uint32_t token;
+  int32_t reserved;
+  const float* peer_flat[NIC_MAX_PEERS];
+  uint32_t* peer_flag[NIC_MAX_PEERS];
+  float* zero_buf;
+  int64_t zero_numel;
+} NicExchange;
+int nic_sym_alloc(NicHandle* h, int64_t bytes, void** ptr, uint8_t ipc_handle[64]);
+int nic_sym_open(NicHandle* h, const uint8_t ipc_handle[64], void** ptr);
+int nic_sym_close(NicHandle* h, void* ptr);
+int nic_sym_free(NicHandle* h, void* ptr);
+/* nic_adam_step_loss with the gradient (and the loss sum) of every element taken as the sum over the peers' buffers. */
+int nic_adam_step_exchange(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                           float grad_scale, const NicExchange* x, const float* loss_sum, float* loss_out, float loss_scale,
+                           void* stream);
+/* Synchronises the device and reports whether any exchange so far timed out waiting for a peer (then clears it). */
+int nic_exchange_status(NicHandle* h, int* timed_out);
+
 /* ---- quantisers (K6) ------------------------------------------------------------------------------------ */
 /* models.quantize4fp (models.py:55-57): dst = floor(src*(2^b-1)+.5)/(2^b-1), separate fp32 mul and add. */
 int nic_quantize4fp(NicHandle* h, const float* src, float* dst, int64_t n, int bits, void* stream);

@@ -48,6 +48,15 @@ class NicAdamTensor(C.Structure):
                 ("clamp_hi", C.c_float)]
 
 
+MAX_PEERS = 16
+
+
+class NicExchange(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("token", C.c_uint32), ("reserved", C.c_int32),
+                ("peer_flat", C.c_void_p * MAX_PEERS), ("peer_flag", C.c_void_p * MAX_PEERS),
+                ("zero_buf", C.c_void_p), ("zero_numel", C.c_int64)]
+
+
 # every symbol include/nic.h declares: name -> (restype, argtypes)
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SYMBOLS = {
@@ -71,6 +80,12 @@ SYMBOLS = {
                             _L, C.POINTER(NicMlpGrad), _P, _P, _P, _P, _I, _P]),
     "nic_adam_step": (_I, [_P, C.POINTER(NicAdamTensor), _I, _F, _F, _F, _F, _I, _P]),
     "nic_adam_step_loss": (_I, [_P, C.POINTER(NicAdamTensor), _I, _F, _F, _F, _F, _I, _P, _P, _F, _P]),
+    "nic_sym_alloc": (_I, [_P, _L, C.POINTER(_P), C.c_char_p]),
+    "nic_sym_open": (_I, [_P, C.c_char_p, C.POINTER(_P)]),
+    "nic_sym_close": (_I, [_P, _P]),
+    "nic_sym_free": (_I, [_P, _P]),
+    "nic_adam_step_exchange": (_I, [_P, C.POINTER(NicAdamTensor), _I, _F, _F, _F, _F, C.POINTER(NicExchange), _P, _P, _F, _P]),
+    "nic_exchange_status": (_I, [_P, C.POINTER(_I)]),
     "nic_quantize4fp": (_I, [_P, _P, _P, _L, _I, _P]),
     "nic_quantize_pack": (_I, [_P, _P, _P, _L, _I, _P]),
     "nic_unpack": (_I, [_P, _P, _P, _L, _I, _P]),
@@ -144,6 +159,52 @@ def debug_counters(device, n=16):
     out = (C.c_int64 * 16)()
     check(h, load_library().nic_debug_counters(h, out, int(n)))
     return [int(v) for v in out[:n]]
+
+
+class SymmetricBuffer:
+    """A float32 device buffer in IPC-shared memory (nic_sym_alloc) that the other ranks of a process group can map.
+    `tensor` aliases the memory (CUDA array interface); `handle` is the 64-byte IPC handle to send to the peers."""
+
+    def __init__(self, device, numel):
+        self.device = torch.device(device)
+        self.numel = int(numel)
+        h = handle(self.device)
+        p = _P()
+        buf = C.create_string_buffer(64)
+        check(h, load_library().nic_sym_alloc(h, self.numel * 4, C.byref(p), buf))
+        self.ptr = int(p.value)
+        self.handle = bytes(buf.raw)
+        self.__cuda_array_interface__ = {"shape": (self.numel,), "typestr": "<f4", "data": (self.ptr, False), "version": 3,
+                                         "strides": None}
+        self.tensor = torch.as_tensor(self, device=self.device)
+        self._peers = []
+
+    def open_peer(self, ipc_handle):
+        """Maps another rank's buffer; returns its device pointer in THIS process."""
+        h = handle(self.device)
+        p = _P()
+        check(h, load_library().nic_sym_open(h, C.c_char_p(ipc_handle), C.byref(p)))
+        self._peers.append(int(p.value))
+        return int(p.value)
+
+    def close(self):
+        h = handle(self.device)
+        lib = load_library()
+        for p in self._peers:
+            lib.nic_sym_close(h, _P(p))
+        self._peers = []
+        if self.ptr:
+            self.tensor = None
+            lib.nic_sym_free(h, _P(self.ptr))
+            self.ptr = 0
+
+
+def exchange_status(device):
+    """True if an exchange kernel on this device timed out waiting for a peer since the last call (synchronises)."""
+    h = handle(device)
+    v = C.c_int(0)
+    check(h, load_library().nic_exchange_status(h, C.byref(v)))
+    return bool(v.value)
 
 
 def set_option(device, option, value):

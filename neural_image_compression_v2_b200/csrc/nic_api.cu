@@ -88,6 +88,7 @@ int nic_destroy(NicHandle* h) {
   if (h->tc_shadow) cudaFree(h->tc_shadow);
   if (h->tc_gscratch) cudaFree(h->tc_gscratch);
   if (h->tc_partials) cudaFree(h->tc_partials);
+  if (h->xch_err) cudaFree(h->xch_err);
   if (h->dbg_counters) cudaFree(h->dbg_counters);
   if (h->adam_desc) cudaFree(h->adam_desc);
   for (int i = 0; i < 2 * NIC_MAX_TIMED; ++i)
@@ -400,6 +401,85 @@ int nic_adam_step_loss(NicHandle* h, const NicAdamTensor* tensors, int count, fl
   NIC_ENTER(h);
   if (count < 1 || !loss_sum || !loss_out) return fail(h, NIC_ERR_ARG, "nic_adam_step_loss: needs tensors and loss buffers");
   return adam_common(h, tensors, count, beta1, beta2, eps, grad_scale, zero_grad, loss_sum, loss_out, loss_scale, st);
+}
+
+int nic_sym_alloc(NicHandle* h, int64_t bytes, void** ptr, uint8_t ipc_handle[64]) {
+  if (!h || !ptr || !ipc_handle || bytes <= 0) return fail(h, NIC_ERR_ARG, "nic_sym_alloc: bad argument");
+  DeviceGuard guard_(h->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  cudaIpcMemHandle_t hd;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) {
+    if (p) cudaFree(p);
+    return fail(h, (int)e, "nic_sym_alloc: %s", cudaGetErrorString(e));
+  }
+  memcpy(ipc_handle, &hd, 64);
+  *ptr = p;
+  return NIC_OK;
+}
+
+int nic_sym_open(NicHandle* h, const uint8_t ipc_handle[64], void** ptr) {
+  if (!h || !ptr || !ipc_handle) return fail(h, NIC_ERR_ARG, "nic_sym_open: bad argument");
+  DeviceGuard guard_(h->device);
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, ipc_handle, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(h, (int)e, "nic_sym_open: %s", cudaGetErrorString(e));
+  return NIC_OK;
+}
+
+int nic_sym_close(NicHandle* h, void* ptr) {
+  if (!h) return fail(nullptr, NIC_ERR_ARG, "handle is NULL");
+  DeviceGuard guard_(h->device);
+  cudaError_t e = ptr ? cudaIpcCloseMemHandle(ptr) : cudaSuccess;
+  if (e != cudaSuccess) return fail(h, (int)e, "nic_sym_close: %s", cudaGetErrorString(e));
+  return NIC_OK;
+}
+
+int nic_sym_free(NicHandle* h, void* ptr) {
+  if (!h) return fail(nullptr, NIC_ERR_ARG, "handle is NULL");
+  DeviceGuard guard_(h->device);
+  cudaError_t e = ptr ? cudaFree(ptr) : cudaSuccess;
+  if (e != cudaSuccess) return fail(h, (int)e, "nic_sym_free: %s", cudaGetErrorString(e));
+  return NIC_OK;
+}
+
+int nic_adam_step_exchange(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                           float grad_scale, const NicExchange* x, const float* loss_sum, float* loss_out, float loss_scale,
+                           void* stream) {
+  NIC_ENTER(h);
+  if (!x || count < 1 || !tensors) return fail(h, NIC_ERR_ARG, "nic_adam_step_exchange: NULL argument");
+  if (x->world < 1 || x->world > NIC_MAX_PEERS || x->rank < 0 || x->rank >= x->world)
+    return fail(h, NIC_ERR_ARG, "nic_adam_step_exchange: rank %d of world %d (max %d)", x->rank, x->world, NIC_MAX_PEERS);
+  for (int r = 0; r < x->world; ++r)
+    if (!x->peer_flat[r] || !x->peer_flag[r]) return fail(h, NIC_ERR_ARG, "nic_adam_step_exchange: peer %d not mapped", r);
+  if ((loss_out != nullptr) != (loss_sum != nullptr)) return fail(h, NIC_ERR_ARG, "nic_adam_step_exchange: loss buffers");
+  if (x->zero_buf && ((((uintptr_t)x->zero_buf) & 15) || (x->zero_numel & 3) || x->zero_numel < 0))
+    return fail(h, NIC_ERR_ARG, "nic_adam_step_exchange: zero_buf must be 16-byte aligned, a multiple of 4 floats");
+  for (int i = 0; i < count; ++i) {
+    const NicAdamTensor& t = tensors[i];
+    if (t.numel < 0 || t.t < 1 || (t.numel > 0 && (!t.p || !t.g || !t.m || !t.v)))
+      return fail(h, NIC_ERR_ARG, "nic_adam_step_exchange: tensor %d invalid", i);
+  }
+  return cuda_fail(h, launch_adam_exchange(h, tensors, count, beta1, beta2, eps, grad_scale, *x, loss_sum, loss_out, loss_scale, st),
+                   "nic_adam_step_exchange");
+}
+
+int nic_exchange_status(NicHandle* h, int* timed_out) {
+  if (!h || !timed_out) return fail(h, NIC_ERR_ARG, "nic_exchange_status: NULL argument");
+  *timed_out = 0;
+  if (!h->xch_err) return NIC_OK;
+  DeviceGuard guard_(h->device);
+  unsigned v = 0;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(&v, h->xch_err, sizeof(v), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(h->xch_err, 0, sizeof(v));
+  if (e != cudaSuccess) return fail(h, (int)e, "nic_exchange_status: %s", cudaGetErrorString(e));
+  *timed_out = (int)v;
+  return NIC_OK;
 }
 
 static int check_bits(NicHandle* h, int bits, const char* who) {

@@ -29,6 +29,7 @@ struct Handle {
   size_t tc_shadow_bytes;
   void* tc_gscratch;         // channel-last fp32 grid-gradient scratch of the tensor-core training step (kept zero)
   size_t tc_gscratch_bytes;
+  unsigned* xch_err;         // device word: an exchange timed out waiting for a peer (nic_exchange_status)
   void* tc_partials;         // per-CTA MLP-gradient partial sums of the tensor-core training step
   size_t tc_partials_bytes;
   int disable_fast2d;        // testing knob: force the general tensor-core kernel
@@ -225,6 +226,9 @@ int launch_train_tc(Handle* h, const DevGeom& g, const MlpDev& m, const MlpGradD
                     float* loss_sum, float* out_save, int precision, cudaStream_t st);
 int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
                 float grad_scale, int zero_grad, float* loss_sum, float* loss_out, float loss_scale, cudaStream_t st);
+int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                         float grad_scale, const NicExchange& x, const float* loss_sum, float* loss_out, float loss_scale,
+                         cudaStream_t st);
 int launch_quantize4fp(Handle* h, const float* src, float* dst, long long n, int bits, cudaStream_t st);
 int launch_quantize_pack(Handle* h, const float* src, uint8_t* codes, long long n, int bits, cudaStream_t st);
 int launch_unpack(Handle* h, const uint8_t* codes, float* dst, long long n, int bits, cudaStream_t st);

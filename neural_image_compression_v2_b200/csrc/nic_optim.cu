@@ -63,6 +63,139 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fused exchange + Adam
+// The exchange step of data-parallel training inside the optimiser kernel (see nic.h: NicExchange).  Every block
+//   1. (block 0,0) publishes this rank's token: the gradients were written by the previous kernel of the stream, a
+//      system-scope release store makes them visible to the peers before the flag;
+//   2. waits (thread 0, acquire loads over NVLink, 2 s timeout) until every rank's flag shows the token;
+//   3. forms each gradient element as the sum of the `world` peer buffers in RANK ORDER — identical bits on every rank —
+//      with cache-volatile 16-byte loads (L1 is not coherent with peer writes), and applies Adam;
+//   4. (row 0 of the grid) clears the other-parity buffer of this rank for its next use.
+struct XchDev {
+  int world, rank;
+  unsigned token;
+  const float* peer_flat[NIC_MAX_PEERS];
+  unsigned* peer_flag[NIC_MAX_PEERS];
+  float* zero_buf;
+  long long zero_numel;
+  unsigned* err;
+  const float* loss_sum;      // inside peer_flat[rank]
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev x) {
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer_flag[x.rank]), "r"(x.token) : "memory");
+    }
+    const long long t0 = clock64();
+    for (int r = 0; r < x.world; ++r) {
+      if (r == x.rank) continue;
+      while ((int)(ld_acquire_sys(x.peer_flag[r]) - x.token) < 0) {
+        if (clock64() - t0 > 4000000000ll) {       // ~2 s: a peer is gone; record it and go on (results are then wrong)
+          atomicExch(x.err, 1u);
+          break;
+        }
+        __nanosleep(200);
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (b.loss_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    const long long off = x.loss_sum - x.peer_flat[x.rank];
+    float s = 0.f;
+    for (int r = 0; r < x.world; ++r) s += __ldcv(x.peer_flat[r] + off);
+    b.loss_out[0] = s * b.loss_scale;
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (blockIdx.y == 0 && x.zero_buf) {             // 16-byte aligned, multiple of 4 floats (FusedTrainer's layout)
+    float4* z4 = reinterpret_cast<float4*>(x.zero_buf);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < x.zero_numel / 4; i += stride)
+      z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const NicAdamTensor& t = b.t[blockIdx.y];
+  const float step_size = b.step_size[blockIdx.y], bc2_sqrt = b.bc2_sqrt[blockIdx.y];
+  const long long goff = t.g - x.peer_flat[x.rank];          // this tensor's offset inside every rank's buffer
+  const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0) && (goff & 3) == 0;
+  const long long n4 = vec ? t.numel / 4 : 0;
+  float4* p4 = reinterpret_cast<float4*>(t.p);
+  float4* m4 = reinterpret_cast<float4*>(t.m);
+  float4* v4 = reinterpret_cast<float4*>(t.v);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < x.world; ++r) {
+      const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[r] + goff) + i);
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    float4 p = p4[i], m = m4[i], v = v4[i];
+    adam_one(p.x, g.x, m.x, v.x, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    adam_one(p.y, g.y, m.y, v.y, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    adam_one(p.z, g.z, m.z, v.z, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    adam_one(p.w, g.w, m.w, v.w, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    p4[i] = p; m4[i] = m; v4[i] = v;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.numel; i += stride) {
+    float g = 0.f;
+    for (int r = 0; r < x.world; ++r) g += __ldcv(x.peer_flat[r] + goff + i);
+    float p = t.p[i], m = t.m[i], v = t.v[i];
+    adam_one(p, g, m, v, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+    t.p[i] = p; t.m[i] = m; t.v[i] = v;
+  }
+}
+
+int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
+                         float grad_scale, const NicExchange& xc, const float* loss_sum, float* loss_out, float loss_scale,
+                         cudaStream_t st) {
+  if (count > NIC_ADAM_BATCH) return NIC_ERR_UNSUPPORTED;      // one launch: the flag protocol runs once per step
+  if (!h->xch_err) {
+    cudaError_t e = cudaMalloc(&h->xch_err, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->xch_err, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  AdamBatch b;
+  b.loss_sum = nullptr;
+  b.loss_out = loss_out;
+  b.loss_scale = loss_scale;
+  b.count = count;
+  b.beta1 = beta1; b.beta2 = beta2; b.eps = eps; b.grad_scale = grad_scale; b.zero_grad = 0;
+  long long maxn = xc.zero_numel;
+  for (int i = 0; i < count; ++i) {
+    b.t[i] = tensors[i];
+    const double bc1 = 1.0 - pow((double)beta1, (double)b.t[i].t), bc2 = 1.0 - pow((double)beta2, (double)b.t[i].t);
+    b.step_size[i] = (float)((double)b.t[i].lr / bc1);
+    b.bc2_sqrt[i] = (float)sqrt(bc2);
+    if (b.t[i].numel > maxn) maxn = b.t[i].numel;
+  }
+  XchDev x;
+  memset(&x, 0, sizeof(x));
+  x.world = xc.world;
+  x.rank = xc.rank;
+  x.token = xc.token;
+  for (int r = 0; r < xc.world; ++r) {
+    x.peer_flat[r] = xc.peer_flat[r];
+    x.peer_flag[r] = (unsigned*)xc.peer_flag[r];
+  }
+  x.zero_buf = xc.zero_buf;
+  x.zero_numel = xc.zero_numel;
+  x.err = h->xch_err;
+  x.loss_sum = loss_sum;
+  long long blocks = (maxn / 4 + 255) / 256 + 1;
+  long long cap = (long long)h->sms * 8;
+  dim3 grid((unsigned)(blocks > cap ? cap : blocks), (unsigned)count);
+  cudaError_t e = launch_pdl(adam_exchange_kernel, grid, dim3(256), 0, st, b, x);
+  h->launches++;
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return (int)e;
+}
+
 int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
                 float grad_scale, int zero_grad, float* loss_sum, float* loss_out, float loss_scale, cudaStream_t st) {
   for (int base = 0; base < count; base += NIC_ADAM_BATCH) {

@@ -489,8 +489,10 @@ class FusedTrainer:
     quantise the grids once epoch > 0.95 N (:227-231); clamp of the two active grids after each step (:269).
     """
 
+    PEER_EXCHANGE_MAX_BYTES = 4 << 20      # one-shot peer reads beat a ring/tree all-reduce only for small buffers
+
     def __init__(self, fp, decoder, num_epochs=None, fp_bits=None, lr_fp=0.01, lr_mlp=0.005, betas=(0.9, 0.999),
-                 eps=1e-8, method=None, level_table=None, process_group=None, seed=0, precision="f32"):
+                 eps=1e-8, method=None, level_table=None, process_group=None, seed=0, precision="f32", exchange="auto"):
         self.fp = [_check_grid(g.detach()) for g in fp]
         self.decoder = decoder
         self.params = [p.detach() for p in decoder.parameters_list()]
@@ -514,21 +516,82 @@ class FusedTrainer:
         self.device = dev
         # one flat gradient buffer per pyramid level: [dG0 | dG1 | dW1 db1 dW2 db2 dW3 db3 | loss] -> one all-reduce
         self._flat = {}
+        # The exchange step under data parallelism: "nccl" = all_reduce(flat) then Adam; "peer" = ONE kernel that reads the
+        # peers' flat buffers over NVLink and applies Adam (nic_adam_step_exchange); "auto" = peer for flat buffers up to
+        # PEER_EXCHANGE_MAX_BYTES when every rank could map every peer, else nccl.
+        if exchange not in ("auto", "nccl", "peer"):
+            raise ValueError("exchange must be 'auto', 'nccl' or 'peer'")
+        self.exchange = exchange
+        self._peer = {}          # level -> symmetric buffers, peer pointers, use count (None: this level uses nccl)
         self.state = {}          # id -> (m, v, t)
         self.q_min = -(pow(2, self.bits) - 1) / pow(2, self.bits + 1)
 
     # -- buffers
     def _level_buffers(self, fl):
         if fl not in self._flat:
-            sizes = [self.fp[2 * fl].numel(), self.fp[2 * fl + 1].numel()] + [p.numel() for p in self.params] + [4]
-            offs, total = [], 0
-            for s in sizes:
-                offs.append(total)
-                total += (s + 3) // 4 * 4          # keep every view 16-byte aligned
+            sizes, offs, total = self._level_layout(fl)          # every view 16-byte aligned
             flat = torch.zeros(total, dtype=torch.float32, device=self.device)
             views = [flat[o:o + s] for o, s in zip(offs, sizes)]
             self._flat[fl] = (flat, views)
         return self._flat[fl]
+
+    def _level_layout(self, fl):
+        sizes = [self.fp[2 * fl].numel(), self.fp[2 * fl + 1].numel()] + [p.numel() for p in self.params] + [4]
+        offs, total = [], 0
+        for s in sizes:
+            offs.append(total)
+            total += (s + 3) // 4 * 4
+        return sizes, offs, total
+
+    def _peer_level(self, fl):
+        """Symmetric double-buffered flat gradient buffers of level `fl`, mapped on every rank (collective on first
+        use: all ranks reach it in the same step because they draw the same LOD sequence).  None -> use nccl."""
+        if fl in self._peer:
+            return self._peer[fl]
+        dist = torch.distributed
+        sizes, offs, total = self._level_layout(fl)
+        want = self.world > 1 and self.world <= L.MAX_PEERS and self.exchange != "nccl" and \
+            (self.exchange == "peer" or total * 4 <= self.PEER_EXCHANGE_MAX_BYTES)
+        ent = None
+        if want:
+            ok, buf, bases = 1, None, []
+            try:
+                buf = L.SymmetricBuffer(self.device, 2 * total + 64)          # [parity 0 | parity 1 | flag words]
+                handles = [None] * self.world
+                dist.all_gather_object(handles, buf.handle, group=self.pg)
+                bases = [buf.ptr if r == self.rank else buf.open_peer(handles[r]) for r in range(self.world)]
+            except Exception:                                                  # no IPC / no peer access on this box
+                ok = 0
+                if buf is None:       # keep the collective below matched even when the allocation itself failed
+                    dist.all_gather_object([None] * self.world, b"", group=self.pg)
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+            if int(flag.item()) == 1:
+                flats = []
+                for par in range(2):
+                    flat = buf.tensor[par * total:(par + 1) * total]
+                    flats.append((flat, [flat[o:o + s] for o, s in zip(offs, sizes)]))
+                ent = {"buf": buf, "bases": bases, "flats": flats, "total": total, "uses": 0, "xch": {}}
+            else:
+                if self.exchange == "peer":
+                    raise RuntimeError("exchange='peer': the ranks could not map each other's buffers (CUDA IPC)")
+                if buf is not None:
+                    buf.close()
+        self._peer[fl] = ent
+        return ent
+
+    def _exchange_desc(self, ent, parity):
+        x = ent["xch"].get(parity)
+        if x is None:
+            x = L.NicExchange()
+            x.world, x.rank = self.world, self.rank
+            for r, base in enumerate(ent["bases"]):
+                x.peer_flat[r] = base + 4 * parity * ent["total"]
+                x.peer_flag[r] = base + 8 * ent["total"]
+            x.zero_buf = ent["bases"][self.rank] + 4 * (1 - parity) * ent["total"]
+            x.zero_numel = ent["total"]
+            ent["xch"][parity] = x
+        return x
 
     def _adam_state(self, key, like):
         if key not in self.state:
@@ -556,14 +619,16 @@ class FusedTrainer:
         sample_number = pow(2, max(0, (8 if self.dim == 2 else var2.CROP_MIP_LEVEL) - lod))
         coord = L.origins_tensor(coord, self.device, self.dim)
         nc = coord.shape[0]
-        # descriptors that only depend on (lod, crops) are built once (host overhead matters at ~0.4 ms per step)
-        key = (lod, nc)
+        peer = self._peer_level(fl) if self.world > 1 else None
+        parity = (peer["uses"] & 1) if peer else 0
+        # descriptors that only depend on (lod, crops) are built once (host overhead matters at ~0.2 ms per step)
+        key = (lod, nc, parity)
         ent = self._cache.get(key)
         if ent is None:
             geom = L.make_geom(self.method, g0, g1, sample_number, nc, _step_log2(lod, fl), lod, var2.PE_CHANNELS,
                                _pe_kind(self.method))
             m = L.make_mlp(self.params)
-            flat, views = self._level_buffers(fl)
+            flat, views = peer["flats"][parity] if peer else self._level_buffers(fl)
             gm = L.make_mlp_grad(views[2:8])
             entries = []
             if not self.frozen:
@@ -604,7 +669,7 @@ class FusedTrainer:
                                       C.byref(gm), L.ptr(None if self.frozen else views[0]),
                                       L.ptr(None if self.frozen else views[1]), L.ptr(views[8]), L.ptr(out),
                                       self.precision, st))
-        if self.world > 1:                                           # the one exchange step of the path
+        if self.world > 1 and not peer:                              # the one exchange step of the path, as a collective
             torch.distributed.all_reduce(flat, group=self.pg)
         # Adam on the tensors that received a gradient this step (per-tensor step counts); the same launch turns the
         # loss sum into the mean (a fresh 1-element tensor per step, so callers may keep the handles) and re-zeroes it
@@ -614,8 +679,16 @@ class FusedTrainer:
             arr[k].lr = lr0 * scale
             arr[k].t = stt[2]
         loss = torch.empty(1, dtype=torch.float32, device=self.device)
-        L.check(h, lib.nic_adam_step_loss(h, arr, len(states), self.betas[0], self.betas[1], self.eps, 1.0, 1,
-                                          L.ptr(views[8]), L.ptr(loss), 1.0 / float(n * self.world * m.cout), st))
+        if peer:                                                     # ... or fused into the optimiser over NVLink peer memory
+            x = self._exchange_desc(peer, parity)
+            peer["uses"] += 1
+            x.token = peer["uses"]
+            L.check(h, lib.nic_adam_step_exchange(h, arr, len(states), self.betas[0], self.betas[1], self.eps, 1.0,
+                                                  C.byref(x), L.ptr(views[8]), L.ptr(loss),
+                                                  1.0 / float(n * self.world * m.cout), st))
+        else:
+            L.check(h, lib.nic_adam_step_loss(h, arr, len(states), self.betas[0], self.betas[1], self.eps, 1.0, 1,
+                                              L.ptr(views[8]), L.ptr(loss), 1.0 / float(n * self.world * m.cout), st))
         loss = loss[0]
         self.epoch += 1
         return loss

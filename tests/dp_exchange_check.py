@@ -1,0 +1,74 @@
+"""Data-parallel training check for >= 2 GPUs (launched by tests/test_gpu_parity.py::test_dp_exchange_* or by hand):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tests/dp_exchange_check.py
+Trains the same model with the exchange step as an NCCL all-reduce and fused into the optimiser over NVLink peer memory
+(nic_adam_step_exchange), from the same initial state, crops and noise, and checks that
+  * the replicas stay bit-identical across ranks in both modes,
+  * the two modes agree to float rounding (the sums are formed in a different order),
+  * no exchange timed out.
+Prints one line `DP_EXCHANGE_OK ...` on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import inputs as I  # noqa: E402
+from neural_image_compression_v2_b200 import _lib as L  # noqa: E402
+from neural_image_compression_v2_b200 import image_compression as ic, var2  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    size, nc = 512, 4
+    var2.update(IMAGE_SIZE=size, TF_NO_MIP=False, MAX_MIP_LEVEL=8)
+    mips = [torch.tensor(m, device=dev) for m in I.box_mips(I.make_image(size, 2, seed=5), 8)]
+    rng = np.random.default_rng(100 + rank)                 # every rank trains on its own crops
+    lods = [0, 2, 0, 1, 2, 0, 0, 1, 3, 0, 1, 0, 2, 0]      # same on every rank; several pyramid levels, both parities
+    batches = []
+    for lod in lods:
+        crop, dsize = 2 ** (8 - lod), size >> lod
+        coord = torch.tensor(rng.integers(0, dsize - crop + 1, (nc, 2)))
+        batches.append((coord, ic.sample_crops(mips[lod], coord, crop), lod))
+    results = {}
+    for mode in ("nccl", "peer"):
+        fp = [torch.tensor(g, device=dev) for g in I.make_grids(size, 2, seed=3)]
+        dec = ic.ColorDecoder(73, 64, 3).to(dev)
+        with torch.no_grad():
+            for p, v in zip(dec.parameters_list(), I.make_mlp(73, seed=4)):
+                p.copy_(torch.tensor(v))
+        tr = ic.FusedTrainer(fp, dec, num_epochs=1000, fp_bits=8, seed=1, precision=sys.argv[1] if len(sys.argv) > 1 else "f16",
+                             exchange=mode)
+        losses = []
+        for coord, tg, lod in batches:
+            losses.append(tr.step(coord, tg, lod))
+        torch.cuda.synchronize()
+        assert not L.exchange_status(dev), "an exchange timed out"
+        if mode == "peer":
+            assert any(v is not None for v in tr._peer.values()), "peer exchange was not used"
+        state = torch.cat([g.reshape(-1) for g in fp] + [p.detach().reshape(-1) for p in dec.parameters_list()])
+        gathered = [torch.empty_like(state) for _ in range(world)]
+        dist.all_gather(gathered, state)
+        for r in range(1, world):
+            assert torch.equal(gathered[0], gathered[r]), f"{mode}: replicas of rank 0 and {r} differ"
+        results[mode] = (state.cpu().numpy(), np.array([float(x) for x in losses]))
+    a, b = results["nccl"], results["peer"]
+    rel = float(np.linalg.norm(a[0] - b[0]) / np.linalg.norm(a[0]))
+    assert rel < 2e-3, f"nccl and peer exchange disagree: rel {rel}"
+    assert np.allclose(a[1], b[1], rtol=2e-2, atol=1e-5), (a[1], b[1])
+    dist.barrier()
+    if rank == 0:
+        print(f"DP_EXCHANGE_OK world {world} rel_l2(nccl, peer) {rel:.2e} final loss {b[1][-1]:.5f}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

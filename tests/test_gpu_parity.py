@@ -1118,3 +1118,19 @@ def test_edge_cases_empty_and_oversized():
                             C.byref(gm), L.ptr(d0), L.ptr(d1), L.ptr(ls), None, L.PREC_F16, L.stream_ptr(dev()))
     assert rc == -2, rc
     torch.cuda.synchronize()
+
+
+def test_dp_exchange_peer_memory_matches_nccl():
+    """Data parallel training on 2 GPUs (skipped on a 1-GPU box): the exchange step fused into the optimiser over NVLink
+    peer memory (nic_adam_step_exchange) against the NCCL all-reduce — bit-identical replicas across ranks in both modes,
+    the two modes equal to rounding, no timeouts.  The check itself lives in tests/dp_exchange_check.py (torchrun)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(here, "dp_exchange_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DP_EXCHANGE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
