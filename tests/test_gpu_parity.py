@@ -4,6 +4,7 @@
 Bar: bit-exact for indices, gathers with the triangular encoding, quantiser codes; rtol 1e-5 for the fp32 MLP path;
 +-1 LSB on 8-bit output for >= 99.9 % of texels and PSNR within 0.05 dB for the f16/bf16 tensor-core path."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
