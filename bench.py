@@ -205,7 +205,11 @@ def bench_train(args, nic, ic, var2, dev, world, rank, dist, barrier):
     rate = world * n * steps / (float(ms.item()) * 1e-3) / 1e6
     tf_peak = peaks()[0]
     kernel_tflops = 3 * FLOP_PER_TEXEL * n * kn / (kms * 1e-3) / 1e12 if kms > 0 else None
+    exchange = tr.exchange_in_use()
+    timed_out = bool(L.exchange_status(dev)) if exchange in ("peer", "mixed") else False
     return {"value": rate, "unit": "Msamples/s", "samples_per_step": world * n, "ms_per_step": float(ms.item()) / steps,
+            "exchange": {"none": "none (1 GPU)", "peer": "fused into Adam over NVLink peer memory (nic_adam_step_exchange)",
+                         "nccl": "NCCL all_reduce + Adam", "mixed": "peer + nccl"}[exchange], "exchange_timed_out": timed_out,
             "precision": args.train_prec, "loss": float(loss), "workload": "train_512x512_8x256x256_crops",
             "kernel_ms": kms / max(kn, 1), "kernel_tflops": kernel_tflops,
             "roofline_frac": (kernel_tflops / tf_peak) if kernel_tflops else None, "flop_per_sample": 3 * FLOP_PER_TEXEL}

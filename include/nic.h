@@ -217,8 +217,8 @@ int nic_adam_step_loss(NicHandle* h, const NicAdamTensor* tensors, int count, fl
  *   nic_sym_alloc: cudaMalloc'ed, zero-filled memory + its 64-byte IPC handle (send it to the other ranks out of band).
  *   nic_sym_open / nic_sym_close: map / unmap another rank's allocation.  nic_sym_free: release one's own.
  * Protocol (FusedTrainer implements it): gradient buffers are double-buffered by use parity; tensors[i].g points into
- * THIS rank's current buffer `peer_flat[rank]`; peer_flat[r] / peer_flag[r] are the same buffer / the 32-bit flag word of
- * rank r; `token` increases by one per use; `zero_buf` (the OTHER parity buffer of this rank, `zero_numel` floats) is
+ * THIS rank's current buffer `peer_flat[rank]`; peer_flat[r] / peer_flag[r] are the same buffer / the flag array (`world`
+ * 32-bit words: slot s is written by rank s) of rank r; `token` increases by one per use; `zero_buf` (the OTHER parity buffer of this rank, `zero_numel` floats) is
  * cleared in the same launch — no peer can still be reading it once every flag shows `token`.  A rank that waits more
  * than ~2 s for a flag records a timeout (nic_exchange_status) and continues, so a lost peer cannot hang the GPU. */
 #define NIC_MAX_PEERS 16

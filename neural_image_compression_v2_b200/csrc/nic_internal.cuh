@@ -29,7 +29,8 @@ struct Handle {
   size_t tc_shadow_bytes;
   void* tc_gscratch;         // channel-last fp32 grid-gradient scratch of the tensor-core training step (kept zero)
   size_t tc_gscratch_bytes;
-  unsigned* xch_err;         // device word: an exchange timed out waiting for a peer (nic_exchange_status)
+  unsigned* xch_err;         // device words: [0] an exchange timed out waiting for a peer (nic_exchange_status), [1] release word
+  unsigned xch_seq;          // launches of the exchange kernel so far
   void* tc_partials;         // per-CTA MLP-gradient partial sums of the tensor-core training step
   size_t tc_partials_bytes;
   int disable_fast2d;        // testing knob: force the general tensor-core kernel

@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b) {
 
 // ------------------------------------------------------------------------------------------------ fused exchange + Adam
 // The exchange step of data-parallel training inside the optimiser kernel (see nic.h: NicExchange).  Every block
-//   1. (block 0,0) publishes this rank's token: the gradients were written by the previous kernel of the stream, a
-//      system-scope release store makes them visible to the peers before the flag;
-//   2. waits (thread 0, acquire loads over NVLink, 2 s timeout) until every rank's flag shows the token;
+//   1. (one warp of block 0,0) pushes this rank's token into every peer's flag array: the gradients were written by the
+//      previous kernel of the stream, a system-scope release store makes them visible to the peers before the flag;
+//   2. waits (local acquire loads, 2 s timeout) until its own flag array shows the token of every rank;
 //   3. forms each gradient element as the sum of the `world` peer buffers in RANK ORDER — identical bits on every rank —
 //      with cache-volatile 16-byte loads (L1 is not coherent with peer writes), and applies Adam;
 //   4. (row 0 of the grid) clears the other-parity buffer of this rank for its next use.
@@ -79,7 +79,10 @@ struct XchDev {
   float* zero_buf;
   long long zero_numel;
   unsigned* err;
+  unsigned* go;               // local word: block (0,0) releases the other blocks once every peer has arrived
+  unsigned go_token;          // ... by storing this launch's sequence number (per handle, monotonic)
   const float* loss_sum;      // inside peer_flat[rank]
+  int dbg;                    // knock-outs (timing experiments only): bit 5 no flag wait, bit 6 read the own buffer only
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -90,29 +93,41 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 
 __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev x) {
   pdl_wait();
-  if (threadIdx.x == 0) {
+  if (!(x.dbg & 32)) {
     if (blockIdx.x == 0 && blockIdx.y == 0) {
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer_flag[x.rank]), "r"(x.token) : "memory");
-    }
-    const long long t0 = clock64();
-    for (int r = 0; r < x.world; ++r) {
-      if (r == x.rank) continue;
-      while ((int)(ld_acquire_sys(x.peer_flag[r]) - x.token) < 0) {
-        if (clock64() - t0 > 4000000000ll) {       // ~2 s: a peer is gone; record it and go on (results are then wrong)
-          atomicExch(x.err, 1u);
-          break;
+      // ONE warp of the grid talks to the peers.  Flags are PUSHED: lane p stores this rank's token into slot `rank` of
+      // peer p's flag array (a fire-and-forget NVLink store), then polls slot p of the LOCAL array — no remote polling,
+      // and all peers are awaited in parallel.  Lane 0 then releases this rank's other blocks through a local word.
+      if (threadIdx.x < 32) {
+        const int p = threadIdx.x;
+        if (p < x.world) {
+          __threadfence_system();
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer_flag[p] + x.rank), "r"(x.token) : "memory");
+          const unsigned* mine = x.peer_flag[x.rank] + p;
+          const long long t0 = clock64();
+          while ((int)(ld_acquire_sys(mine) - x.token) < 0) {
+            if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer is gone; record it and go on (results are then wrong)
+              atomicExch(x.err, 1u);
+              break;
+            }
+          }
         }
-        __nanosleep(200);
+        __syncwarp();
+        if (p == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(x.go), "r"(x.go_token) : "memory");
       }
+    } else if (threadIdx.x == 0) {
+      unsigned v;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(x.go) : "memory");
+      } while ((int)(v - x.go_token) < 0 && clock64() - t0 < 5000000000ll);
     }
-    __threadfence_system();
   }
   __syncthreads();
   if (b.loss_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     const long long off = x.loss_sum - x.peer_flat[x.rank];
     float s = 0.f;
-    for (int r = 0; r < x.world; ++r) s += __ldcv(x.peer_flat[r] + off);
+    for (int r = 0; r < x.world; ++r) s += __ldcv(x.peer_flat[(x.dbg & 64) ? x.rank : r] + off);
     b.loss_out[0] = s * b.loss_scale;
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -132,7 +147,7 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < x.world; ++r) {
-      const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[r] + goff) + i);
+      const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[(x.dbg & 64) ? x.rank : r] + goff) + i);
       g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
     }
     float4 p = p4[i], m = m4[i], v = v4[i];
@@ -155,9 +170,9 @@ int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, flo
                          float grad_scale, const NicExchange& xc, const float* loss_sum, float* loss_out, float loss_scale,
                          cudaStream_t st) {
   if (count > NIC_ADAM_BATCH) return NIC_ERR_UNSUPPORTED;      // one launch: the flag protocol runs once per step
-  if (!h->xch_err) {
-    cudaError_t e = cudaMalloc(&h->xch_err, sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemsetAsync(h->xch_err, 0, sizeof(unsigned), st);
+  if (!h->xch_err) {          // two words: [0] timeout flag, [1] the local release word
+    cudaError_t e = cudaMalloc(&h->xch_err, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->xch_err, 0, 2 * sizeof(unsigned), st);
     if (e != cudaSuccess) return (int)e;
   }
   AdamBatch b;
@@ -186,6 +201,9 @@ int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, flo
   x.zero_buf = xc.zero_buf;
   x.zero_numel = xc.zero_numel;
   x.err = h->xch_err;
+  x.go = h->xch_err + 1;
+  x.go_token = ++h->xch_seq;
+  x.dbg = h->debug_flags;
   x.loss_sum = loss_sum;
   long long blocks = (maxn / 4 + 255) / 256 + 1;
   long long cap = (long long)h->sms * 8;

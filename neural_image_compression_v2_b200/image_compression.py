@@ -580,6 +580,13 @@ class FusedTrainer:
         self._peer[fl] = ent
         return ent
 
+    def exchange_in_use(self):
+        """'none' (single process), 'peer' (every level used so far exchanges over peer memory), 'nccl' or 'mixed'."""
+        if self.world == 1:
+            return "none"
+        kinds = {"peer" if v is not None else "nccl" for v in self._peer.values()}
+        return kinds.pop() if len(kinds) == 1 else ("mixed" if kinds else "nccl")
+
     def _exchange_desc(self, ent, parity):
         x = ent["xch"].get(parity)
         if x is None:
