@@ -104,7 +104,8 @@ int64_t nic_launch_count(const NicHandle* h);
 /* NIC_OPT_LEGACY_FAST2D = 1 selects the first-generation fast-path decode kernel (A/B comparisons in tests). */
 /* NIC_OPT_DEBUG_KNOCKOUT: profiling only (tools/run_decode.py, tools/run_train.py) — decode: bit 0 skips the output
  * stores, bit 1 replaces GELU by a plain pack, bit 2 issues one MMA per layer; training: bit 4 skips the grid-gradient
- * atomics; results are then WRONG on purpose.  Bit 3 only enables the training phase counters (nic_debug_counters) and
+ * atomics, bits 5 / 6 make nic_adam_step_exchange skip the flag wait / read only its own buffer (timing experiments in
+ * tools/dp_timing.py); results are then WRONG on purpose.  Bit 3 only enables the training phase counters (nic_debug_counters) and
  * leaves the results unchanged.  Never set in production. */
 enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3, NIC_OPT_LEGACY_FAST2D = 4,
        NIC_OPT_DEBUG_KNOCKOUT = 100 };

@@ -580,6 +580,15 @@ class FusedTrainer:
         self._peer[fl] = ent
         return ent
 
+    def close(self):
+        """Unmaps the peers' buffers and frees this rank's symmetric buffers (call on every rank, after a barrier)."""
+        for ent in self._peer.values():
+            if ent is not None:
+                ent["flats"], ent["xch"] = [], {}
+                ent["buf"].close()
+        self._peer = {}
+        self._cache.clear()
+
     def exchange_in_use(self):
         """'none' (single process), 'peer' (every level used so far exchanges over peer memory), 'nccl' or 'mixed'."""
         if self.world == 1:

@@ -1121,6 +1121,64 @@ def test_edge_cases_empty_and_oversized():
     torch.cuda.synchronize()
 
 
+def test_exchange_kernel_single_rank_equals_plain_adam():
+    """nic_adam_step_exchange with world = 1 (runs on a 1-GPU box): symmetric buffer allocation and aliasing, the flag
+    protocol against itself, the other-parity clear and the loss bookkeeping — and bit-equality with nic_adam_step_loss
+    on the same gradients (a one-term sum is exact).  The multi-rank behaviour is test_dp_exchange_* below."""
+    n = nic()
+    L = n._lib
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    sizes = [12 * 33 * 33, 73 * 64, 64, 4]          # a grid, W1, b1, the loss slot
+    offs, total = [], 0
+    for sz in sizes:
+        offs.append(total)
+        total += (sz + 3) // 4 * 4
+    buf = L.SymmetricBuffer(dev(), 2 * total + 64)
+    try:
+        assert buf.tensor.data_ptr() == buf.ptr and float(buf.tensor.abs().sum()) == 0.0
+        flat0, flat1 = buf.tensor[:total], buf.tensor[total:2 * total]
+        grad = T(rng.standard_normal(total).astype(np.float32) * 1e-2)
+        results = {}
+        for mode in ("plain", "exchange"):
+            params = [T(rng2) for rng2 in (np.random.default_rng(6).standard_normal(sz).astype(np.float32) * 0.1 for sz in sizes[:3])]
+            ms = [torch.full_like(p, 0.01) for p in params]
+            vs = [torch.full_like(p, 0.001) for p in params]
+            g = grad.clone() if mode == "plain" else flat0
+            if mode == "exchange":
+                flat0.copy_(grad)
+                flat1.fill_(7.0)                     # stale contents of the other parity: must come back cleared
+            arr = (L.NicAdamTensor * 3)()
+            for k in range(3):
+                a = arr[k]
+                a.p, a.g = params[k].data_ptr(), g[offs[k]:].data_ptr()
+                a.m, a.v, a.numel = ms[k].data_ptr(), vs[k].data_ptr(), sizes[k]
+                a.lr, a.t, a.clamp, a.clamp_lo, a.clamp_hi = 0.01, 3, int(k == 0), -0.05, 0.05
+            loss = torch.zeros(1, device=dev())
+            loss_sum = g[offs[3]:offs[3] + 4]
+            h, lib = L.handle(dev()), L.load_library()
+            if mode == "plain":
+                L.check(h, lib.nic_adam_step_loss(h, arr, 3, 0.9, 0.999, 1e-8, 1.0, 0, L.ptr(loss_sum), L.ptr(loss), 0.5,
+                                                  L.stream_ptr(dev())))
+            else:
+                x = L.NicExchange()
+                x.world, x.rank, x.token = 1, 0, 41
+                x.peer_flat[0], x.peer_flag[0] = buf.ptr, buf.ptr + 8 * total
+                x.zero_buf, x.zero_numel = buf.ptr + 4 * total, total
+                L.check(h, lib.nic_adam_step_exchange(h, arr, 3, 0.9, 0.999, 1e-8, 1.0, C.byref(x), L.ptr(loss_sum), L.ptr(loss),
+                                                      0.5, L.stream_ptr(dev())))
+                assert not L.exchange_status(dev())
+                assert float(flat1.abs().sum()) == 0.0
+                assert int(buf.tensor[2 * total:2 * total + 1].view(torch.int32)[0]) == 41       # slot 0 of the flag array
+                assert torch.equal(flat0, grad)                                                   # the current buffer is left alone
+            results[mode] = [t.cpu().numpy() for t in params + ms + vs] + [loss.cpu().numpy()]
+        for a, b in zip(results["plain"], results["exchange"]):
+            assert np.array_equal(a, b)
+        assert abs(float(results["plain"][-1][0]) - 0.5 * float(grad[offs[3]])) < 1e-7
+    finally:
+        buf.close()
+
+
 def test_dp_exchange_peer_memory_matches_nccl():
     """Data parallel training on 2 GPUs (skipped on a 1-GPU box): the exchange step fused into the optimiser over NVLink
     peer memory (nic_adam_step_exchange) against the NCCL all-reduce — bit-identical replicas across ranks in both modes,
