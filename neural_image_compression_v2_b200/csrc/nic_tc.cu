@@ -781,6 +781,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
   const uint32_t aLx = smem_u32(sLx), aLy = smem_u32(sLy), aSel = smem_u32(sSel), aOne = smem_u32(sOne), aAct = smem_u32(sAct);
   const int ny0 = g.n0[1], ny1 = g.n1[1];
   auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(WS_GROUP) : "memory"); };
+  // wait for the group's MMA batch: ONE warp polls the mbarrier, the other three park at the group's named barrier
+  // (a hardware wait: no issue slots) — polling by all four warps was 10 % of the kernel's issued instructions
+  auto group_wait = [&](uint32_t phase) {
+    if (issuer_warp) mbar_wait(bar_full + slot, phase);
+    group_sync();
+  };
   // ---- operand staging: 144 pieces per tile over 128 threads (threads 0..15 take a second piece)
   uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = make_uint4(0, 0, 0, 0);
   auto fetch_piece = [&](int p, int px0, int py0) -> uint4 {
@@ -864,9 +870,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
     const unsigned tile = blockIdx.x + i * gridDim.x;
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
-      mbar_wait(bar_full + slot, ph);
+      group_wait(ph);
       ph ^= 1;
-      __syncwarp();
       tc_fence_after();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -898,9 +903,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
         __syncwarp();
       }
     }
-    mbar_wait(bar_full + slot, ph);
+    group_wait(ph);
     ph ^= 1;
-    __syncwarp();
     tc_fence_after();
     uint32_t acc[16];
     if (cout > 4) tmem_ld16(tD, acc);               // multi-channel outputs (material stacks): up to 16 channels
