@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnic.so")
+LIB_PATH = os.environ.get("NIC_LIB_PATH") or os.path.join(_HERE, "libnic.so")     # override: A/B runs of kernel builds
 
 METHOD_2D, METHOD_3D, METHOD_3D_V2 = 1, 3, 4
 PE_TRIANGULAR, PE_SINUSOIDAL = 0, 1
