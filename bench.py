@@ -27,8 +27,8 @@ SIZE = 4096                      # BASELINE.json configs[1]
 FLOP_PER_TEXEL = 2 * (73 * 64 + 64 * 64 + 64 * 3)      # 17,920
 METRIC, UNIT = "decoded Gtexel/s (4096x4096 RGB full-frame decode)", "Gtexel/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of decode_tc2d_kernel per launch, from the committed ncu --set full capture
-NCU_TRAFFIC_BYTES = 58967552 + 15951616
-NCU_TRAFFIC_SOURCE = "profiles/r01o_decode_tc2d_ws_uniform_issue_metrics.txt"
+NCU_TRAFFIC_BYTES = 58968064 + 12888832
+NCU_TRAFFIC_SOURCE = "profiles/r01q_decode_tc2d_ws_final_metrics.txt"
 
 
 def peaks():
@@ -443,7 +443,7 @@ def run_ours(args):
                          # tools/ubench/mma_rate2.cu: an SS-form M128 x N64 x K16 tcgen05.mma (hidden width 64) holds the
                          # tensor pipe 48.1 cycles (shared-memory operand fetch: 6 KB at 128 B/clk) for 32 cycles of math,
                          # so 0.665 is the ceiling for this kernel's MMA form (TS form: 32.1 cycles).  The kernel itself is
-                         # bound by MUFU: one tanh per hidden activation, 128 per texel, XU pipe 79 % busy (profiles/r01o).
+                         # bound by MUFU: one tanh per hidden activation, 128 per texel, XU pipe 78 % busy (profiles/r01q).
                          "attainable_frac_ss_form_hidden_64": 32.0 / 48.1,
                          "binding_pipe": "xu (MUFU.TANH, 128 per texel): 79 % busy"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

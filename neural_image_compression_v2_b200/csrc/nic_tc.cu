@@ -1015,6 +1015,10 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
   constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
   const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3), aOne = smem_u32(sOne), aAct = smem_u32(sAct);
   auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(GW_GROUP) : "memory"); };
+  auto group_wait = [&](uint32_t phase) {          // one polling warp per group, the others park at the named barrier
+    if (issuer_warp) mbar_wait(bar_full + slot, phase);
+    group_sync();
+  };
   // this thread's 8-byte piece holding features [f, f + 4) of its row (f a multiple of 4)
   auto piece = [&](int f) -> uint2* { return reinterpret_cast<uint2*>(sAct + (f >> 3) * KG + roff + (f & 7) * 2); };
 
@@ -1109,9 +1113,8 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
     // ------------------------------------------------------------------------------------ layers 1, 2: epilogues
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
-      mbar_wait(bar_full + slot, ph);
+      group_wait(ph);
       ph ^= 1;
-      __syncwarp();
       tc_fence_after();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -1142,9 +1145,8 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
       }
     }
     // ------------------------------------------------------------------------------------ output
-    mbar_wait(bar_full + slot, ph);
+    group_wait(ph);
     ph ^= 1;
-    __syncwarp();
     tc_fence_after();
     uint32_t acc[16];
     if (cout > 4) tmem_ld16(tD, acc);
