@@ -159,6 +159,18 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def xu_roofline(kernel_ms, clocks, sm_count):
+    """MUFU (XU pipe) roofline of the decode kernel: the binding pipe for this decoder."""
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+    out = {"pipe": "xu (MUFU)", "ops_per_texel": 134, "lanes_per_clk_per_sm": 16, "ncu_pct_busy": 78.3,
+           "source": "profiles/r01q_decode_tc2d_ws_final_metrics.txt"}
+    if mhz and kernel_ms:
+        peak = sm_count * 16 * mhz * 1e6                      # MUFU results per second
+        achieved = 134.0 * SIZE * SIZE / (kernel_ms * 1e-3)
+        out.update({"peak_gops": peak / 1e9, "achieved_gops": achieved / 1e9, "frac": achieved / peak, "sm_mhz": mhz})
+    return out
+
+
 def bench_train(args, nic, ic, var2, dev, world, rank, dist, barrier):
     """Fused training step at BASELINE config 1 shape: 512^2 image, 8 crops of 256^2 per rank per step (weak DP),
     Philox noise on, one all-reduce of the flat gradient buffer when world > 1, fused Adam + clamp."""
@@ -424,6 +436,7 @@ def run_ours(args):
     if rank == 0:
         tf_peak, hbm_peak, src = peaks()
         kms = kernel_ms / max(kernel_n, 1)
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
         achieved = FLOP_PER_TEXEL * texels / (kms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -445,7 +458,9 @@ def run_ours(args):
                          # so 0.665 is the ceiling for this kernel's MMA form (TS form: 32.1 cycles).  The kernel itself is
                          # bound by MUFU: one tanh per hidden activation, 128 per texel, XU pipe 78 % busy (profiles/r01q).
                          "attainable_frac_ss_form_hidden_64": 32.0 / 48.1,
-                         "binding_pipe": "xu (MUFU.TANH, 128 per texel): 79 % busy"},
+                         # the pipe that actually binds: 134 MUFU per texel (128 tanh + 3 x (ex2, rcp)), 16 lanes/clk/SM.
+                         # sm_count x 16 x SM clock = the XU peak; frac is against nvidia-smi's SM clock sampled under load
+                         "binding_pipe": xu_roofline(kms, clocks, sm_count)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "matches_resident_output": e2e_ok},
             "gpu_launches": int(launches), "clocks": clocks, "numa_node_rank0": numa,
