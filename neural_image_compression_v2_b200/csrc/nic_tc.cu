@@ -656,7 +656,8 @@ __global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, co
 // ================================================================================================ 2-D fast path, v2
 // Warp-specialised persistent form of the kernel above.  Knock-out experiments (NIC option 100, tools/run_decode.py)
 // showed the first versions were bound by the LATENCY of the per-tile chain (epilogue -> barrier -> MMA issue ->
-// ~95 cycles per tcgen05.mma -> commit -> wake-up -> tcgen05.ld), i.e. by how many tiles are in flight, not by any pipe.
+// MMAs (then ~95 cycles each: they were still issued from divergent control flow, see elect_one() in nic_tc_common.cuh)
+// -> commit -> wake-up -> tcgen05.ld), i.e. by how many tiles are in flight, not by any pipe.
 // TMEM caps that number: with the next layer's A operand in TMEM a tile needs 104 columns (4 tiles).  Here the
 // activations go to SHARED memory instead (st.shared in the UMMA K-major core-matrix layout, SS-form MMAs), a tile
 // needs only its 64 accumulator columns, and EIGHT tiles are in flight per SM:
