@@ -34,6 +34,34 @@ def test_library_exports_every_declared_symbol():
     assert nic.load_library().nic_abi_version() == 1
 
 
+def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
+    """include/nic.h compiles as C99 on its own (the boundary has no C++ or torch types) and every struct it declares has
+    the size and field offsets the ctypes binding assumes."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    structs = {"NicGeom": L.NicGeom, "NicMlp": L.NicMlp, "NicMlpGrad": L.NicMlpGrad, "NicAdamTensor": L.NicAdamTensor,
+               "NicExchange": L.NicExchange}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nic.h"', 'int main(void) {']
+    for name, st in structs.items():
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        for field, _ in st._fields_:
+            lines.append(f'  printf("{name} {field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for name, st in structs.items():
+        assert got[(name, "size")] == ctypes.sizeof(st), name
+        for field, _ in st._fields_:
+            assert got[(name, field)] == getattr(st, field).offset, (name, field)
+
+
 def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
