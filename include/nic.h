@@ -101,14 +101,17 @@ int64_t nic_launch_count(const NicHandle* h);
  * tensor-core nic_decode on this handle; if that call prepared its private tables (shadow grids, per-node G1 rows,
  * packed weights) for the same pointers, node counts, step, mip level and precision, they are reused instead of being
  * rebuilt (decoding one frame as several row bands).  Off by default: every call rebuilds from the caller's tensors. */
-/* NIC_OPT_LEGACY_FAST2D = 1 selects the first-generation fast-path decode kernel (A/B comparisons in tests). */
 /* NIC_OPT_DEBUG_KNOCKOUT: profiling only (tools/run_decode.py, tools/run_train.py) — decode: bit 0 skips the output
  * stores, bit 1 replaces GELU by a plain pack, bit 2 issues one MMA per layer; training: bit 4 skips the grid-gradient
  * atomics, bits 5 / 6 make nic_adam_step_exchange skip the flag wait / read only its own buffer (timing experiments in
  * tools/dp_timing.py); results are then WRONG on purpose.  Bit 3 only enables the training phase counters (nic_debug_counters) and
  * leaves the results unchanged.  Never set in production. */
-enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3, NIC_OPT_LEGACY_FAST2D = 4,
-       NIC_OPT_DEBUG_KNOCKOUT = 100 };
+/* NIC_OPT_GELU_POLY: how many of every 8 hidden activations of the fast 2-D tensor-core decode kernel evaluate GELU as a
+ * clamped minimax polynomial on the FMA pipe instead of MUFU.TANH (the kernel is bound by the XU pipe when all of them
+ * use the transcendental).  -1 = the tuned default; 0 = all MUFU (round-1 behaviour); values the library was not built
+ * with return NIC_ERR_UNSUPPORTED from nic_decode.  Both forms stay inside the tensor-core tolerance (+-1 LSB). */
+enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3,
+       NIC_OPT_GELU_POLY = 5, NIC_OPT_DEBUG_KNOCKOUT = 100 };
 int nic_set_option(NicHandle* h, int option, int value);
 /* With NIC_OPT_TIME_KERNELS = 1 every nic_decode / nic_train_step / nic_gather call brackets its DOMINANT kernel
  * (not the small preparation kernels) with CUDA events on the call's stream.  This call synchronises on the recorded

@@ -141,7 +141,7 @@ def handle(device):
 OPT_DISABLE_FAST2D = 1
 OPT_TIME_KERNELS = 2
 OPT_REUSE_PREPARED = 3
-OPT_LEGACY_FAST2D = 4
+OPT_GELU_POLY = 5            # share (of 8) of hidden activations on the polynomial GELU; -1 = tuned default
 OPT_DEBUG_KNOCKOUT = 100     # profiling only (nic.h); bit 3 = training phase counters
 
 

@@ -18,6 +18,7 @@ UNITS = [("nic_api.cu", [], "nic_api.o"), ("nic_f32.cu", [], "nic_f32.o"), ("nic
          ("nic_f32_mlp.cu", ["-DNIC_H=64", "-DNIC_PART=1"], "nic_f32_bwd64.o"),
          ("nic_f32_mlp.cu", ["-DNIC_H=32", "-DNIC_PART=0"], "nic_f32_fwd32.o"),
          ("nic_f32_mlp.cu", ["-DNIC_H=32", "-DNIC_PART=1"], "nic_f32_bwd32.o")]
+EXTRA = os.environ.get("NIC_EXTRA_NVCC_FLAGS", "").split()
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
@@ -46,7 +47,7 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         s, defs, o = job
-        r = subprocess.run([_nvcc()] + NVCC_FLAGS + defs + ["-c", s, "-o", o], capture_output=True, text=True)
+        r = subprocess.run([_nvcc()] + NVCC_FLAGS + EXTRA + defs + ["-c", s, "-o", o], capture_output=True, text=True)
         with open(o + ".log", "w") as f:
             f.write(r.stdout + r.stderr)
         return s, r

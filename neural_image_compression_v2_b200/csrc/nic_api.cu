@@ -74,6 +74,7 @@ int nic_create(int device, NicHandle** out) {
   h->sms = prop.multiProcessorCount;
   h->cc_major = prop.major;
   h->cc_minor = prop.minor;
+  h->gelu_poly = -1;
   strcpy(h->err, "no error");
   *out = h;
   return NIC_OK;
@@ -104,9 +105,13 @@ int nic_set_option(NicHandle* h, int option, int value) {
   if (!h) return fail(nullptr, NIC_ERR_ARG, "handle is NULL");
   if (option == NIC_OPT_DISABLE_FAST2D) { h->disable_fast2d = value != 0; return NIC_OK; }
   if (option == NIC_OPT_DEBUG_KNOCKOUT) { h->debug_flags = value; return NIC_OK; }
-  if (option == NIC_OPT_LEGACY_FAST2D) { h->legacy_fast2d = value != 0; return NIC_OK; }
   if (option == NIC_OPT_REUSE_PREPARED) { h->reuse_prepared = value != 0; return NIC_OK; }
   if (option == NIC_OPT_TIME_KERNELS) { h->time_kernels = value != 0; h->timed_count = 0; return NIC_OK; }
+  if (option == NIC_OPT_GELU_POLY) {
+    if (value < -1 || value > 8) return fail(h, NIC_ERR_ARG, "nic_set_option: NIC_OPT_GELU_POLY takes -1 (default) or 0..8");
+    h->gelu_poly = value;
+    return NIC_OK;
+  }
   return fail(h, NIC_ERR_ARG, "nic_set_option: unknown option %d", option);
 }
 

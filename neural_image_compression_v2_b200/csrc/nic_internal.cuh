@@ -38,10 +38,10 @@ struct Handle {
   int reuse_prepared;        // NIC_OPT_REUSE_PREPARED
   int debug_flags;           // knock-out experiments (option 100), never set in production
   unsigned long long* dbg_counters;   // 16 device counters (nic_debug_counters), allocated on first use
-  int legacy_fast2d;         // NIC_OPT_LEGACY_FAST2D: the first-generation (non warp-specialised) fast-path kernel
+  int gelu_poly;             // NIC_OPT_GELU_POLY: -1 = tuned default, 0..8 = activation pairs (of 8) on the polynomial GELU
   struct PreparedKey {       // what the tables in tc_weights / tc_shadow were last built from
     const void *g0, *g1, *w1, *b1, *w2, *b2, *w3, *b3;
-    int n0[3], n1[3], method, pe_kind, mip, fmt, fast, valid, code_bits;
+    int n0[3], n1[3], method, pe_kind, mip, fmt, fast, valid, code_bits, npoly;
     float step;
   } prepared;
   void* adam_desc;           // device copy of NicAdamTensor descriptors

@@ -3,19 +3,13 @@
 // Reference behaviour: finally_decode_input_* + ColorDecoder.forward inside decode_image
 // (Projects/image_compression.py:54-68, 170-211, 313-327).
 //
-// Shape of the computation per CTA (128 threads, one thread per texel row, 4 CTAs resident per SM so one
-// CTA's epilogue overlaps another's MMA):
-//   tile of 128 texels:
-//     gather   : each thread builds its decoder-input row (fp32), packs it to 16-bit pairs and writes it with
-//                tcgen05.st into TMEM columns [A, A+KX/2)  -> operand A of layer 1 (A-from-TMEM, "TS" MMA).
-//     layer 1  : KX/16 x tcgen05.mma (M=128, N=64, K=16)  A = TMEM, B = W1' in shared memory, D1 -> TMEM.
-//     epilogue : tcgen05.ld D1 -> packed tanh-GELU (x + x*tanh(u); the 1/2 is folded into W2') -> tcgen05.st H1.
-//     layer 2  : 5 x tcgen05.mma, A = H1 (TMEM, K = 64 + bias column block), B = W2'.
-//     epilogue : same -> H2.
-//     layer 3  : 5 x tcgen05.mma (N = 16), B = W3'.   epilogue: sigmoid, quantise, store.
-//   Biases ride in the K dimension: the row carries a constant 1 and the matching column of W' holds the bias
-//   (for layer 1 that column also absorbs the LOD input, which is constant for a launch).
-//   TMEM map (128 columns per CTA): [0,64) accumulator D (fp32), [64,64+KX/2) operand A (16-bit pairs).
+// Two kernels, both ONE persistent CTA per SM made of independent groups of 4 warps (a group = one tile of 128 texels =
+// the MMA M = the TMEM lanes; a group owns 64 accumulator columns of TMEM and its operand buffers in shared memory):
+//   decode_tc2d_ws_kernel   aligned full-resolution 2-D frames; layer 1 re-associated so no input row is ever built;
+//   decode_tc_gws_kernel    everything else (any mip / origin / block shape, both 3-D methods, random-access queries).
+// Per tile: layer 1 (KX/16 or 5 tcgen05.mma, M=128 N=64 K=16, SS form) -> epilogue: tcgen05.ld, packed GELU, st.shared in
+// the UMMA K-major layout -> layer 2 (4 MMAs + 1 bias MMA against a constant ones block) -> epilogue -> layer 3 (N=16)
+// -> sigmoid, quantise, store.  The 1/2 of GELU is folded into the next layer's weights.
 //
 // Algorithmic work: 2*(Cin*64 + 64*64 + 64*Cout) FLOP/texel (17,920 for the 2-D default); tensor-bound roofline.
 #include "nic_tc_common.cuh"
@@ -26,10 +20,10 @@ namespace nic {
 // Operand-B images in global memory, already in the shared-memory UMMA layout (K-major, no swizzle):
 //   byte offset of element (n, k) = (k/8)*LBO + (n/8)*128 + (n%8)*16 + (k%8)*2,  LBO = (Nrows/8)*128.
 // W1': [64 x KX]  col k < cin-1: W1[n][k];  col cin-1: b1[n] + lod*W1[n][cin-1];  rest 0.
-// W2': [64 x 80]  col k < 64: W2[n][k]/2;   col 64: b2[n];  rest 0.
-// W3': [16 x 80]  row n < cout: col k < 64: W3[n][k]/2; col 64: b3[n];  rest 0.
+// W2': [64 x 80]  col k < 64: W2[n][k]/2 (W2[n][k] for hidden columns on the polynomial GELU);   col 64: b2[n];  rest 0.
+// W3': [16 x 80]  row n < cout: col k < 64: W3[n][k]/2 (same rule); col 64: b3[n];  rest 0.
 template <int FMT>
-__global__ void pack_weights_kernel(MlpDev m, float lod, int KX, uint16_t* __restrict__ img) {
+__global__ void pack_weights_kernel(MlpDev m, float lod, int KX, uint16_t* __restrict__ img, int npoly) {
   const int H = 64;
   const int n1 = H * KX, n2 = H * 80, n3 = 16 * 80;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += gridDim.x * blockDim.x) {
@@ -42,22 +36,24 @@ __global__ void pack_weights_kernel(MlpDev m, float lod, int KX, uint16_t* __res
     int n = rem / 8, ke = rem - n * 8;
     int k = kc * 8 + ke;
     float v = 0.f;
+    // hidden column k arrives as 2*gelu (MUFU tanh form) or as gelu (polynomial form, gelu_poly_pair)
+    const float half = gelu_poly_column(k, npoly) ? 1.0f : 0.5f;
     if (which == 0) {
       if (k < m.cin - 1) v = m.w1[n * m.cin + k];
       else if (k == m.cin - 1) v = m.b1[n] + lod * m.w1[n * m.cin + k];
     } else if (which == 1) {
-      if (k < H) v = 0.5f * m.w2[n * H + k];
+      if (k < H) v = half * m.w2[n * H + k];
       else if (k == H) v = m.b2[n];
     } else if (n < m.cout) {
-      if (k < H) v = 0.5f * m.w3[n * H + k];
+      if (k < H) v = half * m.w3[n * H + k];
       else if (k == H) v = m.b3[n];
     }
     img[i] = to16<FMT>(v);
   }
 }
 
-// ------------------------------------------------------------------------------------------------ gather to registers
-// Decoder-input row of one texel for C = 12, PE = 6, built directly as packed 16-bit pairs (the operand-A registers):
+// ------------------------------------------------------------------------------------------------ decoder-input row
+// Decoder-input row of one texel for C = 12, PE = 6 as packed 16-bit pairs (the layer-1 A operand):
 //   pairs [6j, 6j+6)         corner j of G0 (raw copy of the shadow node)
 //   pairs [6*NC0, 6*NC0+6)   sum_j w_j * G1 corner j   (packed fma; w_j exact in f16)
 //   then 3 pairs per axis    positional encoding (shared-memory LUT for the triangular kind)
@@ -82,241 +78,9 @@ __device__ __forceinline__ int node_lin(const int* n, int dim, int x, int y, int
   return dim == 2 ? x * n[1] + y : (x * n[1] + y) * n[2] + z;
 }
 
-template <int METHOD, int FMT>
-__device__ __forceinline__ void gather_row_packed(const DevGeom& g, const ShadowGeom& sg, const int* p,
-                                                  const uint4* __restrict__ pe_lut, int lut_mask, uint32_t* xp) {
-  using S = RowShape<METHOD>;
-  using P = Pair<FMT>;
-  AxisCoord ax[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    ax[a] = axis_coord(p[a], g.step);
-    // memory safety for device-supplied origins (host-known origins are validated): keep i, i+1 inside the grid
-    ax[a].i0 = clampi(ax[a].i0, 0, g.n0[a] - 2 < 0 ? 0 : g.n0[a] - 2);
-    ax[a].i1 = clampi(ax[a].i1, 0, g.n1[a] - 2 < 0 ? 0 : g.n1[a] - 2);
-  }
-  // ---- G0 corners: raw copies
-#pragma unroll
-  for (int j = 0; j < S::NC0; ++j) {
-    const int8_t* d = S::DIM == 2 ? kCorner2D[j] : (METHOD == NIC_METHOD_3D ? kCorner3D[j] : kCorner3Dv2[j]);
-    int dz = S::DIM == 3 ? d[0] : 0;
-    const uint2* node = sg.s0 + 3 * node_lin(g.n0, S::DIM, ax[0].i0 + d[2], ax[1].i0 + d[1], ax[2].i0 + dz);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      uint2 v = __ldg(node + q);
-      xp[6 * j + 2 * q] = v.x;
-      xp[6 * j + 2 * q + 1] = v.y;
-    }
-  }
-  // ---- G1: weighted sum of corners
-  typename P::T2 acc[6];
-#pragma unroll
-  for (int j = 0; j < S::NC1; ++j) {
-    const int8_t* d = S::DIM == 2 ? kCorner2D[j] : kCorner3D[j];
-    int dz = S::DIM == 3 ? d[0] : 0;
-    const uint2* node = sg.s1 + 3 * node_lin(g.n1, S::DIM, ax[0].i1 + d[2], ax[1].i1 + d[1], ax[2].i1 + dz);
-    float f[3];
-    g1_factors(g, j, ax, f);
-    float w = f[0] * f[1];
-    if (S::DIM == 3) w *= f[2];
-    typename P::T2 w2 = P::cst(w);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      uint2 v = __ldg(node + q);
-      typename P::T2 a = *reinterpret_cast<typename P::T2*>(&v.x), b = *reinterpret_cast<typename P::T2*>(&v.y);
-      acc[2 * q] = j == 0 ? __hmul2(a, w2) : __hfma2(a, w2, acc[2 * q]);
-      acc[2 * q + 1] = j == 0 ? __hmul2(b, w2) : __hfma2(b, w2, acc[2 * q + 1]);
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 6; ++q) xp[6 * S::NC0 + q] = *reinterpret_cast<uint32_t*>(&acc[q]);
-  // ---- positional encoding: 3 pairs per axis
-  constexpr int PE0 = 6 * (S::NC0 + 1);
-#pragma unroll
-  for (int a = 0; a < S::DIM; ++a) {
-    if (g.pe_kind == NIC_PE_TRIANGULAR) {
-      uint4 e = pe_lut[p[a] & lut_mask];       // the encoding is periodic in the texel coordinate (period 16/step)
-      xp[PE0 + 3 * a] = e.x;
-      xp[PE0 + 3 * a + 1] = e.y;
-      xp[PE0 + 3 * a + 2] = e.z;
-    } else {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        float arg = __fmul_rn(ax[a].u1, g.pe_div[q]);
-        auto v = P::pack(sinf(arg), cosf(arg));
-        xp[PE0 + 3 * a + q] = *reinterpret_cast<uint32_t*>(&v);
-      }
-    }
-  }
-  // ---- bias carrier and padding.  CIN - 1 is even for all three methods: the 1 sits in the low half of its pair.
-  static_assert((S::CIN - 1) % 2 == 0, "bias column must be the low half of a pair");
-  {
-    auto one = P::pack(1.0f, 0.0f);
-    xp[(S::CIN - 1) / 2] = *reinterpret_cast<uint32_t*>(&one);
-#pragma unroll
-    for (int i = (S::CIN - 1) / 2 + 1; i < S::KX / 2; ++i) xp[i] = 0u;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ the kernel
 constexpr int TC_ROWS = 128;    // texels per tile = MMA M = TMEM lanes
-constexpr int TC_THREADS = 256; // 8 warps: warps w and w+4 share TMEM lane quarter w and split the columns
-constexpr int TC_TMEM_COLS = 128;
-constexpr int TC_COL_D = 0;     // accumulator columns [0, 64)
-constexpr int TC_COL_A = 64;    // operand-A columns   [64, 64 + KX/2)
 constexpr int TC_K2 = 80;       // K of layers 2/3: 64 hidden + the bias block
 constexpr int TC_LUT_MAX = 256; // positional-encoding LUT entries (period 16/step texels)
-
-template <int METHOD, int FMT, typename OutT>
-__global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, ShadowGeom sg,
-                                                                  const long long* __restrict__ origins,
-                                                                  const uint4* __restrict__ wimg, int cout,
-                                                                  int lut_n, OutT* __restrict__ out) {
-  using S = RowShape<METHOD>;
-  using P = Pair<FMT>;
-  constexpr int KX = S::KX;
-  constexpr int HALF = KX / 4;   // operand-A registers per warp group
-  constexpr int W1_BYTES = b_image_bytes(64, KX), W2_BYTES = b_image_bytes(64, TC_K2), W3_BYTES = b_image_bytes(16, TC_K2);
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* sW1 = smem_raw;
-  uint8_t* sW2 = sW1 + W1_BYTES;
-  uint8_t* sW3 = sW2 + W2_BYTES;
-  uint4* sLut = reinterpret_cast<uint4*>(sW3 + W3_BYTES);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sLut + TC_LUT_MAX);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-
-  const int tid = threadIdx.x, warp = uniform_warp_index();
-  const int grp = warp >> 2;                 // 0: columns [0, 32) of D / first half of the row; 1: the rest
-  const int row = tid & (TC_ROWS - 1);       // texel row of the tile = TMEM lane
-  // ---- one-time setup: TMEM allocation, barrier, weight images and PE LUT -> shared memory
-  if (warp == 0) tmem_alloc(tmem_slot, TC_TMEM_COLS);
-  if (tid == 0) mbar_init(mbar, 1);
-  {
-    uint4* dst = reinterpret_cast<uint4*>(smem_raw);
-    constexpr int NV = (W1_BYTES + W2_BYTES + W3_BYTES) / 16;
-    for (int i = tid; i < NV; i += TC_THREADS) dst[i] = __ldg(wimg + i);
-    for (int i = tid; i < lut_n; i += TC_THREADS) {
-      float u1 = __fmul_rn(__fmul_rn((float)i, g.step), 0.5f);
-      uint4 e;
-      auto v0 = P::pack(pe_triangular(u1, 0, 6), pe_triangular(u1, 1, 6));
-      auto v1 = P::pack(pe_triangular(u1, 2, 6), pe_triangular(u1, 3, 6));
-      auto v2 = P::pack(pe_triangular(u1, 4, 6), pe_triangular(u1, 5, 6));
-      e.x = *reinterpret_cast<uint32_t*>(&v0);
-      e.y = *reinterpret_cast<uint32_t*>(&v1);
-      e.z = *reinterpret_cast<uint32_t*>(&v2);
-      e.w = 0u;
-      sLut[i] = e;
-    }
-  }
-  fence_async_smem();            // weights (generic-proxy stores) -> visible to the tensor core (async proxy)
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const uint32_t tD = tmem + TC_COL_D, tA = tmem + TC_COL_A;
-
-  constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
-  constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
-  const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-  uint32_t phase = 0;
-
-  const unsigned ntiles = (unsigned)((g.N + TC_ROWS - 1) / TC_ROWS);
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const unsigned n = tile * TC_ROWS + row;
-    const bool live = n < (unsigned)g.N;
-    // ---- gather: each warp group builds and stores its half of the row (the other half is dead code per branch)
-    {
-      Texel t = texel_of_fast(g, live ? n : (unsigned)g.N - 1, origins);
-      uint32_t xp[KX / 2];
-      if (grp == 0) {
-        gather_row_packed<METHOD, FMT>(g, sg, t.p, sLut, lut_n - 1, xp);
-        store_row_part<HALF>(tA + lane_base, xp);
-      } else {
-        gather_row_packed<METHOD, FMT>(g, sg, t.p, sLut, lut_n - 1, xp);
-        store_row_part<HALF>(tA + lane_base + HALF, xp + HALF);
-      }
-    }
-    tc_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 1
-    if (warp == 0) {               // one warp issues and waits for the MMAs; the others sleep at the barrier below
-      if (elect_one()) {
-        tc_fence_after();
-#pragma unroll
-        for (int kc = 0; kc < KX / 16; ++kc)
-          mma_ts(tD, tA + kc * 8, make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
-        tc_commit(mbar);
-      }
-      __syncwarp();
-      mbar_wait(mbar, phase);
-    }
-    phase ^= 1;
-    __syncthreads();
-    tc_fence_after();
-    // ---- epilogue of layers 1 and 2: D -> 2*gelu -> H (operand A of the next layer), bias block [1, 0, ...]
-#pragma unroll 1
-    for (int layer = 0; layer < 2; ++layer) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint32_t acc[16];
-        tmem_ld16(tD + lane_base + grp * 32 + q * 16, acc);
-        tc_wait_ld();
-        uint32_t hp[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hp[i] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-        tmem_st8(tA + lane_base + grp * 16 + q * 8, hp);
-      }
-      if (layer == 0 && grp == 1) {   // the bias block survives layer 2's epilogue, which rewrites columns [0, 32) only
-        uint32_t ones[8];
-        auto one = P::pack(1.0f, 0.0f);
-        ones[0] = *reinterpret_cast<uint32_t*>(&one);
-#pragma unroll
-        for (int i = 1; i < 8; ++i) ones[i] = 0u;
-        tmem_st8(tA + lane_base + 32, ones);
-      }
-      tc_wait_st();
-      tc_fence_before();
-      __syncthreads();
-      if (warp == 0) {
-        if (elect_one()) {
-          tc_fence_after();
-          const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
-          const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
-#pragma unroll
-          for (int kc = 0; kc < TC_K2 / 16; ++kc)
-            mma_ts(tD, tA + kc * 8, make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
-          tc_commit(mbar);
-        }
-        __syncwarp();
-        mbar_wait(mbar, phase);
-      }
-      phase ^= 1;
-      __syncthreads();
-      tc_fence_after();
-    }
-    // ---- output (warp group 0): sigmoid, optional 8-bit quantisation.  Group 1 moves on to the next gather.
-    if (grp == 0) {
-      uint32_t acc[16];
-      tmem_ld16(tD + lane_base, acc);
-      tc_wait_ld();
-      if (live) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c)
-          if (c < cout) {
-            float z = __uint_as_float(acc[c]);
-            float v = __fdividef(1.0f, 1.0f + __expf(-z));
-            store_out(out + (size_t)n * cout + c, v);
-          }
-      }
-    }
-    // the next tile's tcgen05.st / mma reuse the A and D columns: order them after this tile's tcgen05.ld
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TC_TMEM_COLS);
-}
 
 // ================================================================================================ 2-D fast path
 // Full-resolution 2-D decode (step 1/4, interpolation on, triangular PE, block aligned to 8 x 16 texels): layer 1 is
@@ -325,10 +89,9 @@ __global__ void __launch_bounds__(TC_THREADS, 4) decode_tc_kernel(DevGeom g, Sha
 //      + sum_nodes tent(node, texel) * R[node]                   R[node] = W1[:, 48:60] * G1[node]   (per-node table)
 //      + LUTx[px mod 64] + LUTy[py mod 64]                       LUT = W1[:, 60:72] * PE(p) (+ bias and LOD in LUTx)
 // The last two lines are ONE constant 128 x 32 selector/weight matrix (tent weights, one-hot x, one-hot y) that stays
-// in TMEM for the life of the CTA, times per-tile table rows that are addressed in shared memory as an MN-major B
-// operand.  Row m of a tile is texel (cell = m % 8, within-cell index = m / 8).
+// in shared memory for the life of the CTA, times per-tile table rows that are addressed in shared memory as an MN-major
+// B operand.  Row m of a tile is texel (cell = m % 8, within-cell index = m / 8).
 constexpr int F_TX = 8, F_TY = 16;                 // tile extent in texels (x = first image axis)
-constexpr int F_COL_SEL = 104;                     // TMEM columns [104, 120): the selector matrix (32 halves / row)
 constexpr int F_W1G0 = b_image_bytes(64, 48);      // 6144
 constexpr int F_LUT = 64 * 64 * 2;                 // 8192 per axis
 constexpr int F_IMG = F_W1G0 + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2) + 2 * F_LUT;
@@ -376,7 +139,7 @@ __global__ void __launch_bounds__(128) g1_rows_kernel(MlpDev m, const float* __r
 // Weight images of the fast path: [W1g0 K-major 64x48][W2' 64x80][W3' 16x80][LUTx][LUTy]; LUT element (n, k = p mod 64)
 // at (k/8)*1024 + (n/8)*128 + (k%8)*16 + (n%8)*2  (MN-major B operand, 8 k-rows x 8 n per 128-byte block).
 template <int FMT>
-__global__ void pack_fast_kernel(MlpDev m, float lod, float step, uint16_t* __restrict__ img) {
+__global__ void pack_fast_kernel(MlpDev m, float lod, float step, uint16_t* __restrict__ img, int npoly) {
   const int H = 64, C = 12, PE = 6;
   const int n1 = H * 48, n2 = H * 80, n3 = 16 * 80, nl = 64 * 64;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3 + 2 * nl; i += gridDim.x * blockDim.x) {
@@ -387,9 +150,11 @@ __global__ void pack_fast_kernel(MlpDev m, float lod, float step, uint16_t* __re
       int nrows = which == 2 ? 16 : H;
       int kc = local / (nrows * 8), rem = local - kc * nrows * 8;
       int n = rem / 8, k = kc * 8 + (rem - n * 8);
+      // hidden column k arrives as 2*gelu (MUFU tanh form) or as gelu (polynomial form, gelu_poly_pair)
+      const float half = gelu_poly_column(k, npoly) ? 1.0f : 0.5f;
       if (which == 0) v = m.w1[n * m.cin + k];
-      else if (which == 1) v = k < H ? 0.5f * m.w2[n * H + k] : (k == H ? m.b2[n] : 0.f);
-      else if (n < m.cout) v = k < H ? 0.5f * m.w3[n * H + k] : (k == H ? m.b3[n] : 0.f);
+      else if (which == 1) v = k < H ? half * m.w2[n * H + k] : (k == H ? m.b2[n] : 0.f);
+      else if (n < m.cout) v = k < H ? half * m.w3[n * H + k] : (k == H ? m.b3[n] : 0.f);
     } else {
       int local = i - (n1 + n2 + n3);
       int axis = local / nl;
@@ -404,253 +169,6 @@ __global__ void pack_fast_kernel(MlpDev m, float lod, float step, uint16_t* __re
     }
     img[i] = to16<FMT>(v);
   }
-}
-
-// Fast-path kernel: 512 threads (16 warps: lane quarter = warp % 4, 16-column slice = warp / 4), two tiles in flight
-// per CTA in ping-pong so one tile's MMAs run under the other tile's epilogue; 2 CTAs per SM (256 TMEM columns each).
-//   TMEM: D0 [0,64) D1 [64,128) A0 [128,168) A1 [168,208) SEL [208,224).
-constexpr int F_THREADS = 512;
-constexpr int F_TMEM_COLS = 256;
-constexpr int F_COL_D = 0, F_COL_A = 128, F_COL_S = 208;
-constexpr int F_STAGE = 4096;                      // per-slot staging: [slot][Ag0 1 KB | G1 rows 1 KB]
-
-template <int FMT, typename OutT>
-__global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, const uint2* __restrict__ shadow0,
-                                                                   const uint4* __restrict__ R,
-                                                                   const uint4* __restrict__ wimg, int cout,
-                                                                   unsigned tiles_y, unsigned fd_mul, unsigned fd_shift,
-                                                                   OutT* __restrict__ out) {
-  using P = Pair<FMT>;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* sW = smem_raw + F_STAGE;                 // weight images + LUTs sit ABOVE the staging buffers (LBO = distance)
-  uint8_t* sW1 = sW;
-  uint8_t* sW2 = sW1 + F_W1G0;
-  uint8_t* sW3 = sW2 + b_image_bytes(64, TC_K2);
-  uint8_t* sLx = sW3 + b_image_bytes(16, TC_K2);
-  uint8_t* sLy = sLx + F_LUT;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(sLy + F_LUT);       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
-
-  const int tid = threadIdx.x, warp = uniform_warp_index();
-  const int cs = warp >> 2;                          // which 16 accumulator columns this thread owns
-  const int row = tid & (TC_ROWS - 1);
-  if (warp == 0) tmem_alloc(tmem_slot, F_TMEM_COLS);
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    mbar_init(mbar + 1, 1);
-  }
-  {
-    uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (int i = tid; i < F_IMG / 16; i += F_THREADS) dst[i] = __ldg(wimg + i);
-    for (int i = tid; i < F_STAGE / 16; i += F_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
-  }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-
-  // ---- this thread's texel inside a tile: row m = cell + 8 * within
-  const int cell = row & 7, within = row >> 3;
-  const int lx = 4 * (cell >> 2) + (within >> 2), ly = 4 * (cell & 3) + (within & 3);
-  // ---- constants in TMEM: selector rows (slice-1 warps), bias blocks of both A slots (slice-0 warps)
-  if (cs == 1) {
-    float kx = (float)lx * 0.125f, ky = (float)(ly & 7) * 0.125f;
-    int cy1 = ly >> 3;
-    float sel[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) sel[i] = 0.f;
-#pragma unroll
-    for (int ix = 0; ix < 2; ++ix)
-#pragma unroll
-      for (int iy = 0; iy < 3; ++iy) {
-        float wx = ix ? kx : 1.0f - kx;
-        float wy = iy == cy1 ? 1.0f - ky : (iy == cy1 + 1 ? ky : 0.f);
-        sel[ix * 3 + iy] = wx * wy;
-      }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sel[8 + j] = j == lx ? 1.f : 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) sel[16 + j] = j == ly ? 1.f : 0.f;
-    uint32_t sp[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      auto v = P::pack(sel[2 * i], sel[2 * i + 1]);
-      sp[i] = *reinterpret_cast<uint32_t*>(&v);
-    }
-    tmem_st16(tmem + F_COL_S + lane_base, sp);
-  } else if (cs == 0) {
-    uint32_t ones[8];
-    auto one = P::pack(1.0f, 0.0f);
-    ones[0] = *reinterpret_cast<uint32_t*>(&one);
-#pragma unroll
-    for (int i = 1; i < 8; ++i) ones[i] = 0u;
-    tmem_st8(tmem + F_COL_A + lane_base + 32, ones);
-    tmem_st8(tmem + F_COL_A + 40 + lane_base + 32, ones);
-  }
-  tc_wait_st();
-
-  constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
-  constexpr uint32_t IDESC_64_BMN = make_idesc(FMT, 128, 64, 1);
-  constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
-  const uint32_t aStage = smem_u32(smem_raw), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-  const uint32_t aLx = smem_u32(sLx), aLy = smem_u32(sLy);
-  const int ny0 = g.n0[1], ny1 = g.n1[1];
-  const unsigned ntiles = (unsigned)(g.B[0] / F_TX) * tiles_y;
-  const unsigned npairs = (ntiles + 1) >> 1;
-  uint32_t ph0 = 0, ph1 = 0;
-
-  // ---- staging: thread t < 288 fetches one piece of tile (t >= 144) of the pair
-  const int st_slot = tid >= 144, st_t = tid - 144 * st_slot;
-  const bool st_active = tid < 288;
-  uint4 pre = make_uint4(0, 0, 0, 0);
-  auto tile_origin = [&](unsigned tile, int& px0, int& py0, int& bx0, int& by0) {
-    unsigned tx = fastdiv31(tile, fd_mul, fd_shift), ty = tile - tx * tiles_y;
-    bx0 = (int)tx * F_TX;
-    by0 = (int)ty * F_TY;
-    px0 = g.origin0[0] + bx0;
-    py0 = g.origin0[1] + by0;
-  };
-  auto prefetch = [&](unsigned pair) {
-    unsigned tile = 2 * pair + st_slot;
-    if (!st_active || tile >= ntiles) return;
-    int px0, py0, bx0, by0;
-    tile_origin(tile, px0, py0, bx0, by0);
-    if (st_t < 96) {
-      int c8 = st_t / 12, piece = st_t - c8 * 12;
-      int seg = piece >= 6, off = piece - seg * 6;
-      int nx_ = (px0 >> 2) + (c8 >> 2) + seg, ny_ = (py0 >> 2) + (c8 & 3);
-      uint2 v = __ldg(shadow0 + ((size_t)nx_ * ny0 + ny_) * 3 + off);      // nodes (x, y) and (x, y + 1) are contiguous
-      pre.x = v.x;
-      pre.y = v.y;
-    } else {
-      int t2 = st_t - 96, r6 = t2 >> 3, piece = t2 & 7;
-      int nx_ = (px0 >> 3) + r6 / 3, ny_ = (py0 >> 3) + r6 % 3;
-      pre = __ldg(R + ((size_t)nx_ * ny1 + ny_) * 8 + piece);
-    }
-  };
-  auto commit_stage = [&]() {
-    if (!st_active) return;
-    uint8_t* base = smem_raw + st_slot * 2048;
-    if (st_t < 96) {
-      int c8 = st_t / 12, piece = st_t - c8 * 12;
-      int seg = piece >= 6, off = piece - seg * 6;
-      int k = seg * 24 + off * 4;
-      *reinterpret_cast<uint2*>(base + (k >> 3) * 128 + c8 * 16 + (k & 7) * 2) = make_uint2(pre.x, pre.y);
-    } else {
-      int t2 = st_t - 96, r6 = t2 >> 3, piece = t2 & 7;
-      *reinterpret_cast<uint4*>(base + 1024 + piece * 128 + r6 * 16) = pre;
-    }
-  };
-  // layer 1 of the tile in `slot`: 3 aliased-cell MMAs (G0) + [G1 rows | LUTx] + [LUTy]
-  auto issue_layer1 = [&](int slot, unsigned tile) {
-    int px0, py0, bx0, by0;
-    tile_origin(tile, px0, py0, bx0, by0);
-    const uint32_t tD = tmem + F_COL_D + slot * 64, tS = tmem + F_COL_S;
-    const uint32_t aAg0 = aStage + slot * 2048, aG1 = aAg0 + 1024;
-#pragma unroll
-    for (int kc = 0; kc < 3; ++kc)
-      mma_ss(tD, make_smem_desc(aAg0 + kc * 256, 128, 0), make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
-    const uint32_t lx_grp = aLx + ((px0 & 63) >> 3) * 1024;
-    mma_ts(tD, tS, make_smem_desc(aG1, lx_grp - aG1, SBO), IDESC_64_BMN, 1);
-    mma_ts(tD, tS + 8, make_smem_desc(aLy + ((py0 & 63) >> 3) * 1024, 1024, SBO), IDESC_64_BMN, 1);
-    tc_commit(mbar + slot);
-  };
-  auto issue_layer23 = [&](int slot, int layer) {
-    const uint32_t tD = tmem + F_COL_D + slot * 64, tA = tmem + F_COL_A + slot * 40;
-    const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
-    const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
-#pragma unroll
-    for (int kc = 0; kc < TC_K2 / 16; ++kc)
-      mma_ts(tD, tA + kc * 8, make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
-    tc_commit(mbar + slot);
-  };
-  // epilogue of one hidden layer: this thread's 16 accumulator columns -> 8 packed activations
-  auto epilogue = [&](int slot) {
-    uint32_t acc[16];
-    tmem_ld16(tmem + F_COL_D + slot * 64 + lane_base + cs * 16, acc);
-    tc_wait_ld();
-    uint32_t hp[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) hp[i] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-    tmem_st8(tmem + F_COL_A + slot * 40 + lane_base + cs * 8, hp);
-    tc_wait_st();
-    tc_fence_before();
-  };
-  auto output = [&](int slot, unsigned tile) {
-    if (cs != 0) return;
-    int px0, py0, bx0, by0;
-    tile_origin(tile, px0, py0, bx0, by0);
-    uint32_t acc[16];
-    tmem_ld16(tmem + F_COL_D + slot * 64 + lane_base, acc);
-    tc_wait_ld();
-    const size_t n = (size_t)(bx0 + lx) * g.B[1] + (by0 + ly);
-#pragma unroll
-    for (int c = 0; c < 16; ++c)
-      if (c < cout) store_out(out + n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
-    tc_fence_before();
-  };
-
-  prefetch(blockIdx.x);
-  for (unsigned pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-    const unsigned tA_ = 2 * pair, tB_ = 2 * pair + 1;
-    const bool hasB = tB_ < ntiles;
-    commit_stage();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-      if (elect_one()) {
-        tc_fence_after();
-        issue_layer1(0, tA_);
-        if (hasB) issue_layer1(1, tB_);
-      }
-      __syncwarp();
-    }
-    prefetch(pair + gridDim.x);                 // next pair's operands: in flight during this pair's epilogues
-#pragma unroll 1
-    for (int layer = 0; layer < 2; ++layer) {
-      mbar_wait_sleep(mbar, ph0);
-      ph0 ^= 1;
-      tc_fence_after();
-      epilogue(0);
-      __syncthreads();
-      if (warp == 0) {
-        if (elect_one()) {
-          tc_fence_after();
-          issue_layer23(0, layer);
-        }
-        __syncwarp();
-      }
-      if (hasB) {
-        mbar_wait_sleep(mbar + 1, ph1);
-        ph1 ^= 1;
-        tc_fence_after();
-        epilogue(1);
-      }
-      __syncthreads();
-      if (hasB && warp == 0) {
-        if (elect_one()) {
-          tc_fence_after();
-          issue_layer23(1, layer);
-        }
-        __syncwarp();
-      }
-    }
-    mbar_wait_sleep(mbar, ph0);
-    ph0 ^= 1;
-    tc_fence_after();
-    output(0, tA_);
-    if (hasB) {
-      mbar_wait_sleep(mbar + 1, ph1);
-      ph1 ^= 1;
-      tc_fence_after();
-      output(1, tB_);
-    }
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, F_TMEM_COLS);
 }
 
 // ================================================================================================ 2-D fast path, v2
@@ -671,6 +189,7 @@ __global__ void __launch_bounds__(F_THREADS, 2) decode_tc2d_kernel(DevGeom g, co
 //   * the group stages its own operands: its threads fetch the pieces (8 B of a G0 cell row / 16 B of a G1 node row)
 //     of the tile after next into registers while the current tile is processed.
 constexpr int WS_SLOTS = 8, WS_GROUP = 128, WS_THREADS = WS_SLOTS * WS_GROUP;
+constexpr int WS_NPOLY_F16 = 3, WS_NPOLY_BF16 = 3;   // default share (of 8) of activation pairs on the polynomial GELU
 constexpr int WS_TMEM_COLS = 512;
 constexpr int WS_STAGE = WS_SLOTS * 2 * 2048;       // [slot][buffer][Ag0 1 KB | G1 rows 1 KB]
 constexpr int WS_KG = 16 * 128;                     // bytes of one k-group (8 columns) of a 128-row K-major A operand
@@ -680,6 +199,19 @@ constexpr int WS_OFF_ACT = WS_OFF_ONE + 2 * WS_KG;  // [slot] 128 x 64 activatio
 constexpr int WS_OFF_BAR = WS_OFF_ACT + WS_SLOTS * 8 * WS_KG;
 constexpr int WS_SMEM = WS_OFF_BAR + 256;
 
+// Output activation of the warp-specialised kernels: sigmoid(z) = 1/2 + 1/2 tanh(z/2) — one MUFU instead of ex2 + rcp; the
+// 8-bit code is floor(v * 255 + .5) of exactly the float this kernel would store (separate multiply and add like
+// models.quantize_to_bit), and needs no clamp because v is in [0, 1].
+__device__ __forceinline__ float sigmoid_tanh(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(z * 0.5f));
+  return fmaf(t, 0.5f, 0.5f);
+}
+__device__ __forceinline__ void store_sigmoid(float* p, float z) { *p = sigmoid_tanh(z); }
+__device__ __forceinline__ void store_sigmoid(uint8_t* p, float z) {
+  *p = (uint8_t)__float2uint_rd(__fadd_rn(__fmul_rn(sigmoid_tanh(z), 255.0f), 0.5f));
+}
+
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -687,7 +219,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
                : "memory");
 }
 
-template <int FMT, typename OutT>
+template <int FMT, typename OutT, int NPOLY>
 __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g, const uint2* __restrict__ shadow0,
                                                                        const uint4* __restrict__ R,
                                                                        const uint4* __restrict__ wimg, int cout,
@@ -774,7 +306,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
   const uint32_t tDs = tmem + slot * 64;             // this slot's accumulator columns
   const uint32_t tD = tDs + ((uint32_t)((warp & 3) * 32) << 16);
   uint8_t* sAct = smem_raw + WS_OFF_ACT + slot * 8 * WS_KG;
-  const bool issuer_warp = (warp & 3) == 0;          // its elected lane issues the group's MMAs (uniform control flow)
+  // the group's issuing (and polling) warp: a different lane quarter for consecutive groups, so the eight issuers are
+  // spread over the four SM sub-partitions (warp % 4) instead of all sitting on sub-partition 0
+  const bool issuer_warp = (warp & 3) == (slot & 3);
   constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
   constexpr uint32_t IDESC_64_BMN = make_idesc(FMT, 128, 64, 1);
   constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
@@ -788,68 +322,83 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
     if (issuer_warp) mbar_wait(bar_full + slot, phase);
     group_sync();
   };
-  // ---- operand staging: 144 pieces per tile over 128 threads (threads 0..15 take a second piece)
+  // ---- operand staging: 144 pieces per tile over 128 threads (threads 0..15 take a second piece).  Piece p of a tile:
+  //   p < 96 : 8 bytes of a G0 cell row  (cell c8 = p / 12; the two 24-byte halves of a row are the nodes (x, y) and
+  //            (x, y + 1), contiguous in the channel-last shadow, for x and x + 1);
+  //   p >= 96: 16 bytes of one of the 2 x 3 G1 node rows R[node] the tile touches.
+  // Which piece a thread moves never changes, so everything but the tile's base node is formed once, here: a thread
+  // keeps a pointer (pre-offset by its piece) and its shared-memory offset per piece.
+  const bool g0_piece = gt < 96;                     // warp-uniform (warps 0..2 of a group: G0, warp 3: G1 rows)
+  const uint8_t* src0;                               // this thread's primary piece at tile base 0
+  uint32_t dst0;                                     // and where it goes inside a staging buffer
+  if (g0_piece) {
+    const int c8 = gt / 12, piece = gt - c8 * 12, seg = piece >= 6, off = piece - seg * 6, k = seg * 24 + off * 4;
+    src0 = reinterpret_cast<const uint8_t*>(shadow0 + ((size_t)((c8 >> 2) + seg) * ny0 + (c8 & 3)) * 3 + off);
+    dst0 = (k >> 3) * 128 + c8 * 16 + (k & 7) * 2;
+  } else {
+    const int t2 = gt - 96, r6 = t2 >> 3, piece = t2 & 7;
+    src0 = reinterpret_cast<const uint8_t*>(R + ((size_t)(r6 / 3) * ny1 + r6 % 3) * 8 + piece);
+    dst0 = 1024 + piece * 128 + r6 * 16;
+  }
+  const int r6b = 4 + (gt >> 3);                     // second piece of threads 0..15: G1 rows 4, 5
+  const uint8_t* src1 = reinterpret_cast<const uint8_t*>(R + ((size_t)(r6b / 3) * ny1 + r6b % 3) * 8 + (gt & 7));
+  const uint32_t dst1 = 1024 + (gt & 7) * 128 + r6b * 16;
+  const uint32_t out_thread = (uint32_t)lx * (uint32_t)g.B[1] + (uint32_t)ly;      // this thread's texel inside a tile
   uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = make_uint4(0, 0, 0, 0);
-  auto fetch_piece = [&](int p, int px0, int py0) -> uint4 {
-    if (p < 96) {
-      int c8 = p / 12, piece = p - c8 * 12;
-      int seg = piece >= 6, off = piece - seg * 6;
-      int nx_ = (px0 >> 2) + (c8 >> 2) + seg, ny_ = (py0 >> 2) + (c8 & 3);
-      uint2 v = __ldg(shadow0 + ((size_t)nx_ * ny0 + ny_) * 3 + off);      // nodes (x, y) and (x, y + 1) are contiguous
-      return make_uint4(v.x, v.y, 0, 0);
-    }
-    int t2 = p - 96, r6 = t2 >> 3, piece = t2 & 7;
-    int nx_ = (px0 >> 3) + r6 / 3, ny_ = (py0 >> 3) + r6 % 3;
-    return __ldg(R + ((size_t)nx_ * ny1 + ny_) * 8 + piece);
-  };
-  auto store_piece = [&](uint8_t* base, int p, const uint4& v) {
-    if (p < 96) {
-      int c8 = p / 12, piece = p - c8 * 12;
-      int seg = piece >= 6, off = piece - seg * 6;
-      int k = seg * 24 + off * 4;
-      *reinterpret_cast<uint2*>(base + (k >> 3) * 128 + c8 * 16 + (k & 7) * 2) = make_uint2(v.x, v.y);
-    } else {
-      int t2 = p - 96, r6 = t2 >> 3, piece = t2 & 7;
-      *reinterpret_cast<uint4*>(base + 1024 + piece * 128 + r6 * 16) = v;
-    }
-  };
-  auto fetch = [&](unsigned i) {
+  auto fetch = [&](unsigned i) {          // pieces of tile i -> registers
     if (i >= my_tiles) return;
     int px0, py0, bx0, by0;
     tile_origin(blockIdx.x + i * gridDim.x, px0, py0, bx0, by0);
-    pre0 = fetch_piece(gt, px0, py0);
-    if (gt < 16) pre1 = fetch_piece(128 + gt, px0, py0);
+    const size_t b0 = ((size_t)(px0 >> 2) * ny0 + (py0 >> 2)) * 24, b1 = ((size_t)(px0 >> 3) * ny1 + (py0 >> 3)) * 128;
+    if (g0_piece) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(src0 + b0));
+      pre0 = make_uint4(v.x, v.y, 0, 0);
+    } else {
+      pre0 = __ldg(reinterpret_cast<const uint4*>(src0 + b1));
+    }
+    if (gt < 16) pre1 = __ldg(reinterpret_cast<const uint4*>(src1 + b1));
   };
   auto stage = [&](unsigned i) {          // store the fetched pieces of tile i into its staging buffer
     if (i >= my_tiles) return;
     uint8_t* base = smem_raw + (slot * 2 + ((i / WS_SLOTS) & 1)) * 2048;
-    store_piece(base, gt, pre0);
-    if (gt < 16) store_piece(base, 128 + gt, pre1);
+    if (g0_piece) *reinterpret_cast<uint2*>(base + dst0) = make_uint2(pre0.x, pre0.y);
+    else *reinterpret_cast<uint4*>(base + dst0) = pre0;
+    if (gt < 16) *reinterpret_cast<uint4*>(base + dst1) = pre1;
     fence_async_smem();
   };
+  // Descriptors as 32-bit halves (mma_ss_lohi): everything that does not depend on the tile is formed once, here; per
+  // tile the issuing thread adds the staging-buffer parity and the two LUT groups.
+  constexpr uint32_t HI_SBO = smem_desc_hi(SBO), HI_SBO0 = smem_desc_hi(0);
+  const uint32_t loAg0 = smem_desc_lo(aStage + slot * 2 * 2048, 128);        // + parity * 128 + kc * 16
+  const uint32_t loW1 = smem_desc_lo(aW1, LBO_64);                           // + kc * (2 * LBO_64 >> 4)
+  const uint32_t loSel = smem_desc_lo(aSel, WS_KG);
+  const uint32_t loLy = smem_desc_lo(aLy, 1024);                             // + group * 64
+  const uint32_t loAct = smem_desc_lo(aAct, WS_KG), loOne = smem_desc_lo(aOne, WS_KG);
+  const uint32_t loW2 = smem_desc_lo(aW2, LBO_64), loW3 = smem_desc_lo(aW3, LBO_16);
   auto issue_layer1 = [&](unsigned i) {          // elected lane only; tile i's operands are staged
     int px0, py0, bx0, by0;
     tile_origin(blockIdx.x + i * gridDim.x, px0, py0, bx0, by0);
-    const uint32_t aAg0 = aStage + (slot * 2 + ((i / WS_SLOTS) & 1)) * 2048, aG1 = aAg0 + 1024;
+    const uint32_t par = (i / WS_SLOTS) & 1;
+    const uint32_t aG1 = aStage + (slot * 2 + par) * 2048 + 1024;
 #pragma unroll
     for (int kc = 0; kc < 3; ++kc)
       if (!((dbg & 4) && kc > 0))
-        mma_ss(tDs, make_smem_desc(aAg0 + kc * 256, 128, 0), make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
-    const uint32_t lx_grp = aLx + ((px0 & 63) >> 3) * 1024;
+        mma_ss_lohi(tDs, loAg0 + par * 128 + kc * 16, HI_SBO0, loW1 + kc * (2 * LBO_64 >> 4), HI_SBO, IDESC_64, kc > 0);
     if (!(dbg & 4)) {
-      mma_ss(tDs, make_smem_desc(aSel, WS_KG, SBO), make_smem_desc(aG1, lx_grp - aG1, SBO), IDESC_64_BMN, 1);
-      mma_ss(tDs, make_smem_desc(aSel + 2 * WS_KG, WS_KG, SBO), make_smem_desc(aLy + ((py0 & 63) >> 3) * 1024, 1024, SBO),
-             IDESC_64_BMN, 1);
+      // selector x [G1 rows of this tile | LUTx group]: the B operand's LBO is the distance between the two pieces
+      const uint32_t lx_grp = aLx + ((px0 & 63) >> 3) * 1024;
+      mma_ss_lohi(tDs, loSel, HI_SBO, (aG1 >> 4) | (((lx_grp - aG1) >> 4) << 16), HI_SBO, IDESC_64_BMN, 1);
+      mma_ss_lohi(tDs, loSel + (2 * WS_KG >> 4), HI_SBO, loLy + ((py0 & 63) >> 3) * 64, HI_SBO, IDESC_64_BMN, 1);
     }
     tc_commit(bar_full + slot);
   };
   auto issue_layer23 = [&](int layer) {          // elected lane only: A = this slot's activations (+ the ones block: bias)
-    const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
+    const uint32_t loW = layer == 0 ? loW2 : loW3, stepW = layer == 0 ? (2 * LBO_64 >> 4) : (2 * LBO_16 >> 4);
     const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc)
-      if (!((dbg & 4) && kc > 0)) mma_ss(tDs, make_smem_desc(aAct + kc * 2 * WS_KG, WS_KG, SBO), make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
-    if (!(dbg & 4)) mma_ss(tDs, make_smem_desc(aOne, WS_KG, SBO), make_smem_desc(aW + 4 * 2 * lbo, lbo, SBO), idesc, 1);
+      if (!((dbg & 4) && kc > 0)) mma_ss_lohi(tDs, loAct + kc * (2 * WS_KG >> 4), HI_SBO, loW + kc * stepW, HI_SBO, idesc, kc > 0);
+    if (!(dbg & 4)) mma_ss_lohi(tDs, loOne, HI_SBO, loW + 4 * stepW, HI_SBO, idesc, 1);
     tc_commit(bar_full + slot);
   };
 
@@ -888,7 +437,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) hp[k] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]));
+          for (int k = 0; k < 8; ++k)
+            hp[k] = gelu_poly_pair_sel(k, NPOLY) ? gelu_poly_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]))
+                                                 : gelu2x_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]));
         }
         *reinterpret_cast<uint4*>(sAct + (2 * q) * WS_KG + roff) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
         *reinterpret_cast<uint4*>(sAct + (2 * q + 1) * WS_KG + roff) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
@@ -925,14 +476,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
     {
       int px0, py0, bx0, by0;
       tile_origin(tile, px0, py0, bx0, by0);
-      const size_t n = (size_t)(bx0 + lx) * g.B[1] + (by0 + ly);
+      const size_t n = (size_t)((uint32_t)bx0 * (uint32_t)g.B[1] + (uint32_t)by0 + out_thread);      // < 2^31 (launcher)
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        if (c < cout && !(dbg & 1)) store_out(out + n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+        if (c < cout && !(dbg & 1)) store_sigmoid(out + n * cout + c, __uint_as_float(acc[c]));
       if (cout > 4) {
 #pragma unroll
         for (int c = 4; c < 16; ++c)
-          if (c < cout) store_out(out + n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+          if (c < cout) store_sigmoid(out + n * cout + c, __uint_as_float(acc[c]));
       }
     }
   }
@@ -954,7 +505,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
 //            operand buffer with the next layer's activations;  the groups never meet at a CTA-wide barrier.
 constexpr int GW_GROUP = 128;
 
-template <int METHOD, int FMT, typename OutT>
+template <int METHOD, int FMT, typename OutT, int NPOLY>
 __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 * GW_GROUP, 1)
     decode_tc_gws_kernel(DevGeom g, ShadowGeom sg, const long long* __restrict__ origins, const uint4* __restrict__ wimg,
                          int cout, int lut_n, OutT* __restrict__ out) {
@@ -1011,7 +562,9 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
   const uint32_t tDs = tmem + slot * 64;
   const uint32_t tD = tDs + ((uint32_t)((warp & 3) * 32) << 16);
   uint8_t* sAct = smem_raw + OFF_ACT + slot * ACT_BYTES;
-  const bool issuer_warp = (warp & 3) == 0;          // its elected lane issues the group's MMAs (uniform control flow)
+  // the group's issuing (and polling) warp: a different lane quarter for consecutive groups, so the eight issuers are
+  // spread over the four SM sub-partitions (warp % 4) instead of all sitting on sub-partition 0
+  const bool issuer_warp = (warp & 3) == (slot & 3);
   constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64), IDESC_16 = make_idesc(FMT, 128, 16);
   constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
   const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3), aOne = smem_u32(sOne), aAct = smem_u32(sAct);
@@ -1020,6 +573,9 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
     if (issuer_warp) mbar_wait(bar_full + slot, phase);
     group_sync();
   };
+  constexpr uint32_t HI_SBO = smem_desc_hi(SBO);      // descriptors as 32-bit halves (mma_ss_lohi)
+  const uint32_t loAct = smem_desc_lo(aAct, KG), loOne = smem_desc_lo(aOne, KG);
+  const uint32_t loW1 = smem_desc_lo(aW1, LBO_64), loW2 = smem_desc_lo(aW2, LBO_64), loW3 = smem_desc_lo(aW3, LBO_16);
   // this thread's 8-byte piece holding features [f, f + 4) of its row (f a multiple of 4)
   auto piece = [&](int f) -> uint2* { return reinterpret_cast<uint2*>(sAct + (f >> 3) * KG + roff + (f & 7) * 2); };
 
@@ -1106,7 +662,7 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
         tc_fence_after();
 #pragma unroll
         for (int kc = 0; kc < KX / 16; ++kc)
-          mma_ss(tDs, make_smem_desc(aAct + kc * 2 * KG, KG, SBO), make_smem_desc(aW1 + kc * 2 * LBO_64, LBO_64, SBO), IDESC_64, kc > 0);
+          mma_ss_lohi(tDs, loAct + kc * (2 * KG >> 4), HI_SBO, loW1 + kc * (2 * LBO_64 >> 4), HI_SBO, IDESC_64, kc > 0);
         tc_commit(bar_full + slot);
       }
       __syncwarp();
@@ -1124,7 +680,9 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
         tc_wait_ld();
         uint32_t hp[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) hp[k] = gelu2x_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]));
+        for (int k = 0; k < 8; ++k)
+          hp[k] = gelu_poly_pair_sel(k, NPOLY) ? gelu_poly_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]))
+                                               : gelu2x_pair<FMT>(__uint_as_float(acc[2 * k]), __uint_as_float(acc[2 * k + 1]));
         *reinterpret_cast<uint4*>(sAct + (2 * q) * KG + roff) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
         *reinterpret_cast<uint4*>(sAct + (2 * q + 1) * KG + roff) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
       }
@@ -1134,12 +692,12 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
       if (issuer_warp) {
         if (elect_one()) {
           tc_fence_after();
-          const uint32_t aW = layer == 0 ? aW2 : aW3, lbo = layer == 0 ? LBO_64 : LBO_16;
+          const uint32_t loW = layer == 0 ? loW2 : loW3, stepW = layer == 0 ? (2 * LBO_64 >> 4) : (2 * LBO_16 >> 4);
           const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
 #pragma unroll
           for (int kc = 0; kc < 4; ++kc)
-            mma_ss(tDs, make_smem_desc(aAct + kc * 2 * KG, KG, SBO), make_smem_desc(aW + kc * 2 * lbo, lbo, SBO), idesc, kc > 0);
-          mma_ss(tDs, make_smem_desc(aOne, KG, SBO), make_smem_desc(aW + 4 * 2 * lbo, lbo, SBO), idesc, 1);
+            mma_ss_lohi(tDs, loAct + kc * (2 * KG >> 4), HI_SBO, loW + kc * stepW, HI_SBO, idesc, kc > 0);
+          mma_ss_lohi(tDs, loOne, HI_SBO, loW + 4 * stepW, HI_SBO, idesc, 1);
           tc_commit(bar_full + slot);
         }
         __syncwarp();
@@ -1157,11 +715,11 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
     if (live) {
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        if (c < cout) store_out(out + (size_t)n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+        if (c < cout) store_sigmoid(out + (size_t)n * cout + c, __uint_as_float(acc[c]));
       if (cout > 4) {
 #pragma unroll
         for (int c = 4; c < 16; ++c)
-          if (c < cout) store_out(out + (size_t)n * cout + c, __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c]))));
+          if (c < cout) store_sigmoid(out + (size_t)n * cout + c, __uint_as_float(acc[c]));
       }
     }
     // (every thread passes its own tcgen05.wait::ld above before it reaches the next tile's pre-MMA barrier, so the next
@@ -1175,13 +733,14 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
 // ------------------------------------------------------------------------------------------------ launcher
 // NIC_OPT_REUSE_PREPARED: do the private tables already describe these inputs?
 static Handle::PreparedKey make_key(const DevGeom& g, const MlpDev& m, const float* g0, const float* g1, int fmt, int fast,
-                                    int code_bits = 0) {
+                                    int code_bits = 0, int npoly = 0) {
   Handle::PreparedKey k;
   memset(&k, 0, sizeof(k));
   k.g0 = g0; k.g1 = g1; k.w1 = m.w1; k.b1 = m.b1; k.w2 = m.w2; k.b2 = m.b2; k.w3 = m.w3; k.b3 = m.b3;
   for (int a = 0; a < 3; ++a) { k.n0[a] = g.n0[a]; k.n1[a] = g.n1[a]; }
   k.method = g.method; k.pe_kind = g.pe_kind; k.mip = g.mip; k.fmt = fmt; k.fast = fast; k.valid = 1;
   k.code_bits = code_bits;
+  k.npoly = npoly;
   k.step = g.step;
   return k;
 }
@@ -1207,7 +766,10 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
   uint16_t* s0 = (uint16_t*)h->tc_shadow;
   uint16_t* R = (uint16_t*)((uint8_t*)h->tc_shadow + b0);
   cudaError_t e = cudaSuccess;
-  const Handle::PreparedKey key = make_key(g, m, g0, g1, FMT, 1, h->src_code_bits);
+  // how many of every 8 activation pairs take the polynomial (FMA-pipe) GELU instead of MUFU.TANH: tuned per format so
+  // that the XU and FMA pipes finish together (profiles/r02*); NIC_OPT_GELU_POLY overrides it for A/B runs
+  const int npoly = h->gelu_poly >= 0 ? h->gelu_poly : (FMT == 0 ? WS_NPOLY_F16 : WS_NPOLY_BF16);
+  const Handle::PreparedKey key = make_key(g, m, g0, g1, FMT, 1, h->src_code_bits, npoly);
   if (!prepared_matches(h, key)) {
     h->prepared.valid = 0;
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
@@ -1215,7 +777,7 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
     dim3 grid_r((g.n1[0] + 127) / 128, g.n1[1]);
     g1_rows_kernel<FMT><<<grid_r, 128, 0, st>>>(m, g1, g.n1[0], g.n1[1], R, h->src_code_bits);
     h->launches++;
-    pack_fast_kernel<FMT><<<32, 256, 0, st>>>(m, g.lod, g.step, (uint16_t*)h->tc_weights);
+    pack_fast_kernel<FMT><<<32, 256, 0, st>>>(m, g.lod, g.step, (uint16_t*)h->tc_weights, npoly);
     h->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -1223,37 +785,32 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
   }
   unsigned tiles_y = (unsigned)(g.B[1] / F_TY);
   long long ntiles = (long long)(g.B[0] / F_TX) * tiles_y;
-  if (ntiles >= (1ll << 31)) return NIC_ERR_UNSUPPORTED;
+  if (ntiles >= (1ll << 31) || g.N >= (1ll << 31)) return NIC_ERR_UNSUPPORTED;     // 32-bit texel index in the kernel
   unsigned sh = 0;
   while ((1ull << sh) < tiles_y) ++sh;
   unsigned mul = (unsigned)(((1ull << (31 + sh)) + tiles_y - 1) / tiles_y);
-  if (!h->legacy_fast2d) {
-    // warp-specialised persistent kernel: one CTA per SM (all 512 TMEM columns)
-    static_assert(WS_SMEM <= 227 * 1024, "shared memory budget");
-    auto kern = decode_tc2d_ws_kernel<FMT, OutT>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    int grid = (int)(ntiles < h->sms ? ntiles : h->sms);
-    {
-      KernelTimer timer(h, st);
-      kern<<<grid, WS_THREADS, WS_SMEM, st>>>(g, (const uint2*)s0, (const uint4*)R, (const uint4*)h->tc_weights, m.cout,
-                                               tiles_y, mul, sh, out, h->debug_flags);
-    }
-    h->launches++;
-    return (int)cudaGetLastError();
+  // warp-specialised persistent kernel: one CTA per SM (all 512 TMEM columns)
+  static_assert(WS_SMEM <= 227 * 1024, "shared memory budget");
+  void (*kern)(DevGeom, const uint2*, const uint4*, const uint4*, int, unsigned, unsigned, unsigned, OutT*, int) = nullptr;
+  switch (npoly) {
+    case 0: kern = decode_tc2d_ws_kernel<FMT, OutT, 0>; break;
+    case 3: kern = decode_tc2d_ws_kernel<FMT, OutT, 3>; break;
+#ifdef NIC_GELU_SWEEP
+    case 2: kern = decode_tc2d_ws_kernel<FMT, OutT, 2>; break;
+    case 4: kern = decode_tc2d_ws_kernel<FMT, OutT, 4>; break;
+    case 5: kern = decode_tc2d_ws_kernel<FMT, OutT, 5>; break;
+    case 6: kern = decode_tc2d_ws_kernel<FMT, OutT, 6>; break;
+    case 8: kern = decode_tc2d_ws_kernel<FMT, OutT, 8>; break;
+#endif
+    default: return NIC_ERR_UNSUPPORTED;
   }
-  // 100 KB of dynamic shared memory per CTA caps residency at 2 CTAs/SM = 2 x 256 TMEM columns = all 512.
-  size_t smem = 100 * 1024;
-  static_assert(F_STAGE + F_IMG + 64 <= 100 * 1024, "shared memory budget");
-  auto kern = decode_tc2d_kernel<FMT, OutT>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM);
   if (e != cudaSuccess) return (int)e;
-  long long npairs = (ntiles + 1) / 2, cap = (long long)h->sms * 2;
-  int grid = (int)(npairs < cap ? npairs : cap);
+  int grid = (int)(ntiles < h->sms ? ntiles : h->sms);
   {
     KernelTimer timer(h, st);
-    kern<<<grid, F_THREADS, smem, st>>>(g, (const uint2*)s0, (const uint4*)R, (const uint4*)h->tc_weights, m.cout,
-                                        tiles_y, mul, sh, out);
+    kern<<<grid, WS_THREADS, WS_SMEM, st>>>(g, (const uint2*)s0, (const uint4*)R, (const uint4*)h->tc_weights, m.cout,
+                                             tiles_y, mul, sh, out, h->debug_flags);
   }
   h->launches++;
   return (int)cudaGetLastError();
@@ -1277,14 +834,15 @@ static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float
   uint16_t* s0 = (uint16_t*)h->tc_shadow;
   uint16_t* s1 = (uint16_t*)((uint8_t*)h->tc_shadow + b0);
   cudaError_t e = cudaSuccess;
-  const Handle::PreparedKey key = make_key(g, m, g0, g1, FMT, 0, h->src_code_bits);
+  const int npoly = h->gelu_poly >= 0 ? h->gelu_poly : (FMT == 0 ? WS_NPOLY_F16 : WS_NPOLY_BF16);
+  const Handle::PreparedKey key = make_key(g, m, g0, g1, FMT, 0, h->src_code_bits, npoly);
   if (!prepared_matches(h, key)) {
     h->prepared.valid = 0;
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
     if (e != cudaSuccess) return (int)e;
     e = (cudaError_t)launch_relayout<FMT>(h, g, g1, g.n1, s1, st);
     if (e != cudaSuccess) return (int)e;
-    pack_weights_kernel<FMT><<<16, 256, 0, st>>>(m, g.lod, S::KX, (uint16_t*)h->tc_weights);
+    pack_weights_kernel<FMT><<<16, 256, 0, st>>>(m, g.lod, S::KX, (uint16_t*)h->tc_weights, npoly);
     h->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
@@ -1300,34 +858,23 @@ static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float
   if (g.N >= (1ll << 31) - TC_ROWS) return NIC_ERR_UNSUPPORTED;     // 32-bit sample index in the kernel
   long long ntiles = (g.N + TC_ROWS - 1) / TC_ROWS;
   ShadowGeom sg = {(const uint2*)s0, (const uint2*)s1};
-  if (!h->legacy_fast2d) {
-    // warp-specialised persistent kernel: one CTA per SM, NG groups of 4 warps
-    constexpr int NG = S::KX > 80 ? 5 : 8;
-    constexpr int GSMEM = IMG + TC_LUT_MAX * 16 + 2 * 2048 + NG * (S::KX / 8) * 2048 + 256;
-    static_assert(GSMEM <= 227 * 1024, "shared memory budget");
-    auto kern = decode_tc_gws_kernel<METHOD, FMT, OutT>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM);
-    if (e != cudaSuccess) return (int)e;
-    long long groups = (ntiles + NG - 1) / NG;
-    int grid = (int)(groups < h->sms ? groups : h->sms);
-    {
-      KernelTimer timer(h, st);
-      kern<<<grid, NG * GW_GROUP, GSMEM, st>>>(g, sg, origins, (const uint4*)h->tc_weights, m.cout, lut_n, out);
-    }
-    h->launches++;
-    return (int)cudaGetLastError();
+  // warp-specialised persistent kernel: one CTA per SM, NG groups of 4 warps
+  constexpr int NG = S::KX > 80 ? 5 : 8;
+  constexpr int GSMEM = IMG + TC_LUT_MAX * 16 + 2 * 2048 + NG * (S::KX / 8) * 2048 + 256;
+  static_assert(GSMEM <= 227 * 1024, "shared memory budget");
+  void (*kern)(DevGeom, ShadowGeom, const long long*, const uint4*, int, int, OutT*) = nullptr;
+  switch (npoly) {
+    case 0: kern = decode_tc_gws_kernel<METHOD, FMT, OutT, 0>; break;
+    case 3: kern = decode_tc_gws_kernel<METHOD, FMT, OutT, 3>; break;
+    default: return NIC_ERR_UNSUPPORTED;      // (the NIC_GELU_SWEEP values exist for the fast 2-D kernel only)
   }
-  // first-generation kernel: 56 KB of dynamic shared memory per CTA caps residency at 4 CTAs/SM = 4 x 128 TMEM columns.
-  size_t smem = 56 * 1024;
-  static_assert(IMG + TC_LUT_MAX * 16 + 64 <= 56 * 1024, "shared memory budget");
-  auto kern = decode_tc_kernel<METHOD, FMT, OutT>;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GSMEM);
   if (e != cudaSuccess) return (int)e;
-  long long cap = (long long)h->sms * 4;
-  int grid = (int)(ntiles < cap ? ntiles : cap);
+  long long groups = (ntiles + NG - 1) / NG;
+  int grid = (int)(groups < h->sms ? groups : h->sms);
   {
     KernelTimer timer(h, st);
-    kern<<<grid, TC_THREADS, smem, st>>>(g, sg, origins, (const uint4*)h->tc_weights, m.cout, lut_n, out);
+    kern<<<grid, NG * GW_GROUP, GSMEM, st>>>(g, sg, origins, (const uint4*)h->tc_weights, m.cout, lut_n, out);
   }
   h->launches++;
   return (int)cudaGetLastError();

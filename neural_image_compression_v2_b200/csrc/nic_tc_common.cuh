@@ -69,6 +69,26 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_
       : "memory");
 }
 
+// The same with the two shared-memory descriptors given as 32-bit halves.  The high half of a K-major no-swizzle
+// descriptor (SBO, version bit) is a constant and the low half is (address >> 4) | (LBO >> 4) << 16, so stepping an operand
+// through shared memory is ONE 32-bit add on the low half — the issuing thread of the decode kernels spends ~10 uniform
+// instructions per MMA batch on descriptors this way instead of ~90 when every descriptor is rebuilt from its fields.
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void mma_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
+      "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // One elected lane of a CONVERGED warp.  tcgen05.mma must be issued from warp-uniform control flow with warp-uniform
 // operands: `if (warp_u == X) if (elect_one()) mma(...)` with warp_u = uniform_warp_index() keeps descriptors in uniform
 // registers and the UTCHMMAs back to back (48 cycles each for M128 N64 SS, 32 for TS; tools/ubench/mma_rate2.cu).
@@ -166,6 +186,44 @@ __device__ __forceinline__ uint32_t gelu2x_pair(float a, float b) {
   typename P::T2 h = __hfma2(x, t, x);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// GELU without MUFU (the decode kernels are bound by the XU pipe when every activation costs one MUFU.TANH):
+//   gelu(x) = x * Phi(x),  Phi(x) ~ clamp(1/2 + x * Q(x^2), 0, 1),  Q a minimax polynomial of degree 4 in x^2
+// evaluated on the FMA pipe in packed 16-bit math.  Exhaustively checked over all 63,488 finite f16 inputs against the
+// exact erf GELU (tools/gelu_poly_fit.py): f16 max |err| 4.4e-3 (at |x| ~ 2.8), rms 4.1e-4 for |x| < 4 — the MUFU tanh
+// form has 1.7e-3 / 1.5e-4, bf16 tanh 9.2e-3 / 8.7e-4.  The result is gelu(x), NOT 2*gelu(x) like gelu2x_pair: columns
+// evaluated this way take the next layer's weights unscaled (pack_fast_kernel / gelu_poly_column).
+//   f16 : the degree-4 Q has a positive leading coefficient and x*Q(x^2) stays above 1/2 beyond the fitted range, so no
+//         argument clamp is needed; fma.rn.sat clamps Phi to [0, 1]  (7 FMA-pipe instructions + the pack).
+//   bf16: no .sat form exists and the 8-bit mantissa needs the argument clamped: min(x^2, L^2), fma.relu, min(., 1).
+template <int FMT>
+__device__ __forceinline__ uint32_t gelu_poly_pair(float a, float b) {
+  using P = Pair<FMT>;
+  typename P::T2 x = P::pack(a, b);
+  typename P::T2 s = __hmul2(x, x);
+  typename P::T2 h;
+  if constexpr (FMT == 0) {
+    typename P::T2 q = __hfma2(s, P::cst(1.1074006e-05f), P::cst(-4.2891181e-04f));
+    q = __hfma2(q, s, P::cst(6.8348698e-03f));
+    q = __hfma2(q, s, P::cst(-6.0208798e-02f));
+    q = __hfma2(q, s, P::cst(3.9457067e-01f));
+    h = __hmul2(x, __hfma2_sat(x, q, P::cst(0.5f)));
+  } else {
+    s = __hmin2(s, P::cst(11.56f));
+    typename P::T2 q = __hfma2(s, P::cst(1.1117739e-05f), P::cst(-4.2903416e-04f));
+    q = __hfma2(q, s, P::cst(6.8217828e-03f));
+    q = __hfma2(q, s, P::cst(-6.0079083e-02f));
+    q = __hfma2(q, s, P::cst(3.9425993e-01f));
+    h = __hmul2(x, __hmin2(__hfma2_relu(x, q, P::cst(0.5f)), P::cst(1.0f)));
+  }
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// Which of the 8 activation pairs of a 16-column chunk use gelu_poly_pair when NPOLY of them do (evenly interleaved with
+// the MUFU pairs, so both pipes stay busy), and the same question for a hidden column (weight packing).
+__host__ __device__ constexpr bool gelu_poly_pair_sel(int pair, int npoly) {
+  return ((pair + 1) * npoly) / 8 > (pair * npoly) / 8;
+}
+__host__ __device__ constexpr bool gelu_poly_column(int col, int npoly) { return gelu_poly_pair_sel((col & 15) >> 1, npoly); }
 
 template <int FMT>
 __device__ __forceinline__ uint16_t to16(float v) {

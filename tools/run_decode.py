@@ -12,8 +12,8 @@ from neural_image_compression_v2_b200 import _lib as L  # noqa: E402
 from neural_image_compression_v2_b200 import image_compression as ic, var2  # noqa: E402
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "f16"
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-size = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+reps = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 3
+size = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 4096
 dev = torch.device("cuda:0")
 var2.update(IMAGE_SIZE=size)
 fp = [torch.tensor(g, device=dev) for g in I.make_grids(size, 2, seed=0, no_mip=True, quantized=True)]
@@ -25,8 +25,8 @@ out = torch.empty((size, size, 3), dtype=torch.uint8, device=dev)
 for a in sys.argv:
     if a.startswith("dbg="):
         L.set_option(dev, 100, int(a[4:]))
-if "legacy" in sys.argv:
-    L.set_option(dev, L.OPT_LEGACY_FAST2D, 1)
+    if a.startswith("npoly="):
+        L.set_option(dev, L.OPT_GELU_POLY, int(a[6:]))
 L.set_option(dev, L.OPT_TIME_KERNELS, 1)
 for _ in range(reps):
     ic.decode(fp, dec, 0, precision=prec, out_dtype=torch.uint8, out=out)
