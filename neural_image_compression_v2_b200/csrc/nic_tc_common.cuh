@@ -114,8 +114,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B format fmt (0 f16, 1 bf16), both K-major.
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int b_mn_major = 0) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) |
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int b_mn_major = 0, int d_f16 = 0) {
+  return ((d_f16 ? 0u : 1u) << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -138,6 +138,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// 16 columns of 16-bit accumulators (idesc d_f16) as 8 registers of packed pairs (columns 2i, 2i+1 -> register i)
+__device__ __forceinline__ void tmem_ld8_pack16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
@@ -177,6 +184,16 @@ template <> struct Pair<1> {
 
 // 2*GELU_tanh on a packed pair: x + x*tanh(x*(c1 + c2*x^2)); the factor 1/2 lives in the next layer's weights.
 template <int FMT>
+__device__ __forceinline__ uint32_t gelu2x_packed(uint32_t xin) {
+  using P = Pair<FMT>;
+  typename P::T2 x = *reinterpret_cast<typename P::T2*>(&xin);
+  typename P::T2 x2 = __hmul2(x, x);
+  typename P::T2 p = __hfma2(x2, P::cst(0.0356774081f), P::cst(0.7978845608f));
+  typename P::T2 t = P::tanh2(__hmul2(p, x));
+  typename P::T2 h = __hfma2(x, t, x);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <int FMT>
 __device__ __forceinline__ uint32_t gelu2x_pair(float a, float b) {
   using P = Pair<FMT>;
   typename P::T2 x = P::pack(a, b);
@@ -197,9 +214,16 @@ __device__ __forceinline__ uint32_t gelu2x_pair(float a, float b) {
 //         argument clamp is needed; fma.rn.sat clamps Phi to [0, 1]  (7 FMA-pipe instructions + the pack).
 //   bf16: no .sat form exists and the 8-bit mantissa needs the argument clamped: min(x^2, L^2), fma.relu, min(., 1).
 template <int FMT>
+__device__ __forceinline__ uint32_t gelu_poly_packed(uint32_t xin);
+template <int FMT>
 __device__ __forceinline__ uint32_t gelu_poly_pair(float a, float b) {
+  auto x = Pair<FMT>::pack(a, b);
+  return gelu_poly_packed<FMT>(*reinterpret_cast<uint32_t*>(&x));
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t gelu_poly_packed(uint32_t xin) {
   using P = Pair<FMT>;
-  typename P::T2 x = P::pack(a, b);
+  typename P::T2 x = *reinterpret_cast<typename P::T2*>(&xin);
   typename P::T2 s = __hmul2(x, x);
   typename P::T2 h;
   if constexpr (FMT == 0) {

@@ -14,7 +14,10 @@ from neural_image_compression_v2_b200 import _lib as L  # noqa: E402
 from neural_image_compression_v2_b200 import image_compression as ic, var2  # noqa: E402
 
 dev = torch.device("cuda:0")
-sweep = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 4]
+sweep = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 3]
+for a in sys.argv[2:]:
+    if a.startswith("dbg="):
+        L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, int(a[4:]))
 
 
 def model(size, seed, gain):
