@@ -37,7 +37,9 @@ typedef enum NicStatus {
   NIC_ERR_DEVICE = -3,       /* not an sm_100 device, or handle bound to another device           */
   NIC_ERR_BOUNDS = -4,       /* a host-known origin would index outside the grids                 */
   NIC_ERR_ALIGN = -5,        /* pointer not aligned as documented                                 */
-  NIC_ERR_SCRATCH = -6       /* scratch allocation failed                                         */
+  NIC_ERR_SCRATCH = -6,      /* scratch allocation failed                                         */
+  NIC_ERR_EXCHANGE = -7      /* a data-parallel exchange timed out waiting for a peer (sticky, see
+                                nic_adam_step_exchange): parameters are no longer updated on this handle */
 } NicStatus;
 
 /* COMPRESSION_METHOD of Projects/var2.py:51-55 (2 = 2-D atlas, handled by the caller as method 1). */
@@ -110,8 +112,15 @@ int64_t nic_launch_count(const NicHandle* h);
  * clamped minimax polynomial on the FMA pipe instead of MUFU.TANH (the kernel is bound by the XU pipe when all of them
  * use the transcendental).  -1 = the tuned default; 0 = all MUFU (round-1 behaviour); values the library was not built
  * with return NIC_ERR_UNSUPPORTED from nic_decode.  Both forms stay inside the tensor-core tolerance (+-1 LSB). */
+/* NIC_OPT_EXCHANGE_TIMEOUT_MS: how long nic_adam_step_exchange waits on the device for a peer before it gives up
+ * (default 10,000 ms; raise it when a rank may legitimately stall, e.g. a rank-0 evaluation between steps). */
+/* NIC_OPT_STEP_METRICS = 1: the per-step PSNR bookkeeping of train_models (calculate_psnr(quantize_to_bit(out),
+ * quantize_to_bit(target)), image_compression.py:260-261) without a host sync: nic_train_step additionally accumulates
+ * loss_sum[1] += sum((floor(out*255+.5) - floor(target*255+.5))^2), and nic_adam_step_loss / nic_adam_step_exchange
+ * additionally write loss_out[1] = loss_sum[1] * loss_scale (and clear it).  loss_sum and loss_out must then hold TWO floats.
+ * FusedTrainer points loss_out into a device ring buffer and reads it back every k steps. */
 enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3,
-       NIC_OPT_GELU_POLY = 5, NIC_OPT_DEBUG_KNOCKOUT = 100 };
+       NIC_OPT_GELU_POLY = 5, NIC_OPT_EXCHANGE_TIMEOUT_MS = 6, NIC_OPT_STEP_METRICS = 7, NIC_OPT_DEBUG_KNOCKOUT = 100 };
 int nic_set_option(NicHandle* h, int option, int value);
 /* With NIC_OPT_TIME_KERNELS = 1 every nic_decode / nic_train_step / nic_gather call brackets its DOMINANT kernel
  * (not the small preparation kernels) with CUDA events on the call's stream.  This call synchronises on the recorded
@@ -143,6 +152,33 @@ int nic_scatter(NicHandle* h, const NicGeom* g, const float* dx, const int64_t* 
  * (the reference's `coord`).  size / crop: HOST pointers to dim ints.  Origins are clamped into the image. */
 int nic_sample_crops(NicHandle* h, const float* image, int dim, int channels, const int32_t* size, const int64_t* origins,
                      int num_crops, const int32_t* crop, float* targets, void* stream);
+
+/* random_crop_dataset without the host (image_compression.py:36-49): crop origins are drawn ON THE DEVICE, uniform over the
+ * integers [0, size - crop] per axis like torch.randint (Philox4x32-10, key = seed, counter = (crop index, step); word a of
+ * the block -> axis a), written to origins_out [num_crops, dim] (int64, the reference's `coord`) and used for the target
+ * gather of nic_sample_crops in the same launch.  Data-parallel ranks pass different seeds.  The LOD of the step (which
+ * fixes `image`, `crop` and every launch shape) stays a host integer: FusedTrainer.draw_lod evaluates the reference's
+ * distribution (:29-34) with a counter-based generator, identically on every rank, without touching the device. */
+int nic_sample_crops_random(NicHandle* h, const float* image, int dim, int channels, const int32_t* size, int num_crops,
+                            const int32_t* crop, uint64_t seed, uint64_t step, int64_t* origins_out, float* targets, void* stream);
+
+/* The mip-pyramid builder of the script: transforms.Resize((h, w)) on the 8-bit PIL image followed by ToTensor
+ * (image_compression.py:433-442, 462-469).  src: uint8 [height, width, channels] (PIL / numpy HWC layout).  Reproduces
+ * Pillow's antialiased BILINEAR resample bit for bit: separable triangle filter of support max(scale, 1), fixed-point
+ * coefficients (22 fractional bits), horizontal pass rounded to 8 bits before the vertical pass.  dst_u8 (optional):
+ * [out_height, out_width, channels]; dst_f32 (optional): ToTensor's [channels, out_height, out_width] = u8 / 255.
+ * An init-time call: it synchronises `stream` (host-built coefficient tables live in handle scratch). */
+int nic_resize_bilinear_u8(NicHandle* h, const uint8_t* src, int height, int width, int channels, int out_height, int out_width,
+                           uint8_t* dst_u8, float* dst_f32, void* stream);
+
+/* COMPRESSION_METHOD 2 (a volume flattened into one 2-D image): frame i of frames [num_frames, S, S, channels] (uint8) sits
+ * at atlas rows [r S, (r+1) S), columns [q S, (q+1) S), r = i / (atlas_size / S), q = i % (atlas_size / S)
+ * (image_compression.py:453-460); unused atlas cells are zero.  nic_atlas_unpack is the inverse applied to the decoded
+ * frame (:413-419). */
+int nic_atlas_pack(NicHandle* h, const uint8_t* frames, int num_frames, int frame_size, int channels, int atlas_size,
+                   uint8_t* atlas, void* stream);
+int nic_atlas_unpack(NicHandle* h, const uint8_t* atlas, int atlas_size, int channels, int num_frames, int frame_size,
+                     uint8_t* frames, void* stream);
 
 /* Stand-alone positional encodings, utils.triangular_positional_encoding (utils.py:211-223) and
  * utils.positional_encoding (utils.py:198-208): coord [dim, n] fp32 -> out [pe_channels*dim, n] fp32.
@@ -223,8 +259,12 @@ int nic_adam_step_loss(NicHandle* h, const NicAdamTensor* tensors, int count, fl
  * Protocol (FusedTrainer implements it): gradient buffers are double-buffered by use parity; tensors[i].g points into
  * THIS rank's current buffer `peer_flat[rank]`; peer_flat[r] / peer_flag[r] are the same buffer / the flag array (`world`
  * 32-bit words: slot s is written by rank s) of rank r; `token` increases by one per use; `zero_buf` (the OTHER parity buffer of this rank, `zero_numel` floats) is
- * cleared in the same launch — no peer can still be reading it once every flag shows `token`.  A rank that waits more
- * than ~2 s for a flag records a timeout (nic_exchange_status) and continues, so a lost peer cannot hang the GPU. */
+ * cleared in the same launch — no peer can still be reading it once every flag shows `token`.
+ * A timeout is FATAL and sticky: a rank that waits longer than NIC_OPT_EXCHANGE_TIMEOUT_MS for a peer applies NO update in
+ * that launch nor in any later one (nobody ever consumes a partial sum, a lost peer cannot hang the GPU), and the next
+ * nic_adam_step_exchange on the handle returns NIC_ERR_EXCHANGE without launching.  nic_exchange_status reports and clears the
+ * flag; the caller must re-synchronise the replicas (broadcast parameters + Adam state) before it resumes.  All blocks of the
+ * kernel are co-resident by construction (grid capped by occupancy), so the intra-kernel release cannot deadlock. */
 #define NIC_MAX_PEERS 16
 typedef struct NicExchange {
   int32_t world, rank;
@@ -243,7 +283,7 @@ int nic_sym_free(NicHandle* h, void* ptr);
 int nic_adam_step_exchange(NicHandle* h, const NicAdamTensor* tensors, int count, float beta1, float beta2, float eps,
                            float grad_scale, const NicExchange* x, const float* loss_sum, float* loss_out, float loss_scale,
                            void* stream);
-/* Synchronises the device and reports whether any exchange so far timed out waiting for a peer (then clears it). */
+/* Synchronises the device and reports whether any exchange so far timed out waiting for a peer (then clears the sticky flag). */
 int nic_exchange_status(NicHandle* h, int* timed_out);
 
 /* ---- quantisers (K6) ------------------------------------------------------------------------------------ */

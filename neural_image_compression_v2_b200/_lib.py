@@ -95,6 +95,10 @@ SYMBOLS = {
     "nic_output_to_u8": (_I, [_P, _P, _P, _L, _I, _P]),
     "nic_sse_u8": (_I, [_P, _P, _P, _L, _P, _P]),
     "nic_sample_crops": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
+    "nic_sample_crops_random": (_I, [_P, _P, _I, _I, _P, _I, _P, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "nic_resize_bilinear_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "nic_atlas_pack": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "nic_atlas_unpack": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "nic_positional_encoding": (_I, [_P, _P, _I, _L, _I, _I, _P, _P, _P]),
 }
 
@@ -142,6 +146,9 @@ OPT_DISABLE_FAST2D = 1
 OPT_TIME_KERNELS = 2
 OPT_REUSE_PREPARED = 3
 OPT_GELU_POLY = 5            # share (of 8) of hidden activations on the polynomial GELU; -1 = tuned default
+OPT_EXCHANGE_TIMEOUT_MS = 6  # device-side wait for a peer in nic_adam_step_exchange (default 10 s)
+OPT_STEP_METRICS = 7         # loss_sum / loss_out carry [squared error, squared error of the 8-bit outputs]
+ERR_EXCHANGE = -7
 OPT_DEBUG_KNOCKOUT = 100     # profiling only (nic.h); bit 3 = training phase counters
 
 

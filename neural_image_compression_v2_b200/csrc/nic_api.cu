@@ -47,6 +47,7 @@ const char* nic_status_string(int status) {
     case NIC_ERR_BOUNDS: return "origin would index outside the grids";
     case NIC_ERR_ALIGN: return "misaligned pointer";
     case NIC_ERR_SCRATCH: return "scratch allocation failed";
+    case NIC_ERR_EXCHANGE: return "data-parallel exchange timed out waiting for a peer";
     default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown status";
   }
 }
@@ -90,7 +91,9 @@ int nic_destroy(NicHandle* h) {
   if (h->tc_gscratch) cudaFree(h->tc_gscratch);
   if (h->tc_partials) cudaFree(h->tc_partials);
   if (h->xch_err) cudaFree(h->xch_err);
+  if (h->xch_host_err) cudaFreeHost(h->xch_host_err);
   if (h->dbg_counters) cudaFree(h->dbg_counters);
+  if (h->data_scratch) cudaFree(h->data_scratch);
   if (h->adam_desc) cudaFree(h->adam_desc);
   for (int i = 0; i < 2 * NIC_MAX_TIMED; ++i)
     if (h->timed_ev[i]) cudaEventDestroy(h->timed_ev[i]);
@@ -107,6 +110,12 @@ int nic_set_option(NicHandle* h, int option, int value) {
   if (option == NIC_OPT_DEBUG_KNOCKOUT) { h->debug_flags = value; return NIC_OK; }
   if (option == NIC_OPT_REUSE_PREPARED) { h->reuse_prepared = value != 0; return NIC_OK; }
   if (option == NIC_OPT_TIME_KERNELS) { h->time_kernels = value != 0; h->timed_count = 0; return NIC_OK; }
+  if (option == NIC_OPT_STEP_METRICS) { h->step_metrics = value != 0; return NIC_OK; }
+  if (option == NIC_OPT_EXCHANGE_TIMEOUT_MS) {
+    if (value < 0) return fail(h, NIC_ERR_ARG, "nic_set_option: NIC_OPT_EXCHANGE_TIMEOUT_MS must be >= 0 (0 = default)");
+    h->xch_timeout_ms = value;
+    return NIC_OK;
+  }
   if (option == NIC_OPT_GELU_POLY) {
     if (value < -1 || value > 8) return fail(h, NIC_ERR_ARG, "nic_set_option: NIC_OPT_GELU_POLY takes -1 (default) or 0..8");
     h->gelu_poly = value;
@@ -273,6 +282,57 @@ int nic_sample_crops(NicHandle* h, const float* image, int dim, int channels, co
                    "nic_sample_crops");
 }
 
+int nic_sample_crops_random(NicHandle* h, const float* image, int dim, int channels, const int32_t* size, int num_crops,
+                            const int32_t* crop, uint64_t seed, uint64_t step, int64_t* origins_out, float* targets, void* stream) {
+  NIC_ENTER(h);
+  if ((dim != 2 && dim != 3) || channels < 1 || num_crops < 0 || !size || !crop)
+    return fail(h, NIC_ERR_ARG, "nic_sample_crops_random: dim %d channels %d num_crops %d", dim, channels, num_crops);
+  for (int a = 0; a < dim; ++a)
+    if (size[a] < 1 || crop[a] < 1 || crop[a] > size[a])
+      return fail(h, NIC_ERR_ARG, "nic_sample_crops_random: axis %d size %d crop %d", a, size[a], crop[a]);
+  if (num_crops > 0 && (!image || !origins_out || !targets)) return fail(h, NIC_ERR_ARG, "nic_sample_crops_random: NULL pointer");
+  int rc = launch_sample_crops_random(h, image, dim, channels, size, num_crops, crop, seed, step, (long long*)origins_out, targets, st);
+  if (rc == NIC_ERR_UNSUPPORTED) return fail(h, rc, "nic_sample_crops_random: at most 4096 crops per call");
+  return cuda_fail(h, rc, "nic_sample_crops_random");
+}
+
+int nic_resize_bilinear_u8(NicHandle* h, const uint8_t* src, int height, int width, int channels, int out_height, int out_width,
+                           uint8_t* dst_u8, float* dst_f32, void* stream) {
+  NIC_ENTER(h);
+  if (height < 1 || width < 1 || channels < 1 || out_height < 1 || out_width < 1)
+    return fail(h, NIC_ERR_ARG, "nic_resize_bilinear_u8: %dx%dx%d -> %dx%d", height, width, channels, out_height, out_width);
+  if (!src || (!dst_u8 && !dst_f32)) return fail(h, NIC_ERR_ARG, "nic_resize_bilinear_u8: NULL pointer");
+  int rc = launch_resize_bilinear_u8(h, src, height, width, channels, out_height, out_width, dst_u8, dst_f32, st);
+  if (rc == NIC_ERR_SCRATCH) return fail(h, rc, "nic_resize_bilinear_u8: scratch allocation failed");
+  return cuda_fail(h, rc, "nic_resize_bilinear_u8");
+}
+
+static int check_atlas(NicHandle* h, int num_frames, int frame_size, int channels, int atlas_size, const char* who) {
+  if (num_frames < 0 || frame_size < 1 || channels < 1 || atlas_size < frame_size)
+    return fail(h, NIC_ERR_ARG, "%s: %d frames of %d^2 x %d into %d^2", who, num_frames, frame_size, channels, atlas_size);
+  const long long per_row = atlas_size / frame_size;
+  if (per_row * per_row < num_frames) return fail(h, NIC_ERR_ARG, "%s: %d frames do not fit a %d^2 atlas", who, num_frames, atlas_size);
+  return NIC_OK;
+}
+
+int nic_atlas_pack(NicHandle* h, const uint8_t* frames, int num_frames, int frame_size, int channels, int atlas_size,
+                   uint8_t* atlas, void* stream) {
+  NIC_ENTER(h);
+  if (int rc = check_atlas(h, num_frames, frame_size, channels, atlas_size, "nic_atlas_pack")) return rc;
+  if (!atlas || (num_frames > 0 && !frames)) return fail(h, NIC_ERR_ARG, "nic_atlas_pack: NULL pointer");
+  return cuda_fail(h, launch_atlas(h, const_cast<uint8_t*>(frames), atlas, num_frames, frame_size, channels, atlas_size, 0, st),
+                   "nic_atlas_pack");
+}
+
+int nic_atlas_unpack(NicHandle* h, const uint8_t* atlas, int atlas_size, int channels, int num_frames, int frame_size,
+                     uint8_t* frames, void* stream) {
+  NIC_ENTER(h);
+  if (int rc = check_atlas(h, num_frames, frame_size, channels, atlas_size, "nic_atlas_unpack")) return rc;
+  if (!atlas || (num_frames > 0 && !frames)) return fail(h, NIC_ERR_ARG, "nic_atlas_unpack: NULL pointer");
+  return cuda_fail(h, launch_atlas(h, frames, const_cast<uint8_t*>(atlas), num_frames, frame_size, channels, atlas_size, 1, st),
+                   "nic_atlas_unpack");
+}
+
 int nic_positional_encoding(NicHandle* h, const float* coord, int dim, int64_t n, int pe_channels, int pe_kind,
                             const float* pe_div, float* out, void* stream) {
   NIC_ENTER(h);
@@ -368,6 +428,7 @@ int nic_train_step(NicHandle* h, const NicGeom* g, const float* g0, const float*
   if (noise_bits < 0 || noise_bits > 24) return fail(h, NIC_ERR_ARG, "nic_train_step: noise_bits %d", noise_bits);
   if (precision != NIC_PREC_F32 && precision != NIC_PREC_F16 && precision != NIC_PREC_BF16)
     return fail(h, NIC_ERR_ARG, "nic_train_step: precision %d", precision);
+  d.metrics = h->step_metrics;
   long long denom = (global_n > 0 ? global_n : d.N) * (long long)md.cout;
   float grad_scale = denom > 0 ? (float)(1.0 / (double)denom) : 0.f;
   MlpGradDev gd = {gm->w1, gm->b1, gm->w2, gm->b2, gm->w3, gm->b3};
@@ -469,8 +530,11 @@ int nic_adam_step_exchange(NicHandle* h, const NicAdamTensor* tensors, int count
     if (t.numel < 0 || t.t < 1 || (t.numel > 0 && (!t.p || !t.g || !t.m || !t.v)))
       return fail(h, NIC_ERR_ARG, "nic_adam_step_exchange: tensor %d invalid", i);
   }
-  return cuda_fail(h, launch_adam_exchange(h, tensors, count, beta1, beta2, eps, grad_scale, *x, loss_sum, loss_out, loss_scale, st),
-                   "nic_adam_step_exchange");
+  int rc = launch_adam_exchange(h, tensors, count, beta1, beta2, eps, grad_scale, *x, loss_sum, loss_out, loss_scale, st);
+  if (rc == NIC_ERR_EXCHANGE)
+    return fail(h, rc, "nic_adam_step_exchange: an earlier exchange timed out waiting for a peer; no update has been applied "
+                       "since.  Re-synchronise the replicas and clear the flag with nic_exchange_status");
+  return cuda_fail(h, rc, "nic_adam_step_exchange");
 }
 
 int nic_exchange_status(NicHandle* h, int* timed_out) {
@@ -482,6 +546,10 @@ int nic_exchange_status(NicHandle* h, int* timed_out) {
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(&v, h->xch_err, sizeof(v), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemset(h->xch_err, 0, sizeof(v));
+  if (h->xch_host_err) {
+    if (*reinterpret_cast<volatile unsigned*>(h->xch_host_err)) v = 1u;
+    *h->xch_host_err = 0u;
+  }
   if (e != cudaSuccess) return fail(h, (int)e, "nic_exchange_status: %s", cudaGetErrorString(e));
   *timed_out = (int)v;
   return NIC_OK;

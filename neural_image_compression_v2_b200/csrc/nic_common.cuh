@@ -30,6 +30,7 @@ struct DevGeom {
   long long N;                                    // nblocks*per_block
   // exact division of n < 2^31 by per_block, B[1]*B[2] and B[2]: q = (n * mul) >> (31 + shift)
   unsigned fd_mul[3], fd_shift[3];
+  int metrics;                                    // training: also accumulate the squared error of the 8-bit outputs (loss_sum[1])
 };
 
 // corner tables, (dz,dy,dx) as the reference orders them

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128, 1) mlp_backward_kernel(
   const int jrow = tid % H, part = tid / H;
   const int span1 = (cin + PARTS - 1) / PARTS, k1base = part * span1;
   const int k2base = part * SPAN2;
-  float loss_local = 0.f;
+  float loss_local = 0.f, sse8_local = 0.f;
 
   const long long ntiles = (N + T - 1) / T;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -216,8 +216,13 @@ __global__ void __launch_bounds__(128, 1) mlp_backward_kernel(
       for (int c = 0; c < NIC_MAX_COUT; ++c) {
         float d = 0.f, oc = c < cout ? o[c] : 0.f;
         if (live && c < cout) {
-          d = oc - targets[n * cout + c];
+          const float tc = targets[n * cout + c];
+          d = oc - tc;
           loss_local += d * d;
+          if (g.metrics) {          // calculate_psnr(quantize_to_bit(out), quantize_to_bit(target)), image_compression.py:260-261
+            const float d8 = quant_round(oc, 255.0f) - quant_round(tc, 255.0f);
+            sse8_local += d8 * d8;
+          }
           if (out_save) out_save[n * cout + c] = oc;
         }
         dz3[c] = 2.0f * d * grad_scale * oc * (1.0f - oc);
@@ -334,6 +339,15 @@ __global__ void __launch_bounds__(128, 1) mlp_backward_kernel(
     if ((tid & 31) == 0) sRed[tid >> 5] = v;
     __syncthreads();
     if (tid == 0) atomicAdd(loss_sum, (sRed[0] + sRed[1]) + (sRed[2] + sRed[3]));
+    if (g.metrics) {
+      __syncthreads();
+      v = sse8_local;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if ((tid & 31) == 0) sRed[tid >> 5] = v;
+      __syncthreads();
+      if (tid == 0) atomicAdd(loss_sum + 1, (sRed[0] + sRed[1]) + (sRed[2] + sRed[3]));
+    }
   }
 }
 

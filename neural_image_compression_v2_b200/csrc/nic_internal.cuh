@@ -31,6 +31,10 @@ struct Handle {
   size_t tc_gscratch_bytes;
   unsigned* xch_err;         // device words: [0] an exchange timed out waiting for a peer (nic_exchange_status), [1] release word
   unsigned xch_seq;          // launches of the exchange kernel so far
+  unsigned* xch_host_err;    // mapped pinned host copy of xch_err[0] (read by the next API call without a sync) + its device alias
+  unsigned* xch_host_err_dev;
+  int xch_resident_blocks;   // occupancy-bounded co-resident blocks of adam_exchange_kernel on this device
+  int xch_timeout_ms;        // NIC_OPT_EXCHANGE_TIMEOUT_MS (0 = default 10 s)
   void* tc_partials;         // per-CTA MLP-gradient partial sums of the tensor-core training step
   size_t tc_partials_bytes;
   int disable_fast2d;        // testing knob: force the general tensor-core kernel
@@ -38,6 +42,9 @@ struct Handle {
   int reuse_prepared;        // NIC_OPT_REUSE_PREPARED
   int debug_flags;           // knock-out experiments (option 100), never set in production
   unsigned long long* dbg_counters;   // 16 device counters (nic_debug_counters), allocated on first use
+  int step_metrics;          // NIC_OPT_STEP_METRICS: training steps also accumulate the 8-bit squared error in loss_sum[1]
+  void* data_scratch;        // nic_data.cu: resample coefficient tables + 8-bit intermediate
+  size_t data_scratch_bytes;
   int gelu_poly;             // NIC_OPT_GELU_POLY: -1 = tuned default, 0..8 = activation pairs (of 8) on the polynomial GELU
   struct PreparedKey {       // what the tables in tc_weights / tc_shadow were last built from
     const void *g0, *g1, *w1, *b1, *w2, *b2, *w3, *b3;
@@ -207,6 +214,12 @@ int launch_scatter(Handle* h, const DevGeom& g, const float* dx, const long long
                    cudaStream_t st);
 int launch_sample_crops(Handle* h, const float* img, int dim, int ci, const int* size, const long long* origins, int ncrops,
                         const int* crop, float* out, cudaStream_t st);
+int launch_sample_crops_random(Handle* h, const float* img, int dim, int ci, const int* size, int ncrops, const int* crop,
+                               unsigned long long seed, unsigned long long step, long long* origins_out, float* out,
+                               cudaStream_t st);
+int launch_resize_bilinear_u8(Handle* h, const uint8_t* src, int H, int W, int C, int out_h, int out_w, uint8_t* dst_u8,
+                              float* dst_f32, cudaStream_t st);
+int launch_atlas(Handle* h, uint8_t* frames, uint8_t* atlas, int T, int S, int C, int A, int unpack, cudaStream_t st);
 int launch_pe(Handle* h, const float* coord, int dim, long long n, int PE, int kind, const float* div_host, float* out,
               cudaStream_t st);
 int launch_mlp_forward_f32(Handle* h, const DevGeom* g, const MlpDev& m, const float* g0, const float* g1,

@@ -19,6 +19,7 @@ struct AdamBatch {
   float* loss_sum;      // optional: loss_out[0] = loss_sum[0] * loss_scale; loss_sum[0] = 0  (done by one thread)
   float* loss_out;
   float loss_scale;
+  int metrics;          // loss_sum / loss_out hold two values: [0] squared error, [1] squared error of the 8-bit outputs
 };
 
 __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float beta1, float beta2, float eps,
@@ -37,6 +38,10 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b) {
   if (b.loss_sum && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     b.loss_out[0] = b.loss_sum[0] * b.loss_scale;
     b.loss_sum[0] = 0.f;
+    if (b.metrics) {
+      b.loss_out[1] = b.loss_sum[1] * b.loss_scale;
+      b.loss_sum[1] = 0.f;
+    }
   }
   const NicAdamTensor& t = b.t[blockIdx.y];
   const float step_size = b.step_size[blockIdx.y], bc2_sqrt = b.bc2_sqrt[blockIdx.y];
@@ -67,7 +72,8 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b) {
 // The exchange step of data-parallel training inside the optimiser kernel (see nic.h: NicExchange).  Every block
 //   1. (one warp of block 0,0) pushes this rank's token into every peer's flag array: the gradients were written by the
 //      previous kernel of the stream, a system-scope release store makes them visible to the peers before the flag;
-//   2. waits (local acquire loads, 2 s timeout) until its own flag array shows the token of every rank;
+//   2. waits (local acquire loads; timeout NIC_OPT_EXCHANGE_TIMEOUT_MS, default 10 s, FATAL: see the kernel) until its own
+//      flag array shows the token of every rank;
 //   3. forms each gradient element as the sum of the `world` peer buffers in RANK ORDER — identical bits on every rank —
 //      with cache-volatile 16-byte loads (L1 is not coherent with peer writes), and applies Adam;
 //   4. (row 0 of the grid) clears the other-parity buffer of this rank for its next use.
@@ -78,9 +84,11 @@ struct XchDev {
   unsigned* peer_flag[NIC_MAX_PEERS];
   float* zero_buf;
   long long zero_numel;
-  unsigned* err;
+  unsigned* err;              // device word, sticky: an exchange timed out; no update is applied from then on
+  unsigned* host_err;         // the same flag in mapped pinned host memory: the next API call reads it without a sync
   unsigned* go;               // local word: block (0,0) releases the other blocks once every peer has arrived
   unsigned go_token;          // ... by storing this launch's sequence number (per handle, monotonic)
+  unsigned long long timeout_ns;
   const float* loss_sum;      // inside peer_flat[rank]
   int dbg;                    // knock-outs (timing experiments only): bit 5 no flag wait, bit 6 read the own buffer only
 };
@@ -90,9 +98,31 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void xch_fail(const XchDev& x) {
+  atomicExch(x.err, 1u);
+  if (x.host_err) {
+    *reinterpret_cast<volatile unsigned*>(x.host_err) = 1u;
+    __threadfence_system();
+  }
+}
 
+// A timeout is FATAL for the exchange: the flag is sticky, this launch and every later one leave the parameters, the
+// Adam state and the loss untouched, and the next nic_adam_step_exchange / nic_exchange_status call on the handle returns
+// NIC_ERR_EXCHANGE — the replicas stay consistent (nobody applied a partial sum) until the caller re-synchronises them.
+// The grid is sized to the resident block count (launch_adam_exchange), so block (0,0) is always scheduled.
 __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev x) {
   pdl_wait();
+  __shared__ unsigned s_err;
   if (!(x.dbg & 32)) {
     if (blockIdx.x == 0 && blockIdx.y == 0) {
       // ONE warp of the grid talks to the peers.  Flags are PUSHED: lane p stores this rank's token into slot `rank` of
@@ -100,35 +130,48 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
       // and all peers are awaited in parallel.  Lane 0 then releases this rank's other blocks through a local word.
       if (threadIdx.x < 32) {
         const int p = threadIdx.x;
-        if (p < x.world) {
+        bool bad = ld_acquire_gpu(x.err) != 0u;
+        if (p < x.world && !bad) {          // a rank that has already failed stays silent: its peers time out too
           __threadfence_system();
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer_flag[p] + x.rank), "r"(x.token) : "memory");
           const unsigned* mine = x.peer_flag[x.rank] + p;
-          const long long t0 = clock64();
-          while ((int)(ld_acquire_sys(mine) - x.token) < 0) {
-            if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer is gone; record it and go on (results are then wrong)
-              atomicExch(x.err, 1u);
-              break;
-            }
+          const unsigned long long t0 = globaltimer_ns();
+          unsigned spins = 0;
+          while (!bad && (int)(ld_acquire_sys(mine) - x.token) < 0) {
+            if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > x.timeout_ns) bad = true;     // the peer is gone
           }
         }
-        __syncwarp();
-        if (p == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(x.go), "r"(x.go_token) : "memory");
+        bad = __any_sync(0xffffffffu, bad);
+        if (p == 0) {
+          if (bad) xch_fail(x);
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(x.go), "r"(x.go_token) : "memory");
+        }
       }
     } else if (threadIdx.x == 0) {
-      unsigned v;
-      const long long t0 = clock64();
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(x.go) : "memory");
-      } while ((int)(v - x.go_token) < 0 && clock64() - t0 < 5000000000ll);
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned spins = 0;
+      while ((int)(ld_acquire_gpu(x.go) - x.go_token) < 0) {
+        if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > x.timeout_ns + 1000000000ull) {
+          xch_fail(x);
+          break;
+        }
+      }
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) s_err = ld_acquire_gpu(x.err);
+  __syncthreads();
+  if (s_err) return;             // sticky failure: nothing is updated (see above)
   if (b.loss_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     const long long off = x.loss_sum - x.peer_flat[x.rank];
     float s = 0.f;
     for (int r = 0; r < x.world; ++r) s += __ldcv(x.peer_flat[(x.dbg & 64) ? x.rank : r] + off);
     b.loss_out[0] = s * b.loss_scale;
+    if (b.metrics) {
+      float s8 = 0.f;
+      for (int r = 0; r < x.world; ++r) s8 += __ldcv(x.peer_flat[(x.dbg & 64) ? x.rank : r] + off + 1);
+      b.loss_out[1] = s8 * b.loss_scale;
+    }
   }
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (blockIdx.y == 0 && x.zero_buf) {             // 16-byte aligned, multiple of 4 floats (FusedTrainer's layout)
@@ -170,15 +213,27 @@ int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, flo
                          float grad_scale, const NicExchange& xc, const float* loss_sum, float* loss_out, float loss_scale,
                          cudaStream_t st) {
   if (count > NIC_ADAM_BATCH) return NIC_ERR_UNSUPPORTED;      // one launch: the flag protocol runs once per step
-  if (!h->xch_err) {          // two words: [0] timeout flag, [1] the local release word
+  if (!h->xch_err) {          // two words: [0] sticky timeout flag, [1] the local release word; + the host-visible copy of [0]
     cudaError_t e = cudaMalloc(&h->xch_err, 2 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemsetAsync(h->xch_err, 0, 2 * sizeof(unsigned), st);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->xch_host_err, sizeof(unsigned), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+      *h->xch_host_err = 0u;
+      e = cudaHostGetDevicePointer((void**)&h->xch_host_err_dev, h->xch_host_err, 0);
+    }
+    if (e == cudaSuccess) {
+      int occ = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, adam_exchange_kernel, 256, 0);
+      h->xch_resident_blocks = (occ > 0 ? occ : 1) * h->sms;
+    }
     if (e != cudaSuccess) return (int)e;
   }
+  if (*reinterpret_cast<volatile unsigned*>(h->xch_host_err)) return NIC_ERR_EXCHANGE;     // sticky until nic_exchange_status
   AdamBatch b;
   b.loss_sum = nullptr;
   b.loss_out = loss_out;
   b.loss_scale = loss_scale;
+  b.metrics = h->step_metrics;
   b.count = count;
   b.beta1 = beta1; b.beta2 = beta2; b.eps = eps; b.grad_scale = grad_scale; b.zero_grad = 0;
   long long maxn = xc.zero_numel;
@@ -201,12 +256,17 @@ int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, flo
   x.zero_buf = xc.zero_buf;
   x.zero_numel = xc.zero_numel;
   x.err = h->xch_err;
+  x.host_err = h->xch_host_err_dev;
   x.go = h->xch_err + 1;
   x.go_token = ++h->xch_seq;
+  x.timeout_ns = (unsigned long long)(h->xch_timeout_ms > 0 ? h->xch_timeout_ms : 10000) * 1000000ull;
   x.dbg = h->debug_flags;
   x.loss_sum = loss_sum;
+  // Every block but (0,0) spins until block (0,0) has met the peers, so ALL blocks must be co-resident: the grid is
+  // capped at the occupancy-bounded resident block count (the loops are grid-stride).
   long long blocks = (maxn / 4 + 255) / 256 + 1;
-  long long cap = (long long)h->sms * 8;
+  long long cap = h->xch_resident_blocks / count;
+  if (cap < 1) return NIC_ERR_UNSUPPORTED;
   dim3 grid((unsigned)(blocks > cap ? cap : blocks), (unsigned)count);
   cudaError_t e = launch_pdl(adam_exchange_kernel, grid, dim3(256), 0, st, b, x);
   h->launches++;
@@ -221,6 +281,7 @@ int launch_adam(Handle* h, const NicAdamTensor* tensors, int count, float beta1,
     b.loss_sum = base == 0 ? loss_sum : nullptr;
     b.loss_out = loss_out;
     b.loss_scale = loss_scale;
+    b.metrics = h->step_metrics;
     b.count = count - base < NIC_ADAM_BATCH ? count - base : NIC_ADAM_BATCH;
     b.beta1 = beta1; b.beta2 = beta2; b.eps = eps; b.grad_scale = grad_scale; b.zero_grad = zero_grad;
     long long maxn = 0;

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   constexpr uint32_t ID_BDX = tt_idesc(FMT, 128, NDX, 0, 1);       // dX = dZ1 W1' (N = NDX input columns)
   constexpr uint32_t WG64 = 8 * 128, WG16 = 2 * 128;               // k-group strides of the 64-row / 16-row weight images
   uint32_t phase = 0;
-  float loss_local = 0.f;
+  float loss_local = 0.f, sse8_local = 0.f;
   unsigned tiles_done = 0;
 
   // phase profile (debug): thread 0 adds the cycles since its previous mark to counter `i`
@@ -562,6 +562,10 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         const float o = __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c])));
         const float d = o - tgt[c];
         loss_local += on ? d * d : 0.f;
+        if (g.metrics) {            // squared error of the 8-bit outputs (per-step PSNR, image_compression.py:260-261)
+          const float d8 = quant_round(o, 255.0f) - quant_round(tgt[c], 255.0f);
+          sse8_local += on ? d8 * d8 : 0.f;
+        }
         if (on && save) a.out_save[(size_t)n * a.cout + c] = o;
         dz[c] = on ? TT_LOSS_SCALE * d * o * (1.0f - o) : 0.f;
       }
@@ -572,8 +576,13 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         for (int c = 4; c < 16; ++c) {
           if (c < a.cout) {
             const float o = __fdividef(1.0f, 1.0f + __expf(-__uint_as_float(acc[c])));
-            const float d = o - a.targets[(size_t)n * a.cout + c];
+            const float tv = a.targets[(size_t)n * a.cout + c];
+            const float d = o - tv;
             loss_local += d * d;
+            if (g.metrics) {
+              const float d8 = quant_round(o, 255.0f) - quant_round(tv, 255.0f);
+              sse8_local += d8 * d8;
+            }
             if (save) a.out_save[(size_t)n * a.cout + c] = o;
             dz[c] = TT_LOSS_SCALE * d * o * (1.0f - o);
           }
@@ -812,6 +821,15 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     if (lane == 0) sRed[warp] = v;
     __syncthreads();
     if (tid == 0) atomicAdd(a.loss_sum, ((sRed[0] + sRed[1]) + (sRed[2] + sRed[3])));
+    if (g.metrics) {
+      __syncthreads();
+      v = sse8_local;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) sRed[warp] = v;
+      __syncthreads();
+      if (tid == 0) atomicAdd(a.loss_sum + 1, ((sRed[0] + sRed[1]) + (sRed[2] + sRed[3])));
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -356,6 +356,14 @@ class HostDecodePipeline:
         # ---- upload (buffer k was last read by the decode of frame - 2)
         if self.dec_done[k] is not None:
             self.up_stream.wait_event(self.dec_done[k])
+        else:
+            # first use of buffer k: it was allocated on the caller's stream, and the caching allocator may have handed
+            # out a block whose previous use on that stream is still pending
+            self.up_stream.wait_stream(main)
+            self.copy_stream.wait_stream(main)
+            for t in self.dcodes[k] + list(self.decoders[k].parameters_list()):
+                t.record_stream(self.up_stream)
+            self.out[k].record_stream(self.copy_stream)
         with torch.cuda.stream(self.up_stream):
             for d, c in zip(self.dcodes[k], codes):
                 d.copy_(c, non_blocking=True)
@@ -476,6 +484,88 @@ def random_crop_dataset(datasets, crop_size, num_crops, uniform_distribution, di
     return sample_crops(dataset, coord, re_crop_size), coord, lod
 
 
+def random_crop_dataset_device(datasets, crop_size, num_crops, lod, seed, step, dim=2):
+    """random_crop_dataset (image_compression.py:36-49) with NO host work after the LOD draw: the crop origins are drawn on
+    the device (Philox keyed by (seed, step), uniform over [0, size - crop] like torch.randint) and the targets are
+    gathered in the same launch (nic_sample_crops_random).  `lod` is the step's mip level (FusedTrainer.draw_lod or
+    DataParallelPlan.next_lod).  Returns (inputs [NC, crop^D, C], coord [NC, D] int64 on the device)."""
+    dataset = datasets[lod]
+    if not dataset.is_cuda:
+        raise L.NicError(-3, "dataset must be a CUDA tensor (no CPU fallback)")
+    if dataset.dtype != torch.float32 or not dataset.is_contiguous():
+        raise TypeError("dataset must be contiguous float32")
+    if dataset.dim() != dim + 1:
+        raise ValueError(f"dataset must be [C, {'S, ' * dim}] for dim {dim}")
+    re_crop_size = max(1, crop_size // pow(2, lod))
+    ci = dataset.shape[0]
+    out = torch.empty((num_crops, re_crop_size ** dim, ci), dtype=torch.float32, device=dataset.device)
+    coord = torch.empty((num_crops, dim), dtype=torch.int64, device=dataset.device)
+    size = (C.c_int32 * 3)(*(list(dataset.shape[1:]) + [1] * (3 - dim)))
+    crop = (C.c_int32 * 3)(*([min(re_crop_size, dataset.shape[1 + a]) for a in range(dim)] + [1] * (3 - dim)))
+    h = L.handle(dataset.device)
+    L.check(h, L.load_library().nic_sample_crops_random(h, L.ptr(dataset), dim, ci, C.cast(size, C.c_void_p), num_crops,
+                                                        C.cast(crop, C.c_void_p), int(seed) & (2 ** 64 - 1), int(step),
+                                                        L.ptr(coord), L.ptr(out), L.stream_ptr(dataset.device)))
+    return out, coord
+
+
+# ------------------------------------------------------------------------------------------------ data front end
+def resize_image(image_u8, out_height, out_width, want_u8=False):
+    """transforms.Resize((h, w)) + transforms.ToTensor() on an 8-bit image (image_compression.py:436-441), on the device:
+    `image_u8` uint8 [H, W, C] (PIL / numpy layout) -> float32 [C, h, w] in [0, 1].  Bit-exact with Pillow's antialiased
+    BILINEAR resample (nic_resize_bilinear_u8).  want_u8: also return the 8-bit [h, w, C] image."""
+    if not image_u8.is_cuda:
+        raise L.NicError(-3, "image must be a CUDA tensor (no CPU fallback)")
+    if image_u8.dtype != torch.uint8 or image_u8.dim() != 3 or not image_u8.is_contiguous():
+        raise TypeError("image must be a contiguous uint8 [H, W, C] tensor")
+    hh, ww, cc = image_u8.shape
+    out = torch.empty((cc, out_height, out_width), dtype=torch.float32, device=image_u8.device)
+    out8 = torch.empty((out_height, out_width, cc), dtype=torch.uint8, device=image_u8.device) if want_u8 else None
+    h = L.handle(image_u8.device)
+    L.check(h, L.load_library().nic_resize_bilinear_u8(h, L.ptr(image_u8), hh, ww, cc, out_height, out_width, L.ptr(out8),
+                                                       L.ptr(out), L.stream_ptr(image_u8.device)))
+    return (out, out8) if want_u8 else out
+
+
+def build_mip_pyramid(image_u8, image_size=None, max_mip_level=None):
+    """The `images` list of the script (image_compression.py:433-442): mip i = Resize((S >> i, S >> i)) of the ORIGINAL
+    8-bit image, ToTensor -> float32 [C, S >> i, S >> i] on the device, for i = 0..MAX_MIP_LEVEL."""
+    size = var2.IMAGE_SIZE if image_size is None else image_size
+    top = var2.MAX_MIP_LEVEL if max_mip_level is None else max_mip_level
+    return [resize_image(image_u8, size // pow(2, i), size // pow(2, i)) for i in range(top + 1)]
+
+
+def flatten_movie_to_atlas(movie_u8, image_size=None):
+    """COMPRESSION_METHOD 2 (image_compression.py:453-460): frames [T, S, S, C] uint8 -> one [IMAGE_SIZE, IMAGE_SIZE, C] image,
+    frame i at tile (i // (IMAGE_SIZE // S), i % (IMAGE_SIZE // S)); unused tiles are zero."""
+    if not movie_u8.is_cuda:
+        raise L.NicError(-3, "movie must be a CUDA tensor (no CPU fallback)")
+    if movie_u8.dtype != torch.uint8 or movie_u8.dim() != 4 or movie_u8.shape[1] != movie_u8.shape[2] or not movie_u8.is_contiguous():
+        raise TypeError("movie must be a contiguous uint8 [T, S, S, C] tensor")
+    t, sz, _, cc = movie_u8.shape
+    a = var2.IMAGE_SIZE if image_size is None else image_size
+    atlas = torch.empty((a, a, cc), dtype=torch.uint8, device=movie_u8.device)
+    h = L.handle(movie_u8.device)
+    L.check(h, L.load_library().nic_atlas_pack(h, L.ptr(movie_u8), t, sz, cc, a, L.ptr(atlas), L.stream_ptr(movie_u8.device)))
+    return atlas
+
+
+def unflatten_atlas(image_u8, size_3d=None, num_frames=None):
+    """The inverse on the decoded frame (image_compression.py:410-419): [A, A, C] uint8 -> [T, S, S, C], S = IMAGE_3D_SIZE,
+    T = S frames unless `num_frames` says otherwise."""
+    if not image_u8.is_cuda:
+        raise L.NicError(-3, "image must be a CUDA tensor (no CPU fallback)")
+    if image_u8.dtype != torch.uint8 or image_u8.dim() != 3 or image_u8.shape[0] != image_u8.shape[1] or not image_u8.is_contiguous():
+        raise TypeError("image must be a contiguous uint8 [A, A, C] tensor")
+    sz = var2.IMAGE_3D_SIZE if size_3d is None else size_3d
+    t = sz if num_frames is None else num_frames
+    a, _, cc = image_u8.shape
+    frames = torch.empty((t, sz, sz, cc), dtype=torch.uint8, device=image_u8.device)
+    h = L.handle(image_u8.device)
+    L.check(h, L.load_library().nic_atlas_unpack(h, L.ptr(image_u8), a, cc, t, sz, L.ptr(frames), L.stream_ptr(image_u8.device)))
+    return frames
+
+
 # ------------------------------------------------------------------------------------------------ fused training
 class FusedTrainer:
     """The body of train_models (image_compression.py:215-269) as fused CUDA launches per step:
@@ -492,7 +582,8 @@ class FusedTrainer:
     PEER_EXCHANGE_MAX_BYTES = 4 << 20      # one-shot peer reads beat a ring/tree all-reduce only for small buffers
 
     def __init__(self, fp, decoder, num_epochs=None, fp_bits=None, lr_fp=0.01, lr_mlp=0.005, betas=(0.9, 0.999),
-                 eps=1e-8, method=None, level_table=None, process_group=None, seed=0, precision="f32", exchange="auto"):
+                 eps=1e-8, method=None, level_table=None, process_group=None, seed=0, precision="f32", exchange="auto",
+                 metrics_ring=4096, data_parallel=True, exchange_timeout_ms=None):
         self.fp = [_check_grid(g.detach()) for g in fp]
         self.decoder = decoder
         self.params = [p.detach() for p in decoder.parameters_list()]
@@ -504,7 +595,7 @@ class FusedTrainer:
         self.table = feature_pyramid_mip_levels() if level_table is None else level_table
         self.pg = process_group
         self.world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        if data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self.seed = seed
         self.rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
@@ -514,6 +605,8 @@ class FusedTrainer:
         self.frozen = False
         dev = self.fp[0].device
         self.device = dev
+        if exchange_timeout_ms is not None:      # how long the fused exchange waits on the device for a peer (default 10 s)
+            L.set_option(dev, L.OPT_EXCHANGE_TIMEOUT_MS, int(exchange_timeout_ms))
         # one flat gradient buffer per pyramid level: [dG0 | dG1 | dW1 db1 dW2 db2 dW3 db3 | loss] -> one all-reduce
         self._flat = {}
         # The exchange step under data parallelism: "nccl" = all_reduce(flat) then Adam; "peer" = ONE kernel that reads the
@@ -525,6 +618,19 @@ class FusedTrainer:
         self._peer = {}          # level -> symmetric buffers, peer pointers, use count (None: this level uses nccl)
         self.state = {}          # id -> (m, v, t)
         self.q_min = -(pow(2, self.bits) - 1) / pow(2, self.bits + 1)
+        # per-step metrics stay on the device (the reference syncs with loss.item() every step, :275): every step writes
+        # (loss, mse of the 8-bit outputs) into a ring slot; flush_metrics() reads the steps since the last flush at once
+        self.metrics_ring = max(16, int(metrics_ring))
+        self._ring = torch.zeros((self.metrics_ring, 2), dtype=torch.float32, device=dev)
+        self._ring_base = 0      # first step held by the current ring tensor
+        self._flushed = 0        # steps already returned by flush_metrics
+        self._old_rings = []     # (base, tensor) of rings that still hold unflushed steps
+        from .parallel import DataParallelPlan
+        self._plan = DataParallelPlan(var2.MAX_MIP_LEVEL, var2.UNIFORM_DISTRIBUTION_RATE, seed=seed, rank=self.rank,
+                                      world=self.world, group=process_group)
+        self._checked_uniform = False
+        self._sample_stream = None
+        self._prefetched = None  # the sampler launch of the NEXT step (step_sampled)
 
     # -- buffers
     def _level_buffers(self, fl):
@@ -581,7 +687,16 @@ class FusedTrainer:
         return ent
 
     def close(self):
-        """Unmaps the peers' buffers and frees this rank's symmetric buffers (call on every rank, after a barrier)."""
+        """Unmaps the peers' buffers and frees this rank's symmetric buffers (call on every rank, after a barrier).
+        Raises if an exchange timed out since the last check (the replicas then stopped updating, see nic.h)."""
+        used_peer = any(v is not None for v in self._peer.values())
+        failed = used_peer and L.exchange_status(self.device)
+        self._close_buffers()
+        if failed:
+            raise L.NicError(L.ERR_EXCHANGE, "a data-parallel exchange timed out waiting for a peer; parameters were not "
+                                             "updated from that step on")
+
+    def _close_buffers(self):
         for ent in self._peer.values():
             if ent is not None:
                 ent["flats"], ent["xch"] = [], {}
@@ -635,6 +750,16 @@ class FusedTrainer:
         sample_number = pow(2, max(0, (8 if self.dim == 2 else var2.CROP_MIP_LEVEL) - lod))
         coord = L.origins_tensor(coord, self.device, self.dim)
         nc = coord.shape[0]
+        if self.world > 1 and not self._checked_uniform:
+            # every rank must pass the same (lod, crop count): the gradient denominator is n * world, and the peer
+            # buffers and flag tokens are keyed per level.  Checked on the first step (all ranks are here together);
+            # draw_lod() / step_sampled() make it true by construction afterwards.
+            chk = torch.tensor([lod, -lod, nc, -nc], dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(chk, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            mx = chk.tolist()
+            if mx[0] != -mx[1] or mx[2] != -mx[3]:
+                raise ValueError(f"data-parallel step: ranks disagree on (lod, crops): lod {-mx[1]}..{mx[0]}, crops {-mx[3]}..{mx[2]}")
+            self._checked_uniform = True
         peer = self._peer_level(fl) if self.world > 1 else None
         parity = (peer["uses"] & 1) if peer else 0
         # descriptors that only depend on (lod, crops) are built once (host overhead matters at ~0.2 ms per step)
@@ -680,6 +805,76 @@ class FusedTrainer:
                 noise_bits = self.bits
         h = L.handle(self.device)
         st = L.stream_ptr(self.device)
+        lib.nic_set_option(h, L.OPT_STEP_METRICS, 1)
+        try:
+            return self._launch_step(lib, h, st, geom, m, g0, g1, coord, targets, noise_t, noise_bits, epoch, n, gm, views,
+                                     out, peer, parity, flat, states, arr)
+        finally:
+            lib.nic_set_option(h, L.OPT_STEP_METRICS, 0)
+
+    def _ring_slot(self, epoch):
+        if epoch - self._ring_base >= self.metrics_ring:       # ring full: a FRESH tensor, so handles returned earlier stay valid
+            self._old_rings.append((self._ring_base, self._ring))
+            self._ring = torch.zeros((self.metrics_ring, 2), dtype=torch.float32, device=self.device)
+            self._ring_base = epoch
+        return self._ring[epoch - self._ring_base]
+
+    def flush_metrics(self):
+        """The per-step scalars the reference logs (image_compression.py:275-279) for every step since the last flush, with
+        ONE device-to-host copy: a list of (step, loss, psnr) where psnr = calculate_psnr of the 8-bit-rounded outputs and
+        targets (:260-261; 10 log10(256^2 / mse8))."""
+        res = []
+        rings = self._old_rings + [(self._ring_base, self._ring)]
+        for base, ring in rings:
+            lo, hi = max(self._flushed, base), min(self.epoch, base + self.metrics_ring)
+            if hi <= lo:
+                continue
+            vals = ring[lo - base:hi - base].cpu().tolist()
+            for i, (loss, mse8) in enumerate(vals):
+                res.append((lo + i, loss, float("inf") if mse8 == 0 else 10.0 * math.log10(65536.0 / mse8)))
+        self._old_rings = []
+        self._flushed = self.epoch
+        return res
+
+    def draw_lod(self):
+        """The step's LOD with the reference's distribution (image_compression.py:221-226 + :29-34), identical on every
+        rank of the process group (a shared counter-free host stream: no device work, no collective)."""
+        return self._plan.next_lod()
+
+    def step_sampled(self, datasets, crop_size=None, num_crops=None, noise=None):
+        """One whole iteration of train_models' loop body: LOD draw, device-side crop sampling + target gather
+        (random_crop_dataset), fused step.  `datasets`: the mip list (build_mip_pyramid).  Returns (loss, lod).
+        The sampler of step i + 1 is launched on a side stream BEFORE step i is enqueued (its inputs — the image and a
+        Philox counter — do not depend on the step), so it runs in the shadow of step i's small kernels instead of
+        between two steps."""
+        crop = (var2.CROP_SIZE if crop_size is None else crop_size)
+        nc = var2.NUM_CROPS if num_crops is None else num_crops
+        key = (id(datasets), crop, nc)
+        if self._sample_stream is None:
+            self._sample_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+
+        def launch(index):
+            lod = self.draw_lod()
+            with torch.cuda.stream(self._sample_stream):     # (its buffers are allocated on that stream, too)
+                targets, coord = random_crop_dataset_device(datasets, crop, nc, lod, self.seed + 7919 * self.rank + 1, index,
+                                                            dim=self.dim)
+                done = torch.cuda.Event()
+                done.record(self._sample_stream)
+            targets.record_stream(main)
+            coord.record_stream(main)
+            return key, index, lod, targets, coord, done
+
+        cur = self._prefetched
+        if cur is None or cur[0] != key or cur[1] != self.epoch:
+            cur = launch(self.epoch)
+        self._prefetched = launch(self.epoch + 1)
+        _, _, lod, targets, coord, done = cur
+        main.wait_event(done)
+        return self.step(coord, targets, lod, noise=noise), lod
+
+    def _launch_step(self, lib, h, st, geom, m, g0, g1, coord, targets, noise_t, noise_bits, epoch, n, gm, views, out, peer,
+                     parity, flat, states, arr):
         L.check(h, lib.nic_train_step(h, C.byref(geom), L.ptr(g0), L.ptr(g1), L.ptr(coord), C.byref(m), L.ptr(targets),
                                       L.ptr(noise_t), noise_bits, self.seed + 7919 * self.rank, epoch, n * self.world,
                                       C.byref(gm), L.ptr(None if self.frozen else views[0]),
@@ -694,7 +889,7 @@ class FusedTrainer:
             stt[2] += 1
             arr[k].lr = lr0 * scale
             arr[k].t = stt[2]
-        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        loss = self._ring_slot(epoch)                                # [loss, mse of the 8-bit outputs]
         if peer:                                                     # ... or fused into the optimiser over NVLink peer memory
             x = self._exchange_desc(peer, parity)
             peer["uses"] += 1

@@ -396,3 +396,129 @@ def calculate_psnr(a, b, num_bits=8):
         return float("inf")
     peak = 2.0 ** num_bits
     return 10.0 * math.log10(peak * peak / mse)
+
+
+# ------------------------------------------------------------------------------------------------ data front end
+def pil_bilinear_coeffs(in_size, out_size):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc for the BILINEAR filter (src/libImaging/Resample.c, Pillow is
+    the third-party dependency behind transforms.Resize at image_compression.py:436): per output index the first input
+    index, the tap count and the fixed-point (22 fractional bits) weights.  Double arithmetic in Pillow's order."""
+    scale = filterscale = float(in_size) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int64)
+    kk = np.zeros((out_size, ksize), np.int64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        k = []
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            a = -a if a < 0.0 else a
+            w = 1.0 - a if a < 1.0 else 0.0
+            k.append(w)
+            ww += w
+        for x in range(xmax):
+            if ww != 0.0:
+                k[x] /= ww
+            kk[xx, x] = int(-0.5 + k[x] * (1 << 22)) if k[x] < 0 else int(0.5 + k[x] * (1 << 22))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def pil_resize_bilinear(img, out_h, out_w):
+    """transforms.Resize((out_h, out_w)) on an 8-bit PIL image, img uint8 [H, W, C] -> uint8 [out_h, out_w, C]:
+    horizontal pass, rounding to 8 bits, vertical pass (ImagingResample).  image_compression.py:433-442."""
+    img = np.asarray(img, np.uint8)
+    h, w, _ = img.shape
+    cur = img.astype(np.int64)
+    if out_w != w:
+        b, kk = pil_bilinear_coeffs(w, out_w)
+        nxt = np.zeros((h, out_w, img.shape[2]), np.int64)
+        for xx in range(out_w):
+            lo, n = b[xx]
+            acc = (1 << 21) + np.tensordot(cur[:, lo:lo + n, :], kk[xx, :n], axes=([1], [0]))
+            nxt[:, xx, :] = np.clip(acc >> 22, 0, 255)
+        cur = nxt
+    if out_h != h:
+        b, kk = pil_bilinear_coeffs(h, out_h)
+        nxt = np.zeros((out_h, cur.shape[1], img.shape[2]), np.int64)
+        for yy in range(out_h):
+            lo, n = b[yy]
+            acc = (1 << 21) + np.tensordot(kk[yy, :n], cur[lo:lo + n], axes=([0], [0]))
+            nxt[yy] = np.clip(acc >> 22, 0, 255)
+        cur = nxt
+    return cur.astype(np.uint8)
+
+
+def to_tensor(img_u8):
+    """transforms.ToTensor: uint8 [H, W, C] -> float32 [C, H, W] / 255 (image_compression.py:437)."""
+    return (np.transpose(np.asarray(img_u8, np.uint8), (2, 0, 1)).astype(F32) / F32(255.0)).astype(F32)
+
+
+def philox4x32_10(seed, offset, counter):
+    """Philox4x32-10 (Salmon et al. 2011) as the device code evaluates it (csrc/nic_internal.cuh: philox4x32): key = seed,
+    counter words (counter lo, counter hi, offset lo, offset hi) -> four 32-bit words."""
+    m32 = 0xFFFFFFFF
+    k0, k1 = seed & m32, (seed >> 32) & m32
+    c0, c1, c2, c3 = counter & m32, (counter >> 32) & m32, offset & m32, (offset >> 32) & m32
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        hi0, lo0, hi1, lo1 = p0 >> 32, p0 & m32, p1 >> 32, p1 & m32
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ k0) & m32, lo1, (hi0 ^ c3 ^ k1) & m32, lo0
+        k0, k1 = (k0 + 0x9E3779B9) & m32, (k1 + 0xBB67AE85) & m32
+    return c0, c1, c2, c3
+
+
+def random_crop_origins(seed, step, num_crops, size, crop):
+    """Crop origins of the device-side sampler: origin[a] = floor(U_a * (size[a] - crop[a] + 1)), U_a = word a of
+    Philox(seed, offset=step, counter=crop index) / 2^32 — uniform over the integers [0, size - crop], the distribution
+    of torch.randint(0, size - crop + 1) at image_compression.py:40-41."""
+    out = np.zeros((num_crops, len(size)), np.int64)
+    for b in range(num_crops):
+        r = philox4x32_10(seed, step, b)
+        for a in range(len(size)):
+            out[b, a] = (r[a] * (size[a] - crop[a] + 1)) >> 32
+    return out
+
+
+def crop_targets(dataset, coord, crop):
+    """Target slices of random_crop_dataset (image_compression.py:42-47): dataset [C, S, S(, S)] -> [NC, crop^D, C]."""
+    dim = dataset.ndim - 1
+    out = []
+    for o in np.asarray(coord):
+        sl = (slice(None),) + tuple(slice(int(o[a]), int(o[a]) + crop) for a in range(dim))
+        out.append(dataset[sl].reshape(dataset.shape[0], -1).T)
+    return np.stack(out)
+
+
+def atlas_pack(frames, atlas_size):
+    """COMPRESSION_METHOD 2 flatten (image_compression.py:453-460): frames uint8 [T, S, S, C] -> [A, A, C]."""
+    t, s, _, c = frames.shape
+    per = atlas_size // s
+    atlas = np.zeros((atlas_size, atlas_size, c), np.uint8)
+    for i in range(t):
+        row, col = i // per, i % per
+        atlas[row * s:(row + 1) * s, col * s:(col + 1) * s, :] = frames[i]
+    return atlas
+
+
+def atlas_unpack(atlas, size, num_frames=None):
+    """The inverse on the decoded image (image_compression.py:410-419)."""
+    t = size if num_frames is None else num_frames
+    per = atlas.shape[0] // size
+    out = np.zeros((t, size, size, atlas.shape[2]), np.uint8)
+    for x in range(t):
+        row, col = x // per, x % per
+        out[x] = atlas[row * size:(row + 1) * size, col * size:(col + 1) * size, :]
+    return out

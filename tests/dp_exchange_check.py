@@ -5,7 +5,11 @@ Trains the same model with the exchange step as an NCCL all-reduce and fused int
 (nic_adam_step_exchange), from the same initial state, crops and noise, and checks that
   * the replicas stay bit-identical across ranks in both modes,
   * the two modes agree to float rounding (the sums are formed in a different order),
-  * no exchange timed out.
+  * no exchange timed out,
+  * N ranks x b crops == ONE rank x N b crops (fp32 path, no noise): the data-parallel trajectory equals the single-device
+    trajectory on the concatenated batch to float rounding,
+  * a lost peer is FATAL, not silent: when one rank skips a step the others time out, apply no update, and their next
+    step raises NIC_ERR_EXCHANGE.
 Prints one line `DP_EXCHANGE_OK ...` on rank 0."""
 import os
 import sys
@@ -64,10 +68,75 @@ def main():
     rel = float(np.linalg.norm(a[0] - b[0]) / np.linalg.norm(a[0]))
     assert rel < 2e-3, f"nccl and peer exchange disagree: rel {rel}"
     assert np.allclose(a[1], b[1], rtol=2e-2, atol=1e-5), (a[1], b[1])
+    rel1 = dp_equals_single_device(rank, world, dev, mips)
+    fatal_timeout(rank, world, dev, mips)
     dist.barrier()
     if rank == 0:
-        print(f"DP_EXCHANGE_OK world {world} rel_l2(nccl, peer) {rel:.2e} final loss {b[1][-1]:.5f}")
+        print(f"DP_EXCHANGE_OK world {world} rel_l2(nccl, peer) {rel:.2e} final loss {b[1][-1]:.5f} "
+              f"rel_l2(dp, single device) {rel1:.2e} lost-peer timeout fatal: yes")
     dist.destroy_process_group()
+
+
+def fresh_model(dev, size):
+    fp = [torch.tensor(g, device=dev) for g in I.make_grids(size, 2, seed=3)]
+    dec = ic.ColorDecoder(73, 64, 3).to(dev)
+    with torch.no_grad():
+        for p, v in zip(dec.parameters_list(), I.make_mlp(73, seed=4)):
+            p.copy_(torch.tensor(v))
+    return fp, dec
+
+
+def dp_equals_single_device(rank, world, dev, mips, size=512, nc=2, steps=6):
+    """Every rank: `steps` fp32 steps, data parallel on its own crops AND alone on the crops of ALL ranks."""
+    rng = np.random.default_rng(7)
+    lods = [0, 1, 0, 2, 1, 0][:steps]
+    out = {}
+    for mode in ("dp", "single"):
+        fp, dec = fresh_model(dev, size)
+        tr = ic.FusedTrainer(fp, dec, num_epochs=1000, fp_bits=8, seed=1, precision="f32", exchange="peer",
+                             data_parallel=mode == "dp")
+        r2 = np.random.default_rng(8)
+        for lod in lods:
+            crop, dsize = 2 ** (8 - lod), size >> lod
+            allc = torch.tensor(r2.integers(0, dsize - crop + 1, (world * nc, 2)))       # the same draw on every rank
+            coord = allc[rank * nc:(rank + 1) * nc] if mode == "dp" else allc
+            tr.step(coord, ic.sample_crops(mips[lod], coord, crop), lod, noise=False)
+        torch.cuda.synchronize()
+        out[mode] = torch.cat([g.reshape(-1) for g in fp] + [p.detach().reshape(-1) for p in dec.parameters_list()]).cpu().numpy()
+        if mode == "dp":
+            dist.barrier()
+            tr.close()
+    rel = float(np.linalg.norm(out["dp"] - out["single"]) / np.linalg.norm(out["single"]))
+    assert rel < 1e-5, f"data parallel and single-device trajectories differ: rel {rel}"
+    return rel
+
+
+def fatal_timeout(rank, world, dev, mips, size=512, nc=2):
+    """The last rank skips one step.  Every other rank must time out (300 ms here), leave its parameters untouched, and get
+    NIC_ERR_EXCHANGE from its next step."""
+    fp, dec = fresh_model(dev, size)
+    tr = ic.FusedTrainer(fp, dec, num_epochs=1000, fp_bits=8, seed=1, precision="f16", exchange="peer", exchange_timeout_ms=300)
+    coord = torch.tensor(np.random.default_rng(9 + rank).integers(0, size - 256 + 1, (nc, 2)))
+    tg = ic.sample_crops(mips[0], coord, 256)
+    tr.step(coord, tg, 0)                                   # a good step (maps the peer buffers)
+    torch.cuda.synchronize()
+    dist.barrier()
+    before = torch.cat([g.reshape(-1) for g in fp] + [p.detach().reshape(-1) for p in dec.parameters_list()]).clone()
+    if rank != world - 1:
+        tr.step(coord, tg, 0)                               # the peer never arrives
+        torch.cuda.synchronize()
+        after = torch.cat([g.reshape(-1) for g in fp] + [p.detach().reshape(-1) for p in dec.parameters_list()])
+        assert torch.equal(before, after), "a timed-out exchange must not update the parameters"
+        try:
+            tr.step(coord, tg, 0)
+            raise AssertionError("the step after a timed-out exchange must raise")
+        except L.NicError as e:
+            assert e.status == L.ERR_EXCHANGE, e
+        assert L.exchange_status(dev), "nic_exchange_status must report the timeout"
+        assert not L.exchange_status(dev), "... and clear it"
+    dist.barrier()
+    tr._close_buffers()
+    L.set_option(dev, L.OPT_EXCHANGE_TIMEOUT_MS, 0)
 
 
 if __name__ == "__main__":
