@@ -789,7 +789,7 @@ def run_lut_65(args, env):
                          "inputs": "int64 [Q, 3] coordinates resident in HBM (4 distinct chunks per rank, cycled)"},
               "points_equal_dense_decode": ok,
               "roofline": {"bound": "tensor", "achieved": value * FLOP_M3 / 1e3, "peak": tf_peak * world, "unit": "TFLOP/s",
-                           "frac": value * FLOP_M3 / 1e3 / (tf_peak * world), "kernel_ms_per_step_rank0": kms * steps / max(kn, 1) if kn else None,
+                           "frac": value * FLOP_M3 / 1e3 / (tf_peak * world), "kernel_ms_per_step_rank0": kms / steps if kn else None,
                            "kernel": "decode_tc_gws_kernel<3> (queries)", "traffic": None}})
 
 
