@@ -278,8 +278,9 @@ int nic_sample_crops(NicHandle* h, const float* image, int dim, int channels, co
   for (int a = 0; a < dim; ++a)
     if (size[a] < 1 || crop[a] < 0 || crop[a] > size[a]) return fail(h, NIC_ERR_ARG, "nic_sample_crops: axis %d size %d crop %d", a, size[a], crop[a]);
   if (num_crops > 0 && (!image || !origins || !targets)) return fail(h, NIC_ERR_ARG, "nic_sample_crops: NULL pointer");
-  return cuda_fail(h, launch_sample_crops(h, image, dim, channels, size, (const long long*)origins, num_crops, crop, targets, st),
-                   "nic_sample_crops");
+  int rc = launch_sample_crops(h, image, dim, channels, size, (const long long*)origins, num_crops, crop, targets, st);
+  if (rc == NIC_ERR_UNSUPPORTED) return fail(h, rc, "nic_sample_crops: num_crops * 12 + 1 KB * (channels | 1) must fit 48 KB of shared memory");
+  return cuda_fail(h, rc, "nic_sample_crops");
 }
 
 int nic_sample_crops_random(NicHandle* h, const float* image, int dim, int channels, const int32_t* size, int num_crops,
@@ -292,7 +293,7 @@ int nic_sample_crops_random(NicHandle* h, const float* image, int dim, int chann
       return fail(h, NIC_ERR_ARG, "nic_sample_crops_random: axis %d size %d crop %d", a, size[a], crop[a]);
   if (num_crops > 0 && (!image || !origins_out || !targets)) return fail(h, NIC_ERR_ARG, "nic_sample_crops_random: NULL pointer");
   int rc = launch_sample_crops_random(h, image, dim, channels, size, num_crops, crop, seed, step, (long long*)origins_out, targets, st);
-  if (rc == NIC_ERR_UNSUPPORTED) return fail(h, rc, "nic_sample_crops_random: at most 4096 crops per call");
+  if (rc == NIC_ERR_UNSUPPORTED) return fail(h, rc, "nic_sample_crops_random: num_crops * 12 + 1 KB * (channels | 1) must fit 48 KB of shared memory");
   return cuda_fail(h, rc, "nic_sample_crops_random");
 }
 

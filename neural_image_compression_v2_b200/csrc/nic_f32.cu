@@ -47,37 +47,7 @@ __global__ void __launch_bounds__(256) scatter_flat_kernel(DevGeom g, const floa
 // ===================================================================================================== crop targets
 // random_crop_dataset's target gather (image_compression.py:44-47): image [Ci, S0, S1(, S2)] -> targets
 // [num_crops, crop^D, Ci] (sample-major, channels last), crop origins read from the device `coord` tensor.
-__global__ void __launch_bounds__(256) sample_crops_kernel(const float* __restrict__ img, int dim, int ci, int s0, int s1,
-                                                           int s2, const long long* __restrict__ origins, int c0, int c1,
-                                                           int c2, long long total, float* __restrict__ out) {
-  const long long per = (long long)c0 * c1 * c2, plane = (long long)s0 * s1 * s2;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long n = e / ci;
-    const int c = (int)(e - n * ci);
-    const long long b = n / per;
-    long long r = n - b * per;
-    const int i2 = (int)(r % c2);
-    r /= c2;
-    const int i1 = (int)(r % c1), i0 = (int)(r / c1);
-    int p0 = (int)origins[b * dim] + i0, p1 = (int)origins[b * dim + 1] + i1, p2 = dim == 3 ? (int)origins[b * dim + 2] + i2 : 0;
-    p0 = clampi(p0, 0, s0 - 1);
-    p1 = clampi(p1, 0, s1 - 1);
-    p2 = clampi(p2, 0, s2 - 1);
-    out[e] = __ldg(img + c * plane + ((long long)p0 * s1 + p1) * s2 + p2);
-  }
-}
-
-int launch_sample_crops(Handle* h, const float* img, int dim, int ci, const int* size, const long long* origins, int ncrops,
-                        const int* crop, float* out, cudaStream_t st) {
-  const int s2 = dim == 3 ? size[2] : 1, c2 = dim == 3 ? crop[2] : 1;
-  const long long total = (long long)ncrops * crop[0] * crop[1] * c2 * ci;
-  if (total == 0) return NIC_OK;
-  long long blocks = (total + 255) / 256, cap = (long long)h->sms * 16;
-  sample_crops_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, st>>>(img, dim, ci, size[0], size[1], s2, origins, crop[0],
-                                                                       crop[1], c2, total, out);
-  h->launches++;
-  return (int)cudaGetLastError();
-}
+// (the target gather of random_crop_dataset lives in nic_data.cu: sample_crops_tile_kernel)
 
 // ===================================================================================================== stand-alone PE
 struct PeDiv { float d[NIC_MAX_PE]; };

@@ -178,13 +178,16 @@ __device__ __forceinline__ void scatter_column(const DevGeom& g, float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
+#ifndef NIC_PHILOX_ROUNDS
+#define NIC_PHILOX_ROUNDS 10
+#endif
 __device__ __forceinline__ uint4 philox4x32(unsigned long long seed, unsigned long long offset,
                                             unsigned long long counter) {
   unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
   unsigned int c0 = (unsigned int)counter, c1 = (unsigned int)(counter >> 32);
   unsigned int c2 = (unsigned int)offset, c3 = (unsigned int)(offset >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < NIC_PHILOX_ROUNDS; ++r) {
     unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;

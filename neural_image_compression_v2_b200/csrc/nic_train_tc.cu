@@ -91,26 +91,28 @@ __device__ __forceinline__ void pack_train_weights_item(int i, const MlpDev& m, 
 }
 
 // dg[c][y][x] += scale * s[(x*ny + y)*C + c];  s <- 0   (channel-last fp32 scratch -> the caller's channel-major grid)
+// Tile = 32 nodes along x  x  GR_TF along y, all channels: the scratch is read in runs of GR_TF * C contiguous floats, the
+// gradient is written in 128-byte runs along x, every loop runs over the whole tile in parallel.
+constexpr int GR_TF = 8;
 __global__ void __launch_bounds__(256) grad_relayout_add_kernel(float* __restrict__ s, float* __restrict__ dg, int C, int nx,
                                                                 int ny, float scale) {
-  extern __shared__ float tile_f[];            // [C][32][33]
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
-  const int yw = ny - y0 < 32 ? ny - y0 : 32;
-  for (int xi = 0; xi < 32 && x0 + xi < nx; ++xi) {
-    float* row = s + ((size_t)(x0 + xi) * ny + y0) * C;
-    for (int i = threadIdx.x; i < yw * C; i += blockDim.x) {
-      int yi = i / C, c = i - yi * C;
-      tile_f[(c * 32 + yi) * 33 + xi] = row[i];
-      row[i] = 0.f;
-    }
+  extern __shared__ float tile_f[];            // [GR_TF * C][33]
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * GR_TF;
+  const int yw = ny - y0 < GR_TF ? ny - y0 : GR_TF, xw = nx - x0 < 32 ? nx - x0 : 32;
+  const int run = yw * C;
+  for (int i = threadIdx.x; i < xw * run; i += blockDim.x) {
+    const int xi = i / run, e = i - xi * run;        // e = yi * C + c
+    float* p = s + ((size_t)(x0 + xi) * ny + y0) * C + e;
+    const float v = *p;
+    tile_f[e * 33 + xi] = v;
+    if (v != 0.f) *p = 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 1024; i += blockDim.x) {
-    int c = i >> 10, r = i & 1023, yi = r >> 5, xi = r & 31;
-    int x = x0 + xi, y = y0 + yi;
-    if (x < nx && y < ny) {
-      float v = tile_f[(c * 32 + yi) * 33 + xi];
-      if (v != 0.f) dg[((size_t)c * ny + y) * nx + x] += scale * v;
+  for (int i = threadIdx.x; i < C * GR_TF * 32; i += blockDim.x) {
+    const int c = i / (GR_TF * 32), r = i - c * (GR_TF * 32), yi = r >> 5, xi = r & 31;
+    if (xi < xw && yi < yw) {
+      const float v = tile_f[(yi * C + c) * 33 + xi];
+      if (v != 0.f) dg[((size_t)c * ny + y0 + yi) * nx + x0 + xi] += scale * v;
     }
   }
 }
@@ -948,7 +950,11 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
     gs1 = (float*)((uint8_t*)h->tc_gscratch + ((gb0 + 255) & ~(size_t)255));
   }
   cudaError_t e = cudaSuccess;
-  const bool small = nodes0 <= (1 << 20) || g.dim == 3;        // the tiled relayout / relayout-add kernels are 2-D only
+  // The one-thread-per-element side kernels read / write the channel-major grids with a stride of a whole plane between
+  // neighbouring threads: fine (and one launch each) while the grids are L2-resident and tiny — [12, 129, 129] at config 1 —
+  // but 19 + 40 us per step on [12, 513, 513] (2048^2 image).  From 160^2 nodes on, the tiled (shared-memory transposing)
+  // relayout / relayout-add kernels take over (2-D only).
+  const bool small = nodes0 <= 160 * 160 || g.dim == 3;
   TrainSideArgs sa;
   memset(&sa, 0, sizeof(sa));
   sa.g0 = g0;
@@ -1053,11 +1059,10 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (dg0 && !small) {
-    size_t smem = (size_t)g.C * 32 * 33 * sizeof(float);
-    e = cudaFuncSetAttribute(grad_relayout_add_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    grad_relayout_add_kernel<<<dim3((g.n0[0] + 31) / 32, (g.n0[1] + 31) / 32), 256, smem, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sa.scale);
-    grad_relayout_add_kernel<<<dim3((g.n1[0] + 31) / 32, (g.n1[1] + 31) / 32), 256, smem, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sa.scale);
+    size_t smem = (size_t)g.C * GR_TF * 33 * sizeof(float);
+    if (smem > 48 * 1024) return NIC_ERR_UNSUPPORTED;
+    grad_relayout_add_kernel<<<dim3((g.n0[0] + 31) / 32, (g.n0[1] + GR_TF - 1) / GR_TF), 256, smem, st>>>(gs0, dg0, g.C, g.n0[0], g.n0[1], sa.scale);
+    grad_relayout_add_kernel<<<dim3((g.n1[0] + 31) / 32, (g.n1[1] + GR_TF - 1) / GR_TF), 256, smem, st>>>(gs1, dg1, g.C, g.n1[0], g.n1[1], sa.scale);
     h->launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

@@ -844,9 +844,14 @@ def test_train_tc_multi_lod_trajectory_tracks_f32(tc_prec):
     assert runs["f32"][1] == runs[tc_prec][1]                      # per-tensor Adam step counts
     assert runs["f32"][3] and runs[tc_prec][3]                      # both froze + quantised the grids at 95 %
     for a, b in zip(runs["f32"][2], runs[tc_prec][2]):
-        # quantised grids: codes may differ by one level (f16; two for bf16's 8-bit mantissa) where the two trajectories
-        # straddle a rounding boundary
-        assert float((a - b).abs().max()) <= (1.0 if tc_prec == "f16" else 2.0) / 255 + 1e-6
+        # quantised grids: codes may differ by one level where the two trajectories straddle a rounding boundary.  With
+        # bf16 operands (8 mantissa bits) the sign of a near-zero gradient can flip, and ONE Adam step moves a grid value by
+        # up to lr = 0.01 = 2.5 codes either way: >= 99 % of the codes within one level, none further than 8
+        d = (a - b).abs()
+        if tc_prec == "f16":
+            assert float(d.max()) <= 1.0 / 255 + 1e-6
+        else:
+            assert float((d <= 1.0 / 255 + 1e-6).float().mean()) >= 0.99 and float(d.max()) <= 8.0 / 255 + 1e-6
         assert float(((a - b).abs() > 1e-6).float().mean()) < 0.05
 
 
