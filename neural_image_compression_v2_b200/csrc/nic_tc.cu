@@ -22,8 +22,11 @@ namespace nic {
 // W1': [64 x KX]  col k < cin-1: W1[n][k];  col cin-1: b1[n] + lod*W1[n][cin-1];  rest 0.
 // W2': [64 x 80]  col k < 64: W2[n][k]/2 (W2[n][k] for hidden columns on the polynomial GELU);   col 64: b2[n];  rest 0.
 // W3': [16 x 80]  row n < cout: col k < 64: W3[n][k]/2 (same rule); col 64: b3[n];  rest 0.
+// (code-resident path, decode_codes_smem_kernel: the A operand holds the integer grid codes minus their offset, so the
+//  grid columns k < grid_cols of W1 carry the 1 / (2^bits - 1) of models.load4fp: gscale.)
 template <int FMT>
-__global__ void pack_weights_kernel(MlpDev m, float lod, int KX, uint16_t* __restrict__ img, int npoly) {
+__global__ void pack_weights_kernel(MlpDev m, float lod, int KX, uint16_t* __restrict__ img, int npoly, int grid_cols = 0,
+                                    float gscale = 1.0f) {
   const int H = 64;
   const int n1 = H * KX, n2 = H * 80, n3 = 16 * 80;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2 + n3; i += gridDim.x * blockDim.x) {
@@ -39,7 +42,7 @@ __global__ void pack_weights_kernel(MlpDev m, float lod, int KX, uint16_t* __res
     // hidden column k arrives as 2*gelu (MUFU tanh form) or as gelu (polynomial form, gelu_poly_pair)
     const float half = gelu_poly_column(k, npoly) ? 1.0f : 0.5f;
     if (which == 0) {
-      if (k < m.cin - 1) v = m.w1[n * m.cin + k];
+      if (k < m.cin - 1) v = k < grid_cols ? __fmul_rn(m.w1[n * m.cin + k], gscale) : m.w1[n * m.cin + k];
       else if (k == m.cin - 1) v = m.b1[n] + lod * m.w1[n * m.cin + k];
     } else if (which == 1) {
       if (k < H) v = half * m.w2[n * H + k];
@@ -754,6 +757,263 @@ __global__ void __launch_bounds__(RowShape<METHOD>::KX > 80 ? 5 * GW_GROUP : 8 *
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ================================================================================================ code-resident queries
+// Random-access decode of a SMALL model straight from its saved uint8 codes (BASELINE config 4: a 65^3 colour LUT, 1e9
+// query points): both grids live in SHARED MEMORY as channel-last codes for the life of the CTA (18^3 + 10^3 nodes x 12
+// bytes = 82 KB), so a query's 16 corner reads are shared-memory loads instead of 48 uncoalesced 8-byte global loads —
+// with the grids in global memory a tile of 128 queries costs ~6,000 L1 wavefronts (one 32-byte sector per thread and
+// load), which is what bounds decode_tc_gws_kernel at 6 Gquery/s.  The A operand holds the INTEGER codes minus their
+// offset (bytes -> exact f16 integers through 0x6400 | b = 1024 + b), and 1 / (2^bits - 1) rides in W1 (pack_weights_kernel
+// gscale).  f16 only (the byte trick needs 11 mantissa bits); otherwise the structure of decode_tc_gws_kernel with NG = 3.
+constexpr int CQ_NG = 3;
+template <int METHOD>
+__host__ __device__ constexpr int cq_fixed_smem() {
+  using S = RowShape<METHOD>;
+  return b_image_bytes(64, S::KX) + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2) + TC_LUT_MAX * 16 + 2 * 2048 +
+         CQ_NG * (S::KX / 8) * 2048 + 256;
+}
+
+template <int METHOD, typename OutT, int NPOLY>
+__global__ void __launch_bounds__(CQ_NG * GW_GROUP, 1)
+    decode_codes_smem_kernel(DevGeom g, const uint8_t* __restrict__ codes0, const uint8_t* __restrict__ codes1, int code_off,
+                             int bytes0, const long long* __restrict__ origins, const uint4* __restrict__ wimg, int cout,
+                             int lut_n, OutT* __restrict__ out) {
+  using S = RowShape<METHOD>;
+  constexpr int FMT = 0;
+  using P = Pair<FMT>;
+  constexpr int KX = S::KX, NG = CQ_NG, THREADS = NG * GW_GROUP;
+  constexpr int W1_BYTES = b_image_bytes(64, KX), W2_BYTES = b_image_bytes(64, TC_K2), W3_BYTES = b_image_bytes(16, TC_K2);
+  constexpr int KG = 16 * 128;
+  constexpr int OFF_LUT = W1_BYTES + W2_BYTES + W3_BYTES, OFF_ONE = OFF_LUT + TC_LUT_MAX * 16, OFF_ACT = OFF_ONE + 2 * KG;
+  constexpr int ACT_BYTES = (KX / 8) * KG, OFF_BAR = OFF_ACT + NG * ACT_BYTES, OFF_GRID = OFF_BAR + 256;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* sW1 = smem_raw;
+  uint8_t* sW2 = sW1 + W1_BYTES;
+  uint8_t* sW3 = sW2 + W2_BYTES;
+  uint4* sLut = reinterpret_cast<uint4*>(smem_raw + OFF_LUT);
+  uint8_t* sOne = smem_raw + OFF_ONE;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + NG);
+  uint8_t* sG0 = smem_raw + OFF_GRID;                  // codes, channel-last: [x][y][z][12]
+  uint8_t* sG1 = sG0 + bytes0;                         // (bytes0 is a multiple of 16)
+
+  const int tid = threadIdx.x, warp = uniform_warp_index(), lane = tid & 31;
+  const int slot = warp >> 2;
+  const int row = 32 * (warp & 3) + lane;
+  const int roff = (row >> 3) * 128 + (row & 7) * 16;
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 0)
+    for (int s = 0; s < NG; ++s) mbar_init(bar_full + s, 1);
+  {
+    uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+    for (int i = tid; i < OFF_LUT / 16; i += THREADS) dst[i] = __ldg(wimg + i);
+    for (int i = tid; i < lut_n; i += THREADS) {
+      float u1 = __fmul_rn(__fmul_rn((float)i, g.step), 0.5f);
+      uint4 e;
+      auto v0 = P::pack(pe_triangular(u1, 0, 6), pe_triangular(u1, 1, 6));
+      auto v1 = P::pack(pe_triangular(u1, 2, 6), pe_triangular(u1, 3, 6));
+      auto v2 = P::pack(pe_triangular(u1, 4, 6), pe_triangular(u1, 5, 6));
+      e.x = *reinterpret_cast<uint32_t*>(&v0);
+      e.y = *reinterpret_cast<uint32_t*>(&v1);
+      e.z = *reinterpret_cast<uint32_t*>(&v2);
+      e.w = 0u;
+      sLut[i] = e;
+    }
+    if (slot == 0) {
+      auto one = P::pack(1.0f, 0.0f);
+      *reinterpret_cast<uint4*>(sOne + roff) = make_uint4(*reinterpret_cast<uint32_t*>(&one), 0, 0, 0);
+      *reinterpret_cast<uint4*>(sOne + KG + roff) = make_uint4(0, 0, 0, 0);
+    }
+    // the caller's codes are channel-major [C][z][y][x] (x fastest): read them linearly (coalesced), store channel-last
+    for (int which = 0; which < 2; ++which) {
+      const uint8_t* src = which == 0 ? codes0 : codes1;
+      uint8_t* dstg = which == 0 ? sG0 : sG1;
+      const int* nn = which == 0 ? g.n0 : g.n1;
+      const int nx = nn[0], ny = nn[1], nz = S::DIM == 3 ? nn[2] : 1;
+      const int plane = nx * ny * nz;
+      for (int i = tid; i < 12 * plane; i += THREADS) {
+        const int c = i / plane, r = i - c * plane;               // r = (z * ny + y) * nx + x
+        const int x = r % nx, yz = r / nx, y = yz % ny, z = yz / ny;
+        dstg[((x * ny + y) * nz + z) * 12 + c] = __ldg(src + i);
+      }
+    }
+  }
+  fence_async_smem();
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tDs = tmem + slot * 64;
+  const uint32_t tD = tDs + ((uint32_t)((warp & 3) * 32) << 16);
+  uint8_t* sAct = smem_raw + OFF_ACT + slot * ACT_BYTES;
+  const bool issuer_warp = (warp & 3) == (slot & 3);
+  constexpr uint32_t IDESC_64 = make_idesc(FMT, 128, 64, 0, 1), IDESC_16 = make_idesc(FMT, 128, 16);
+  constexpr uint32_t LBO_64 = (64 / 8) * 128, LBO_16 = (16 / 8) * 128, SBO = 128;
+  const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3), aOne = smem_u32(sOne), aAct = smem_u32(sAct);
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "n"(GW_GROUP) : "memory"); };
+  auto group_wait = [&](uint32_t phase) {
+    if (issuer_warp) mbar_wait(bar_full + slot, phase);
+    group_sync();
+  };
+  constexpr uint32_t HI_SBO = smem_desc_hi(SBO);
+  const uint32_t loAct = smem_desc_lo(aAct, KG), loOne = smem_desc_lo(aOne, KG);
+  const uint32_t loW1 = smem_desc_lo(aW1, LBO_64), loW2 = smem_desc_lo(aW2, LBO_64), loW3 = smem_desc_lo(aW3, LBO_16);
+  auto piece = [&](int f) -> uint2* { return reinterpret_cast<uint2*>(sAct + (f >> 3) * KG + roff + (f & 7) * 2); };
+  // four code bytes -> two packed pairs of exact f16 integers (code - offset)
+  const __half2 neg = __float2half2_rn(-(1024.0f + (float)code_off));
+  auto pair_lo = [&](uint32_t w) {
+    const uint32_t v = __byte_perm(w, 0x64646464u, 0x5140);
+    return __hadd2(*reinterpret_cast<const __half2*>(&v), neg);
+  };
+  auto pair_hi = [&](uint32_t w) {
+    const uint32_t v = __byte_perm(w, 0x64646464u, 0x5342);
+    return __hadd2(*reinterpret_cast<const __half2*>(&v), neg);
+  };
+  auto bits2 = [](__half2 v) { return *reinterpret_cast<uint32_t*>(&v); };
+
+  const unsigned ntiles = (unsigned)((g.N + TC_ROWS - 1) / TC_ROWS);
+  const int lut_mask = lut_n - 1;
+  uint32_t ph = 0;
+  for (unsigned tile = blockIdx.x + gridDim.x * slot; tile < ntiles; tile += gridDim.x * NG) {
+    const unsigned n = tile * TC_ROWS + row;
+    const bool live = n < (unsigned)g.N;
+    {
+      Texel t = texel_of_fast(g, live ? n : (unsigned)g.N - 1, origins);
+      AxisCoord ax[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ax[a] = axis_coord(t.p[a], g.step);
+        ax[a].i0 = clampi(ax[a].i0, 0, g.n0[a] - 2 < 0 ? 0 : g.n0[a] - 2);
+        ax[a].i1 = clampi(ax[a].i1, 0, g.n1[a] - 2 < 0 ? 0 : g.n1[a] - 2);
+      }
+#pragma unroll
+      for (int j = 0; j < S::NC0; ++j) {             // G0 corners: 12 code bytes -> 12 features
+        const int8_t* d = S::DIM == 2 ? kCorner2D[j] : (METHOD == NIC_METHOD_3D ? kCorner3D[j] : kCorner3Dv2[j]);
+        const int dz = S::DIM == 3 ? d[0] : 0;
+        const uint32_t* node = reinterpret_cast<const uint32_t*>(sG0 + 12 * node_lin(g.n0, S::DIM, ax[0].i0 + d[2], ax[1].i0 + d[1], ax[2].i0 + dz));
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const uint32_t w = node[q];
+          *piece(12 * j + 4 * q) = make_uint2(bits2(pair_lo(w)), bits2(pair_hi(w)));
+        }
+      }
+      __half2 acc[6];                                 // G1: weighted sum of corners
+#pragma unroll
+      for (int j = 0; j < S::NC1; ++j) {
+        const int8_t* d = S::DIM == 2 ? kCorner2D[j] : kCorner3D[j];
+        const int dz = S::DIM == 3 ? d[0] : 0;
+        const uint32_t* node = reinterpret_cast<const uint32_t*>(sG1 + 12 * node_lin(g.n1, S::DIM, ax[0].i1 + d[2], ax[1].i1 + d[1], ax[2].i1 + dz));
+        float f[3];
+        g1_factors(g, j, ax, f);
+        float wgt = f[0] * f[1];
+        if (S::DIM == 3) wgt *= f[2];
+        const __half2 w2 = __float2half2_rn(wgt);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const uint32_t w = node[q];
+          acc[2 * q] = j == 0 ? __hmul2(pair_lo(w), w2) : __hfma2(pair_lo(w), w2, acc[2 * q]);
+          acc[2 * q + 1] = j == 0 ? __hmul2(pair_hi(w), w2) : __hfma2(pair_hi(w), w2, acc[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) *piece(12 * S::NC0 + 4 * q) = make_uint2(bits2(acc[2 * q]), bits2(acc[2 * q + 1]));
+      constexpr int T0 = 12 * (S::NC0 + 1), NTAIL = (KX - T0) / 2;
+      uint32_t tail[NTAIL];
+#pragma unroll
+      for (int i = 0; i < NTAIL; ++i) tail[i] = 0u;
+#pragma unroll
+      for (int a = 0; a < S::DIM; ++a) {
+        if (g.pe_kind == NIC_PE_TRIANGULAR) {
+          uint4 e = sLut[t.p[a] & lut_mask];
+          tail[3 * a] = e.x;
+          tail[3 * a + 1] = e.y;
+          tail[3 * a + 2] = e.z;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            float arg = __fmul_rn(ax[a].u1, g.pe_div[q]);
+            auto v = P::pack(sinf(arg), cosf(arg));
+            tail[3 * a + q] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        }
+      }
+      {
+        auto one = P::pack(1.0f, 0.0f);
+        tail[(S::CIN - 1 - T0) / 2] = *reinterpret_cast<uint32_t*>(&one);
+      }
+#pragma unroll
+      for (int i = 0; i < NTAIL / 2; ++i) *piece(T0 + 4 * i) = make_uint2(tail[2 * i], tail[2 * i + 1]);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    group_sync();
+    if (issuer_warp) {
+      if (elect_one()) {
+        tc_fence_after();
+#pragma unroll
+        for (int kc = 0; kc < KX / 16; ++kc)
+          mma_ss_lohi(tDs, loAct + kc * (2 * KG >> 4), HI_SBO, loW1 + kc * (2 * LBO_64 >> 4), HI_SBO, IDESC_64, kc > 0);
+        tc_commit(bar_full + slot);
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {
+      group_wait(ph);
+      ph ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t acc[8], hp[8];
+        tmem_ld8_pack16(tD + 16 * q, acc);
+        tc_wait_ld();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hp[k] = gelu_poly_pair_sel(k, NPOLY) ? gelu_poly_packed<FMT>(acc[k]) : gelu2x_packed<FMT>(acc[k]);
+        *reinterpret_cast<uint4*>(sAct + (2 * q) * KG + roff) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(sAct + (2 * q + 1) * KG + roff) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      group_sync();
+      if (issuer_warp) {
+        if (elect_one()) {
+          tc_fence_after();
+          const uint32_t loW = layer == 0 ? loW2 : loW3, stepW = layer == 0 ? (2 * LBO_64 >> 4) : (2 * LBO_16 >> 4);
+          const uint32_t idesc = layer == 0 ? IDESC_64 : IDESC_16;
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc)
+            mma_ss_lohi(tDs, loAct + kc * (2 * KG >> 4), HI_SBO, loW + kc * stepW, HI_SBO, idesc, kc > 0);
+          mma_ss_lohi(tDs, loOne, HI_SBO, loW + 4 * stepW, HI_SBO, idesc, 1);
+          tc_commit(bar_full + slot);
+        }
+        __syncwarp();
+      }
+    }
+    group_wait(ph);
+    ph ^= 1;
+    tc_fence_after();
+    uint32_t acc[16];
+    if (cout > 4) tmem_ld16(tD, acc);
+    else tmem_ld4(tD, acc);
+    tc_wait_ld();
+    tc_fence_before();
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < cout) store_sigmoid(out + (size_t)n * cout + c, __uint_as_float(acc[c]));
+      if (cout > 4) {
+#pragma unroll
+        for (int c = 4; c < 16; ++c)
+          if (c < cout) store_sigmoid(out + (size_t)n * cout + c, __uint_as_float(acc[c]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ launcher
 // NIC_OPT_REUSE_PREPARED: do the private tables already describe these inputs?
 static Handle::PreparedKey make_key(const DevGeom& g, const MlpDev& m, const float* g0, const float* g1, int fmt, int fast,
@@ -776,6 +1036,56 @@ static bool fast2d_eligible(const DevGeom& g, const long long* origins) {
   return g.method == NIC_METHOD_2D && g.step == 0.25f && g.interp && g.pe_kind == NIC_PE_TRIANGULAR && !origins &&
          g.nblocks == 1 && g.B[0] % F_TX == 0 && g.B[1] % F_TY == 0 && g.origin0[0] % F_TX == 0 &&
          g.origin0[1] % F_TY == 0 && g.B[0] > 0 && g.B[1] > 0;
+}
+
+// Random-access queries (1-texel blocks) on a model given as uint8 codes whose two grids fit shared memory next to three
+// operand buffers: the code-resident kernel.  Returns -1000 when the call does not qualify (the caller falls through).
+template <int METHOD, typename OutT>
+static int launch_codes_smem(Handle* h, const DevGeom& g, const MlpDev& m, const uint8_t* c0, const uint8_t* c1,
+                             const long long* origins, OutT* out, cudaStream_t st) {
+  using S = RowShape<METHOD>;
+  const long long nodes0 = plane_size_host(g.n0, g.dim), nodes1 = plane_size_host(g.n1, g.dim);
+  const long long bytes0 = (nodes0 * 12 + 15) & ~15ll, bytes1 = (nodes1 * 12 + 15) & ~15ll;
+  const long long smem = cq_fixed_smem<METHOD>() + bytes0 + bytes1;
+  const int bits = h->src_code_bits;
+  if (!origins || g.per_block != 1 || bits < 1 || bits > 8 || smem > 227 * 1024 || h->disable_fast2d) return -1000;
+  int rc = ensure_scratch(&h->tc_weights, &h->tc_weights_bytes, 64 * 1024);
+  if (rc) return rc;
+  const int npoly = h->gelu_poly >= 0 ? h->gelu_poly : WS_NPOLY_F16;
+  const Handle::PreparedKey key = make_key(g, m, (const float*)c0, (const float*)c1, 0, 2, bits, npoly);
+  if (!prepared_matches(h, key)) {
+    h->prepared.valid = 0;
+    pack_weights_kernel<0><<<16, 256, 0, st>>>(m, g.lod, S::KX, (uint16_t*)h->tc_weights, npoly, 12 * (S::NC0 + 1),
+                                               1.0f / (float)((1 << bits) - 1));
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    memcpy(&h->prepared, &key, sizeof(key));
+  }
+  int lut_n = 1;
+  {
+    float period = 16.0f / g.step;
+    while (lut_n < period && lut_n < TC_LUT_MAX) lut_n <<= 1;
+    if (g.pe_kind == NIC_PE_TRIANGULAR && (float)lut_n < period) return NIC_ERR_UNSUPPORTED;
+  }
+  if (g.N >= (1ll << 31) - TC_ROWS) return NIC_ERR_UNSUPPORTED;
+  void (*kern)(DevGeom, const uint8_t*, const uint8_t*, int, int, const long long*, const uint4*, int, int, OutT*) = nullptr;
+  switch (npoly) {
+    case 0: kern = decode_codes_smem_kernel<METHOD, OutT, 0>; break;
+    case 3: kern = decode_codes_smem_kernel<METHOD, OutT, 3>; break;
+    default: return NIC_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const long long ntiles = (g.N + TC_ROWS - 1) / TC_ROWS, groups = (ntiles + CQ_NG - 1) / CQ_NG;
+  const int grid = (int)(groups < h->sms ? groups : h->sms);
+  {
+    KernelTimer timer(h, st);
+    kern<<<grid, CQ_NG * GW_GROUP, (size_t)smem, st>>>(g, c0, c1, (1 << (bits - 1)) - 1, (int)bytes0, origins,
+                                                        (const uint4*)h->tc_weights, m.cout, lut_n, out);
+  }
+  h->launches++;
+  return (int)cudaGetLastError();
 }
 
 template <int FMT, typename OutT>
@@ -846,6 +1156,13 @@ static int launch_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const float
   using S = RowShape<METHOD>;
   if constexpr (METHOD == NIC_METHOD_2D) {
     if (fast2d_eligible(g, origins) && !h->disable_fast2d) return launch_fast2d<FMT, OutT>(h, g, m, g0, g1, out, st);
+  }
+  if constexpr (METHOD == NIC_METHOD_3D && FMT == 0) {       // small models given as codes, random-access queries
+    if (h->src_code_bits > 0) {
+      const int crc = launch_codes_smem<METHOD, OutT>(h, g, m, reinterpret_cast<const uint8_t*>(g0),
+                                                      reinterpret_cast<const uint8_t*>(g1), origins, out, st);
+      if (crc != -1000) return crc;
+    }
   }
   constexpr int IMG = b_image_bytes(64, S::KX) + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2);
   int rc = ensure_scratch(&h->tc_weights, &h->tc_weights_bytes, 64 * 1024);

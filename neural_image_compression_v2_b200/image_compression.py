@@ -295,6 +295,36 @@ def decode_points(fp, decoder, coords, mip_level=0, precision=None, out_dtype=to
     return out
 
 
+def decode_points_codes(codes, decoder, coords, num_bits, mip_level=0, precision="f16", out_dtype=torch.uint8, method=None,
+                        level_table=None):
+    """`decode_points` straight from the saved model (`codes`: the uint8 list of fp_savable, one code per byte): the
+    deployment form of a colour LUT (BASELINE config 4).  When both active grids fit into shared memory next to the
+    operand buffers (a 65^3 LUT: 18^3 + 10^3 nodes = 82 KB of codes) and the precision is f16, the queries run on the
+    code-resident kernel (decode_codes_smem_kernel: corner reads are shared-memory loads, models.load4fp is folded into the
+    first layer); otherwise on the general tensor-core kernel with the de-quantisation fused into the grid read."""
+    method = _method() if method is None else method
+    dim = 2 if method == L.METHOD_2D else 3
+    table = feature_pyramid_mip_levels() if level_table is None else level_table
+    fl = table[mip_level]
+    c0, c1 = codes[fl * 2], codes[fl * 2 + 1]
+    for c in (c0, c1):
+        if not c.is_cuda or c.dtype != torch.uint8 or not c.is_contiguous():
+            raise TypeError("codes must be contiguous uint8 CUDA tensors")
+    coords = L.origins_tensor(coords, c0.device, dim)
+    params = [p.detach().contiguous() for p in decoder.parameters_list()]
+    m = L.make_mlp(params)
+    q = coords.shape[0]
+    if q >= 2 ** 31 - 128:
+        raise ValueError("at most 2^31 - 129 queries per call; split the batch")
+    geom = L.make_geom(method, c0, c1, 1, q, _step_log2(mip_level, fl), mip_level, var2.PE_CHANNELS, _pe_kind(method))
+    out = torch.empty((q, m.cout), dtype=out_dtype, device=c0.device)
+    h = L.handle(c0.device)
+    L.check(h, L.load_library().nic_decode_codes(h, C.byref(geom), L.ptr(c0), L.ptr(c1), num_bits, L.ptr(coords), C.byref(m),
+                                                 L.ptr(out), L.DT_U8 if out_dtype == torch.uint8 else L.DT_F32,
+                                                 L.PRECISIONS[precision.lower()], L.stream_ptr(c0.device)))
+    return out
+
+
 class DecodeSession:
     """A model that is decoded many times (regions, mips, repeated frames): the private tensor-core tables (16-bit
     channel-last shadow grids, per-node G1 rows, packed weight images) are built by the first `decode` and REUSED by the

@@ -187,3 +187,45 @@ def test_data_parallel_gradient_algebra_on_one_device():
     for a, c in zip(single[0] + [single[1], single[2]], summed[0] + [summed[1], summed[2]]):
         np.testing.assert_allclose(c.cpu().numpy(), a.cpu().numpy(), rtol=2e-5, atol=1e-9)
     assert abs(float(single[3][0]) - float(summed[3][0])) <= 1e-5 * float(single[3][0])
+
+
+def test_code_resident_queries_match_dense_decode():
+    """BASELINE config 4 in deployment form: random-access queries on a 65^3 LUT given as uint8 codes run on the
+    code-resident kernel (grids in shared memory, load4fp folded into layer 1).  Against the fp32 reference-exact decode of
+    the de-quantised grids: +-1 LSB for >= 99.9 % (north-star tolerance); against the general tensor-core kernel (same
+    queries, grids in global memory): identical up to the rounding of the folded weights (>= 99.9 % equal +-1).  FP_BITS 8
+    and 4; triangular PE, interpolation on (mip 0) and off (a step == 2 level)."""
+    n = nic()
+    ic, fp_def, L = n.image_compression, n.fp_def, n._lib
+    configure(IMAGE_SIZE=64, IMAGE_DIMENSION=3, COMPRESSION_METHOD=3, CROP_MIP_LEVEL=3)
+    rng = np.random.default_rng(194)
+    params = I.make_mlp(127, seed=195, gain=2.0)
+    dec = make_decoder(params)
+    table = {0: 0, 3: 0}
+    for bits in (8, 4):
+        lo, hi = I.q_range(bits)
+        grids = [rng.uniform(lo, hi, (12, 18, 18, 18)).astype(np.float32), rng.uniform(lo, hi, (12, 10, 10, 10)).astype(np.float32)]
+        fp = [T(a) for a in grids]
+        codes = fp_def.fp_savable(fp, bits)
+        loaded = fp_def.fp_load(codes, bits)
+        for mip, size in ((0, 65), (3, 8)):                    # mip 3 on level 0: step 2, no interpolation (fp_def.py:136)
+            dense = ic.decode(loaded, dec, mip, size=size, precision="f32", out_dtype=torch.uint8, level_table=table)
+            q = rng.integers(0, size, (20011, 3))
+            q[:3] = [[size - 1] * 3, [0, 0, size - 1], [size - 1, 0, 0]]
+            qt = torch.tensor(q)
+            pts = ic.decode_points_codes(codes, dec, qt, bits, mip, precision="f16", level_table=table)
+            want = dense[q[:, 0], q[:, 1], q[:, 2]]
+            within1, same, worst = lsb_stats(pts.cpu().numpy(), want.cpu().numpy())
+            assert within1 >= 0.999 and worst <= 2, (bits, mip, within1, same, worst)
+            L.set_option(dev(), L.OPT_DISABLE_FAST2D, 1)         # the same call on the general kernel
+            try:
+                gen = ic.decode_points_codes(codes, dec, qt, bits, mip, precision="f16", level_table=table)
+            finally:
+                L.set_option(dev(), L.OPT_DISABLE_FAST2D, 0)
+            w1, s1, m1 = lsb_stats(pts.cpu().numpy(), gen.cpu().numpy())
+            assert w1 >= 0.999 and m1 <= 2, (bits, mip, w1, s1, m1)
+    # float output and an empty batch
+    out = ic.decode_points_codes(codes, dec, qt[:100], 4, 0, precision="f16", out_dtype=torch.float32, level_table=table)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (100, 3) and float(out.min()) >= 0 and float(out.max()) <= 1
+    assert ic.decode_points_codes(codes, dec, torch.zeros((0, 3), dtype=torch.int64), 4, 0, level_table=table).shape == (0, 3)
+    configure()
