@@ -9,6 +9,9 @@ from . import _lib as L
 from .models import load4fp, quantize4fp, save4fp
 
 
+# the names `from ... import *` hands to the reference script
+__all__ = ["return_2_power", "return_pyramid_levels", "create_pyramid_mip_levels", "create_pyramid", "create_pyramid_3d", "fp_quantize_clamp", "fp_quantize", "fp_all_quantize", "fp_savable", "fp_load", "fp_savable_packed", "fp_load_packed", "fp_freeze"]
+
 def return_2_power(base_size):
     """fp_def.py:8-15."""
     count = 0

@@ -6,6 +6,9 @@ import torch
 from . import _lib as L
 
 
+# the names `from ... import *` hands to the reference script
+__all__ = ["quantize4fp", "quantize_torch", "quantize", "save4fp", "load4fp", "quantize_clamp", "quantize_to_bit", "output_to_u8"]
+
 def _run_f2f(fn_name, tensor, bits):
     t = tensor.detach()
     if t.dtype != torch.float32:
@@ -76,7 +79,13 @@ def quantize_clamp(tensor, num_bits=8):
 
 
 def quantize_to_bit(array, num_bits=8):
-    """models.py:38-40 — float image in [0,1] -> float values 0..2^b-1 (round half up)."""
+    """models.py:38-40 — float image in [0,1] -> float values 0..2^b-1 (round half up).  The script calls it on a HOST numpy
+    image (image_compression.py:406): such an input makes the round trip through the device (there is no host arithmetic
+    in this package) and comes back as a float32 numpy array, like the reference's."""
+    if isinstance(array, np.ndarray):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = torch.as_tensor(np.ascontiguousarray(array, dtype=np.float32), device=dev)
+        return output_to_u8(t, num_bits).to(torch.float32).cpu().numpy()
     return output_to_u8(array, num_bits).to(torch.float32)
 
 

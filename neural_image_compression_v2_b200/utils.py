@@ -9,6 +9,9 @@ import torch
 from . import _lib as L
 
 
+# the names `from ... import *` hands to the reference script
+__all__ = ["triangular_positional_encoding", "positional_encoding", "tri", "calculate_psnr", "bits2dtype_torch", "bits2dtype_np"]
+
 def _pe(coord, num_channels, device, dtype, kind):
     if isinstance(coord, (tuple, list)):
         coord = torch.stack([c.reshape(-1) for c in coord])
