@@ -218,8 +218,17 @@ struct TrainArgs {
   unsigned long long* prof;   // NULL, or 16 device counters: cycles per phase seen by thread 0 (nic_debug_counters)
 };
 
-template <int FMT, int METHOD>
+// FS ("fast scatter", 2-D, step 1/4, interpolation on, crop rows of whole tiles): the grid-gradient reduction over the samples
+// that share a node runs ON THE TENSOR CORE.  A tile is 128 consecutive texels of one image row, so its samples touch <= 33
+// consecutive G0 node rows and <= 17 G1 node rows; with the selector matrix S [128 samples x 80 slots] (slot < 40: one-hot
+// G0 node row of the sample; 40 + q / 58 + q: its G1 node row q weighted by (1 - ky) / ky)
+//     T = S^T dZ1           (8 MMAs, reduction over the samples: S is an MN-major A operand exactly like the weight gradients)
+//     U = T W1'             (4 MMAs: the dX GEMM applied to 80 slot rows instead of 128 sample rows)
+// and U's rows leave as fp32 red.global.add.v4 — no dX epilogue, no shuffles, no 16-bit packing of the gradients.  S is
+// written into the H1 buffer (dead once D2 has been accumulated), T (16 bit) into the DZ buffer.
+template <int FMT, int METHOD, int FS = 0>
 __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc_kernel(DevGeom g, TrainArgs a) {
+  static_assert(!FS || METHOD == NIC_METHOD_2D, "the tensor-core scatter covers the 2-D method");
   using P = Pair<FMT>;
   using TS = TrainShape<METHOD>;
   constexpr int DIM = TS::DIM, CIN = TS::CIN, NC0 = TS::NC0, NC1 = TS::NC1, K1 = TS::K1, SGX = TS::SGX, NDX = TS::NDX, C0 = TS::C0;
@@ -362,6 +371,135 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       g1_factors(g, j, ax, f);
       return DIM == 2 ? f[0] * f[1] : f[0] * f[1] * f[2];
     };
+    constexpr bool PACKED_ROW = FMT == 0 && METHOD == NIC_METHOD_2D;
+    if constexpr (PACKED_ROW) {
+      // f16, 2-D: the row is assembled as PACKED 16-bit words, never as fp32 values.  The G0 corners go from the shadow grid to
+      // the operand buffer as loaded (one packed add for the noise, no conversions), G1 is interpolated with packed FMAs (the
+      // result is rounded to f16 anyway), only the 12 encoding values are converted.  Same Philox counters and the same
+      // feature <-> noise-byte mapping as the generic path below.
+      auto ldg2 = [](const uint2* p) {
+        uint2 v;
+        asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+        return v;
+      };
+      auto as_h2 = [](uint32_t v) { return *reinterpret_cast<const __half2*>(&v); };
+      auto bits2 = [](__half2 v) { return *reinterpret_cast<uint32_t*>(&v); };
+      const bool gen = !a.noise && a.noise_amp > 0.f;
+      const __half2 nsc = __float2half2_rn(a.noise_amp * (1.0f / 256.0f)), nhs = __float2half2_rn(a.noise_amp * (0.5f / 256.0f));
+      auto noise16 = [&](int b16, uint32_t* nzw) {
+        const uint4 r = philox4x32(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(8 * wg + b16));
+        const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          nzw[2 * k] = noise_h2(__byte_perm(wds[k], 0x64646464u, 0x5140), nsc, nhs);
+          nzw[2 * k + 1] = noise_h2(__byte_perm(wds[k], 0x64646464u, 0x5342), nsc, nhs);
+        }
+      };
+      auto add_inj = [&](uint32_t w, float n0, float n1) {     // injected fp32 noise (parity tests)
+        const float2 x = __half22float2(as_h2(w));
+        return bits2(__floats2half2_rn(x.x + n0, x.y + n1));
+      };
+      auto wait_prev = [&] {          // the previous tile's deferred D1 += dZ1^T X~ still reads X~ (and the H2 buffer)
+        if (tiles_done > 0) {
+          mbar_wait_sleep(mbar2, phase2);
+          phase2 ^= 1;
+        }
+      };
+      if (wg == 0) {                  // features [0, 48): the four raw G0 corners
+        uint32_t w[24];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const uint2 v = ldg2(a.s0 + 3 * (size_t)(node0 + off0(j)) + q);
+            w[6 * j + 2 * q] = v.x;
+            w[6 * j + 2 * q + 1] = v.y;
+          }
+        if (a.noise) {
+          const float* nz = a.noise + (size_t)nc * CIN;
+#pragma unroll
+          for (int i = 0; i < 24; ++i) w[i] = add_inj(w[i], nz[2 * i], nz[2 * i + 1]);
+        } else if (gen) {
+#pragma unroll
+          for (int b16 = 0; b16 < 3; ++b16) {
+            uint32_t nzw[8];
+            noise16(b16, nzw);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[8 * b16 + i] = bits2(__hadd2(as_h2(w[8 * b16 + i]), as_h2(nzw[i])));
+          }
+        }
+        wait_prev();
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          *reinterpret_cast<uint4*>(sX + roffx + c * 128) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      } else {                        // features [48, 80): G1 (12), PE (12), LOD, bias carrier, zero padding
+        uint2 raw1[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) raw1[3 * j + q] = ldg2(a.s1 + 3 * (size_t)(node1 + off1(j)) + q);
+        uint32_t w[16];
+        {
+          __half2 acc[6];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __half2 wj = __float2half2_rn(w1(j));
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              acc[2 * q] = j == 0 ? __hmul2(wj, as_h2(raw1[3 * j + q].x)) : __hfma2(wj, as_h2(raw1[3 * j + q].x), acc[2 * q]);
+              acc[2 * q + 1] = j == 0 ? __hmul2(wj, as_h2(raw1[3 * j + q].y)) : __hfma2(wj, as_h2(raw1[3 * j + q].y), acc[2 * q + 1]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) w[i] = bits2(acc[i]);
+        }
+        if (g.pe_kind == NIC_PE_TRIANGULAR) {
+#pragma unroll
+          for (int d = 0; d < 2; ++d)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              w[6 + 3 * d + r] = bits2(__floats2half2_rn(pe_triangular(ax[d].u1, 2 * r, 6), pe_triangular(ax[d].u1, 2 * r + 1, 6)));
+        } else {
+#pragma unroll 1
+          for (int d = 0; d < 2; ++d) {
+#pragma unroll 1
+            for (int h = 0; h < 3; ++h) {
+              float sv, cv;
+              sincosf(__fmul_rn(ax[d].u1, g.pe_div[h]), &sv, &cv);
+              const uint32_t pv = bits2(__floats2half2_rn(sv, cv));
+#pragma unroll
+              for (int i = 0; i < 6; ++i)
+                if (i == 3 * d + h) w[6 + i] = pv;
+            }
+          }
+        }
+        float lodv = g.lod;
+        if (a.noise) {
+          const float* nz = a.noise + (size_t)nc * CIN + 48;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) w[i] = add_inj(w[i], nz[2 * i], nz[2 * i + 1]);
+          lodv += nz[24];
+          w[12] = bits2(__floats2half2_rn(lodv, 1.0f));          // (LOD, bias carrier: not an input, no noise)
+        } else {
+          w[12] = bits2(__floats2half2_rn(lodv, 1.0f));
+          if (gen) {
+            uint32_t nzw[8];
+            noise16(0, nzw);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = bits2(__hadd2(as_h2(w[i]), as_h2(nzw[i])));
+            noise16(1, nzw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[8 + i] = bits2(__hadd2(as_h2(w[8 + i]), as_h2(nzw[i])));
+            w[12] = bits2(__hadd2(as_h2(w[12]), as_h2(nzw[4] & 0x0000FFFFu)));      // no noise beyond the real input columns
+          }
+        }
+        w[13] = w[14] = w[15] = 0u;
+        wait_prev();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(sX + roffx + (6 + c) * 128) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      }
+    } else {
     constexpr int NCW0 = 8 * C0 / 12;          // G0 corners gathered by warp-group 0 (4 / 6); the rest go to warp-group 1
     constexpr int R0 = 12 * (NC0 - NCW0);      // ... which therefore starts with R0 raw G0 features (0 / 24)
     {
@@ -503,6 +641,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         }
       }
     }
+    }
     mark(0);
     // ------------------------------------------------------------------------------------------ forward
     // d h'/d z of this thread's 32 hidden columns, layers 1 and 2.  The two layer loops below are FULLY unrolled: with a
@@ -532,6 +671,10 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
           else gd2[4 * f + i] = gg;
         }
         *reinterpret_cast<uint4*>(dstb + f * 128) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      }
+      if (FS && layer == 0 && a.dgs0) {      // the previous tile's selector matrix overwrote H1's bias carrier / padding
+        auto one = P::pack(1.0f, 0.0f);
+        *reinterpret_cast<uint4*>(sH1 + roff80 + (8 + wg) * 128) = make_uint4(wg == 0 ? *reinterpret_cast<uint32_t*>(&one) : 0u, 0, 0, 0);
       }
       mark(layer == 0 ? 2 : 4);
       if (layer == 0) {
@@ -632,16 +775,19 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         *reinterpret_cast<uint4*>(dstb + f * 128) = make_uint4(dp[0], dp[1], dp[2], dp[3]);
       }
       mark(layer == 1 ? 8 : 10);
+      const bool fs = FS && a.dgs0;
       if (layer == 1) {
-        run_mmas2(      // dH1 = dZ2 W2'  and (deferred)  D2 += DZ^T [H1 | 1]   (rows 16..79 = hidden units)
-            [&] {
+        auto issue_dh1 = [&] {
 #pragma unroll
-              for (int kc = 0; kc < 4; ++kc)
-                mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
-                       make_smem_desc(aW2 + kc * 256, 128, WG64), ID_B64, kc > 0);
-            },
-            [&] { issue_wgrad(TT_COL_D2, aDZ, aH1, TT_SG80, ID_G80); }, false);
-      } else {
+          for (int kc = 0; kc < 4; ++kc)
+            mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
+                   make_smem_desc(aW2 + kc * 256, 128, WG64), ID_B64, kc > 0);
+        };
+        // dH1 = dZ2 W2'  and  D2 += DZ^T [H1 | 1]   (rows 16..79 = hidden units): deferred, unless the selector matrix is about
+        // to overwrite H1 (FS) — then it is part of the awaited batch
+        if (fs) run_mmas2([&] { issue_dh1(); issue_wgrad(TT_COL_D2, aDZ, aH1, TT_SG80, ID_G80); }, [] {}, false);
+        else run_mmas2(issue_dh1, [&] { issue_wgrad(TT_COL_D2, aDZ, aH1, TT_SG80, ID_G80); }, false);
+      } else if (!fs) {
         run_mmas2(      // dX = dZ1 W1' (grid columns only)  and (deferred)  D1 += dZ1^T X~   (rows 0..63 = hidden units)
             [&] {
               if (a.dgs0) {
@@ -656,7 +802,125 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       mark(layer == 1 ? 9 : 11);
     }
     // ------------------------------------------------------------------------------------------ grid-gradient scatter
-    if (a.dgs0) {
+    if (FS && a.dgs0) {
+      // ---- selector matrix S -> H1 buffer.  This thread: sample `row`; warp-group 0 writes slots [0, 40), 1 writes [40, 80).
+      const AxisCoord ayf = axis_coord(t.p[1] - row, g.step);       // first sample of the tile (same image row)
+      const int base0 = clampi(ayf.i0, 0, g.n0[1] - 2 < 0 ? 0 : g.n0[1] - 2);
+      const int base1 = clampi(ayf.i1, 0, g.n1[1] - 2 < 0 ? 0 : g.n1[1] - 2);
+      {
+        auto h16 = [](float v) -> uint32_t {
+          auto p2 = P::pack(v, 0.0f);
+          return *reinterpret_cast<uint32_t*>(&p2) & 0xFFFFu;
+        };
+        // (slot, value) pairs of this thread's half of the row; a slot outside [0, 40) never matches (invalid origins)
+        int sa, sb;
+        uint32_t va, vb;
+        if (wg == 0) {
+          sa = clampi(ax[1].i0 - base0, 0, 39);
+          va = h16(1.0f);
+          sb = -1;
+          vb = 0u;
+        } else {
+          const int q = clampi(ax[1].i1 - base1, 0, 17);
+          sa = q;                                                  // slots 40 + q: weight 1 - ky (corner dy = 0)
+          va = h16(__fsub_rn(1.0f, ax[1].k));
+          sb = 18 + q;                                             // slots 58 + q: weight ky (corner dy = 1)
+          vb = h16(ax[1].k);
+        }
+        if (!live) va = vb = 0u;
+        // one or two non-zero halves in 80 bytes: position them with shifts instead of comparing every slot
+        const int ca = sa >> 3, cb = sb >> 3;                      // chunk (16 bytes = 8 slots) of each entry; cb = -1: none
+        const uint32_t wa = va << ((sa & 1) * 16), wb = vb << ((sb & 1) * 16);
+        const int ia = (sa >> 1) & 3, ib = (sb >> 1) & 3;          // word inside the chunk
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          const uint32_t xa = c == ca ? wa : 0u, xb = c == cb ? wb : 0u;
+          uint4 v;
+          v.x = (ia == 0 ? xa : 0u) | (ib == 0 ? xb : 0u);
+          v.y = (ia == 1 ? xa : 0u) | (ib == 1 ? xb : 0u);
+          v.z = (ia == 2 ? xa : 0u) | (ib == 2 ? xb : 0u);
+          v.w = (ia == 3 ? xa : 0u) | (ib == 3 ? xb : 0u);
+          *reinterpret_cast<uint4*>(sH1 + roff80 + (5 * wg + c) * 128) = v;
+        }
+      }
+      // ---- T = S^T dZ1 (awaited)  and (deferred)  D1 += dZ1^T X~
+      run_mmas2(
+          [&] {
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc)
+              mma_ss(tmem + TT_COL_D, make_smem_desc(aH1 + kc * 2 * TT_SG80, TT_SG80, 128),
+                     make_smem_desc(aH2 + kc * 2 * TT_SG80, TT_SG80, 128), tt_idesc(FMT, 128, 64, 1, 1), kc > 0);
+          },
+          [&] { issue_wgrad(TT_COL_D1, aH2, aX, SGX, ID_GX); }, true);
+      mark(11);
+      // ---- T (rows = slots) -> 16 bit, K-major A operand in the DZ buffer (dZ2 / dZ3 are dead: D2, D3 and dH1 are complete)
+      {
+        uint32_t acc[32];
+        tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
+        tc_wait_ld();
+        if (row < 80) {
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            uint32_t tp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              auto v = P::pack(__uint_as_float(acc[8 * f + 2 * i]), __uint_as_float(acc[8 * f + 2 * i + 1]));
+              tp[i] = *reinterpret_cast<uint32_t*>(&v);
+            }
+            *reinterpret_cast<uint4*>(sDZ + roff80 + (wg * 4 + f) * 128) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
+          }
+        }
+      }
+      // ---- U = T W1'  (the dX GEMM on slot rows)
+      run_mmas([&] {
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc)
+          mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + 2 * kc * 128, 128, TT_SG80), make_smem_desc(aW1 + kc * 256, 128, WG64),
+                 ID_BDX, kc > 0);
+      });
+      // ---- rows of U -> the channel-last fp32 gradient scratch.  Row r < 40: G0 node row base0 + r, columns [12 j, +12) =
+      // corner j = (dy, dx) -> node (x0 + dx, base0 + r + dy); rows 40 + q / 58 + q: G1 node row base1 + q (+ 1), columns
+      // [48, 60), times wx(dx) for the two x nodes.  Warp-group 0 holds columns [0, 32), 1 holds [32, 64).
+      {
+        uint32_t acc[32];
+        tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
+        tc_wait_ld();
+        auto red4f = [](float* dst, float x0, float x1, float x2, float x3) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
+        };
+        const int nslot0 = clampi(axis_coord(t.p[1] - row + TT_ROWS - 1, g.step).i0, 0, g.n0[1] - 2 < 0 ? 0 : g.n0[1] - 2) - base0 + 1;
+        const int nslot1 = clampi(axis_coord(t.p[1] - row + TT_ROWS - 1, g.step).i1, 0, g.n1[1] - 2 < 0 ? 0 : g.n1[1] - 2) - base1 + 1;
+        if (!(a.dbg & 16)) {
+          if (row < nslot0 && row < 40) {
+#pragma unroll
+            for (int gi = 0; gi < 8; ++gi) {
+              const int col = 32 * wg + 4 * gi;
+              if (col < 48) {
+                const int j = col / 12, q = (col - 12 * j) >> 2, dy = j & 1, dx = j >> 1;
+                float* dst = a.dgs0 + ((size_t)(ax[0].i0 + dx) * g.n0[1] + (base0 + row + dy)) * 12 + 4 * q;
+                red4f(dst, __uint_as_float(acc[4 * gi]), __uint_as_float(acc[4 * gi + 1]), __uint_as_float(acc[4 * gi + 2]),
+                      __uint_as_float(acc[4 * gi + 3]));
+              }
+            }
+          } else if (wg == 1 && row >= 40 && row < 76) {
+            const int dy = row >= 58, q = row - 40 - 18 * dy;
+            if (q < nslot1) {
+              const float kx = ax[0].k;
+#pragma unroll
+              for (int dx = 0; dx < 2; ++dx) {
+                const float wx = dx ? kx : __fsub_rn(1.0f, kx);
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                  float* dst = a.dgs1 + ((size_t)(ax[0].i1 + dx) * g.n1[1] + (base1 + q + dy)) * 12 + 4 * part;
+                  red4f(dst, wx * __uint_as_float(acc[16 + 4 * part]), wx * __uint_as_float(acc[17 + 4 * part]),
+                        wx * __uint_as_float(acc[18 + 4 * part]), wx * __uint_as_float(acc[19 + 4 * part]));
+                }
+              }
+            }
+          }
+        }
+      }
+    } else if (a.dgs0) {
       constexpr int HW = NDX / 2;                     // dX columns read by each warp-group: [HW wg, HW wg + HW)
       uint32_t acc[HW];
 #pragma unroll
@@ -1018,7 +1282,12 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
     }
     a.prof = h->dbg_counters;
   }
-  auto kern = train_tc_kernel<FMT, METHOD>;
+  void (*kern)(DevGeom, TrainArgs) = train_tc_kernel<FMT, METHOD, 0>;
+  if constexpr (METHOD == NIC_METHOD_2D) {
+    // full-resolution crops whose rows are whole tiles: the node reduction of the scatter runs on the tensor core
+    // (NIC_OPT_DEBUG_KNOCKOUT bit 8 keeps the shuffle path for A/B runs)
+    if (dg0 && g.step == 0.25f && g.interp && g.B[1] % TT_ROWS == 0 && !(h->debug_flags & 256)) kern = train_tc_kernel<FMT, METHOD, 1>;
+  }
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TrainShape<METHOD>::SMEM);
   if (e != cudaSuccess) return (int)e;
   if (g.N >= (1ll << 27)) return NIC_ERR_UNSUPPORTED;          // Philox counter packs (sample << 4 | block)

@@ -30,6 +30,9 @@ tg = ic.sample_crops(img, coord, crop)
 noise_arg = False if "nonoise" in sys.argv else None
 if "frozen" in sys.argv:
     tr.frozen = True
+dbg_extra = sum(int(a[4:]) for a in sys.argv if a.startswith("dbg="))      # e.g. dbg=256: shuffle scatter instead of the MMA scatter
+if dbg_extra:
+    L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, dbg_extra)
 for _ in range(3):
     tr.step(coord, tg, 0, noise=noise_arg)
 torch.cuda.synchronize()
