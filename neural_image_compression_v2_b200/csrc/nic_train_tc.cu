@@ -330,6 +330,56 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   };
   uint32_t phase2 = 0;
 
+  // FS: the last GEMM of a tile (U = T W1') is NOT awaited at the end of the tile — its rows are scattered after the NEXT
+  // tile's gather, which hides that round trip; the geometry the scatter needs travels in these registers.
+  bool u_pending = false;
+  int u_x0 = 0, u_x1 = 0, u_base0 = 0, u_base1 = 0, u_nslot0 = 0, u_nslot1 = 0;
+  float u_kx = 0.f;
+  // rows of U -> the channel-last fp32 gradient scratch.  Row r < 40: G0 node row base0 + r, columns [12 j, +12) = corner
+  // j = (dy, dx) -> node (x0 + dx, base0 + r + dy); rows 40 + q / 58 + q: G1 node row base1 + q (+ 1), columns [48, 60), times
+  // wx(dx) for the two x nodes.  Warp-group 0 holds columns [0, 32), 1 holds [32, 64).
+  auto fs_scatter_rows = [&] {
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    uint32_t acc[32];
+    tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
+    tc_wait_ld();
+    auto red4f = [](float* dst, float x0, float x1, float x2, float x3) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
+    };
+    if (!(a.dbg & 16)) {
+      if (row < u_nslot0 && row < 40) {
+#pragma unroll
+        for (int gi = 0; gi < 8; ++gi) {
+          const int col = 32 * wg + 4 * gi;
+          if (col < 48) {
+            const int j = col / 12, q = (col - 12 * j) >> 2, dy = j & 1, dx = j >> 1;
+            float* dst = a.dgs0 + ((size_t)(u_x0 + dx) * g.n0[1] + (u_base0 + row + dy)) * 12 + 4 * q;
+            red4f(dst, __uint_as_float(acc[4 * gi]), __uint_as_float(acc[4 * gi + 1]), __uint_as_float(acc[4 * gi + 2]),
+                  __uint_as_float(acc[4 * gi + 3]));
+          }
+        }
+      } else if (wg == 1 && row >= 40 && row < 76) {
+        const int dy = row >= 58, q = row - 40 - 18 * dy;
+        if (q < u_nslot1) {
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const float wx = dx ? u_kx : __fsub_rn(1.0f, u_kx);
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+              float* dst = a.dgs1 + ((size_t)(u_x1 + dx) * g.n1[1] + (u_base1 + q + dy)) * 12 + 4 * part;
+              red4f(dst, wx * __uint_as_float(acc[16 + 4 * part]), wx * __uint_as_float(acc[17 + 4 * part]),
+                    wx * __uint_as_float(acc[18 + 4 * part]), wx * __uint_as_float(acc[19 + 4 * part]));
+            }
+          }
+        }
+      }
+    }
+    u_pending = false;
+    tc_fence_before();          // the next MMAs into D are ordered after these tcgen05.ld by the barrier of run_mmas
+  };
+
   const unsigned ntiles = (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS);
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tiles_done) {
     const unsigned n = tile * TT_ROWS + row;
@@ -642,6 +692,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       }
     }
     }
+    if (FS && u_pending) fs_scatter_rows();     // the previous tile's gradient rows (its last GEMM ran under this gather)
     mark(0);
     // ------------------------------------------------------------------------------------------ forward
     // d h'/d z of this thread's 32 hidden columns, layers 1 and 2.  The two layer loops below are FULLY unrolled: with a
@@ -871,55 +922,29 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
           }
         }
       }
-      // ---- U = T W1'  (the dX GEMM on slot rows)
-      run_mmas([&] {
+      // ---- U = T W1'  (the dX GEMM on slot rows): issued, NOT awaited (fs_scatter_rows after the next tile's gather)
+      fence_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        if (elect_one()) {
+          tc_fence_after();
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc)
-          mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + 2 * kc * 128, 128, TT_SG80), make_smem_desc(aW1 + kc * 256, 128, WG64),
-                 ID_BDX, kc > 0);
-      });
-      // ---- rows of U -> the channel-last fp32 gradient scratch.  Row r < 40: G0 node row base0 + r, columns [12 j, +12) =
-      // corner j = (dy, dx) -> node (x0 + dx, base0 + r + dy); rows 40 + q / 58 + q: G1 node row base1 + q (+ 1), columns
-      // [48, 60), times wx(dx) for the two x nodes.  Warp-group 0 holds columns [0, 32), 1 holds [32, 64).
-      {
-        uint32_t acc[32];
-        tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
-        tc_wait_ld();
-        auto red4f = [](float* dst, float x0, float x1, float x2, float x3) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x0), "f"(x1), "f"(x2), "f"(x3) : "memory");
-        };
-        const int nslot0 = clampi(axis_coord(t.p[1] - row + TT_ROWS - 1, g.step).i0, 0, g.n0[1] - 2 < 0 ? 0 : g.n0[1] - 2) - base0 + 1;
-        const int nslot1 = clampi(axis_coord(t.p[1] - row + TT_ROWS - 1, g.step).i1, 0, g.n1[1] - 2 < 0 ? 0 : g.n1[1] - 2) - base1 + 1;
-        if (!(a.dbg & 16)) {
-          if (row < nslot0 && row < 40) {
-#pragma unroll
-            for (int gi = 0; gi < 8; ++gi) {
-              const int col = 32 * wg + 4 * gi;
-              if (col < 48) {
-                const int j = col / 12, q = (col - 12 * j) >> 2, dy = j & 1, dx = j >> 1;
-                float* dst = a.dgs0 + ((size_t)(ax[0].i0 + dx) * g.n0[1] + (base0 + row + dy)) * 12 + 4 * q;
-                red4f(dst, __uint_as_float(acc[4 * gi]), __uint_as_float(acc[4 * gi + 1]), __uint_as_float(acc[4 * gi + 2]),
-                      __uint_as_float(acc[4 * gi + 3]));
-              }
-            }
-          } else if (wg == 1 && row >= 40 && row < 76) {
-            const int dy = row >= 58, q = row - 40 - 18 * dy;
-            if (q < nslot1) {
-              const float kx = ax[0].k;
-#pragma unroll
-              for (int dx = 0; dx < 2; ++dx) {
-                const float wx = dx ? kx : __fsub_rn(1.0f, kx);
-#pragma unroll
-                for (int part = 0; part < 3; ++part) {
-                  float* dst = a.dgs1 + ((size_t)(ax[0].i1 + dx) * g.n1[1] + (base1 + q + dy)) * 12 + 4 * part;
-                  red4f(dst, wx * __uint_as_float(acc[16 + 4 * part]), wx * __uint_as_float(acc[17 + 4 * part]),
-                        wx * __uint_as_float(acc[18 + 4 * part]), wx * __uint_as_float(acc[19 + 4 * part]));
-                }
-              }
-            }
-          }
+          for (int kc = 0; kc < 4; ++kc)
+            mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + 2 * kc * 128, 128, TT_SG80), make_smem_desc(aW1 + kc * 256, 128, WG64),
+                   ID_BDX, kc > 0);
+          tc_commit(mbar);
         }
+        __syncwarp();
       }
+      u_pending = true;
+      u_x0 = ax[0].i0;
+      u_x1 = ax[0].i1;
+      u_base0 = base0;
+      u_base1 = base1;
+      u_kx = ax[0].k;
+      u_nslot0 = clampi(axis_coord(t.p[1] - row + TT_ROWS - 1, g.step).i0, 0, g.n0[1] - 2 < 0 ? 0 : g.n0[1] - 2) - base0 + 1;
+      u_nslot1 = clampi(axis_coord(t.p[1] - row + TT_ROWS - 1, g.step).i1, 0, g.n1[1] - 2 < 0 ? 0 : g.n1[1] - 2) - base1 + 1;
     } else if (a.dgs0) {
       constexpr int HW = NDX / 2;                     // dX columns read by each warp-group: [HW wg, HW wg + HW)
       uint32_t acc[HW];
@@ -1019,6 +1044,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     if (a.prof && tid == 0) atomicAdd(a.prof + 15, 1ull);
     tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
   }
+  if (FS && u_pending) fs_scatter_rows();       // the last tile's gradient rows
   // -------------------------------------------------------------------------------------------- flush: MLP gradients
   pdl_launch_dependents();       // train_finish_kernel may be scheduled now; it waits for this grid to complete
   if (a.prof && tid == 0) prof_t = clock64();

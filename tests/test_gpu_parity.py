@@ -501,7 +501,10 @@ def test_fused_training_2d_sequence_golden():
     for i in range(6):
         np.testing.assert_allclose(pr[i], z[f"param{i}"], rtol=0, atol=2e-3)
     for i in range(len(fp)):
-        np.testing.assert_allclose(fp[i].reshape(-1)[z[f"grid{i}_idx"]], z[f"grid{i}_val"], rtol=0, atol=2e-3)
+        # the grids were quantised at the freeze: a value that sits on a rounding boundary may land one code (1/255) away
+        # when the float atomics of the scatter add up in another order — allowed for at most 0.1 % of the sampled values
+        d = np.abs(fp[i].reshape(-1)[z[f"grid{i}_idx"]] - z[f"grid{i}_val"])
+        assert d.max() <= 1.0 / 255 + 2e-3 and (d <= 2e-3).mean() >= 0.999, (i, d.max(), (d <= 2e-3).mean())
     for i in (6, 7):       # never-active level: untouched by Adam, then quantised -> bit-exact
         assert np.array_equal(fp[i].reshape(-1)[z[f"grid{i}_idx"]], z[f"grid{i}_val"])
     # per-tensor step counts (reference: grids of inactive levels keep t = 0)
