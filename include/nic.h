@@ -106,7 +106,8 @@ int64_t nic_launch_count(const NicHandle* h);
 /* NIC_OPT_DEBUG_KNOCKOUT: profiling only (tools/run_decode.py, tools/run_train.py) — decode: bit 0 skips the output
  * stores, bit 1 replaces GELU by a plain pack, bit 2 issues one MMA per layer; training: bit 4 skips the grid-gradient
  * atomics, bits 5 / 6 make nic_adam_step_exchange skip the flag wait / read only its own buffer (timing experiments in
- * tools/dp_timing.py); results are then WRONG on purpose.  Bit 3 only enables the training phase counters (nic_debug_counters) and
+ * tools/dp_timing.py), bit 8 keeps the shuffle-based grid scatter where the tensor-core scatter would run (results stay correct:
+ * A/B timing); results are otherwise WRONG on purpose.  Bit 3 only enables the training phase counters (nic_debug_counters) and
  * leaves the results unchanged.  Never set in production. */
 /* NIC_OPT_GELU_POLY: how many of every 8 hidden activations of the fast 2-D tensor-core decode kernel evaluate GELU as a
  * clamped minimax polynomial on the FMA pipe instead of MUFU.TANH (the kernel is bound by the XU pipe when all of them

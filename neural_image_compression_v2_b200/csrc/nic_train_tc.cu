@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TS::OFF_MISC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   uint64_t* mbar2 = mbar + 2;                     // completion of the LAST deferred batch of a tile (D1 += dZ1^T X~)
+  uint64_t* mbar3 = reinterpret_cast<uint64_t*>(smem + TS::OFF_MISC + 64);      // FS: completion of D2 (H1 may be overwritten)
   float* sRed = reinterpret_cast<float*>(smem + TS::OFF_MISC + 32);      // [8] loss partials
 
   const int tid = threadIdx.x, warp = uniform_warp_index(), lane = tid & 31;     // warp: provably uniform (MMA issue)
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   if (tid == 0) {
     mbar_init(mbar, 1);
     mbar_init(mbar2, 1);
+    mbar_init(mbar3, 1);
   }
   {
     // zero the activation / delta buffers once (padding features must be finite), then the constant-1 bias features
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       mma_ss(tmem + dcol, make_smem_desc(abuf + kc * 2 * TT_SG80, TT_SG80, 128),
              make_smem_desc(bbuf + kc * 2 * sgb, sgb, 128), idesc, (tiles_done > 0 || kc > 0) ? 1u : 0u);
   };
-  uint32_t phase2 = 0;
+  uint32_t phase2 = 0, phase3 = 0;
 
   // FS: the last GEMM of a tile (U = T W1') is NOT awaited at the end of the tile — its rows are scattered after the NEXT
   // tile's gather, which hides that round trip; the geometry the scatter needs travels in these registers.
@@ -834,10 +836,14 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
             mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
                    make_smem_desc(aW2 + kc * 256, 128, WG64), ID_B64, kc > 0);
         };
-        // dH1 = dZ2 W2'  and  D2 += DZ^T [H1 | 1]   (rows 16..79 = hidden units): deferred, unless the selector matrix is about
-        // to overwrite H1 (FS) — then it is part of the awaited batch
-        if (fs) run_mmas2([&] { issue_dh1(); issue_wgrad(TT_COL_D2, aDZ, aH1, TT_SG80, ID_G80); }, [] {}, false);
-        else run_mmas2(issue_dh1, [&] { issue_wgrad(TT_COL_D2, aDZ, aH1, TT_SG80, ID_G80); }, false);
+        // dH1 = dZ2 W2'  and (deferred)  D2 += DZ^T [H1 | 1]   (rows 16..79 = hidden units).  FS: the selector matrix will
+        // overwrite H1, so D2 signals its own mbarrier, awaited after the dZ1 epilogue
+        run_mmas2(issue_dh1,
+                  [&] {
+                    issue_wgrad(TT_COL_D2, aDZ, aH1, TT_SG80, ID_G80);
+                    if (fs) tc_commit(mbar3);
+                  },
+                  false);
       } else if (!fs) {
         run_mmas2(      // dX = dZ1 W1' (grid columns only)  and (deferred)  D1 += dZ1^T X~   (rows 0..63 = hidden units)
             [&] {
@@ -879,6 +885,8 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
           vb = h16(ax[1].k);
         }
         if (!live) va = vb = 0u;
+        mbar_wait(mbar3, phase3);        // D2 += DZ^T [H1 | 1] has read H1 (it ran under the dZ1 epilogue)
+        phase3 ^= 1;
         // one or two non-zero halves in 80 bytes: position them with shifts instead of comparing every slot
         const int ca = sa >> 3, cb = sb >> 3;                      // chunk (16 bytes = 8 slots) of each entry; cb = -1: none
         const uint32_t wa = va << ((sa & 1) * 16), wb = vb << ((sb & 1) * 16);
