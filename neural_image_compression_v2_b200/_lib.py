@@ -149,6 +149,7 @@ OPT_GELU_POLY = 5            # share (of 8) of hidden activations on the polynom
 OPT_EXCHANGE_TIMEOUT_MS = 6  # device-side wait for a peer in nic_adam_step_exchange (default 10 s)
 OPT_STEP_METRICS = 7         # loss_sum / loss_out carry [squared error, squared error of the 8-bit outputs]
 ERR_EXCHANGE = -7
+ERR_UNSUPPORTED = -2
 OPT_DEBUG_KNOCKOUT = 100     # profiling only (nic.h); bit 3 = training phase counters
 
 

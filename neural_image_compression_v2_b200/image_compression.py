@@ -223,7 +223,7 @@ def decode(fp, decoder, mip_level=0, size=None, origin=None, precision=None, out
     m = L.make_mlp(params)
     geom = L.make_geom(method, g0, g1, block, 1, _step_log2(mip_level, fl), mip_level, var2.PE_CHANNELS,
                        _pe_kind(method), origin0=origin)
-    prec = L.PRECISIONS[(precision or var2.DECODE_PRECISION).lower()]
+    pname = (precision or var2.DECODE_PRECISION).lower()
     if out_dtype not in (torch.float32, torch.uint8):
         raise TypeError("out_dtype must be torch.float32 or torch.uint8")
     shape = block + (m.cout,)
@@ -232,9 +232,14 @@ def decode(fp, decoder, mip_level=0, size=None, origin=None, precision=None, out
     elif tuple(out.shape) != shape or out.dtype != out_dtype or not out.is_contiguous():
         raise ValueError(f"out must be a contiguous {out_dtype} tensor of shape {shape}")
     h = L.handle(g0.device)
-    L.check(h, L.load_library().nic_decode(h, C.byref(geom), L.ptr(g0), L.ptr(g1), None, C.byref(m), L.ptr(out),
-                                           L.DT_U8 if out_dtype == torch.uint8 else L.DT_F32, prec,
-                                           L.stream_ptr(g0.device)))
+    # "auto": the tensor-core kernels where they exist (C = 12, PE = 6, hidden 64), else the reference-exact CUDA-core kernel
+    for prec in (("f16", "f32") if pname == "auto" else (pname,)):
+        rc = L.load_library().nic_decode(h, C.byref(geom), L.ptr(g0), L.ptr(g1), None, C.byref(m), L.ptr(out),
+                                         L.DT_U8 if out_dtype == torch.uint8 else L.DT_F32, L.PRECISIONS[prec],
+                                         L.stream_ptr(g0.device))
+        if not (rc == L.ERR_UNSUPPORTED and pname == "auto" and prec != "f32"):
+            break
+    L.check(h, rc)
     return out
 
 
@@ -630,7 +635,14 @@ class FusedTrainer:
         self.seed = seed
         self.rank = torch.distributed.get_rank(process_group) if self.world > 1 else 0
         self._cache = {}
-        self.precision = L.PRECISIONS[precision.lower()]     # "f32" reference-exact; "f16"/"bf16" tcgen05 path
+        # "f32" reference-exact; "f16" / "bf16" tcgen05 path; "auto": f16 where the tensor-core kernels exist (C = 12, PE = 6,
+        # hidden 64, <= 16 outputs), else f32 — decided once, from the shapes
+        if precision.lower() == "auto":
+            c_ok = self.fp[0].shape[0] == 12 and var2.PE_CHANNELS == 6
+            m_ok = self.params[0].shape[0] == 64 and self.params[4].shape[0] <= 16
+            precision = "f16" if (c_ok and m_ok) else "f32"
+        self.precision_name = precision.lower()
+        self.precision = L.PRECISIONS[precision.lower()]
         self.epoch = 0
         self.frozen = False
         dev = self.fp[0].device

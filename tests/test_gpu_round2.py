@@ -335,3 +335,34 @@ def test_integration_import_swap_recipe_runs_the_script_flow(tmp_path):
                                 O.quantize_to_bit(ref01, 8).astype(np.float32))
     assert psnr_ref > 18.0 and abs(psnr - psnr_ref) <= 0.3, (psnr, psnr_ref)
     configure()
+
+
+def test_precision_auto_uses_tensor_cores_where_they_exist():
+    """precision="auto": a reference user who changes FEATURE_PYRAMID_CHANNELS / HIDDEN_LAYER_CHANNELS (var2.py:68-72) keeps a
+    working call — the tensor-core kernels cover C = 12, PE = 6, hidden 64; anything else runs on the reference-exact
+    CUDA-core kernel instead of failing with NIC_ERR_UNSUPPORTED."""
+    n = nic()
+    ic = n.image_compression
+    size = 256
+    configure(IMAGE_SIZE=size)
+    rng = np.random.default_rng(301)
+    lo, hi = I.q_range(8)
+    for C_, hidden in ((12, 64), (8, 64), (12, 32)):
+        configure(IMAGE_SIZE=size, FEATURE_PYRAMID_CHANNELS=C_, HIDDEN_LAYER_CHANNELS=hidden)
+        grids = [rng.uniform(lo, hi, (C_, 65, 65)).astype(np.float32), rng.uniform(lo, hi, (C_, 33, 33)).astype(np.float32)]
+        cin = C_ * 5 + 13
+        params = I.make_mlp(cin, hidden=hidden, seed=302, gain=2.0)
+        fp, dec = [T(a) for a in grids], make_decoder(params)
+        table = O.create_pyramid_mip_levels(size, size // 4)
+        ref = O.decode_block(grids, params, size, 0, table, 1, pe_channels=6).reshape(size, size, 3)
+        out = ic.decode(fp, dec, 0, precision="auto").cpu().numpy()
+        tol = 4e-3 if (C_, hidden) == (12, 64) else 2e-6          # tensor-core path / reference-exact path
+        assert np.abs(out - ref).max() <= tol, (C_, hidden, np.abs(out - ref).max())
+        if (C_, hidden) != (12, 64):
+            with pytest.raises(n._lib.NicError):
+                ic.decode(fp, dec, 0, precision="f16")
+        tr = ic.FusedTrainer(fp, dec, num_epochs=10, fp_bits=8, precision="auto")
+        assert tr.precision_name == ("f16" if (C_, hidden) == (12, 64) else "f32")
+        loss = tr.step(torch.zeros((1, 2), dtype=torch.int64), T(rng.random((256 * 256, 3)).astype(np.float32)), 0, noise=False)
+        assert np.isfinite(float(loss))
+    configure()
