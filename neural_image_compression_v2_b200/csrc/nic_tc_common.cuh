@@ -275,14 +275,15 @@ __device__ __forceinline__ float grid_value(const float* __restrict__ src, long 
   return __fdiv_rn(z, (float)((1 << code_bits) - 1));
 }
 
-constexpr int RL_TF = 8;        // tile: 32 nodes along x  x  RL_TF nodes along the output-fast axis f, all channels
-template <int FMT>
+// tile: 32 nodes along x  x  RL_TF nodes along the output-fast axis f, all channels.  RL_TF = 32 writes 768-byte runs and is
+// the faster one once the grid yields enough blocks (1025^2 nodes: 1,089 blocks, 20 us against 36 us with RL_TF = 8); on
+// smaller grids (513^2: 289 blocks of 48 serial loads per thread, 28 us) RL_TF = 8 gives 4x the blocks.
+template <int FMT, int RL_TF>
 __global__ void __launch_bounds__(256) relayout_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C,
                                                        int nx, int nf, int no, long long sf, long long so,
                                                        long long plane, int code_bits) {
   // blockIdx.z = the third axis.  tile[e * 33 + xi] with e = fi * C + c = the element's position in output row xi:
-  // conflict-free both ways.  (Tiles used to be 32 x 32 nodes: 289 blocks of 48 serial loads per thread on a 513^2 grid,
-  // 28 us; 32 x 8 gives 4x the blocks and a quarter of the serial work.)
+  // conflict-free both ways.
   extern __shared__ uint16_t tile[];           // [RL_TF * C][33]
   const int x0 = blockIdx.x * 32, f0 = blockIdx.y * RL_TF, o = blockIdx.z;
   for (int i = threadIdx.x; i < C * RL_TF * 32; i += blockDim.x) {
@@ -358,9 +359,19 @@ static inline int launch_relayout(Handle* h, const DevGeom& g, const float* src,
   const int nx = nodes[0], nf = dim == 2 ? nodes[1] : nodes[2], no = dim == 2 ? 1 : nodes[1];
   const long long sf = dim == 2 ? nx : (long long)nodes[1] * nx, so = dim == 2 ? 0 : nx;
   const long long plane = (long long)nx * nodes[1] * (dim == 2 ? 1 : nodes[2]);
-  dim3 grid((nx + 31) / 32, (nf + RL_TF - 1) / RL_TF, no);
-  size_t smem = (size_t)g.C * RL_TF * 33 * sizeof(uint16_t);
-  relayout_kernel<FMT><<<grid, 256, smem, st>>>(src, dst, g.C, nx, nf, no, sf, so, plane, h->src_code_bits);
+  const bool tall = (long long)((nx + 31) / 32) * ((nf + 31) / 32) * no >= 4ll * h->sms;
+  const int tf = tall ? 32 : 8;
+  dim3 grid((nx + 31) / 32, (nf + tf - 1) / tf, no);
+  size_t smem = (size_t)g.C * tf * 33 * sizeof(uint16_t);
+  if (tall) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(relayout_kernel<FMT, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    relayout_kernel<FMT, 32><<<grid, 256, smem, st>>>(src, dst, g.C, nx, nf, no, sf, so, plane, h->src_code_bits);
+  } else {
+    relayout_kernel<FMT, 8><<<grid, 256, smem, st>>>(src, dst, g.C, nx, nf, no, sf, so, plane, h->src_code_bits);
+  }
   h->launches++;
   return (int)cudaGetLastError();
 }
