@@ -114,7 +114,7 @@ int64_t nic_launch_count(const NicHandle* h);
  * use the transcendental).  -1 = the tuned default; 0 = all MUFU (round-1 behaviour); values the library was not built
  * with return NIC_ERR_UNSUPPORTED from nic_decode.  Both forms stay inside the tensor-core tolerance (+-1 LSB). */
 /* NIC_OPT_EXCHANGE_TIMEOUT_MS: how long nic_adam_step_exchange waits on the device for a peer before it gives up
- * (default 10,000 ms; raise it when a rank may legitimately stall, e.g. a rank-0 evaluation between steps). */
+ * (default 10,000 ms, counted in SM clock cycles at 2 GHz; raise it when a rank may legitimately stall, e.g. a rank-0 evaluation between steps). */
 /* NIC_OPT_STEP_METRICS = 1: the per-step PSNR bookkeeping of train_models (calculate_psnr(quantize_to_bit(out),
  * quantize_to_bit(target)), image_compression.py:260-261) without a host sync: nic_train_step additionally accumulates
  * loss_sum[1] += sum((floor(out*255+.5) - floor(target*255+.5))^2), and nic_adam_step_loss / nic_adam_step_exchange

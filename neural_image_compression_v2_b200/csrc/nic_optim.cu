@@ -88,7 +88,14 @@ struct XchDev {
   unsigned* host_err;         // the same flag in mapped pinned host memory: the next API call reads it without a sync
   unsigned* go;               // local word: block (0,0) releases the other blocks once every peer has arrived
   unsigned go_token;          // ... by storing this launch's sequence number (per handle, monotonic)
-  unsigned long long timeout_ns;
+  long long timeout_cycles;   // SM clock cycles (clock64: %globaltimer reads by every block cost ~20 us per launch)
+  // Work decomposition: "virtual blocks" of 256 items (an item = one float4 of a tensor, or one float of its unaligned tail /
+  // of an unaligned tensor), tensor i owning virtual blocks [vb_start[i], vb_start[i + 1]); the blocks after vb_start[count]
+  // clear zero_buf.  Every thread handles ONE item of ONE tensor per round, so the peer loads of ALL tensors are in flight at
+  // once (a block that walks the tensors one after the other pays the ~2 us NVLink round trip once per tensor: +17 us per
+  // step on 2 GPUs).
+  int vb_start[NIC_ADAM_BATCH + 2];
+  unsigned char vec[NIC_ADAM_BATCH];
   const float* loss_sum;      // inside peer_flat[rank]
   int dbg;                    // knock-outs (timing experiments only): bit 5 no flag wait, bit 6 read the own buffer only
 };
@@ -102,11 +109,6 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
 }
 __device__ __forceinline__ void xch_fail(const XchDev& x) {
   atomicExch(x.err, 1u);
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
   pdl_wait();
   __shared__ unsigned s_err;
   if (!(x.dbg & 32)) {
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
+    if (blockIdx.x == 0) {
       // ONE warp of the grid talks to the peers.  Flags are PUSHED: lane p stores this rank's token into slot `rank` of
       // peer p's flag array (a fire-and-forget NVLink store), then polls slot p of the LOCAL array — no remote polling,
       // and all peers are awaited in parallel.  Lane 0 then releases this rank's other blocks through a local word.
@@ -135,10 +137,9 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
           __threadfence_system();
           asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer_flag[p] + x.rank), "r"(x.token) : "memory");
           const unsigned* mine = x.peer_flag[x.rank] + p;
-          const unsigned long long t0 = globaltimer_ns();
-          unsigned spins = 0;
+          const long long t0 = clock64();
           while (!bad && (int)(ld_acquire_sys(mine) - x.token) < 0) {
-            if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > x.timeout_ns) bad = true;     // the peer is gone
+            if (clock64() - t0 > x.timeout_cycles) bad = true;     // the peer is gone
           }
         }
         bad = __any_sync(0xffffffffu, bad);
@@ -148,10 +149,9 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
         }
       }
     } else if (threadIdx.x == 0) {
-      const unsigned long long t0 = globaltimer_ns();
-      unsigned spins = 0;
+      const long long t0 = clock64();
       while ((int)(ld_acquire_gpu(x.go) - x.go_token) < 0) {
-        if ((++spins & 255u) == 0u && globaltimer_ns() - t0 > x.timeout_ns + 1000000000ull) {
+        if (clock64() - t0 > x.timeout_cycles + 2000000000ll) {
           xch_fail(x);
           break;
         }
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
   if (threadIdx.x == 0) s_err = ld_acquire_gpu(x.err);
   __syncthreads();
   if (s_err) return;             // sticky failure: nothing is updated (see above)
-  if (b.loss_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+  if (b.loss_out && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long off = x.loss_sum - x.peer_flat[x.rank];
     float s = 0.f;
     for (int r = 0; r < x.world; ++r) s += __ldcv(x.peer_flat[(x.dbg & 64) ? x.rank : r] + off);
@@ -173,39 +173,45 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
       b.loss_out[1] = s8 * b.loss_scale;
     }
   }
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  if (blockIdx.y == 0 && x.zero_buf) {             // 16-byte aligned, multiple of 4 floats (FusedTrainer's layout)
-    float4* z4 = reinterpret_cast<float4*>(x.zero_buf);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < x.zero_numel / 4; i += stride)
-      z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  const NicAdamTensor& t = b.t[blockIdx.y];
-  const float step_size = b.step_size[blockIdx.y], bc2_sqrt = b.bc2_sqrt[blockIdx.y];
-  const long long goff = t.g - x.peer_flat[x.rank];          // this tensor's offset inside every rank's buffer
-  const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0) && (goff & 3) == 0;
-  const long long n4 = vec ? t.numel / 4 : 0;
-  float4* p4 = reinterpret_cast<float4*>(t.p);
-  float4* m4 = reinterpret_cast<float4*>(t.m);
-  float4* v4 = reinterpret_cast<float4*>(t.v);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < x.world; ++r) {
-      const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[(x.dbg & 64) ? x.rank : r] + goff) + i);
-      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+  const int total_vb = x.vb_start[b.count + 1];
+  for (int vb = blockIdx.x; vb < total_vb; vb += gridDim.x) {
+    if (vb >= x.vb_start[b.count]) {               // zero_buf: 16-byte aligned, multiple of 4 floats (FusedTrainer's layout)
+      const long long i = (long long)(vb - x.vb_start[b.count]) * 256 + threadIdx.x;
+      if (i < x.zero_numel / 4) reinterpret_cast<float4*>(x.zero_buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
     }
-    float4 p = p4[i], m = m4[i], v = v4[i];
-    adam_one(p.x, g.x, m.x, v.x, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
-    adam_one(p.y, g.y, m.y, v.y, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
-    adam_one(p.z, g.z, m.z, v.z, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
-    adam_one(p.w, g.w, m.w, v.w, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
-    p4[i] = p; m4[i] = m; v4[i] = v;
-  }
-  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.numel; i += stride) {
-    float g = 0.f;
-    for (int r = 0; r < x.world; ++r) g += __ldcv(x.peer_flat[r] + goff + i);
-    float p = t.p[i], m = t.m[i], v = t.v[i];
-    adam_one(p, g, m, v, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
-    t.p[i] = p; t.m[i] = m; t.v[i] = v;
+    int ti = 0;
+    while (vb >= x.vb_start[ti + 1]) ++ti;
+    const NicAdamTensor& t = b.t[ti];
+    const float step_size = b.step_size[ti], bc2_sqrt = b.bc2_sqrt[ti];
+    const long long goff = t.g - x.peer_flat[x.rank];          // this tensor's offset inside every rank's buffer
+    const long long n4 = x.vec[ti] ? t.numel / 4 : 0;
+    const long long item = (long long)(vb - x.vb_start[ti]) * 256 + threadIdx.x;
+    if (item < n4) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < x.world; ++r) {
+        const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[(x.dbg & 64) ? x.rank : r] + goff) + item);
+        g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+      }
+      float4* p4 = reinterpret_cast<float4*>(t.p);
+      float4* m4 = reinterpret_cast<float4*>(t.m);
+      float4* v4 = reinterpret_cast<float4*>(t.v);
+      float4 p = p4[item], m = m4[item], v = v4[item];
+      adam_one(p.x, g.x, m.x, v.x, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+      adam_one(p.y, g.y, m.y, v.y, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+      adam_one(p.z, g.z, m.z, v.z, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+      adam_one(p.w, g.w, m.w, v.w, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+      p4[item] = p; m4[item] = m; v4[item] = v;
+    } else {
+      const long long i = n4 * 4 + (item - n4);
+      if (i < t.numel) {
+        float g = 0.f;
+        for (int r = 0; r < x.world; ++r) g += __ldcv(x.peer_flat[(x.dbg & 64) ? x.rank : r] + goff + i);
+        float p = t.p[i], m = t.m[i], v = t.v[i];
+        adam_one(p, g, m, v, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
+        t.p[i] = p; t.m[i] = m; t.v[i] = v;
+      }
+    }
   }
 }
 
@@ -236,13 +242,11 @@ int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, flo
   b.metrics = h->step_metrics;
   b.count = count;
   b.beta1 = beta1; b.beta2 = beta2; b.eps = eps; b.grad_scale = grad_scale; b.zero_grad = 0;
-  long long maxn = xc.zero_numel;
   for (int i = 0; i < count; ++i) {
     b.t[i] = tensors[i];
     const double bc1 = 1.0 - pow((double)beta1, (double)b.t[i].t), bc2 = 1.0 - pow((double)beta2, (double)b.t[i].t);
     b.step_size[i] = (float)((double)b.t[i].lr / bc1);
     b.bc2_sqrt[i] = (float)sqrt(bc2);
-    if (b.t[i].numel > maxn) maxn = b.t[i].numel;
   }
   XchDev x;
   memset(&x, 0, sizeof(x));
@@ -259,15 +263,28 @@ int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, flo
   x.host_err = h->xch_host_err_dev;
   x.go = h->xch_err + 1;
   x.go_token = ++h->xch_seq;
-  x.timeout_ns = (unsigned long long)(h->xch_timeout_ms > 0 ? h->xch_timeout_ms : 10000) * 1000000ull;
+  x.timeout_cycles = (long long)(h->xch_timeout_ms > 0 ? h->xch_timeout_ms : 10000) * 2000000ll;      // at <= 2 GHz: >= the requested time
   x.dbg = h->debug_flags;
   x.loss_sum = loss_sum;
   // Every block but (0,0) spins until block (0,0) has met the peers, so ALL blocks must be co-resident: the grid is
   // capped at the occupancy-bounded resident block count (the loops are grid-stride).
-  long long blocks = (maxn / 4 + 255) / 256 + 1;
-  long long cap = h->xch_resident_blocks / count;
-  if (cap < 1) return NIC_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)(blocks > cap ? cap : blocks), (unsigned)count);
+  long long vb = 0;
+  for (int i = 0; i < count; ++i) {
+    const NicAdamTensor& t = b.t[i];
+    const long long goff = t.g - xc.peer_flat[xc.rank];
+    const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0) && (goff & 3) == 0;
+    const long long items = vec ? t.numel / 4 + t.numel % 4 : t.numel;
+    x.vec[i] = vec ? 1 : 0;
+    x.vb_start[i] = (int)vb;
+    vb += (items + 255) / 256;
+  }
+  x.vb_start[count] = (int)vb;
+  vb += (xc.zero_numel / 4 + 255) / 256;
+  x.vb_start[count + 1] = (int)vb;
+  if (vb >= (1ll << 31)) return NIC_ERR_UNSUPPORTED;
+  long long blocks = vb < 1 ? 1 : vb;
+  long long cap = h->xch_resident_blocks;
+  dim3 grid((unsigned)(blocks > cap ? cap : blocks));
   cudaError_t e = launch_pdl(adam_exchange_kernel, grid, dim3(256), 0, st, b, x);
   h->launches++;
   if (e == cudaSuccess) e = cudaGetLastError();
