@@ -120,8 +120,13 @@ int64_t nic_launch_count(const NicHandle* h);
  * loss_sum[1] += sum((floor(out*255+.5) - floor(target*255+.5))^2), and nic_adam_step_loss / nic_adam_step_exchange
  * additionally write loss_out[1] = loss_sum[1] * loss_scale (and clear it).  loss_sum and loss_out must then hold TWO floats.
  * FusedTrainer points loss_out into a device ring buffer and reads it back every k steps. */
+/* NIC_OPT_STATIC_TILES = 1: the tensor-core training kernel walks its tiles in a static round-robin order instead of handing
+ * them out through an atomic counter.  The decoder gradients are per-CTA sums added in a fixed order, so with a static order
+ * two runs on the same inputs give bit-identical decoder gradients; the default (dynamic) order balances the CTAs (-10 % kernel
+ * time at config 1) and is reproducible to fp32 rounding only — like the grid gradients, which are float atomics either way. */
 enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3,
-       NIC_OPT_GELU_POLY = 5, NIC_OPT_EXCHANGE_TIMEOUT_MS = 6, NIC_OPT_STEP_METRICS = 7, NIC_OPT_DEBUG_KNOCKOUT = 100 };
+       NIC_OPT_GELU_POLY = 5, NIC_OPT_EXCHANGE_TIMEOUT_MS = 6, NIC_OPT_STEP_METRICS = 7, NIC_OPT_STATIC_TILES = 8,
+       NIC_OPT_DEBUG_KNOCKOUT = 100 };
 int nic_set_option(NicHandle* h, int option, int value);
 /* With NIC_OPT_TIME_KERNELS = 1 every nic_decode / nic_train_step / nic_gather call brackets its DOMINANT kernel
  * (not the small preparation kernels) with CUDA events on the call's stream.  This call synchronises on the recorded

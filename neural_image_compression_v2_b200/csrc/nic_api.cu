@@ -111,6 +111,7 @@ int nic_set_option(NicHandle* h, int option, int value) {
   if (option == NIC_OPT_REUSE_PREPARED) { h->reuse_prepared = value != 0; return NIC_OK; }
   if (option == NIC_OPT_TIME_KERNELS) { h->time_kernels = value != 0; h->timed_count = 0; return NIC_OK; }
   if (option == NIC_OPT_STEP_METRICS) { h->step_metrics = value != 0; return NIC_OK; }
+  if (option == NIC_OPT_STATIC_TILES) { h->static_tiles = value != 0; return NIC_OK; }
   if (option == NIC_OPT_EXCHANGE_TIMEOUT_MS) {
     if (value < 0) return fail(h, NIC_ERR_ARG, "nic_set_option: NIC_OPT_EXCHANGE_TIMEOUT_MS must be >= 0 (0 = default)");
     h->xch_timeout_ms = value;

@@ -42,6 +42,7 @@ struct Handle {
   int reuse_prepared;        // NIC_OPT_REUSE_PREPARED
   int debug_flags;           // knock-out experiments (option 100), never set in production
   unsigned long long* dbg_counters;   // 16 device counters (nic_debug_counters), allocated on first use
+  int static_tiles;          // NIC_OPT_STATIC_TILES: static tile order in the tensor-core training kernel
   int step_metrics;          // NIC_OPT_STEP_METRICS: training steps also accumulate the 8-bit squared error in loss_sum[1]
   void* data_scratch;        // nic_data.cu: resample coefficient tables + 8-bit intermediate
   size_t data_scratch_bytes;

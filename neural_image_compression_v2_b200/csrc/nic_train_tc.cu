@@ -215,6 +215,8 @@ struct TrainArgs {
   float* partials;            // [gridDim.x][pstride]: this CTA's MLP-gradient sums (w1 | b1 | w2 | b2 | w3 | b3), plain stores
   int pstride;
   int dbg;                    // knock-out experiments (NIC_OPT_DEBUG_KNOCKOUT): bit 4 skips the grid-gradient REDs
+  unsigned* tile_ctr;         // dynamic tile scheduler: next tile to hand out minus gridDim.x (zeroed by train_prep_kernel);
+                              // NULL: static round-robin (NIC_OPT_STATIC_TILES: run-to-run identical decoder gradients)
   unsigned long long* prof;   // NULL, or 16 device counters: cycles per phase seen by thread 0 (nic_debug_counters)
 };
 
@@ -243,8 +245,17 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   uint64_t* mbar2 = mbar + 2;                     // completion of the LAST deferred batch of a tile (D1 += dZ1^T X~)
   uint64_t* mbar3 = reinterpret_cast<uint64_t*>(smem + TS::OFF_MISC + 64);      // FS: completion of D2 (H1 may be overwritten)
   float* sRed = reinterpret_cast<float*>(smem + TS::OFF_MISC + 32);      // [8] loss partials
+  volatile unsigned* sTile = reinterpret_cast<volatile unsigned*>(smem + TS::OFF_MISC + 96);      // [2] next tile (dynamic scheduler)
 
   const int tid = threadIdx.x, warp = uniform_warp_index(), lane = tid & 31;     // warp: provably uniform (MMA issue)
+  // timeline (debug, bit 9 with bit 3): nanosecond stamps of CTA entry / first tile / flush / exit, min and max over the CTAs
+  const bool tl = a.prof && (a.dbg & 512);
+  auto gtime = [] {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+  };
+  const unsigned long long tl_entry = tl ? gtime() : 0ull;
   const int wg = warp >> 2;                       // column half of the epilogues / row half of the gather
   const int row = tid & (TT_ROWS - 1);            // sample of the tile = TMEM lane
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -294,7 +305,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   long long prof_t = a.prof ? clock64() : 0;
   const long long prof_start = prof_t;
   auto mark = [&](int i) {
-    if (a.prof && tid == 0) {
+    if (a.prof && !tl && tid == 0) {
       const long long t = clock64();
       atomicAdd(a.prof + i, (unsigned long long)(t - prof_t));
       prof_t = t;
@@ -383,7 +394,20 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   };
 
   const unsigned ntiles = (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS);
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tiles_done) {
+  if (tl && tid == 0) {
+    const unsigned long long t = gtime();
+    atomicMax(a.prof + 0, ~tl_entry);
+    atomicMax(a.prof + 1, tl_entry);
+    atomicMax(a.prof + 2, ~t);
+    atomicMax(a.prof + 3, t);
+  }
+  // Tiles are handed out by an atomic counter: the CTAs of one launch finish their static share up to 20 % apart (13 or 14
+  // tiles each at config 1, and the per-tile time varies from SM to SM), and the kernel ends with the slowest.  Thread 0
+  // fetches the next index at the top of a tile; it reaches the others through shared memory, several barriers later.
+  unsigned tile = blockIdx.x;
+  for (; tile < ntiles; ++tiles_done) {
+    unsigned tile_next = tile + gridDim.x;
+    if (a.tile_ctr && tid == 0) tile_next = atomicAdd(a.tile_ctr, 1u) + gridDim.x;
     const unsigned n = tile * TT_ROWS + row;
     const bool live = n < (unsigned)g.N;
     const unsigned nc = live ? n : (unsigned)g.N - 1;
@@ -707,6 +731,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
                ID_F64, kc > 0);
     });
     mark(1);
+    if (tid == 0) sTile[tiles_done & 1] = tile_next;
 #pragma unroll
     for (int layer = 0; layer < 2; ++layer) {
       uint32_t acc[32];
@@ -1049,13 +1074,19 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       }
     }
     mark(12);
-    if (a.prof && tid == 0) atomicAdd(a.prof + 15, 1ull);
+    if (a.prof && !tl && tid == 0) atomicAdd(a.prof + 15, 1ull);
     tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
+    tile = sTile[tiles_done & 1];
   }
   if (FS && u_pending) fs_scatter_rows();       // the last tile's gradient rows
   // -------------------------------------------------------------------------------------------- flush: MLP gradients
   pdl_launch_dependents();       // train_finish_kernel may be scheduled now; it waits for this grid to complete
   if (a.prof && tid == 0) prof_t = clock64();
+  if (tl && tid == 0) {
+    const unsigned long long t = gtime();
+    atomicMax(a.prof + 4, ~t);
+    atomicMax(a.prof + 5, t);
+  }
   if (tiles_done > 0) mbar_wait_sleep(mbar2, phase2);       // the last tile's deferred D1 batch (and everything before it)
   __syncthreads();
   tc_fence_after();
@@ -1063,13 +1094,13 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     // Every CTA writes its sums to its OWN slice with plain stores (each element exactly once); mlp_grad_reduce_kernel
     // adds the slices up in a fixed order.  (296 CTAs x 9,091 atomicAdds onto the same 9,091 addresses took a fifth of
     // the kernel, and made the MLP gradients depend on the order of arrival.)
+    // Slice layout (TRANSPOSED, so that the 32 lanes = 32 consecutive accumulator rows of a store write one 128-byte run):
+    //   [K1' = CIN + 1 columns][64 hidden units]  dW1 (column CIN: db1)  |  [65][64]  dW2 (column 64: db2)  |  [cout][64] dW3 | db3
     const float fs = a.flush_scale;
     float* part = a.partials + (size_t)blockIdx.x * a.pstride;
-    float* p_w1 = part;
-    float* p_b1 = p_w1 + 64 * CIN;
-    float* p_w2 = p_b1 + 64;
-    float* p_b2 = p_w2 + 64 * 64;
-    float* p_w3 = p_b2 + 64;
+    float* p_w1t = part;
+    float* p_w2t = p_w1t + 64 * (CIN + 1);
+    float* p_w3 = p_w2t + 64 * 65;
     float* p_b3 = p_w3 + 64 * a.cout;
     // D3^T: rows 0..63 = hidden unit h, row 64 = the bias feature; columns c < cout: dW3'[c][h] (W3' = W3/2) / db3[c]
     // D2: rows 16..79 = hidden unit j = row - 16; columns 0..63 = dW2'[j][k] (W2' = W2/2), 64 = db2[j];
@@ -1102,14 +1133,9 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         const int col = c0 + i;
         const float v = __uint_as_float(acc[i]) * fs;
         if (which == 1) {
-          if (row >= 16 && row < 80) {
-            const int j = row - 16;
-            if (col < 64) p_w2[j * 64 + col] = 0.5f * v;
-            else if (col == 64) p_b2[j] = v;
-          }
-        } else if (row < 64) {
-          if (col < CIN) p_w1[row * CIN + col] = v;
-          else if (col == CIN) p_b1[row] = v;
+          if (row >= 16 && row < 80 && col <= 64) p_w2t[col * 64 + row - 16] = col < 64 ? 0.5f * v : v;
+        } else if (row < 64 && col <= CIN) {
+          p_w1t[col * 64 + row] = v;
         }
       }
     }
@@ -1134,7 +1160,12 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   tc_fence_before();
   __syncthreads();
   mark(13);                    // the flush, once per CTA
-  if (a.prof && tid == 0) atomicAdd(a.prof + 14, (unsigned long long)(clock64() - prof_start));      // CTA lifetime
+  if (a.prof && !tl && tid == 0) atomicAdd(a.prof + 14, (unsigned long long)(clock64() - prof_start));      // CTA lifetime
+  if (tl && tid == 0) {
+    const unsigned long long t = gtime();
+    atomicMax(a.prof + 6, ~t);
+    atomicMax(a.prof + 7, t);
+  }
   if (warp == 0) tmem_dealloc(tmem, TS::TMEM);
 }
 
@@ -1161,9 +1192,17 @@ __device__ __forceinline__ void mlp_grad_reduce_block(int block, const float* __
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < TF_LANES; ++k) t += red[k][tx];
-    const int n_w1 = 64 * cin, o_b1 = n_w1, o_w2 = o_b1 + 64, o_b2 = o_w2 + 4096, o_w3 = o_b2 + 64, o_b3 = o_w3 + 64 * cout;
-    float* dst = i < o_b1 ? gm.w1 + i : (i < o_w2 ? gm.b1 + (i - o_b1) : (i < o_b2 ? gm.w2 + (i - o_w2) : (i < o_w3 ? gm.b2 + (i - o_b2)
-                 : (i < o_b3 ? gm.w3 + (i - o_w3) : gm.b3 + (i - o_b3)))));
+    const int o_w2t = 64 * (cin + 1), o_w3 = o_w2t + 64 * 65, o_b3 = o_w3 + 64 * cout;      // the slice layout of train_tc_kernel
+    float* dst;
+    if (i < o_w2t) {
+      const int col = i >> 6, r = i & 63;
+      dst = col < cin ? gm.w1 + r * cin + col : gm.b1 + r;
+    } else if (i < o_w3) {
+      const int col = (i - o_w2t) >> 6, r = (i - o_w2t) & 63;
+      dst = col < 64 ? gm.w2 + r * 64 + col : gm.b2 + r;
+    } else {
+      dst = i < o_b3 ? gm.w3 + (i - o_w3) : gm.b3 + (i - o_b3);
+    }
     *dst += t;
   }
 }
@@ -1191,11 +1230,13 @@ struct TrainSideArgs {
   int C, n0[3], n1[3];        // nodes per axis (x, y, z), z = 1 in 2-D
   long long t0, t1;           // elements of G0 / G1 handled here (0: the tiled kernels do the grids)
   int nb_items;               // finish: blocks [0, nb_items) walk the grid elements, the rest reduce the partial sums
+  unsigned* tile_ctr;         // prep: the training kernel's tile counter, reset every step
 };
 
 template <int FMT>
 __global__ void __launch_bounds__(256) train_prep_kernel(TrainSideArgs p) {
   pdl_launch_dependents();       // train_tc_kernel's prologue (TMEM allocation, shared-memory clear) may start
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.tile_ctr = 0u;
   const long long nw = 64 * p.K1 + 64 * 80 + 16 * 80, total = p.t0 + p.t1 + nw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     if (i < p.t0) relayout_small_item<FMT>(i, p.g0, p.s0, p.C, p.n0[0], p.n0[1], p.n0[2]);
@@ -1260,6 +1301,7 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   sa.s0 = s0;
   sa.s1 = s1;
   sa.img = (uint16_t*)h->tc_weights;
+  sa.tile_ctr = (unsigned*)((uint8_t*)h->tc_weights + 60 * 1024);       // behind the weight images (<= 29 KB)
   sa.m = m;
   sa.K1 = TrainShape<METHOD>::K1;
   sa.C = g.C;
@@ -1308,6 +1350,7 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   a.steps0 = s0n;
   a.steps1 = s0n + 1 > 5 ? 5 : s0n + 1;
   a.dbg = h->debug_flags;
+  a.tile_ctr = h->static_tiles ? nullptr : sa.tile_ctr;
   if (h->debug_flags & 8) {
     if (!h->dbg_counters) {
       e = cudaMalloc(&h->dbg_counters, 16 * 8);

@@ -675,9 +675,10 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
 
 def test_train_tc_mlp_gradients_deterministic_and_phase_counters():
     """The tensor-core step sums the decoder gradients in a fixed order (per-CTA partial sums + an ordered reduction):
-    two runs on the same inputs give bit-identical MLP gradients, outputs and per-sample results.  (The grid gradients
-    are scattered with float atomics and are only reproducible to rounding.)  Also exercises nic_debug_counters: the
-    phase profile counts every tile exactly once."""
+    with a static tile order (NIC_OPT_STATIC_TILES) two runs on the same inputs give bit-identical MLP gradients, outputs
+    and per-sample results; with the default dynamic tile scheduler the MLP gradients agree to fp32 rounding.  (The grid
+    gradients are scattered with float atomics and are only reproducible to rounding.)  Also exercises
+    nic_debug_counters: the phase profile counts every tile exactly once."""
     n = nic()
     L = n._lib
     import ctypes as C
@@ -697,7 +698,8 @@ def test_train_tc_mlp_gradients_deterministic_and_phase_counters():
     L.set_option(dev(), L.OPT_DEBUG_KNOCKOUT, 8)
     L.debug_counters(dev())
     try:
-        for rep in range(2):
+        for rep in range(3):
+            L.set_option(dev(), L.OPT_STATIC_TILES, 1 if rep < 2 else 0)
             g = [torch.zeros_like(p) for p in pt]
             gm = L.make_mlp_grad(g)
             d0, d1 = torch.zeros_like(g0t), torch.zeros_like(g1t)
@@ -712,9 +714,11 @@ def test_train_tc_mlp_gradients_deterministic_and_phase_counters():
             runs.append(([t.cpu().numpy() for t in g], o.cpu().numpy(), d0.cpu().numpy(), d1.cpu().numpy()))
     finally:
         L.set_option(dev(), L.OPT_DEBUG_KNOCKOUT, 0)
-    for a, b in zip(runs[0][0], runs[1][0]):
+        L.set_option(dev(), L.OPT_STATIC_TILES, 0)
+    for a, b, c in zip(runs[0][0], runs[1][0], runs[2][0]):
         assert np.array_equal(a, b)
-    assert np.array_equal(runs[0][1], runs[1][1])
+        assert _rel_l2(c, a) < 1e-5                      # dynamic tile order: the same sums in another order
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][1], runs[2][1])
     assert _rel_l2(runs[0][2], runs[1][2]) < 1e-5 and _rel_l2(runs[0][3], runs[1][3]) < 1e-5
 
 

@@ -67,3 +67,19 @@ if "phases" in sys.argv:
     print(f"phase profile: {tiles} tiles, {tot / tiles:.0f} cycles per tile per CTA")
     for i, nme in enumerate(names):
         print(f"  {nme:12s} {c[i] / tiles:8.0f} cycles  {100.0 * c[i] / tot:5.1f} %")
+
+if "timeline" in sys.argv:
+    # nanosecond stamps (globaltimer) of one launch: CTA entry / first tile / flush start / exit, min and max over the CTAs
+    L.set_option(dev, L.OPT_TIME_KERNELS, 1)
+    L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, 8 | 512 | dbg_extra)
+    tr.step(coord, tg, 0, noise=noise_arg)
+    L.debug_counters(dev)
+    for rep in range(3):
+        tr.step(coord, tg, 0, noise=noise_arg)
+        c = [x & 0xFFFFFFFFFFFFFFFF for x in L.debug_counters(dev)]
+        inv = lambda v: (~v) & 0xFFFFFFFFFFFFFFFF
+        t0 = inv(c[0])
+        names = ["entry min", "entry max", "loop min", "loop max", "flush min", "flush max", "exit min", "exit max"]
+        vals = [inv(c[0]), c[1], inv(c[2]), c[3], inv(c[4]), c[5], inv(c[6]), c[7]]
+        print("timeline (us from the first CTA entry): " + ", ".join(f"{n} {(v - t0) / 1e3:.1f}" for n, v in zip(names, vals)))
+    L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, 0)
