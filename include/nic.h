@@ -121,9 +121,9 @@ int64_t nic_launch_count(const NicHandle* h);
  * additionally write loss_out[1] = loss_sum[1] * loss_scale (and clear it).  loss_sum and loss_out must then hold TWO floats.
  * FusedTrainer points loss_out into a device ring buffer and reads it back every k steps. */
 /* NIC_OPT_STATIC_TILES = 1: the tensor-core training kernel walks its tiles in a static round-robin order instead of handing
- * them out through an atomic counter.  The decoder gradients are per-CTA sums added in a fixed order, so with a static order
- * two runs on the same inputs give bit-identical decoder gradients; the default (dynamic) order balances the CTAs (-10 % kernel
- * time at config 1) and is reproducible to fp32 rounding only — like the grid gradients, which are float atomics either way. */
+ * them out through an atomic counter (A/B timing of the scheduler: the dynamic order balances the CTAs, -7 % kernel time at
+ * config 1).  Either way the decoder gradients are reproducible to fp32 rounding, like the grid gradients (float atomics): the
+ * tile slots of a CTA share their weight-gradient accumulators. */
 enum { NIC_OPT_DISABLE_FAST2D = 1, NIC_OPT_TIME_KERNELS = 2, NIC_OPT_REUSE_PREPARED = 3,
        NIC_OPT_GELU_POLY = 5, NIC_OPT_EXCHANGE_TIMEOUT_MS = 6, NIC_OPT_STEP_METRICS = 7, NIC_OPT_STATIC_TILES = 8,
        NIC_OPT_DEBUG_KNOCKOUT = 100 };

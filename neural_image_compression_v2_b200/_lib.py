@@ -150,7 +150,7 @@ OPT_EXCHANGE_TIMEOUT_MS = 6  # device-side wait for a peer in nic_adam_step_exch
 OPT_STEP_METRICS = 7         # loss_sum / loss_out carry [squared error, squared error of the 8-bit outputs]
 ERR_EXCHANGE = -7
 ERR_UNSUPPORTED = -2
-OPT_STATIC_TILES = 8         # static tile order in the tensor-core training kernel (bit-reproducible decoder gradients)
+OPT_STATIC_TILES = 8         # static tile order in the tensor-core training kernel (A/B timing of the dynamic scheduler)
 OPT_DEBUG_KNOCKOUT = 100     # profiling only (nic.h); bit 3 = training phase counters
 
 

@@ -38,6 +38,7 @@ constexpr int TT_H = 64, TT_K2 = 80;
 constexpr int TT_SG80 = 10 * 128;          // sample-group stride of an 80-feature activation / delta buffer (bytes)
 constexpr int TT_W2 = 64 * 80 * 2, TT_W3 = 16 * 80 * 2;
 constexpr int TT_ACT = 16 * TT_SG80;       // 20480
+constexpr int TT_SG16 = 2 * 128, TT_DZ3 = 16 * TT_SG16;       // dZ3: 16 output features per sample, sample-group stride 256 B
 // Everything that depends on the decoder-input width.  2-D: Cin = 5C + 2 PE + 1 = 73 and 3-D "v2" (method 4): 79 both
 // fit K1 = 80 (with the bias carrier) -> 106 KB smem, 240 TMEM columns, two CTAs per SM;  3-D method 3: Cin = 9C + 3 PE
 // + 1 = 127 -> K1 = 128, dX is 108 columns wide (N = 128), 122 KB smem, 352 TMEM columns, one CTA per SM.
@@ -51,15 +52,24 @@ template <int METHOD> struct TrainShape {
   static constexpr int NDX = 12 * (NC0 + 1) <= 64 ? 64 : 128;      // N of the dX GEMM = width of the D accumulator
   static constexpr int C0 = METHOD == NIC_METHOD_3D ? 9 : 6;       // feature groups (of 8) gathered by warp-group 0
   static constexpr int XV = 8 * C0 > K1 - 8 * C0 ? 8 * C0 : K1 - 8 * C0;
-  static constexpr int COL_D = 0, COL_D1 = NDX, COL_D2 = COL_D1 + K1, COL_D3 = COL_D2 + 80;       // D3 (transposed): 16 columns
-  static constexpr int TMEM = COL_D3 + 16 <= 256 ? 256 : 512, CTAS = TMEM == 256 ? 2 : 1;
+  // One persistent CTA per SM runs NSLOT tiles at a time, each on its own 256 threads ("slot": own activation buffers, own D
+  // accumulator, own mbarriers and named barrier); the weight images and the three weight-gradient accumulators D1, D2, D3
+  // are shared by the slots.  K1 = 80: three slots (768 threads, <= 80 registers); K1 = 128: one.
+  static constexpr int NSLOT = K1 == 80 ? 3 : 1;
+  static constexpr int THREADS = NSLOT * TT_THREADS;
+  static constexpr int COL_D = 0, COL_D1 = NSLOT * NDX, COL_D2 = COL_D1 + K1, COL_D3 = COL_D2 + 80;       // D3 (transposed): 16 columns
+  static constexpr int COL_GD = COL_D3 + 16;           // NSLOT > 1: d h1'/d z1 of a tile parks here between forward and backward (32 columns per slot)
+  static constexpr int TMEM = COL_GD + (NSLOT > 1 ? 32 * NSLOT : 0) <= 256 ? 256 : 512;
   static constexpr int WIMG = W1BYTES + TT_W2 + TT_W3;
-  static constexpr int OFF_W1 = 0, OFF_W2 = W1BYTES, OFF_W3 = OFF_W2 + TT_W2, OFF_X = OFF_W3 + TT_W3;
-  static constexpr int OFF_H1 = OFF_X + XBYTES, OFF_H2 = OFF_H1 + TT_ACT, OFF_DZ = OFF_H2 + TT_ACT;
+  static constexpr int OFF_W1 = 0, OFF_W2 = W1BYTES, OFF_W3 = OFF_W2 + TT_W2, OFF_SLOT0 = OFF_W3 + TT_W3;
+  // A slot: X~ | B1 | B2 | dZ3.   B1: H1, then the selector matrix S, then T (FS).  B2: H2, then dZ2, then dZ1 — each
+  // overwrite waits for the deferred weight-gradient batch that still reads the previous content (D3, D2).
   // MN-major A operands with M = 128 read 16 feature groups per sample group from buffers that hold 10: groups 10..15
-  // alias the start of the next sample group (finite garbage -> accumulator rows 80..127, never read); for the last
-  // sample group that is 768 bytes past the buffer, hence the zeroed pad after DZ (H2's overrun lands in DZ).
-  static constexpr int OFF_PAD = OFF_DZ + TT_ACT, OFF_MISC = OFF_PAD + 1024, SMEM = OFF_MISC + 256;
+  // alias the start of the next sample group (accumulator rows 80..127, never read); for the last sample group that is 768
+  // bytes past the buffer: B1's overrun lands in B2, B2's in dZ3 (4 KB).
+  static constexpr int SOFF_X = 0, SOFF_B1 = XBYTES, SOFF_B2 = SOFF_B1 + TT_ACT, SOFF_DZ3 = SOFF_B2 + TT_ACT;
+  static constexpr int SLOT_BYTES = SOFF_DZ3 + TT_DZ3;
+  static constexpr int OFF_MISC = OFF_SLOT0 + NSLOT * SLOT_BYTES, SMEM = OFF_MISC + 128 * NSLOT + 64;
 };
 constexpr float TT_LOSS_SCALE = 64.0f;
 
@@ -229,25 +239,31 @@ struct TrainArgs {
 // and U's rows leave as fp32 red.global.add.v4 — no dX epilogue, no shuffles, no 16-bit packing of the gradients.  S is
 // written into the H1 buffer (dead once D2 has been accumulated), T (16 bit) into the DZ buffer.
 template <int FMT, int METHOD, int FS = 0>
-__global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc_kernel(DevGeom g, TrainArgs a) {
+__global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kernel(DevGeom g, TrainArgs a) {
   static_assert(!FS || METHOD == NIC_METHOD_2D, "the tensor-core scatter covers the 2-D method");
   using P = Pair<FMT>;
   using TS = TrainShape<METHOD>;
   constexpr int DIM = TS::DIM, CIN = TS::CIN, NC0 = TS::NC0, NC1 = TS::NC1, K1 = TS::K1, SGX = TS::SGX, NDX = TS::NDX, C0 = TS::C0;
-  constexpr int TT_COL_D = TS::COL_D, TT_COL_D1 = TS::COL_D1, TT_COL_D2 = TS::COL_D2, TT_COL_D3 = TS::COL_D3;
+  constexpr int NSLOT = TS::NSLOT;
+  constexpr bool GD_TMEM = NSLOT > 1;             // d h1'/d z1 parks in tensor memory instead of 16 registers
+  constexpr int TT_COL_D1 = TS::COL_D1, TT_COL_D2 = TS::COL_D2, TT_COL_D3 = TS::COL_D3;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sX = smem + TS::OFF_X;
-  uint8_t* sH1 = smem + TS::OFF_H1;
-  uint8_t* sH2 = smem + TS::OFF_H2;
-  uint8_t* sDZ = smem + TS::OFF_DZ;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + TS::OFF_MISC);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-  uint64_t* mbar2 = mbar + 2;                     // completion of the LAST deferred batch of a tile (D1 += dZ1^T X~)
-  uint64_t* mbar3 = reinterpret_cast<uint64_t*>(smem + TS::OFF_MISC + 64);      // FS: completion of D2 (H1 may be overwritten)
-  float* sRed = reinterpret_cast<float*>(smem + TS::OFF_MISC + 32);      // [8] loss partials
-  volatile unsigned* sTile = reinterpret_cast<volatile unsigned*>(smem + TS::OFF_MISC + 96);      // [2] next tile (dynamic scheduler)
-
-  const int tid = threadIdx.x, warp = uniform_warp_index(), lane = tid & 31;     // warp: provably uniform (MMA issue)
+  const int warp_cta = uniform_warp_index();      // provably uniform (MMA issue)
+  const int slot = warp_cta >> 3, warp = warp_cta & 7;
+  const int tid = threadIdx.x & (TT_THREADS - 1), lane = tid & 31;
+  uint8_t* sSlot = smem + TS::OFF_SLOT0 + slot * TS::SLOT_BYTES;
+  uint8_t* sX = sSlot + TS::SOFF_X;
+  uint8_t* sH1 = sSlot + TS::SOFF_B1;             // B1: H1 | S | T
+  uint8_t* sH2 = sSlot + TS::SOFF_B2;             // B2: H2 | dZ2 | dZ1
+  uint8_t* sDZ3 = sSlot + TS::SOFF_DZ3;
+  uint8_t* sMisc = smem + TS::OFF_MISC + 128 * slot;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(sMisc);          // completion of the awaited batch of a stage
+  uint64_t* mbar2 = mbar + 1;                     // completion of the LAST deferred batch of a tile (D1 += dZ1^T X~): X~, B2 free
+  uint64_t* mbar3 = mbar + 2;                     // completion of D2 (B1 = H1 and B2 = dZ2 may be overwritten)
+  uint64_t* mbar4 = mbar + 3;                     // completion of D3 (B2 = H2 may be overwritten)
+  float* sRed = reinterpret_cast<float*>(sMisc + 32);           // [8] loss partials
+  volatile unsigned* sTile = reinterpret_cast<volatile unsigned*>(sMisc + 64);      // [2] next tile (dynamic scheduler)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TS::OFF_MISC + 128 * NSLOT);
   // timeline (debug, bit 9 with bit 3): nanosecond stamps of CTA entry / first tile / flush / exit, min and max over the CTAs
   const bool tl = a.prof && (a.dbg & 512);
   auto gtime = [] {
@@ -259,22 +275,28 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   const int wg = warp >> 2;                       // column half of the epilogues / row half of the gather
   const int row = tid & (TT_ROWS - 1);            // sample of the tile = TMEM lane
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  // byte offset of this sample's 16-byte chunk inside a feature group, for the two buffer widths
+  // byte offset of this sample's 16-byte chunk inside a feature group, for the three buffer widths
   const int roff80 = (row >> 3) * TT_SG80 + (row & 7) * 16, roffx = (row >> 3) * SGX + (row & 7) * 16;
+  const int roff16 = (row >> 3) * TT_SG16 + (row & 7) * 16;
+  auto slot_sync = [&] {                          // barrier of the 256 threads of this slot
+    if (NSLOT == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(TT_THREADS) : "memory");
+  };
 
-  if (warp == 0) tmem_alloc(tmem_slot, TS::TMEM);
+  if (warp_cta == 0) tmem_alloc(tmem_slot, TS::TMEM);
   if (tid == 0) {
     mbar_init(mbar, 1);
     mbar_init(mbar2, 1);
     mbar_init(mbar3, 1);
+    mbar_init(mbar4, 1);
   }
   {
     // zero the activation / delta buffers once (padding features must be finite), then the constant-1 bias features
-    uint4* act = reinterpret_cast<uint4*>(smem + TS::OFF_X);
-    for (int i = tid; i < (TS::XBYTES + 3 * TT_ACT + 1024) / 16; i += TT_THREADS) act[i] = make_uint4(0, 0, 0, 0);
+    uint4* act = reinterpret_cast<uint4*>(smem + TS::OFF_SLOT0);
+    for (int i = threadIdx.x; i < NSLOT * TS::SLOT_BYTES / 16; i += TS::THREADS) act[i] = make_uint4(0, 0, 0, 0);
     pdl_wait();                  // everything above overlaps the tail of train_prep_kernel; its outputs are read from here on
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < TS::WIMG / 16; i += TT_THREADS) dst[i] = __ldg(a.wimg + i);
+    for (int i = threadIdx.x; i < TS::WIMG / 16; i += TS::THREADS) dst[i] = __ldg(a.wimg + i);
   }
   __syncthreads();
   if (wg == 0) {
@@ -288,8 +310,21 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t TT_COL_D = (uint32_t)(slot * NDX);       // this slot's D accumulator
+  if (slot == 0 && wg == 0) {
+    // D1, D2, D3 are shared by the slots and accumulate from the first MMA on: clear them here
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+    for (int c = TT_COL_D1; c < TT_COL_D3 + 16; c += 16) tmem_st16(tmem + lane_base + c, z);
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   const uint32_t aW1 = smem_u32(smem + TS::OFF_W1), aW2 = smem_u32(smem + TS::OFF_W2), aW3 = smem_u32(smem + TS::OFF_W3);
-  const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aDZ = smem_u32(sDZ);
+  const uint32_t aX = smem_u32(sX), aH1 = smem_u32(sH1), aH2 = smem_u32(sH2), aDZ3 = smem_u32(sDZ3);
   constexpr uint32_t ID_F64 = tt_idesc(FMT, 128, 64, 0, 0), ID_F16 = tt_idesc(FMT, 128, 16, 0, 0);
   constexpr uint32_t ID_B64 = tt_idesc(FMT, 128, 64, 0, 1);        // delta propagation: A K-major, B = W'^T (MN-major view)
   constexpr uint32_t ID_G16 = tt_idesc(FMT, 128, 16, 1, 1);        // D3^T = [H2|1]^T dZ3
@@ -302,10 +337,11 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   unsigned tiles_done = 0;
 
   // phase profile (debug): thread 0 adds the cycles since its previous mark to counter `i`
+  const bool prof0 = a.prof && threadIdx.x == 0;      // thread 0 of slot 0
   long long prof_t = a.prof ? clock64() : 0;
   const long long prof_start = prof_t;
   auto mark = [&](int i) {
-    if (a.prof && !tl && tid == 0) {
+    if (prof0 && !tl) {
       const long long t = clock64();
       atomicAdd(a.prof + i, (unsigned long long)(t - prof_t));
       prof_t = t;
@@ -318,7 +354,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   auto run_mmas2 = [&](auto&& issue, auto&& deferred, bool last) {
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    slot_sync();
     if (warp == 0) {               // uniform branch + elected lane: operands stay in uniform registers (nic_tc_common.cuh)
       if (elect_one()) {
         tc_fence_after();
@@ -339,9 +375,9 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
 #pragma unroll
     for (int kc = 0; kc < 8; ++kc)
       mma_ss(tmem + dcol, make_smem_desc(abuf + kc * 2 * TT_SG80, TT_SG80, 128),
-             make_smem_desc(bbuf + kc * 2 * sgb, sgb, 128), idesc, (tiles_done > 0 || kc > 0) ? 1u : 0u);
+             make_smem_desc(bbuf + kc * 2 * sgb, sgb, 128), idesc, 1u);
   };
-  uint32_t phase2 = 0, phase3 = 0;
+  uint32_t phase2 = 0, phase3 = 0, phase4 = 0;
 
   // FS: the last GEMM of a tile (U = T W1') is NOT awaited at the end of the tile — its rows are scattered after the NEXT
   // tile's gather, which hides that round trip; the geometry the scatter needs travels in these registers.
@@ -394,7 +430,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   };
 
   const unsigned ntiles = (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS);
-  if (tl && tid == 0) {
+  if (tl && prof0) {
     const unsigned long long t = gtime();
     atomicMax(a.prof + 0, ~tl_entry);
     atomicMax(a.prof + 1, tl_entry);
@@ -404,10 +440,10 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
   // Tiles are handed out by an atomic counter: the CTAs of one launch finish their static share up to 20 % apart (13 or 14
   // tiles each at config 1, and the per-tile time varies from SM to SM), and the kernel ends with the slowest.  Thread 0
   // fetches the next index at the top of a tile; it reaches the others through shared memory, several barriers later.
-  unsigned tile = blockIdx.x;
+  unsigned tile = blockIdx.x * NSLOT + slot;
   for (; tile < ntiles; ++tiles_done) {
-    unsigned tile_next = tile + gridDim.x;
-    if (a.tile_ctr && tid == 0) tile_next = atomicAdd(a.tile_ctr, 1u) + gridDim.x;
+    unsigned tile_next = tile + gridDim.x * NSLOT;
+    if (a.tile_ctr && tid == 0) tile_next = atomicAdd(a.tile_ctr, 1u) + gridDim.x * NSLOT;
     const unsigned n = tile * TT_ROWS + row;
     const bool live = n < (unsigned)g.N;
     const unsigned nc = live ? n : (unsigned)g.N - 1;
@@ -418,7 +454,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         if (c < a.cout)       // volatile: keep the load HERE (the compiler would sink it to its use, 2,000 cycles later)
           asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(tgt[c]) : "l"(a.targets + (size_t)n * a.cout + c));
     }
-    if (a.prof && tid == 0) prof_t = clock64();
+    if (prof0) prof_t = clock64();
     // ------------------------------------------------------------------------------------------ gather + noise -> X~
     Texel t = texel_of_fast(g, nc, a.origins);
     AxisCoord ax[3];
@@ -754,6 +790,10 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         auto one = P::pack(1.0f, 0.0f);
         *reinterpret_cast<uint4*>(sH1 + roff80 + (8 + wg) * 128) = make_uint4(wg == 0 ? *reinterpret_cast<uint32_t*>(&one) : 0u, 0, 0, 0);
       }
+      if (GD_TMEM && layer == 0) {           // park d h1'/d z1 in tensor memory until the backward pass
+        tmem_st16(tmem + TS::COL_GD + slot * 32 + wg * 16 + lane_base, gd1);
+        tc_wait_st();
+      }
       mark(layer == 0 ? 2 : 4);
       if (layer == 0) {
         run_mmas([&] {
@@ -815,7 +855,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       for (int f = 0; f < 2; ++f) {
         auto p0 = P::pack(dz[8 * f], dz[8 * f + 1]), p1 = P::pack(dz[8 * f + 2], dz[8 * f + 3]);
         auto p2 = P::pack(dz[8 * f + 4], dz[8 * f + 5]), p3 = P::pack(dz[8 * f + 6], dz[8 * f + 7]);
-        *reinterpret_cast<uint4*>(sDZ + roff80 + f * 128) =
+        *reinterpret_cast<uint4*>(sDZ3 + roff16 + f * 128) =
             make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
                        *reinterpret_cast<uint32_t*>(&p3));
       }
@@ -823,13 +863,14 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     mark(6);
     // ------------------------------------------------------------------------------------------ backward
     // dH2 = dZ3 W3' (K = 16 output features) and D3^T += [H2 | 1]^T dZ3.
-    run_mmas2([&] { mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ, 128, TT_SG80), make_smem_desc(aW3, 128, WG16), ID_B64, 0); },
+    run_mmas2([&] { mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ3, 128, TT_SG16), make_smem_desc(aW3, 128, WG16), ID_B64, 0); },
               [&] {
                 // D3^T [H2 feature x output c] += [H2|1]^T (MN-major A, M = 128 aliased) . dZ3 (MN-major B, N = 16)
 #pragma unroll
                 for (int kc = 0; kc < 8; ++kc)
                   mma_ss(tmem + TT_COL_D3, make_smem_desc(aH2 + kc * 2 * TT_SG80, TT_SG80, 128),
-                         make_smem_desc(aDZ + kc * 2 * TT_SG80, TT_SG80, 128), ID_G16, (tiles_done > 0 || kc > 0) ? 1u : 0u);
+                         make_smem_desc(aDZ3 + kc * 2 * TT_SG16, TT_SG16, 128), ID_G16, 1u);
+                tc_commit(mbar4);      // D3 has read H2: dZ2 may overwrite it
               },
               false);
     mark(7);
@@ -838,35 +879,46 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       uint32_t acc[32];
       tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
       tc_wait_ld();
-      // dZ2 -> DZ features [16, 80);  dZ1 -> the H2 buffer, features [0, 64) (H2 is dead once D3 has been accumulated, and
-      // DZ is still being read by the deferred D2 += dZ2^T [H1|1]).  H2's constant-1 feature 64 is left alone.
-      uint8_t* dstb = layer == 1 ? sDZ + roff80 + (2 + wg * 4) * 128 : sH2 + roff80 + (wg * 4) * 128;
-#pragma unroll
-      for (int f = 0; f < 4; ++f) {
-        uint32_t dp[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 gg = unpack2<FMT>(layer == 1 ? gd2[4 * f + i] : gd1[4 * f + i]);
-          auto v = P::pack(__uint_as_float(acc[8 * f + 2 * i]) * gg.x, __uint_as_float(acc[8 * f + 2 * i + 1]) * gg.y);
-          dp[i] = *reinterpret_cast<uint32_t*>(&v);
-        }
-        *reinterpret_cast<uint4*>(dstb + f * 128) = make_uint4(dp[0], dp[1], dp[2], dp[3]);
+      // dZ2, then dZ1 -> B2, features [0, 64) (H2 / dZ2 are dead once D3 / D2 have been accumulated: awaited HERE, after the
+      // arithmetic).  B2's constant-1 feature 64 is left alone.
+      uint8_t* dstb = sH2 + roff80 + (wg * 4) * 128;
+      uint32_t gdl[16];
+      if (layer == 0 && GD_TMEM) {
+        tmem_ld16(tmem + TS::COL_GD + slot * 32 + wg * 16 + lane_base, gdl);
+        tc_wait_ld();
       }
+      uint32_t dp[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 gg = unpack2<FMT>(layer == 1 ? gd2[i] : (GD_TMEM ? gdl[i] : gd1[i]));
+        auto v = P::pack(__uint_as_float(acc[2 * i]) * gg.x, __uint_as_float(acc[2 * i + 1]) * gg.y);
+        dp[i] = *reinterpret_cast<uint32_t*>(&v);
+      }
+      if (layer == 1) {
+        mbar_wait(mbar4, phase4);
+        phase4 ^= 1;
+      } else {
+        mbar_wait(mbar3, phase3);
+        phase3 ^= 1;
+      }
+      tc_fence_after();
+#pragma unroll
+      for (int f = 0; f < 4; ++f) *reinterpret_cast<uint4*>(dstb + f * 128) = make_uint4(dp[4 * f], dp[4 * f + 1], dp[4 * f + 2], dp[4 * f + 3]);
       mark(layer == 1 ? 8 : 10);
       const bool fs = FS && a.dgs0;
       if (layer == 1) {
         auto issue_dh1 = [&] {
 #pragma unroll
           for (int kc = 0; kc < 4; ++kc)
-            mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + (2 + 2 * kc) * 128, 128, TT_SG80),
+            mma_ss(tmem + TT_COL_D, make_smem_desc(aH2 + 2 * kc * 128, 128, TT_SG80),
                    make_smem_desc(aW2 + kc * 256, 128, WG64), ID_B64, kc > 0);
         };
-        // dH1 = dZ2 W2'  and (deferred)  D2 += DZ^T [H1 | 1]   (rows 16..79 = hidden units).  FS: the selector matrix will
-        // overwrite H1, so D2 signals its own mbarrier, awaited after the dZ1 epilogue
+        // dH1 = dZ2 W2'  and (deferred)  D2 += dZ2^T [H1 | 1]   (rows 0..63 = hidden units).  dZ1 will overwrite dZ2 (and the
+        // selector matrix H1), so D2 signals its own mbarrier, awaited in the dZ1 epilogue
         run_mmas2(issue_dh1,
                   [&] {
-                    issue_wgrad(TT_COL_D2, aDZ, aH1, TT_SG80, ID_G80);
-                    if (fs) tc_commit(mbar3);
+                    issue_wgrad(TT_COL_D2, aH2, aH1, TT_SG80, ID_G80);
+                    tc_commit(mbar3);
                   },
                   false);
       } else if (!fs) {
@@ -910,8 +962,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
           vb = h16(ax[1].k);
         }
         if (!live) va = vb = 0u;
-        mbar_wait(mbar3, phase3);        // D2 += DZ^T [H1 | 1] has read H1 (it ran under the dZ1 epilogue)
-        phase3 ^= 1;
+        // (D2 += dZ2^T [H1 | 1] has read H1: awaited in the dZ1 epilogue)
         // one or two non-zero halves in 80 bytes: position them with shifts instead of comparing every slot
         const int ca = sa >> 3, cb = sb >> 3;                      // chunk (16 bytes = 8 slots) of each entry; cb = -1: none
         const uint32_t wa = va << ((sa & 1) * 16), wb = vb << ((sb & 1) * 16);
@@ -937,7 +988,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
           },
           [&] { issue_wgrad(TT_COL_D1, aH2, aX, SGX, ID_GX); }, true);
       mark(11);
-      // ---- T (rows = slots) -> 16 bit, K-major A operand in the DZ buffer (dZ2 / dZ3 are dead: D2, D3 and dH1 are complete)
+      // ---- T (rows = slots) -> 16 bit, K-major A operand in B1 (the selector matrix is dead: T = S^T dZ1 is complete)
       {
         uint32_t acc[32];
         tmem_ld32(tmem + TT_COL_D + lane_base + wg * 32, acc);
@@ -951,20 +1002,20 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
               auto v = P::pack(__uint_as_float(acc[8 * f + 2 * i]), __uint_as_float(acc[8 * f + 2 * i + 1]));
               tp[i] = *reinterpret_cast<uint32_t*>(&v);
             }
-            *reinterpret_cast<uint4*>(sDZ + roff80 + (wg * 4 + f) * 128) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
+            *reinterpret_cast<uint4*>(sH1 + roff80 + (wg * 4 + f) * 128) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
           }
         }
       }
       // ---- U = T W1'  (the dX GEMM on slot rows): issued, NOT awaited (fs_scatter_rows after the next tile's gather)
       fence_async_smem();
       tc_fence_before();
-      __syncthreads();
+      slot_sync();
       if (warp == 0) {
         if (elect_one()) {
           tc_fence_after();
 #pragma unroll
           for (int kc = 0; kc < 4; ++kc)
-            mma_ss(tmem + TT_COL_D, make_smem_desc(aDZ + 2 * kc * 128, 128, TT_SG80), make_smem_desc(aW1 + kc * 256, 128, WG64),
+            mma_ss(tmem + TT_COL_D, make_smem_desc(aH1 + 2 * kc * 128, 128, TT_SG80), make_smem_desc(aW1 + kc * 256, 128, WG64),
                    ID_BDX, kc > 0);
           tc_commit(mbar);
         }
@@ -1074,23 +1125,24 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
       }
     }
     mark(12);
-    if (a.prof && !tl && tid == 0) atomicAdd(a.prof + 15, 1ull);
+    if (a.prof && !tl && tid == 0) atomicAdd(a.prof + 15, 1ull);      // (every slot counts its tiles)
     tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
     tile = sTile[tiles_done & 1];
   }
   if (FS && u_pending) fs_scatter_rows();       // the last tile's gradient rows
   // -------------------------------------------------------------------------------------------- flush: MLP gradients
   pdl_launch_dependents();       // train_finish_kernel may be scheduled now; it waits for this grid to complete
-  if (a.prof && tid == 0) prof_t = clock64();
-  if (tl && tid == 0) {
+  if (prof0) prof_t = clock64();
+  if (tl && prof0) {
     const unsigned long long t = gtime();
     atomicMax(a.prof + 4, ~t);
     atomicMax(a.prof + 5, t);
   }
   if (tiles_done > 0) mbar_wait_sleep(mbar2, phase2);       // the last tile's deferred D1 batch (and everything before it)
-  __syncthreads();
+  tc_fence_before();
+  __syncthreads();               // all slots: every MMA of the CTA is complete
   tc_fence_after();
-  if (tiles_done > 0) {
+  {
     // Every CTA writes its sums to its OWN slice with plain stores (each element exactly once); mlp_grad_reduce_kernel
     // adds the slices up in a fixed order.  (296 CTAs x 9,091 atomicAdds onto the same 9,091 addresses took a fifth of
     // the kernel, and made the MLP gradients depend on the order of arrival.)
@@ -1103,10 +1155,10 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
     float* p_w3 = p_w2t + 64 * 65;
     float* p_b3 = p_w3 + 64 * a.cout;
     // D3^T: rows 0..63 = hidden unit h, row 64 = the bias feature; columns c < cout: dW3'[c][h] (W3' = W3/2) / db3[c]
-    // D2: rows 16..79 = hidden unit j = row - 16; columns 0..63 = dW2'[j][k] (W2' = W2/2), 64 = db2[j];
-    // D1: rows 0..63 = hidden unit j (dZ1 lives in the H2 buffer's features 0..63); columns 0..72 = dW1[j][cin], 73 = db1[j].
-    // Warp-group 0 reads columns [0,48), 1 reads [48,80).
-    if (wg == 0) {
+    // D2: rows 0..63 = hidden unit j; columns 0..63 = dW2'[j][k] (W2' = W2/2), 64 = db2[j];
+    // D1: rows 0..63 = hidden unit j (dZ2 and dZ1 live in B2's features 0..63); columns 0..72 = dW1[j][cin], 73 = db1[j].
+    // Warp-group 0 reads columns [0,48), 1 reads [48,80).  Slot 0 flushes D3 and D2, slot 1 (if any) D1.
+    if (wg == 0 && slot == 0) {
       uint32_t acc[16];
       tmem_ld16(tmem + TT_COL_D3 + lane_base, acc);
       tc_wait_ld();
@@ -1119,6 +1171,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         }
     }
     for (int which = 1; which < 3; ++which) {
+      if (slot != (NSLOT > 1 ? which - 1 : 0)) continue;
       const uint32_t dcol = which == 1 ? TT_COL_D2 : TT_COL_D1;
       const int width = which == 1 ? 80 : K1;                            // 80-wide: wg 0 reads [0,48), wg 1 [48,80); 128: halves
       const int c0 = width == 80 ? wg * 48 : wg * 64, cw = width == 80 ? (wg == 0 ? 48 : 32) : 64;
@@ -1133,7 +1186,7 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
         const int col = c0 + i;
         const float v = __uint_as_float(acc[i]) * fs;
         if (which == 1) {
-          if (row >= 16 && row < 80 && col <= 64) p_w2t[col * 64 + row - 16] = col < 64 ? 0.5f * v : v;
+          if (row < 64 && col <= 64) p_w2t[col * 64 + row] = col < 64 ? 0.5f * v : v;
         } else if (row < 64 && col <= CIN) {
           p_w1t[col * 64 + row] = v;
         }
@@ -1145,28 +1198,28 @@ __global__ void __launch_bounds__(TT_THREADS, TrainShape<METHOD>::CTAS) train_tc
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (lane == 0) sRed[warp] = v;
-    __syncthreads();
+    slot_sync();
     if (tid == 0) atomicAdd(a.loss_sum, ((sRed[0] + sRed[1]) + (sRed[2] + sRed[3])));
     if (g.metrics) {
-      __syncthreads();
+      slot_sync();
       v = sse8_local;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
       if (lane == 0) sRed[warp] = v;
-      __syncthreads();
+      slot_sync();
       if (tid == 0) atomicAdd(a.loss_sum + 1, ((sRed[0] + sRed[1]) + (sRed[2] + sRed[3])));
     }
   }
   tc_fence_before();
   __syncthreads();
   mark(13);                    // the flush, once per CTA
-  if (a.prof && !tl && tid == 0) atomicAdd(a.prof + 14, (unsigned long long)(clock64() - prof_start));      // CTA lifetime
-  if (tl && tid == 0) {
+  if (prof0 && !tl) atomicAdd(a.prof + 14, (unsigned long long)(clock64() - prof_start));      // CTA lifetime
+  if (tl && prof0) {
     const unsigned long long t = gtime();
     atomicMax(a.prof + 6, ~t);
     atomicMax(a.prof + 7, t);
   }
-  if (warp == 0) tmem_dealloc(tmem, TS::TMEM);
+  if (warp_cta == 0) tmem_dealloc(tmem, TS::TMEM);
 }
 
 // gm.* += sum over the CTAs' slices, in a fixed order (deterministic).  One block of 256 threads = 32 elements x 8 slice
@@ -1368,18 +1421,19 @@ static int launch_train_tc_t(Handle* h, const DevGeom& g, const MlpDev& m, const
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TrainShape<METHOD>::SMEM);
   if (e != cudaSuccess) return (int)e;
   if (g.N >= (1ll << 27)) return NIC_ERR_UNSUPPORTED;          // Philox counter packs (sample << 4 | block)
+  constexpr int NSLOT = TrainShape<METHOD>::NSLOT;
   long long ntiles = (g.N + TT_ROWS - 1) / TT_ROWS;
-  const long long cap = (long long)TrainShape<METHOD>::CTAS * h->sms;        // resident CTAs (two per SM when K1 = 80)
-  int grid = (int)(ntiles < cap ? ntiles : cap);
+  const long long want = (ntiles + NSLOT - 1) / NSLOT, cap = h->sms;          // one persistent CTA per SM, NSLOT tiles in flight each
+  int grid = (int)(want < cap ? want : cap);
   a.pstride = 64 * m.cin + 64 + 64 * 64 + 64 + 64 * m.cout + m.cout;
   rc = ensure_scratch(&h->tc_partials, &h->tc_partials_bytes, (size_t)grid * a.pstride * sizeof(float));
   if (rc) return rc;
   a.partials = (float*)h->tc_partials;
   if (h->time_kernels) {          // the event records between the kernels rule out a programmatic launch
     KernelTimer timer(h, st);
-    kern<<<grid, TT_THREADS, TrainShape<METHOD>::SMEM, st>>>(g, a);
+    kern<<<grid, TrainShape<METHOD>::THREADS, TrainShape<METHOD>::SMEM, st>>>(g, a);
   } else {
-    e = launch_pdl(kern, dim3(grid), dim3(TT_THREADS), TrainShape<METHOD>::SMEM, st, g, a);
+    e = launch_pdl(kern, dim3(grid), dim3(TrainShape<METHOD>::THREADS), TrainShape<METHOD>::SMEM, st, g, a);
     if (e != cudaSuccess) return (int)e;
   }
   h->launches++;

@@ -674,11 +674,11 @@ def test_train_tc_step_vs_oracle_fp64(prec, case):
 
 
 def test_train_tc_mlp_gradients_deterministic_and_phase_counters():
-    """The tensor-core step sums the decoder gradients in a fixed order (per-CTA partial sums + an ordered reduction):
-    with a static tile order (NIC_OPT_STATIC_TILES) two runs on the same inputs give bit-identical MLP gradients, outputs
-    and per-sample results; with the default dynamic tile scheduler the MLP gradients agree to fp32 rounding.  (The grid
-    gradients are scattered with float atomics and are only reproducible to rounding.)  Also exercises
-    nic_debug_counters: the phase profile counts every tile exactly once."""
+    """The tensor-core step keeps the decoder gradients as per-CTA sums in tensor memory and adds the CTAs' slices in a
+    fixed order; the three tile slots of a CTA accumulate into the same accumulators in the order the tensor pipe takes
+    their batches, so two runs on the same inputs agree to fp32 rounding (static or dynamic tile order), while outputs and
+    per-sample results are bit-identical.  (The grid gradients are scattered with float atomics: rounding, too.)  Also
+    exercises nic_debug_counters: the phase profile counts every tile exactly once."""
     n = nic()
     L = n._lib
     import ctypes as C
@@ -716,8 +716,7 @@ def test_train_tc_mlp_gradients_deterministic_and_phase_counters():
         L.set_option(dev(), L.OPT_DEBUG_KNOCKOUT, 0)
         L.set_option(dev(), L.OPT_STATIC_TILES, 0)
     for a, b, c in zip(runs[0][0], runs[1][0], runs[2][0]):
-        assert np.array_equal(a, b)
-        assert _rel_l2(c, a) < 1e-5                      # dynamic tile order: the same sums in another order
+        assert _rel_l2(b, a) < 1e-5 and _rel_l2(c, a) < 1e-5         # the same sums in another order
     assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][1], runs[2][1])
     assert _rel_l2(runs[0][2], runs[1][2]) < 1e-5 and _rel_l2(runs[0][3], runs[1][3]) < 1e-5
 
