@@ -890,8 +890,9 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
       uint32_t dp[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float2 gg = unpack2<FMT>(layer == 1 ? gd2[i] : (GD_TMEM ? gdl[i] : gd1[i]));
-        auto v = P::pack(__uint_as_float(acc[2 * i]) * gg.x, __uint_as_float(acc[2 * i + 1]) * gg.y);
+        // dZ = dH * g' in packed 16-bit math (the product is rounded to 16 bits for the next MMA anyway; dH carries the loss scale)
+        const uint32_t ggw = layer == 1 ? gd2[i] : (GD_TMEM ? gdl[i] : gd1[i]);
+        auto v = __hmul2(P::pack(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1])), *reinterpret_cast<const typename P::T2*>(&ggw));
         dp[i] = *reinterpret_cast<uint32_t*>(&v);
       }
       if (layer == 1) {
