@@ -179,16 +179,13 @@ __device__ __forceinline__ void scatter_column(const DevGeom& g, float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
-#ifndef NIC_PHILOX_ROUNDS
-#define NIC_PHILOX_ROUNDS 10
-#endif
-__device__ __forceinline__ uint4 philox4x32(unsigned long long seed, unsigned long long offset,
-                                            unsigned long long counter) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32_r(unsigned long long seed, unsigned long long offset, unsigned long long counter) {
   unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
   unsigned int c0 = (unsigned int)counter, c1 = (unsigned int)(counter >> 32);
   unsigned int c2 = (unsigned int)offset, c3 = (unsigned int)(offset >> 32);
 #pragma unroll
-  for (int r = 0; r < NIC_PHILOX_ROUNDS; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     unsigned int n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -196,6 +193,9 @@ __device__ __forceinline__ uint4 philox4x32(unsigned long long seed, unsigned lo
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint4 philox4x32(unsigned long long seed, unsigned long long offset, unsigned long long counter) {
+  return philox4x32_r<10>(seed, offset, counter);
 }
 
 // Quantisation noise of image_compression.py:250: (U[0,1) - 0.5) / 2^bits for element `idx` of step `step`.

@@ -69,9 +69,13 @@ template <int METHOD> struct TrainShape {
   // bytes past the buffer: B1's overrun lands in B2, B2's in dZ3 (4 KB).
   static constexpr int SOFF_X = 0, SOFF_B1 = XBYTES, SOFF_B2 = SOFF_B1 + TT_ACT, SOFF_DZ3 = SOFF_B2 + TT_ACT;
   static constexpr int SLOT_BYTES = SOFF_DZ3 + TT_DZ3;
-  static constexpr int OFF_MISC = OFF_SLOT0 + NSLOT * SLOT_BYTES, SMEM = OFF_MISC + 128 * NSLOT + 64;
+  static constexpr int OFF_MISC = OFF_SLOT0 + NSLOT * SLOT_BYTES, OFF_PELUT = OFF_MISC + 128 * NSLOT + 64, SMEM = OFF_PELUT + 1024;
 };
 constexpr float TT_LOSS_SCALE = 64.0f;
+// The quantisation dither takes 8 bits per feature from Philox4x32 with SEVEN rounds — the fewest that pass BigCrush (Salmon et
+// al., SC'11; ten is the library default with its safety margin).  73 bytes per sample are five calls; at ten rounds the
+// generator was 9 % of the kernel's instructions.  (The crop sampler keeps the ten-round generator of the known-answer test.)
+constexpr int TT_NOISE_ROUNDS = 7;
 
 // Instruction descriptor with explicit operand majors (bit 15: A is MN-major, bit 16: B is MN-major).
 __host__ __device__ constexpr uint32_t tt_idesc(int fmt, int M, int N, int a_mn, int b_mn) {
@@ -262,7 +266,10 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
   uint64_t* mbar3 = mbar + 2;                     // completion of D2 (B1 = H1 and B2 = dZ2 may be overwritten)
   uint64_t* mbar4 = mbar + 3;                     // completion of D3 (B2 = H2 may be overwritten)
   float* sRed = reinterpret_cast<float*>(sMisc + 32);           // [8] loss partials
-  volatile unsigned* sTile = reinterpret_cast<volatile unsigned*>(sMisc + 64);      // [2] next tile (dynamic scheduler)
+  // [2] x {tile, px, py0, -}: the next tile (dynamic scheduler) and, FS, the image coordinates of its first texel — worked out
+  // by thread 0 of the slot one tile ahead (the tile's 128 texels are consecutive in y), not by every thread
+  volatile int* sInfo = reinterpret_cast<volatile int*>(sMisc + 64);
+  const uint4* sPE = reinterpret_cast<const uint4*>(smem + TS::OFF_PELUT);      // FS: triangular encoding of p mod 64 (3 packed words)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TS::OFF_MISC + 128 * NSLOT);
   // timeline (debug, bit 9 with bit 3): nanosecond stamps of CTA entry / first tile / flush / exit, min and max over the CTAs
   const bool tl = a.prof && (a.dbg & 512);
@@ -304,6 +311,41 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
     const uint32_t o = *reinterpret_cast<uint32_t*>(&one);
     *reinterpret_cast<uint4*>(sH1 + roff80 + 8 * 128) = make_uint4(o, 0, 0, 0);     // feature 64 = 1
     *reinterpret_cast<uint4*>(sH2 + roff80 + 8 * 128) = make_uint4(o, 0, 0, 0);
+  }
+  // FS: first texel of a tile (b = crop, then x, then the tile's 128 y)
+  auto tile_first_texel = [&](unsigned tl_, int& px, int& py0) {
+    px = py0 = 0;
+    if (tl_ < (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS)) {
+      const unsigned tpb = (unsigned)g.per_block >> 7, tpr = (unsigned)g.B[1] >> 7;
+      const unsigned b = tl_ / tpb, r = tl_ - b * tpb, ix = r / tpr;
+      px = (int)a.origins[2 * (size_t)b] + (int)ix;
+      py0 = (int)a.origins[2 * (size_t)b + 1] + (int)((r - ix * tpr) << 7);
+    }
+  };
+  // The scheduler runs on ONE otherwise idle thread per slot (thread 128: warp-group 1 has nothing to do while warp-group 0
+  // evaluates the loss), two tiles ahead: during tile k it holds the index of tile k + 1, asks the counter for tile k + 2 and —
+  // the two memory round trips overlap — looks up the first texel of tile k + 1.  (Fetching in thread 0 at the top of a tile
+  // cost 1,500 cycles per tile: at 80 registers the compiler spills the returned index at once, i.e. waits for the atomic.)
+  const unsigned tile_stride = gridDim.x * NSLOT;
+  unsigned sched_next = blockIdx.x * NSLOT + slot + tile_stride;      // tile k + 1 (thread 128 only)
+  if (tid == 128 && a.tile_ctr) sched_next = atomicAdd(a.tile_ctr, 1u) + tile_stride;
+  if (FS) {
+    if (tid == 0) {
+      int px, py0;
+      const unsigned t0 = blockIdx.x * NSLOT + slot;
+      tile_first_texel(t0, px, py0);
+      sInfo[4] = (int)t0, sInfo[5] = px, sInfo[6] = py0;
+    }
+    if (threadIdx.x < 64 && g.pe_kind == NIC_PE_TRIANGULAR) {
+      const float u1 = __fmul_rn(__fmul_rn((float)threadIdx.x, g.step), 0.5f);
+      uint32_t w[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        auto v = P::pack(pe_triangular(u1, 2 * r, 6), pe_triangular(u1, 2 * r + 1, 6));
+        w[r] = *reinterpret_cast<uint32_t*>(&v);
+      }
+      reinterpret_cast<uint4*>(smem + TS::OFF_PELUT)[threadIdx.x] = make_uint4(w[0], w[1], w[2], 0u);
+    }
   }
   fence_async_smem();
   tc_fence_before();
@@ -442,10 +484,8 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
   // fetches the next index at the top of a tile; it reaches the others through shared memory, several barriers later.
   unsigned tile = blockIdx.x * NSLOT + slot;
   for (; tile < ntiles; ++tiles_done) {
-    unsigned tile_next = tile + gridDim.x * NSLOT;
-    if (a.tile_ctr && tid == 0) tile_next = atomicAdd(a.tile_ctr, 1u) + gridDim.x * NSLOT;
     const unsigned n = tile * TT_ROWS + row;
-    const bool live = n < (unsigned)g.N;
+    const bool live = FS ? true : n < (unsigned)g.N;           // FS: crop rows are whole tiles
     const unsigned nc = live ? n : (unsigned)g.N - 1;
     float tgt[4] = {0.f, 0.f, 0.f, 0.f};           // targets of the first 4 outputs: loaded now, used after the forward pass
     if (wg == 0 && live) {
@@ -454,9 +494,17 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
         if (c < a.cout)       // volatile: keep the load HERE (the compiler would sink it to its use, 2,000 cycles later)
           asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(tgt[c]) : "l"(a.targets + (size_t)n * a.cout + c));
     }
-    if (prof0) prof_t = clock64();
+    if (prof0 && tiles_done == 0) prof_t = clock64();      // later tiles: the gather phase starts at the end of the previous tile
     // ------------------------------------------------------------------------------------------ gather + noise -> X~
-    Texel t = texel_of_fast(g, nc, a.origins);
+    Texel t;
+    if constexpr (FS) {
+      t.b = 0;
+      t.p[0] = sInfo[4 * ((tiles_done & 1) ^ 1) + 1];
+      t.p[1] = sInfo[4 * ((tiles_done & 1) ^ 1) + 2] + row;
+      t.p[2] = 0;
+    } else {
+      t = texel_of_fast(g, nc, a.origins);
+    }
     AxisCoord ax[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -499,7 +547,7 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
       const bool gen = !a.noise && a.noise_amp > 0.f;
       const __half2 nsc = __float2half2_rn(a.noise_amp * (1.0f / 256.0f)), nhs = __float2half2_rn(a.noise_amp * (0.5f / 256.0f));
       auto noise16 = [&](int b16, uint32_t* nzw) {
-        const uint4 r = philox4x32(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(8 * wg + b16));
+        const uint4 r = philox4x32_r<TT_NOISE_ROUNDS>(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(8 * wg + b16));
         const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -565,7 +613,10 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
 #pragma unroll
           for (int i = 0; i < 6; ++i) w[i] = bits2(acc[i]);
         }
-        if (g.pe_kind == NIC_PE_TRIANGULAR) {
+        if (FS && g.pe_kind == NIC_PE_TRIANGULAR) {        // step 1/4: the encoding has period 64 in the texel coordinate
+          const uint4 lx = sPE[t.p[0] & 63], ly = sPE[t.p[1] & 63];
+          w[6] = lx.x, w[7] = lx.y, w[8] = lx.z, w[9] = ly.x, w[10] = ly.y, w[11] = ly.z;
+        } else if (g.pe_kind == NIC_PE_TRIANGULAR) {
 #pragma unroll
           for (int d = 0; d < 2; ++d)
 #pragma unroll
@@ -718,7 +769,7 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
 #pragma unroll
         for (int i = 0; i < 8; ++i) nzw[i] = 0u;
         if (gen && 16 * b16 < ncols) {
-          const uint4 r = philox4x32(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(8 * wg + b16));
+          const uint4 r = philox4x32_r<TT_NOISE_ROUNDS>(a.seed, a.step, ((unsigned long long)nc << 4) | (unsigned)(8 * wg + b16));
           const uint32_t wds[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -767,7 +818,6 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
                ID_F64, kc > 0);
     });
     mark(1);
-    if (tid == 0) sTile[tiles_done & 1] = tile_next;
 #pragma unroll
     for (int layer = 0; layer < 2; ++layer) {
       uint32_t acc[32];
@@ -859,6 +909,13 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
             make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
                        *reinterpret_cast<uint32_t*>(&p3));
       }
+    } else if (tid == 128) {         // the tile scheduler (see the prologue)
+      const unsigned t1 = sched_next;
+      sched_next = a.tile_ctr ? atomicAdd(a.tile_ctr, 1u) + tile_stride : t1 + tile_stride;
+      int px = 0, py0 = 0;
+      if (FS) tile_first_texel(t1, px, py0);
+      volatile int* d = sInfo + 4 * (tiles_done & 1);
+      d[0] = (int)t1, d[1] = px, d[2] = py0;
     }
     mark(6);
     // ------------------------------------------------------------------------------------------ backward
@@ -1127,8 +1184,9 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
     }
     mark(12);
     if (a.prof && !tl && tid == 0) atomicAdd(a.prof + 15, 1ull);      // (every slot counts its tiles)
-    tc_fence_before();          // next tile's MMAs overwrite D: order them after this tile's tcgen05.ld
-    tile = sTile[tiles_done & 1];
+    // (the next tile's first MMA batch is preceded by tcgen05.fence::before_thread_sync + the slot barrier in run_mmas, which
+    // orders it after this tile's tcgen05.ld)
+    tile = (unsigned)sInfo[4 * (tiles_done & 1)];
   }
   if (FS && u_pending) fs_scatter_rows();       // the last tile's gradient rows
   // -------------------------------------------------------------------------------------------- flush: MLP gradients
