@@ -99,43 +99,81 @@ constexpr int F_W1G0 = b_image_bytes(64, 48);      // 6144
 constexpr int F_LUT = 64 * 64 * 2;                 // 8192 per axis
 constexpr int F_IMG = F_W1G0 + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2) + 2 * F_LUT;
 
-// R[node][n] = sum_c W1[n][4C + c] * G1[c][node], stored [x][y][64] 16-bit (128 B per node).  One thread per node:
-// 12 coalesced loads, 64 x 12 fma against weights broadcast from shared memory, one 128-byte row out.
+// R[node][n] = sum_c W1[n][4C + c] * G1[c][node], stored [x][y][64] 16-bit (128 B per node).  Blocks of 8 (x) x 16 (y) nodes;
+// a thread owns 16 of the 64 outputs of TWO nodes that are neighbours along y (32 accumulators: four blocks per SM).  The patch
+// of the channel-major source grid ([c][y][x], x fastest) goes through shared memory, and the four threads of a node together
+// with their neighbours along y — the fast axis of R — write runs of 2 KB.  (The first version had one thread per node with 64
+// accumulators, 128 threads along x: every 16-byte store of a warp went to 32 different lines 64 KB apart and two warps per
+// scheduler could not hide the shared-memory weight loads: 52 us for a 513 x 513 grid, half of the table build of a 4096^2 frame.)
+// Persistent blocks (the 64 x 12 weights are fetched once per block, not once per 128 nodes), and a block's next patch is
+// in flight in registers while it works on the current one.
+constexpr int G1R_TX = 8, G1R_TY = 16;
 template <int FMT>
-__global__ void __launch_bounds__(128) g1_rows_kernel(MlpDev m, const float* __restrict__ g1, int nx, int ny,
-                                                      uint16_t* __restrict__ R, int code_bits) {
-  constexpr int C = 12;
-  __shared__ float w[C * 64];                 // [c][n]
+__global__ void __launch_bounds__(256, 3) g1_rows_kernel(MlpDev m, const float* __restrict__ g1, int nx, int ny,
+                                                         uint16_t* __restrict__ R, int code_bits) {
+  constexpr int C = 12, PER = C * G1R_TY * G1R_TX / 256;    // patch elements per thread (6)
+  __shared__ __align__(16) float w[C * 64];                 // [c][n]
+  __shared__ float patch[C][G1R_TY][G1R_TX + 1];            // [c][y][x]
   for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) w[(i % C) * 64 + i / C] = m.w1[(i / C) * m.cin + 4 * C + (i % C)];
-  __syncthreads();
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= nx) return;
-  const size_t nodes = (size_t)nx * ny, node = (size_t)y * nx + x;
-  float acc[64];
+  const int tiles_x = (nx + G1R_TX - 1) / G1R_TX, tiles_y = (ny + G1R_TY - 1) / G1R_TY, ntiles = tiles_x * tiles_y;
+  const size_t nodes = (size_t)nx * ny;
+  float pf[PER];
+  auto fetch = [&](int tile) {
+    const int x0 = (tile / tiles_y) * G1R_TX, y0 = (tile % tiles_y) * G1R_TY;
 #pragma unroll
-  for (int n = 0; n < 64; ++n) acc[n] = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    float g = grid_value(g1, (long long)(c * nodes + node), code_bits);
-    const float4* wr = reinterpret_cast<const float4*>(w + c * 64);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      float4 ww = wr[q];
-      acc[4 * q] = fmaf(g, ww.x, acc[4 * q]);
-      acc[4 * q + 1] = fmaf(g, ww.y, acc[4 * q + 1]);
-      acc[4 * q + 2] = fmaf(g, ww.z, acc[4 * q + 2]);
-      acc[4 * q + 3] = fmaf(g, ww.w, acc[4 * q + 3]);
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int c = i / (G1R_TY * G1R_TX), r = i - c * (G1R_TY * G1R_TX), yl = r / G1R_TX, xl = r - yl * G1R_TX;
+      const int x = x0 + xl, y = y0 + yl;
+      pf[k] = (x < nx && y < ny) ? grid_value(g1, (long long)(c * nodes + (size_t)y * nx + x), code_bits) : 0.f;
     }
-  }
-  uint4* dst = reinterpret_cast<uint4*>(R + ((size_t)x * ny + y) * 64);
+  };
+  const int oq = threadIdx.x & 3, pair = threadIdx.x >> 2, xl = pair >> 3, yl = 2 * (pair & 7);
+  int tile = blockIdx.x;
+  if (tile < ntiles) fetch(tile);
+  for (; tile < ntiles; tile += gridDim.x) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    uint4 v;
-    v.x = to16<FMT>(acc[8 * q]) | ((uint32_t)to16<FMT>(acc[8 * q + 1]) << 16);
-    v.y = to16<FMT>(acc[8 * q + 2]) | ((uint32_t)to16<FMT>(acc[8 * q + 3]) << 16);
-    v.z = to16<FMT>(acc[8 * q + 4]) | ((uint32_t)to16<FMT>(acc[8 * q + 5]) << 16);
-    v.w = to16<FMT>(acc[8 * q + 6]) | ((uint32_t)to16<FMT>(acc[8 * q + 7]) << 16);
-    dst[q] = v;
+    for (int k = 0; k < PER; ++k) (&patch[0][0][0])[((threadIdx.x + 256 * k) / G1R_TX) * (G1R_TX + 1) + (threadIdx.x + 256 * k) % G1R_TX] = pf[k];
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
+    const int x = (tile / tiles_y) * G1R_TX + xl, y = (tile % tiles_y) * G1R_TY + yl;
+    if (x < nx && y < ny) {
+      float acc[2][16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) acc[0][n] = acc[1][n] = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float ga = patch[c][yl][xl], gb = patch[c][yl + 1][xl];
+        const float4* wr = reinterpret_cast<const float4*>(w + c * 64 + 16 * oq);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = wr[q];
+          acc[0][4 * q] = fmaf(ga, ww.x, acc[0][4 * q]);
+          acc[0][4 * q + 1] = fmaf(ga, ww.y, acc[0][4 * q + 1]);
+          acc[0][4 * q + 2] = fmaf(ga, ww.z, acc[0][4 * q + 2]);
+          acc[0][4 * q + 3] = fmaf(ga, ww.w, acc[0][4 * q + 3]);
+          acc[1][4 * q] = fmaf(gb, ww.x, acc[1][4 * q]);
+          acc[1][4 * q + 1] = fmaf(gb, ww.y, acc[1][4 * q + 1]);
+          acc[1][4 * q + 2] = fmaf(gb, ww.z, acc[1][4 * q + 2]);
+          acc[1][4 * q + 3] = fmaf(gb, ww.w, acc[1][4 * q + 3]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (y + k >= ny) break;
+        uint4* dst = reinterpret_cast<uint4*>(R + ((size_t)x * ny + y + k) * 64 + 16 * oq);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint4 v;
+          v.x = to16<FMT>(acc[k][8 * q]) | ((uint32_t)to16<FMT>(acc[k][8 * q + 1]) << 16);
+          v.y = to16<FMT>(acc[k][8 * q + 2]) | ((uint32_t)to16<FMT>(acc[k][8 * q + 3]) << 16);
+          v.z = to16<FMT>(acc[k][8 * q + 4]) | ((uint32_t)to16<FMT>(acc[k][8 * q + 5]) << 16);
+          v.w = to16<FMT>(acc[k][8 * q + 6]) | ((uint32_t)to16<FMT>(acc[k][8 * q + 7]) << 16);
+          dst[q] = v;
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1112,8 +1150,9 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
     h->prepared.valid = 0;
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
     if (e != cudaSuccess) return (int)e;
-    dim3 grid_r((g.n1[0] + 127) / 128, g.n1[1]);
-    g1_rows_kernel<FMT><<<grid_r, 128, 0, st>>>(m, g1, g.n1[0], g.n1[1], R, h->src_code_bits);
+    const long long tiles_r = (long long)((g.n1[0] + G1R_TX - 1) / G1R_TX) * ((g.n1[1] + G1R_TY - 1) / G1R_TY);
+    const long long cap_r = 3ll * h->sms;
+    g1_rows_kernel<FMT><<<(int)(tiles_r < cap_r ? tiles_r : cap_r), 256, 0, st>>>(m, g1, g.n1[0], g.n1[1], R, h->src_code_bits);
     h->launches++;
     pack_fast_kernel<FMT><<<32, 256, 0, st>>>(m, g.lod, g.step, (uint16_t*)h->tc_weights, npoly);
     h->launches++;
