@@ -327,8 +327,9 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
   // the two memory round trips overlap — looks up the first texel of tile k + 1.  (Fetching in thread 0 at the top of a tile
   // cost 1,500 cycles per tile: at 80 registers the compiler spills the returned index at once, i.e. waits for the atomic.)
   const unsigned tile_stride = gridDim.x * NSLOT;
-  unsigned sched_next = blockIdx.x * NSLOT + slot + tile_stride;      // tile k + 1 (thread 128 only)
-  if (tid == 128 && a.tile_ctr) sched_next = atomicAdd(a.tile_ctr, 1u) + tile_stride;
+  const unsigned ntiles = (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS);
+  volatile unsigned* sSched = reinterpret_cast<volatile unsigned*>(sMisc + 96);      // tile k + 1 (thread 128 only)
+  if (tid == 128) sSched[0] = a.tile_ctr ? atomicAdd(a.tile_ctr, 1u) + tile_stride : blockIdx.x * NSLOT + slot + tile_stride;
   if (FS) {
     if (tid == 0) {
       int px, py0;
@@ -471,7 +472,6 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
     tc_fence_before();          // the next MMAs into D are ordered after these tcgen05.ld by the barrier of run_mmas
   };
 
-  const unsigned ntiles = (unsigned)((g.N + TT_ROWS - 1) / TT_ROWS);
   if (tl && prof0) {
     const unsigned long long t = gtime();
     atomicMax(a.prof + 0, ~tl_entry);
@@ -910,12 +910,24 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
                        *reinterpret_cast<uint32_t*>(&p3));
       }
     } else if (tid == 128) {         // the tile scheduler (see the prologue)
-      const unsigned t1 = sched_next;
-      sched_next = a.tile_ctr ? atomicAdd(a.tile_ctr, 1u) + tile_stride : t1 + tile_stride;
-      int px = 0, py0 = 0;
-      if (FS) tile_first_texel(t1, px, py0);
+      // tile k + 1 and its crop origin, and the request for tile k + 2: the origin load is issued BEFORE the atomic and nothing
+      // uses either result until both are in flight, so the two round trips overlap inside the loss phase; the atomic's result
+      // goes straight to shared memory.  (Requesting earlier — before the layer-3 wait — and posting here was slower: a result
+      // that has to survive a long wait in a register is spilled at once, i.e. awaited at the point of issue.)
+      const unsigned t1 = sSched[0];
+      long long ox = 0, oy = 0;
+      unsigned ix = 0, iy0 = 0;
+      if (FS && t1 < ntiles) {
+        const unsigned tpb = (unsigned)g.per_block >> 7, tpr = (unsigned)g.B[1] >> 7;
+        const unsigned b = t1 / tpb, r = t1 - b * tpb;
+        ix = r / tpr;
+        iy0 = (r - ix * tpr) << 7;
+        asm volatile("ld.global.nc.v2.s64 {%0, %1}, [%2];" : "=l"(ox), "=l"(oy) : "l"(a.origins + 2 * (size_t)b));
+      }
+      const unsigned t2 = a.tile_ctr ? atomicAdd(a.tile_ctr, 1u) + tile_stride : t1 + tile_stride;
       volatile int* d = sInfo + 4 * (tiles_done & 1);
-      d[0] = (int)t1, d[1] = px, d[2] = py0;
+      d[0] = (int)t1, d[1] = (int)ox + (int)ix, d[2] = (int)oy + (int)iy0;
+      sSched[0] = t2;
     }
     mark(6);
     // ------------------------------------------------------------------------------------------ backward

@@ -33,6 +33,8 @@ if "frozen" in sys.argv:
 dbg_extra = sum(int(a[4:]) for a in sys.argv if a.startswith("dbg="))      # e.g. dbg=256: shuffle scatter instead of the MMA scatter
 if dbg_extra:
     L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, dbg_extra)
+if "static" in sys.argv:            # static round-robin tile order instead of the atomic counter
+    L.set_option(dev, L.OPT_STATIC_TILES, 1)
 for _ in range(3):
     tr.step(coord, tg, 0, noise=noise_arg)
 torch.cuda.synchronize()
