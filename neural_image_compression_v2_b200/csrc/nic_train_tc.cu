@@ -1033,20 +1033,13 @@ __global__ void __launch_bounds__(TrainShape<METHOD>::THREADS, 1) train_tc_kerne
         }
         if (!live) va = vb = 0u;
         // (D2 += dZ2^T [H1 | 1] has read H1: awaited in the dZ1 epilogue)
-        // one or two non-zero halves in 80 bytes: position them with shifts instead of comparing every slot
-        const int ca = sa >> 3, cb = sb >> 3;                      // chunk (16 bytes = 8 slots) of each entry; cb = -1: none
-        const uint32_t wa = va << ((sa & 1) * 16), wb = vb << ((sb & 1) * 16);
-        const int ia = (sa >> 1) & 3, ib = (sb >> 1) & 3;          // word inside the chunk
+        // one or two non-zero 16-bit entries in this thread's 80 bytes: five zero chunks, then the entries as 4-byte words on top
+        // (same thread, same addresses: program order)
+        uint8_t* srow = sH1 + roff80 + 5 * wg * 128;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          const uint32_t xa = c == ca ? wa : 0u, xb = c == cb ? wb : 0u;
-          uint4 v;
-          v.x = (ia == 0 ? xa : 0u) | (ib == 0 ? xb : 0u);
-          v.y = (ia == 1 ? xa : 0u) | (ib == 1 ? xb : 0u);
-          v.z = (ia == 2 ? xa : 0u) | (ib == 2 ? xb : 0u);
-          v.w = (ia == 3 ? xa : 0u) | (ib == 3 ? xb : 0u);
-          *reinterpret_cast<uint4*>(sH1 + roff80 + (5 * wg + c) * 128) = v;
-        }
+        for (int c = 0; c < 5; ++c) *reinterpret_cast<uint4*>(srow + c * 128) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint32_t*>(srow + (sa >> 3) * 128 + ((sa >> 1) & 3) * 4) = va << ((sa & 1) * 16);
+        if (sb >= 0) *reinterpret_cast<uint32_t*>(srow + (sb >> 3) * 128 + ((sb >> 1) & 3) * 4) = vb << ((sb & 1) * 16);
       }
       // ---- T = S^T dZ1 (awaited)  and (deferred)  D1 += dZ1^T X~
       run_mmas2(
