@@ -60,11 +60,30 @@ __global__ void __launch_bounds__(256) sample_crops_tile_kernel(const float* __r
   for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const long long n = chunk * 256 + threadIdx.x;
     if (n < nsamples) {
-      const int b = (int)(n / per);
-      long long r = n - (long long)b * per;
-      const int i2 = (int)(r % c2);
-      r /= c2;
-      const int i1 = (int)(r % c1), i0 = (int)(r / c1);
+      int b, i0, i1, i2;
+      if (nsamples < (1ll << 31)) {            // 32-bit index math (three 64-bit divisions were most of this kernel's instructions)
+        const unsigned un = (unsigned)n, uper = (unsigned)per;
+        const unsigned ub = un / uper;
+        unsigned r = un - ub * uper;
+        b = (int)ub;
+        if (c2 == 1) {
+          i2 = 0;
+        } else {
+          const unsigned q = r / (unsigned)c2;
+          i2 = (int)(r - q * (unsigned)c2);
+          r = q;
+        }
+        const unsigned q1 = r / (unsigned)c1;
+        i1 = (int)(r - q1 * (unsigned)c1);
+        i0 = (int)q1;
+      } else {
+        b = (int)(n / per);
+        long long r = n - (long long)b * per;
+        i2 = (int)(r % c2);
+        r /= c2;
+        i1 = (int)(r % c1);
+        i0 = (int)(r / c1);
+      }
       const float* p = img + ((long long)(s_org[3 * b] + i0) * s1 + (s_org[3 * b + 1] + i1)) * s2 + (s_org[3 * b + 2] + i2);
       for (int c = 0; c < ci; ++c) tile[threadIdx.x * pitch + c] = __ldg(p + c * plane);
     }
