@@ -21,9 +21,12 @@ x = torch.empty((size * size, 73), dtype=td, device=dev)
 geom = L.make_geom(L.METHOD_2D, fp[0], fp[1], size, 1, -2, 0, 6, L.PE_TRIANGULAR)
 h, lib = L.handle(dev), L.load_library()
 L.set_option(dev, L.OPT_TIME_KERNELS, 1)
+dbg = sum(int(a[4:]) for a in sys.argv if a.startswith("dbg="))     # 16-bit kernel: 1 no row build, 2 no bulk store, 16 / 32: 1 / 4 rows per interval
+if dbg:
+    L.set_option(dev, L.OPT_DEBUG_KNOCKOUT, dbg)
 for _ in range(reps):
     L.check(h, lib.nic_gather(h, C.byref(geom), L.ptr(fp[0]), L.ptr(fp[1]), None, L.ptr(x), code, L.stream_ptr(dev)))
 torch.cuda.synchronize()
 ms, n = L.kernel_time_ms(dev)
 b = 73 * x.element_size() + 12 * 4 * (1 / 16 + 1 / 64)
-print(f"{dt}: {ms / n:.3f} ms/launch, {b * size * size / (ms / n * 1e-3) / 1e9:.0f} GB/s algorithmic")
+print(f"{dt} dbg={dbg}: {ms / n:.3f} ms/launch, {b * size * size / (ms / n * 1e-3) / 1e9:.0f} GB/s algorithmic")
