@@ -260,13 +260,17 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
                : "memory");
 }
 
-template <int FMT, typename OutT, int NPOLY>
+// CO = 3: the production instance for RGB outputs (no knock-out flags, channel count folded: the per-tile integer work of
+// the generic instance — three uniform branches per channel, the output pointer re-read per store — was 100 of the 755
+// instructions per texel, profiles/r02f); CO = 0: any channel count <= 16, honours NIC_OPT_DEBUG_KNOCKOUT.
+template <int FMT, typename OutT, int NPOLY, int CO>
 __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g, const uint2* __restrict__ shadow0,
                                                                        const uint4* __restrict__ R,
-                                                                       const uint4* __restrict__ wimg, int cout,
+                                                                       const uint4* __restrict__ wimg, int cout_arg,
                                                                        unsigned tiles_y, unsigned fd_mul, unsigned fd_shift,
-                                                                       OutT* __restrict__ out, int dbg) {
+                                                                       OutT* __restrict__ out, int dbg_arg) {
   using P = Pair<FMT>;
+  const int cout = CO ? CO : cout_arg, dbg = CO ? 0 : dbg_arg;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sW = smem_raw + WS_STAGE;                // weight images + LUTs sit ABOVE the staging buffers (LBO = distance)
   uint8_t* sW1 = sW;
@@ -395,7 +399,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
     if (i >= my_tiles) return;
     int px0, py0, bx0, by0;
     tile_origin(blockIdx.x + i * gridDim.x, px0, py0, bx0, by0);
-    const size_t b0 = ((size_t)(px0 >> 2) * ny0 + (py0 >> 2)) * 24, b1 = ((size_t)(px0 >> 3) * ny1 + (py0 >> 3)) * 128;
+    // byte offsets of the tile's base nodes: the launcher guarantees both tables are smaller than 4 GB
+    const uint32_t b0 = ((uint32_t)(px0 >> 2) * (uint32_t)ny0 + (uint32_t)(py0 >> 2)) * 24u;
+    const uint32_t b1 = ((uint32_t)(px0 >> 3) * (uint32_t)ny1 + (uint32_t)(py0 >> 3)) * 128u;
     if (g0_piece) {
       const uint2 v = __ldg(reinterpret_cast<const uint2*>(src0 + b0));
       pre0 = make_uint4(v.x, v.y, 0, 0);
@@ -532,13 +538,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) decode_tc2d_ws_kernel(DevGeom g
       int px0, py0, bx0, by0;
       tile_origin(tile, px0, py0, bx0, by0);
       const size_t n = (size_t)((uint32_t)bx0 * (uint32_t)g.B[1] + (uint32_t)by0 + out_thread);      // < 2^31 (launcher)
+      if constexpr (CO == 3) {
+        OutT* o = out + n * 3;
+        store_sigmoid(o, __uint_as_float(acc[0]));
+        store_sigmoid(o + 1, __uint_as_float(acc[1]));
+        store_sigmoid(o + 2, __uint_as_float(acc[2]));
+      } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < cout && !(dbg & 1)) store_sigmoid(out + n * cout + c, __uint_as_float(acc[c]));
-      if (cout > 4) {
+        for (int c = 0; c < 4; ++c)
+          if (c < cout && !(dbg & 1)) store_sigmoid(out + n * cout + c, __uint_as_float(acc[c]));
+        if (cout > 4) {
 #pragma unroll
-        for (int c = 4; c < 16; ++c)
-          if (c < cout) store_sigmoid(out + n * cout + c, __uint_as_float(acc[c]));
+          for (int c = 4; c < 16; ++c)
+            if (c < cout) store_sigmoid(out + n * cout + c, __uint_as_float(acc[c]));
+        }
       }
     }
   }
@@ -1168,16 +1181,18 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
   unsigned mul = (unsigned)(((1ull << (31 + sh)) + tiles_y - 1) / tiles_y);
   // warp-specialised persistent kernel: one CTA per SM (all 512 TMEM columns)
   static_assert(WS_SMEM <= 227 * 1024, "shared memory budget");
+  if (b0 >= (1ull << 32) || b1 >= (1ull << 32)) return NIC_ERR_UNSUPPORTED;          // 32-bit table offsets in the kernel
   void (*kern)(DevGeom, const uint2*, const uint4*, const uint4*, int, unsigned, unsigned, unsigned, OutT*, int) = nullptr;
+  const bool rgb = m.cout == 3 && h->debug_flags == 0;       // the specialised instance; anything else takes the generic one
   switch (npoly) {
-    case 0: kern = decode_tc2d_ws_kernel<FMT, OutT, 0>; break;
-    case 3: kern = decode_tc2d_ws_kernel<FMT, OutT, 3>; break;
+    case 0: kern = decode_tc2d_ws_kernel<FMT, OutT, 0, 0>; break;
+    case 3: kern = rgb ? decode_tc2d_ws_kernel<FMT, OutT, 3, 3> : decode_tc2d_ws_kernel<FMT, OutT, 3, 0>; break;
 #ifdef NIC_GELU_SWEEP
-    case 2: kern = decode_tc2d_ws_kernel<FMT, OutT, 2>; break;
-    case 4: kern = decode_tc2d_ws_kernel<FMT, OutT, 4>; break;
-    case 5: kern = decode_tc2d_ws_kernel<FMT, OutT, 5>; break;
-    case 6: kern = decode_tc2d_ws_kernel<FMT, OutT, 6>; break;
-    case 8: kern = decode_tc2d_ws_kernel<FMT, OutT, 8>; break;
+    case 2: kern = decode_tc2d_ws_kernel<FMT, OutT, 2, 0>; break;
+    case 4: kern = decode_tc2d_ws_kernel<FMT, OutT, 4, 0>; break;
+    case 5: kern = decode_tc2d_ws_kernel<FMT, OutT, 5, 0>; break;
+    case 6: kern = decode_tc2d_ws_kernel<FMT, OutT, 6, 0>; break;
+    case 8: kern = decode_tc2d_ws_kernel<FMT, OutT, 8, 0>; break;
 #endif
     default: return NIC_ERR_UNSUPPORTED;
   }
