@@ -353,7 +353,7 @@ def bench_train(args, env, nic, ic, var2):
     fp = [torch.tensor(g, device=dev) for g in I.make_grids(size, 2, seed=3, no_mip=True)]
     dec = make_decoder(ic, torch, dev, I.make_mlp(73, seed=4))
     train_prec = args.train_prec or "f16"
-    tr = ic.FusedTrainer(fp, dec, num_epochs=100000, fp_bits=8, seed=1, precision=train_prec)
+    tr = ic.FusedTrainer(fp, dec, num_epochs=100000, fp_bits=8, seed=1, precision=train_prec, exchange=args.exchange)
     img = I.make_image(size, 2, seed=5)
     img8 = torch.tensor(np.ascontiguousarray(np.floor(np.transpose(img, (1, 2, 0)) * 255 + 0.5).astype(np.uint8)), device=dev)
     pyr = ic.build_mip_pyramid(img8)                   # [3, 512, 512] float32 (TF_NO_MIP: one level)
@@ -398,13 +398,14 @@ def bench_train(args, env, nic, ic, var2):
     res = {"value": rate, "unit": "Msamples/s", "samples_per_step": world * n, "ms_per_step": ms / steps,
            "ms_per_step_presampled": ms_pre / steps, "sampling": "inside the timed region (host LOD draw, device-side origins + target gather)",
            "exchange": {"none": "none (1 GPU)", "peer": "fused into Adam over NVLink peer memory (nic_adam_step_exchange)",
+                        "sliced": "fused into Adam over NVLink peer memory, sliced (reduce-scatter + all-gather by peer loads / stores)",
                         "nccl": "NCCL all_reduce + Adam", "mixed": "peer + nccl"}[exchange],
            "precision": train_prec, "loss": float(loss), "psnr_8bit_last_step_db": metrics[-1][2] if metrics else None,
            "workload": "train_512x512_8x256x256_crops", "kernel_ms": kms / max(kn, 1), "kernel_tflops": kernel_tflops,
            "roofline_frac": (kernel_tflops / tf_peak) if kernel_tflops else None, "flop_per_sample": 3 * FLOP_2D}
     if world > 1:
         res["replicas_identical"] = replicas_identical(env, [t for t in tr.fp] + [p.detach() for p in dec.parameters_list()])
-        res["exchange_timed_out"] = bool(L.exchange_status(dev)) if exchange in ("peer", "mixed") else False
+        res["exchange_timed_out"] = bool(L.exchange_status(dev)) if exchange in ("peer", "sliced", "mixed") else False
     env.barrier()
     tr.close()
     return res
@@ -680,7 +681,8 @@ def run_train_2048(args, env):
     """BASELINE config 3: a 2048^2 multi-channel material texture stack (9 channels) with mip levels 0..11, data-parallel
     training on the tensor-core path, 8 crops per rank per step, LOD drawn per step with the reference's distribution
     (the same on every rank), device-side sampling inside the timed region.  Level 0's flat gradient buffer is 15.8 MB:
-    above FusedTrainer.PEER_EXCHANGE_MAX_BYTES, so its exchange is the NCCL all-reduce; smaller levels use the fused peer exchange."""
+    above FusedTrainer.PEER_EXCHANGE_MAX_BYTES, so with more than two ranks its exchange runs sliced inside the Adam kernel
+    (`--exchange nccl` times the NCCL all-reduce baseline instead); smaller levels use the one-shot fused exchange."""
     from neural_image_compression_v2_b200 import _lib as L
     from neural_image_compression_v2_b200 import image_compression as ic
     from neural_image_compression_v2_b200 import fp_def, var2
@@ -701,7 +703,7 @@ def run_train_2048(args, env):
     fp = [p.detach() for p in fp]
     dec = ic.ColorDecoder(73, 64, cout).to(dev)
     prec = args.train_prec or "bf16"                                   # config 3 names bf16
-    tr = ic.FusedTrainer(fp, dec, num_epochs=1000000, fp_bits=8, seed=3, precision=prec)
+    tr = ic.FusedTrainer(fp, dec, num_epochs=1000000, fp_bits=8, seed=3, precision=prec, exchange=args.exchange)
     steps = max(args.steps, 100)
     for _ in range(max(args.warmup, 20)):                              # touches most levels (peer buffers are mapped on first use)
         tr.step_sampled(pyr)
@@ -722,7 +724,7 @@ def run_train_2048(args, env):
     flop = 3 * 2 * (73 * 64 + 64 * 64 + 64 * cout)
     value = world * samples / (ms * 1e-3) / 1e6
     exchange = tr.exchange_in_use()
-    timed_out = bool(L.exchange_status(dev)) if exchange in ("peer", "mixed") else False
+    timed_out = bool(L.exchange_status(dev)) if exchange in ("peer", "sliced", "mixed") else False
     env.emit({"metric": "train Msamples/s (2048^2 x 9-channel material stack with mips, data parallel)", "value": value,
               "unit": "Msamples/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 20), "ms_per_step": ms / steps,
               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
@@ -887,6 +889,8 @@ def main():
     ap.add_argument("--cpu-baseline-tiles", type=int, default=48,
                     help="cpu_baseline leg: 1024^2 tiles decoded on the host cores (48 = three frames, ~10 s on 16 cores)")
     ap.add_argument("--e2e-bands", type=int, default=4, help="row bands per frame of the host-to-host pipeline")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer", "sliced"],
+                    help="training workloads at N > 1: the data-parallel exchange (FusedTrainer)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the gather, 3-D and training side benchmarks")
     args = ap.parse_args()

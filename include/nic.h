@@ -272,10 +272,14 @@ int nic_adam_step_loss(NicHandle* h, const NicAdamTensor* tensors, int count, fl
  * flag; the caller must re-synchronise the replicas (broadcast parameters + Adam state) before it resumes.  All blocks of the
  * kernel are co-resident by construction (grid capped by occupancy), so the intra-kernel release cannot deadlock. */
 #define NIC_MAX_PEERS 16
+#define NIC_EXCHANGE_ONE_SHOT 0   /* every rank reads all `world` buffers (small buffers: one handshake) */
+#define NIC_EXCHANGE_SLICED 1     /* rank r sums slice r of all buffers and writes it back to all; second handshake; Adam from
+                                     the own buffer: 2 (world-1)/world of the buffer crosses NVLink per rank instead of world-1
+                                     times.  The flag array then needs 2 NIC_MAX_PEERS words, and peer_flat must be writable. */
 typedef struct NicExchange {
   int32_t world, rank;
   uint32_t token;
-  int32_t reserved;
+  int32_t reserved;           /* mode: NIC_EXCHANGE_ONE_SHOT or NIC_EXCHANGE_SLICED */
   const float* peer_flat[NIC_MAX_PEERS];
   uint32_t* peer_flag[NIC_MAX_PEERS];
   float* zero_buf;

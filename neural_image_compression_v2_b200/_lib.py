@@ -51,6 +51,9 @@ class NicAdamTensor(C.Structure):
 MAX_PEERS = 16
 
 
+EXCHANGE_ONE_SHOT, EXCHANGE_SLICED = 0, 1      # NicExchange.reserved (nic.h: NIC_EXCHANGE_*)
+
+
 class NicExchange(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("token", C.c_uint32), ("reserved", C.c_int32),
                 ("peer_flat", C.c_void_p * MAX_PEERS), ("peer_flag", C.c_void_p * MAX_PEERS),

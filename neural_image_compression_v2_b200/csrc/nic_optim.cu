@@ -98,6 +98,12 @@ struct XchDev {
   unsigned char vec[NIC_ADAM_BATCH];
   const float* loss_sum;      // inside peer_flat[rank]
   int dbg;                    // knock-outs (timing experiments only): bit 5 no flag wait, bit 6 read the own buffer only
+  // Sliced (two-phase) mode for buffers too large to read world times: rank r sums slice r of every buffer and writes
+  // the sums back into ALL buffers; after a second handshake every rank applies Adam from its own, now reduced, buffer.
+  int sliced;
+  long long flat_numel;       // floats in one flat buffer (multiple of 4)
+  unsigned* go2;              // local release word of the second handshake
+  unsigned* arrive;           // local counter: blocks of this grid that finished their part of the slice
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -122,54 +128,102 @@ __device__ __forceinline__ void xch_fail(const XchDev& x) {
 // Adam state and the loss untouched, and the next nic_adam_step_exchange / nic_exchange_status call on the handle returns
 // NIC_ERR_EXCHANGE — the replicas stay consistent (nobody applied a partial sum) until the caller re-synchronises them.
 // The grid is sized to the resident block count (launch_adam_exchange), so block (0,0) is always scheduled.
+// One cross-rank handshake of the grid (see the kernel's header): block 0's first warp exchanges tokens with the peers
+// through flag slots [slot0, slot0 + world) and releases the other blocks through `go`; on return (after the caller's
+// __syncthreads) every rank's writes before ITS handshake are visible to this block's cache-volatile loads.
+__device__ __forceinline__ void xch_handshake(const XchDev& x, int slot0, unsigned* go) {
+  if (blockIdx.x == 0) {
+    // ONE warp of the grid talks to the peers.  Flags are PUSHED: lane p stores this rank's token into slot `rank` of
+    // peer p's flag array (a fire-and-forget NVLink store), then polls slot p of the LOCAL array — no remote polling,
+    // and all peers are awaited in parallel.  Lane 0 then releases this rank's other blocks through a local word.
+    if (threadIdx.x < 32) {
+      const int p = threadIdx.x;
+      bool bad = ld_acquire_gpu(x.err) != 0u;
+      if (p < x.world && !bad) {          // a rank that has already failed stays silent: its peers time out too
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer_flag[p] + slot0 + x.rank), "r"(x.token) : "memory");
+        const unsigned* mine = x.peer_flag[x.rank] + slot0 + p;
+        const long long t0 = clock64();
+        while (!bad && (int)(ld_acquire_sys(mine) - x.token) < 0) {
+          if (clock64() - t0 > x.timeout_cycles) bad = true;     // the peer is gone
+        }
+      }
+      bad = __any_sync(0xffffffffu, bad);
+      if (p == 0) {
+        if (bad) xch_fail(x);
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(x.go_token) : "memory");
+      }
+    }
+  } else if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_gpu(go) - x.go_token) < 0) {
+      if (clock64() - t0 > x.timeout_cycles + 2000000000ll) {
+        xch_fail(x);
+        break;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev x) {
   pdl_wait();
   __shared__ unsigned s_err;
-  if (!(x.dbg & 32)) {
-    if (blockIdx.x == 0) {
-      // ONE warp of the grid talks to the peers.  Flags are PUSHED: lane p stores this rank's token into slot `rank` of
-      // peer p's flag array (a fire-and-forget NVLink store), then polls slot p of the LOCAL array — no remote polling,
-      // and all peers are awaited in parallel.  Lane 0 then releases this rank's other blocks through a local word.
-      if (threadIdx.x < 32) {
-        const int p = threadIdx.x;
-        bool bad = ld_acquire_gpu(x.err) != 0u;
-        if (p < x.world && !bad) {          // a rank that has already failed stays silent: its peers time out too
-          __threadfence_system();
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.peer_flag[p] + x.rank), "r"(x.token) : "memory");
-          const unsigned* mine = x.peer_flag[x.rank] + p;
-          const long long t0 = clock64();
-          while (!bad && (int)(ld_acquire_sys(mine) - x.token) < 0) {
-            if (clock64() - t0 > x.timeout_cycles) bad = true;     // the peer is gone
-          }
+  if (!(x.dbg & 32)) xch_handshake(x, 0, x.go);
+  if (x.sliced) {
+    // ---- phase 1: reduce-scatter by peer reads + all-gather by peer writes.  Rank r owns the float4 items
+    // [n4 * r / world, n4 * (r + 1) / world) of the flat buffer: it forms their sum over the ranks IN RANK ORDER and stores
+    // it into every rank's buffer, so that all replicas consume the same bits.  Nobody else touches slice r of any buffer
+    // between the two handshakes (slice q of this rank's buffer is read and rewritten by rank q alone).
+    __syncthreads();
+    if (threadIdx.x == 0) s_err = ld_acquire_gpu(x.err);
+    __syncthreads();
+    if (!s_err) {
+      const long long n4 = x.flat_numel / 4, lo = n4 * x.rank / x.world, hi = n4 * (x.rank + 1) / x.world;
+      for (long long it = lo + (long long)blockIdx.x * 256 + threadIdx.x; it < hi; it += (long long)gridDim.x * 256) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < x.world; ++r) {
+          const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[r]) + it);
+          g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
         }
-        bad = __any_sync(0xffffffffu, bad);
-        if (p == 0) {
-          if (bad) xch_fail(x);
-          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(x.go), "r"(x.go_token) : "memory");
-        }
-      }
-    } else if (threadIdx.x == 0) {
-      const long long t0 = clock64();
-      while ((int)(ld_acquire_gpu(x.go) - x.go_token) < 0) {
-        if (clock64() - t0 > x.timeout_cycles + 2000000000ll) {
-          xch_fail(x);
-          break;
-        }
+        for (int r = 0; r < x.world; ++r) reinterpret_cast<float4*>(const_cast<float*>(x.peer_flat[r]))[it] = g;
       }
     }
+    // every block of this grid has stored its sums -> second handshake -> the whole reduced gradient is in the LOCAL buffer
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (blockIdx.x != 0) {
+        atomicAdd(x.arrive, 1u);
+      } else {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(x.arrive) < gridDim.x - 1) {
+          if (clock64() - t0 > x.timeout_cycles + 2000000000ll) {
+            xch_fail(x);
+            break;
+          }
+        }
+        *x.arrive = 0u;            // for the next launch (nobody adds again before this grid has completed)
+        __threadfence_system();
+      }
+    }
+    __syncthreads();
+    xch_handshake(x, NIC_MAX_PEERS, x.go2);
   }
   __syncthreads();
   if (threadIdx.x == 0) s_err = ld_acquire_gpu(x.err);
   __syncthreads();
   if (s_err) return;             // sticky failure: nothing is updated (see above)
+  // one-shot: every element is the sum over the peers' buffers; sliced: the own buffer already holds the reduced gradient
+  const bool own = x.sliced || (x.dbg & 64);
+  const int nsrc = x.sliced ? 1 : x.world;
   if (b.loss_out && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long off = x.loss_sum - x.peer_flat[x.rank];
     float s = 0.f;
-    for (int r = 0; r < x.world; ++r) s += __ldcv(x.peer_flat[(x.dbg & 64) ? x.rank : r] + off);
+    for (int r = 0; r < nsrc; ++r) s += __ldcv(x.peer_flat[own ? x.rank : r] + off);
     b.loss_out[0] = s * b.loss_scale;
     if (b.metrics) {
       float s8 = 0.f;
-      for (int r = 0; r < x.world; ++r) s8 += __ldcv(x.peer_flat[(x.dbg & 64) ? x.rank : r] + off + 1);
+      for (int r = 0; r < nsrc; ++r) s8 += __ldcv(x.peer_flat[own ? x.rank : r] + off + 1);
       b.loss_out[1] = s8 * b.loss_scale;
     }
   }
@@ -189,8 +243,8 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
     const long long item = (long long)(vb - x.vb_start[ti]) * 256 + threadIdx.x;
     if (item < n4) {
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < x.world; ++r) {
-        const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[(x.dbg & 64) ? x.rank : r] + goff) + item);
+      for (int r = 0; r < nsrc; ++r) {
+        const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[own ? x.rank : r] + goff) + item);
         g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
       }
       float4* p4 = reinterpret_cast<float4*>(t.p);
@@ -206,7 +260,7 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
       const long long i = n4 * 4 + (item - n4);
       if (i < t.numel) {
         float g = 0.f;
-        for (int r = 0; r < x.world; ++r) g += __ldcv(x.peer_flat[(x.dbg & 64) ? x.rank : r] + goff + i);
+        for (int r = 0; r < nsrc; ++r) g += __ldcv(x.peer_flat[own ? x.rank : r] + goff + i);
         float p = t.p[i], m = t.m[i], v = t.v[i];
         adam_one(p, g, m, v, b.beta1, b.beta2, b.eps, b.grad_scale, step_size, bc2_sqrt, t.clamp, t.clamp_lo, t.clamp_hi);
         t.p[i] = p; t.m[i] = m; t.v[i] = v;
@@ -220,8 +274,8 @@ int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, flo
                          cudaStream_t st) {
   if (count > NIC_ADAM_BATCH) return NIC_ERR_UNSUPPORTED;      // one launch: the flag protocol runs once per step
   if (!h->xch_err) {          // two words: [0] sticky timeout flag, [1] the local release word; + the host-visible copy of [0]
-    cudaError_t e = cudaMalloc(&h->xch_err, 2 * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemsetAsync(h->xch_err, 0, 2 * sizeof(unsigned), st);
+    cudaError_t e = cudaMalloc(&h->xch_err, 4 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->xch_err, 0, 4 * sizeof(unsigned), st);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->xch_host_err, sizeof(unsigned), cudaHostAllocMapped);
     if (e == cudaSuccess) {
       *h->xch_host_err = 0u;
@@ -263,6 +317,11 @@ int launch_adam_exchange(Handle* h, const NicAdamTensor* tensors, int count, flo
   x.host_err = h->xch_host_err_dev;
   x.go = h->xch_err + 1;
   x.go_token = ++h->xch_seq;
+  x.sliced = xc.reserved == NIC_EXCHANGE_SLICED;
+  x.flat_numel = xc.zero_numel;
+  x.go2 = h->xch_err + 2;
+  x.arrive = h->xch_err + 3;
+  if (x.sliced && (xc.zero_numel & 3)) return NIC_ERR_ARG;
   x.timeout_cycles = (long long)(h->xch_timeout_ms > 0 ? h->xch_timeout_ms : 10000) * 2000000ll;      // at <= 2 GHz: >= the requested time
   x.dbg = h->debug_flags;
   x.loss_sum = loss_sum;

@@ -614,7 +614,8 @@ class FusedTrainer:
     quantise the grids once epoch > 0.95 N (:227-231); clamp of the two active grids after each step (:269).
     """
 
-    PEER_EXCHANGE_MAX_BYTES = 4 << 20      # one-shot peer reads beat a ring/tree all-reduce only for small buffers
+    PEER_EXCHANGE_MAX_BYTES = 4 << 20      # above this (and more than two ranks) the fused exchange runs sliced: see _peer_level
+    PEER_SYMMETRIC_MAX_BYTES = 1 << 30     # "auto" keeps nccl for flat buffers beyond this (symmetric memory is allocated twice)
 
     def __init__(self, fp, decoder, num_epochs=None, fp_bits=None, lr_fp=0.01, lr_mlp=0.005, betas=(0.9, 0.999),
                  eps=1e-8, method=None, level_table=None, process_group=None, seed=0, precision="f32", exchange="auto",
@@ -654,8 +655,11 @@ class FusedTrainer:
         # The exchange step under data parallelism: "nccl" = all_reduce(flat) then Adam; "peer" = ONE kernel that reads the
         # peers' flat buffers over NVLink and applies Adam (nic_adam_step_exchange); "auto" = peer for flat buffers up to
         # PEER_EXCHANGE_MAX_BYTES when every rank could map every peer, else nccl.
-        if exchange not in ("auto", "nccl", "peer"):
-            raise ValueError("exchange must be 'auto', 'nccl' or 'peer'")
+        # A one-shot exchange reads all `world` buffers on every rank; beyond PEER_EXCHANGE_MAX_BYTES (and two ranks) the
+        # kernel runs SLICED: rank r sums slice r of every buffer, writes it back to all of them, second handshake, Adam
+        # from the own buffer — 2 (world-1)/world of the buffer per rank over NVLink ("sliced" forces that mode).
+        if exchange not in ("auto", "nccl", "peer", "sliced"):
+            raise ValueError("exchange must be 'auto', 'nccl', 'peer' or 'sliced'")
         self.exchange = exchange
         self._peer = {}          # level -> symmetric buffers, peer pointers, use count (None: this level uses nccl)
         self.state = {}          # id -> (m, v, t)
@@ -699,7 +703,9 @@ class FusedTrainer:
         dist = torch.distributed
         sizes, offs, total = self._level_layout(fl)
         want = self.world > 1 and self.world <= L.MAX_PEERS and self.exchange != "nccl" and \
-            (self.exchange == "peer" or total * 4 <= self.PEER_EXCHANGE_MAX_BYTES)
+            (self.exchange != "auto" or total * 4 <= self.PEER_SYMMETRIC_MAX_BYTES)
+        sliced = self.exchange == "sliced" or (self.exchange != "nccl" and self.world > 2 and
+                                               total * 4 > self.PEER_EXCHANGE_MAX_BYTES)
         ent = None
         if want:
             ok, buf, bases = 1, None, []
@@ -719,10 +725,11 @@ class FusedTrainer:
                 for par in range(2):
                     flat = buf.tensor[par * total:(par + 1) * total]
                     flats.append((flat, [flat[o:o + s] for o, s in zip(offs, sizes)]))
-                ent = {"buf": buf, "bases": bases, "flats": flats, "total": total, "uses": 0, "xch": {}}
+                ent = {"buf": buf, "bases": bases, "flats": flats, "total": total, "uses": 0, "xch": {},
+                       "mode": L.EXCHANGE_SLICED if sliced else L.EXCHANGE_ONE_SHOT}
             else:
-                if self.exchange == "peer":
-                    raise RuntimeError("exchange='peer': the ranks could not map each other's buffers (CUDA IPC)")
+                if self.exchange in ("peer", "sliced"):
+                    raise RuntimeError(f"exchange='{self.exchange}': the ranks could not map each other's buffers (CUDA IPC)")
                 if buf is not None:
                     buf.close()
         self._peer[fl] = ent
@@ -747,17 +754,18 @@ class FusedTrainer:
         self._cache.clear()
 
     def exchange_in_use(self):
-        """'none' (single process), 'peer' (every level used so far exchanges over peer memory), 'nccl' or 'mixed'."""
+        """'none' (single process), 'peer' / 'sliced' (every level used so far exchanges over peer memory, one-shot / sliced),
+        'nccl' or 'mixed'."""
         if self.world == 1:
             return "none"
-        kinds = {"peer" if v is not None else "nccl" for v in self._peer.values()}
+        kinds = {"nccl" if v is None else ("sliced" if v["mode"] == L.EXCHANGE_SLICED else "peer") for v in self._peer.values()}
         return kinds.pop() if len(kinds) == 1 else ("mixed" if kinds else "nccl")
 
     def _exchange_desc(self, ent, parity):
         x = ent["xch"].get(parity)
         if x is None:
             x = L.NicExchange()
-            x.world, x.rank = self.world, self.rank
+            x.world, x.rank, x.reserved = self.world, self.rank, ent["mode"]
             for r, base in enumerate(ent["bases"]):
                 x.peer_flat[r] = base + 4 * parity * ent["total"]
                 x.peer_flag[r] = base + 8 * ent["total"]

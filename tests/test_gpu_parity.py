@@ -1143,8 +1143,9 @@ def test_edge_cases_empty_and_oversized():
 
 def test_exchange_kernel_single_rank_equals_plain_adam():
     """nic_adam_step_exchange with world = 1 (runs on a 1-GPU box): symmetric buffer allocation and aliasing, the flag
-    protocol against itself, the other-parity clear and the loss bookkeeping — and bit-equality with nic_adam_step_loss
-    on the same gradients (a one-term sum is exact).  The multi-rank behaviour is test_dp_exchange_* below."""
+    protocol against itself (one-shot and sliced: both handshakes, the grid-wide arrive counter, the write-back), the
+    other-parity clear and the loss bookkeeping — and bit-equality with nic_adam_step_loss on the same gradients (a
+    one-term sum is exact).  The multi-rank behaviour is test_dp_exchange_* below."""
     n = nic()
     L = n._lib
     import ctypes as C
@@ -1160,12 +1161,12 @@ def test_exchange_kernel_single_rank_equals_plain_adam():
         flat0, flat1 = buf.tensor[:total], buf.tensor[total:2 * total]
         grad = T(rng.standard_normal(total).astype(np.float32) * 1e-2)
         results = {}
-        for mode in ("plain", "exchange"):
+        for mode in ("plain", "exchange", "sliced"):
             params = [T(rng2) for rng2 in (np.random.default_rng(6).standard_normal(sz).astype(np.float32) * 0.1 for sz in sizes[:3])]
             ms = [torch.full_like(p, 0.01) for p in params]
             vs = [torch.full_like(p, 0.001) for p in params]
             g = grad.clone() if mode == "plain" else flat0
-            if mode == "exchange":
+            if mode != "plain":
                 flat0.copy_(grad)
                 flat1.fill_(7.0)                     # stale contents of the other parity: must come back cleared
             arr = (L.NicAdamTensor * 3)()
@@ -1182,18 +1183,22 @@ def test_exchange_kernel_single_rank_equals_plain_adam():
                                                   L.stream_ptr(dev())))
             else:
                 x = L.NicExchange()
-                x.world, x.rank, x.token = 1, 0, 41
+                x.world, x.rank, x.token = 1, 0, 41 if mode == "exchange" else 42
+                x.reserved = L.EXCHANGE_SLICED if mode == "sliced" else L.EXCHANGE_ONE_SHOT
                 x.peer_flat[0], x.peer_flag[0] = buf.ptr, buf.ptr + 8 * total
                 x.zero_buf, x.zero_numel = buf.ptr + 4 * total, total
                 L.check(h, lib.nic_adam_step_exchange(h, arr, 3, 0.9, 0.999, 1e-8, 1.0, C.byref(x), L.ptr(loss_sum), L.ptr(loss),
                                                       0.5, L.stream_ptr(dev())))
                 assert not L.exchange_status(dev())
                 assert float(flat1.abs().sum()) == 0.0
-                assert int(buf.tensor[2 * total:2 * total + 1].view(torch.int32)[0]) == 41       # slot 0 of the flag array
-                assert torch.equal(flat0, grad)                                                   # the current buffer is left alone
+                flags = buf.tensor[2 * total:2 * total + 32].view(torch.int32)
+                assert int(flags[0]) == x.token                                                   # slot 0 of the flag array
+                if mode == "sliced":
+                    assert int(flags[16]) == 42                                                   # ... and of the second handshake
+                assert torch.equal(flat0, grad)       # one-shot leaves the buffer alone; a one-rank slice sum rewrites the same bits
             results[mode] = [t.cpu().numpy() for t in params + ms + vs] + [loss.cpu().numpy()]
-        for a, b in zip(results["plain"], results["exchange"]):
-            assert np.array_equal(a, b)
+        for a, b, c in zip(results["plain"], results["exchange"], results["sliced"]):
+            assert np.array_equal(a, b) and np.array_equal(a, c)
         assert abs(float(results["plain"][-1][0]) - 0.5 * float(grad[offs[3]])) < 1e-7
     finally:
         buf.close()
