@@ -711,13 +711,16 @@ def run_train_2048(args, env):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     samples, lods = 0, []
     s.record()
+    t_host = time.perf_counter()
     for _ in range(steps):
         _, lod = tr.step_sampled(pyr)
         lods.append(lod)
         samples += nc * (max(1, 256 >> lod)) ** 2
+    t_host = time.perf_counter() - t_host
     e.record()
     env.barrier()
     ms = env.max_over_ranks(s.elapsed_time(e))
+    host_ms = env.max_over_ranks(1e3 * t_host) / steps                 # enqueue time of a step (no sync inside the loop)
     metrics = tr.flush_metrics()
     ident = replicas_identical(env, list(tr.fp) + [p.detach() for p in dec.parameters_list()]) if world > 1 else None
     tf_peak = peaks()[0]
@@ -733,6 +736,7 @@ def run_train_2048(args, env):
                          "sampling": "inside the timed region"},
               "samples_timed_per_rank": samples, "lod_histogram": {str(k): lods.count(k) for k in sorted(set(lods))},
               "exchange": exchange, "exchange_timed_out": timed_out, "replicas_identical": ident,
+              "host_enqueue_ms_per_step": host_ms,
               "loss_last": metrics[-1][1] if metrics else None, "psnr_8bit_last_step_db": metrics[-1][2] if metrics else None,
               "roofline": {"bound": "tensor", "achieved": value * flop / 1e6, "peak": tf_peak * world, "unit": "TFLOP/s",
                            "frac": value * flop / 1e6 / (tf_peak * world), "flop_per_sample": flop, "traffic": None,

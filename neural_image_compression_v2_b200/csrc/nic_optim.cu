@@ -179,13 +179,34 @@ __global__ void __launch_bounds__(256) adam_exchange_kernel(AdamBatch b, XchDev 
     __syncthreads();
     if (!s_err) {
       const long long n4 = x.flat_numel / 4, lo = n4 * x.rank / x.world, hi = n4 * (x.rank + 1) / x.world;
-      for (long long it = lo + (long long)blockIdx.x * 256 + threadIdx.x; it < hi; it += (long long)gridDim.x * 256) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      // Consecutive 16-byte items per warp (512-byte runs per peer); UN items per thread and round keep UN * world
+      // independent peer loads in flight per thread (knock-out bit 7 of NIC_OPT_DEBUG_KNOCKOUT: one item per round).
+      constexpr int UN = 4;
+      const long long stride = (long long)gridDim.x * 256;
+      const int un = (x.dbg & 128) ? 1 : UN;
+      for (long long it0 = lo + (long long)blockIdx.x * 256 + threadIdx.x; it0 < hi; it0 += stride * un) {
+        float4 g[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < x.world; ++r) {
-          const float4 q = __ldcv(reinterpret_cast<const float4*>(x.peer_flat[r]) + it);
-          g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+          const float4* src = reinterpret_cast<const float4*>(x.peer_flat[r]);
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const long long it = it0 + u * stride;
+            if (u < un && it < hi) {
+              const float4 q = __ldcv(src + it);
+              g[u].x += q.x; g[u].y += q.y; g[u].z += q.z; g[u].w += q.w;
+            }
+          }
         }
-        for (int r = 0; r < x.world; ++r) reinterpret_cast<float4*>(const_cast<float*>(x.peer_flat[r]))[it] = g;
+        for (int r = 0; r < x.world; ++r) {
+          float4* dst = reinterpret_cast<float4*>(const_cast<float*>(x.peer_flat[r]));
+#pragma unroll
+          for (int u = 0; u < UN; ++u) {
+            const long long it = it0 + u * stride;
+            if (u < un && it < hi) dst[it] = g[u];
+          }
+        }
       }
     }
     // every block of this grid has stored its sums -> second handshake -> the whole reduced gradient is in the LOCAL buffer
