@@ -23,6 +23,30 @@ constexpr int GT_C = 12, GT_PE = 6, GT_CIN = 73;
 
 __device__ __forceinline__ uint32_t gt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// L2 residency hints: the grids (63 MB at 4096^2) are re-read by neighbouring super-tiles while 2.4-4.9 GB of X stream
+// through the same L2 — node loads ask to be evicted last, the row stores first (profiles/r02k: without the hints the
+// kernel read 209 MB from DRAM for 66 MB of grids, and reads interleaved with a write stream cost more than their bytes).
+__device__ __forceinline__ uint64_t gt_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t gt_policy_stream() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float gt_ldg_keep(const float* a, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void gt_bulk_store(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem),
+               "r"(bytes), "l"(pol)
+               : "memory");
+}
+
 template <typename OutT> struct Pack16;
 template <> struct Pack16<__half> {
   static __device__ __forceinline__ uint32_t two(float a, float b) {
@@ -120,6 +144,7 @@ __global__ void __launch_bounds__(GT_T) gather_tile_kernel(DevGeom g, const floa
   // 16-bit rows: warp-uniform texel parity (see header); fp32 rows: thread = texel, lanes stride 73 words (== 9 mod 32)
   const int par = sizeof(OutT) == 2 ? (warp & 1) : 0;
   const int t = sizeof(OutT) == 2 ? 64 * (warp >> 1) + 2 * lane + par : tid;
+  const uint64_t pol_keep = gt_policy_keep(), pol_stream = gt_policy_stream();
   const long long ps0 = (long long)g.n0[0] * g.n0[1], ps1 = (long long)g.n1[0] * g.n1[1];
   const unsigned xgroups = (unsigned)g.B[0] / GT_R;
   const unsigned tiles_per_block = xgroups * tiles_per_row;
@@ -150,11 +175,11 @@ __global__ void __launch_bounds__(GT_T) gather_tile_kernel(DevGeom g, const floa
   };
   auto load0 = [&](int yn, const AxisCoord& axf, const AxisCoord& ayf) -> float {
     const int gx = clampi(axf.i0 + xn0_, 0, g.n0[0] - 1), gy = clampi(ayf.i0 + yn, 0, g.n0[1] - 1);
-    return __ldg(g0 + c0_ * ps0 + (long long)gy * g.n0[0] + gx);
+    return gt_ldg_keep(g0 + c0_ * ps0 + (long long)gy * g.n0[0] + gx, pol_keep);
   };
   auto load1 = [&](int yn, const AxisCoord& axf, const AxisCoord& ayf) -> float {
     const int gx = clampi(axf.i1 + xn1_, 0, g.n1[0] - 1), gy = clampi(ayf.i1 + yn, 0, g.n1[1] - 1);
-    return __ldg(g1 + c1_ * ps1 + (long long)gy * g.n1[0] + gx);
+    return gt_ldg_keep(g1 + c1_ * ps1 + (long long)gy * g.n1[0] + gx, pol_keep);
   };
   auto prefetch = [&](unsigned tile) {
     if (tile >= ntiles) return;
@@ -284,9 +309,7 @@ __global__ void __launch_bounds__(GT_T) gather_tile_kernel(DevGeom g, const floa
         // sample index of this row's first texel: block b, x row xg*GT_R + row, y run `run`
         const size_t n0 = (size_t)b * (size_t)g.per_block + ((size_t)xg * GT_R + row) * (size_t)g.B[1] + (size_t)run * GT_T;
         OutT* dst = x + n0 * GT_CIN;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(gt_smem_u32(stage)),
-                     "r"(STAGE_BYTES)
-                     : "memory");
+        gt_bulk_store(dst, gt_smem_u32(stage), STAGE_BYTES, pol_stream);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
@@ -351,6 +374,7 @@ __global__ void __launch_bounds__(GT_T, 4) gather_tile16_kernel(DevGeom g, const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int par = warp & 1;                                  // warp-uniform texel parity
   const int t = 64 * (warp >> 1) + 2 * lane + par;
+  const uint64_t pol_keep = gt_policy_keep(), pol_stream = gt_policy_stream();
   const unsigned xgroups = (unsigned)g.B[0] / R;
   const unsigned tiles_per_block = xgroups * tiles_per_row;
   constexpr float step = 1.0f / (float)(1 << SL);
@@ -388,13 +412,13 @@ __global__ void __launch_bounds__(GT_T, 4) gather_tile16_kernel(DevGeom g, const
     const float* colp = gcol0 + min(gx0 + xn0_, n0x - 1);
 #pragma unroll
     for (int k = 0; k < PRE0; ++k)
-      if (k0 + k < k1) dst[k] = __ldg(colp + min(gy0 + yA0 + (k0 + k) * ys0, n0y1) * n0x);
+      if (k0 + k < k1) dst[k] = gt_ldg_keep(colp + min(gy0 + yA0 + (k0 + k) * ys0, n0y1) * n0x, pol_keep);
   };
   auto loads1 = [&](int gx1, int gy1, int k0, int k1, float* dst) {
     const float* colp = gcol1 + min(gx1 + xn1_, n1x - 1);
 #pragma unroll
     for (int k = 0; k < PRE1; ++k)
-      if (k0 + k < k1) dst[k] = __ldg(colp + min(gy1 + yA1 + (k0 + k) * ys1, n1y1) * n1x);
+      if (k0 + k < k1) dst[k] = gt_ldg_keep(colp + min(gy1 + yA1 + (k0 + k) * ys1, n1y1) * n1x, pol_keep);
   };
   const int nk0 = stager0 ? (np0 - yA0 + ys0 - 1) / ys0 : 0, nk1 = stager1 ? (np1 - yA1 + ys1 - 1) / ys1 : 0;   // nodes per thread
   auto prefetch = [&](unsigned tile) {
@@ -603,10 +627,7 @@ __global__ void __launch_bounds__(GT_T, 4) gather_tile16_kernel(DevGeom g, const
       __syncthreads();
       if (tid == 0) {
         OutT* dst = x + (n_first + (size_t)row * (size_t)g.B[1]) * GT_CIN;
-        if (!(dbg & 2))
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(gt_smem_u32(stage)),
-                       "r"(STAGE_BYTES)
-                       : "memory");
+        if (!(dbg & 2)) gt_bulk_store(dst, gt_smem_u32(stage), STAGE_BYTES, pol_stream);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }

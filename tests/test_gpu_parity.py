@@ -170,7 +170,9 @@ def test_gather_tile_kernel_equals_flat_kernel():
     cases = [  # (fl, mip, block, num_blocks, origins)
         (0, 0, (512, 512), 1, None), (0, 0, (40, 384), 1, (9, 128)), (0, 1, (256, 256), 1, None), (0, 2, (128, 128), 1, None),
         (0, 0, (256, 256), 3, rng.integers(0, 257, (3, 2))), (0, 1, (128, 128), 5, rng.integers(0, 129, (5, 2))),
-        (0, 2, (64, 128), 1, (64, 0))]
+        (0, 2, (64, 128), 1, (64, 0)),
+        # block heights that are not multiples of 8: the 16-bit kernel's 4-row super-tiles at steps 1/4 and 1/2
+        (0, 0, (12, 256), 1, (3, 128)), (0, 1, (20, 128), 2, rng.integers(0, 100, (2, 2)))]
     for fl, mip, block, nb, org in cases:
         g0, g1 = fp[2 * fl], fp[2 * fl + 1]
         o0 = org if (org is not None and nb == 1 and not isinstance(org, np.ndarray)) else None
