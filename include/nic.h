@@ -108,7 +108,10 @@ int64_t nic_launch_count(const NicHandle* h);
  * atomics, bits 5 / 6 make nic_adam_step_exchange skip the flag wait / read only its own buffer (timing experiments in
  * tools/dp_timing.py), bit 8 keeps the shuffle-based grid scatter where the tensor-core scatter would run (results stay correct:
  * A/B timing); results are otherwise WRONG on purpose.  Bit 3 only enables the training phase counters (nic_debug_counters) and
- * leaves the results unchanged.  Never set in production. */
+ * leaves the results unchanged.  nic_gather (16-bit rows, tools/run_gather.py): bit 0 skips the row build, bit 1 the bulk
+ * stores, bit 4 keeps 4-row super-tiles, bit 6 the run-time-geometry kernel.  nic_adam_step_exchange (sliced): bit 7 reduces
+ * one item per thread and round.  Any non-zero value makes nic_decode's fast path run its generic instance instead of the
+ * RGB-specialised one (same results: A/B timing).  Never set in production. */
 /* NIC_OPT_GELU_POLY: how many of every 8 hidden activations of the fast 2-D tensor-core decode kernel evaluate GELU as a
  * clamped minimax polynomial on the FMA pipe instead of MUFU.TANH (the kernel is bound by the XU pipe when all of them
  * use the transcendental).  -1 = the tuned default; 0 = all MUFU (round-1 behaviour); values the library was not built
