@@ -112,9 +112,16 @@ template <int FMT>
 __global__ void __launch_bounds__(256, 3) g1_rows_kernel(MlpDev m, const float* __restrict__ g1, int nx, int ny,
                                                          uint16_t* __restrict__ R, int code_bits) {
   constexpr int C = 12, PER = C * G1R_TY * G1R_TX / 256;    // patch elements per thread (6)
-  __shared__ __align__(16) float w[C * 64];                 // [c][n]
+  // [c][n / 16][16 + 4]: the four 64-byte output groups of a channel sit 80 bytes apart, so the 16-byte loads of the four
+  // threads of a node hit four different bank groups (a stride of 64 bytes puts groups 0 / 2 and 1 / 3 on the same banks: every
+  // weight load took two wavefronts, and the kernel waits on shared-memory latency — short-scoreboard stall 7.4, profiles/r02m)
+  constexpr int WS = 20, WC = 4 * WS;
+  __shared__ __align__(16) float w[C * WC];
   __shared__ float patch[C][G1R_TY][G1R_TX + 1];            // [c][y][x]
-  for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) w[(i % C) * 64 + i / C] = m.w1[(i / C) * m.cin + 4 * C + (i % C)];
+  for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) {
+    const int n = i / C, c = i % C;
+    w[c * WC + (n >> 4) * WS + (n & 15)] = m.w1[n * m.cin + 4 * C + c];
+  }
   const int tiles_x = (nx + G1R_TX - 1) / G1R_TX, tiles_y = (ny + G1R_TY - 1) / G1R_TY, ntiles = tiles_x * tiles_y;
   const size_t nodes = (size_t)nx * ny;
   float pf[PER];
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(256, 3) g1_rows_kernel(MlpDev m, const float* 
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float ga = patch[c][yl][xl], gb = patch[c][yl + 1][xl];
-        const float4* wr = reinterpret_cast<const float4*>(w + c * 64 + 16 * oq);
+        const float4* wr = reinterpret_cast<const float4*>(w + c * WC + WS * oq);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 ww = wr[q];
