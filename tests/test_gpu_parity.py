@@ -196,6 +196,29 @@ def test_gather_tile_kernel_equals_flat_kernel():
     assert np.array_equal(X, O.create_decoder_input(grids, coord, 0, 0, 1))
 
 
+def test_gather_full_frame_16bit_rows_are_the_fp32_rows_rounded_once():
+    """K1 at BASELINE's full size (4096^2 texels, 2.45 GB of f16 / bf16 X): every value of the 16-bit tile kernel (patch
+    staged already rounded, x-weighted G1 rows) equals the fp32 tile kernel's value rounded once — the size-independent form
+    of the small-case oracle check above."""
+    import ctypes as C
+    n = nic()
+    L = n._lib
+    size = 4096
+    grids = I.make_grids(size, 2, seed=80, no_mip=True, quantized=True)
+    fp = [T(a) for a in grids]
+    h, lib = L.handle(dev()), L.load_library()
+    geom = L.make_geom(L.METHOD_2D, fp[0], fp[1], size, 1, -2, 0, 6, L.PE_TRIANGULAR)
+    x32 = torch.empty((size * size, 73), dtype=torch.float32, device=dev())
+    L.check(h, lib.nic_gather(h, C.byref(geom), L.ptr(fp[0]), L.ptr(fp[1]), None, L.ptr(x32), L.DT_F32, L.stream_ptr(dev())))
+    for dt, td in ((L.DT_F16, torch.float16), (L.DT_BF16, torch.bfloat16)):
+        x16 = torch.full((size * size, 73), -7.0, dtype=td, device=dev())
+        L.check(h, lib.nic_gather(h, C.byref(geom), L.ptr(fp[0]), L.ptr(fp[1]), None, L.ptr(x16), dt, L.stream_ptr(dev())))
+        rows = 1 << 20
+        for r0 in range(0, size * size, rows):
+            assert torch.equal(x16[r0:r0 + rows], x32[r0:r0 + rows].to(td)), (td, r0)
+        del x16
+
+
 def test_gather_scatter_adjoint():
     """<gather(G), dX> == <G, scatter(dX)> on the grid columns (linearity / transpose property)."""
     ic = nic().image_compression
