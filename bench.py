@@ -313,7 +313,8 @@ def pcie_floor(env, h2d_bytes, d2h_bytes, iters=6):
     s1, s2 = torch.cuda.Stream(device=env.dev), torch.cuda.Stream(device=env.dev)
     res = {}
     for name, do_in, do_out in (("both", True, True), ("h2d_only", True, False), ("d2h_only", False, True)):
-        for rep in range(2):                 # the first round warms up
+        vals = []
+        for rep in range(4):                 # the first round warms up; the median of the other three is kept
             env.barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -331,7 +332,8 @@ def pcie_floor(env, h2d_bytes, d2h_bytes, iters=6):
             main.wait_stream(s2)
             b.record()
             env.barrier()
-            res[name] = env.max_over_ranks(a.elapsed_time(b)) / iters
+            vals.append(env.max_over_ranks(a.elapsed_time(b)) / iters)
+        res[name] = sorted(vals[1:])[1]
     return {"ms_per_frame": res["both"], "gtexel_s": env.world * SIZE * SIZE / (res["both"] * 1e-3) / 1e9,
             "h2d_gbs_per_rank": h2d_bytes / (res["h2d_only"] * 1e-3) / 1e9,
             "d2h_gbs_per_rank": d2h_bytes / (res["d2h_only"] * 1e-3) / 1e9,
@@ -543,14 +545,19 @@ def run_decode_4096(args, env):
     pipe.finish()
     env.barrier()
     k2 = max(3, args.steps)                  # the same K steps as `value`; pipeline fill and drain are inside the timed region
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(k2):
-        e2e_step()
-    pipe.finish()                            # every frame of the timed region is in host memory before the stop event
-    e.record()
-    env.barrier()
-    e2e_ms = env.max_over_ranks(s.elapsed_time(e)) / k2
+    # Three timed regions of K steps each, the MEDIAN reported and all three listed: the copies share the host's PCIe root
+    # and memory with whatever else runs on the box, and a 20 ms region is short enough to be hit by one transient.
+    e2e_runs = []
+    for _ in range(3):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(k2):
+            e2e_step()
+        pipe.finish()                        # every frame of the timed region is in host memory before the stop event
+        e.record()
+        env.barrier()
+        e2e_runs.append(env.max_over_ranks(s.elapsed_time(e)) / k2)
+    e2e_ms = sorted(e2e_runs)[1]
     e2e_value = world * texels / (e2e_ms * 1e-3) / 1e9
     e2e_ok = bool(torch.equal(host_out.to(dev), out))
     floor = pcie_floor(env, h2d, d2h)
@@ -591,7 +598,8 @@ def run_decode_4096(args, env):
                          "attainable_frac_ss_form_hidden_64": 32.0 / 48.1,
                          "binding_pipe": xu_roofline(kms, clocks, sm_count, npoly, rec)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_frame": e2e_ms, "matches_resident_output": e2e_ok, "pcie_floor": floor,
+                    "ms_per_frame": e2e_ms, "ms_per_frame_runs": e2e_runs, "timing": "median of three timed regions of K steps",
+                    "matches_resident_output": e2e_ok, "pcie_floor": floor,
                     "frac_of_pcie_floor": floor["ms_per_frame"] / e2e_ms},
             "gpu_launches": int(main["launches"]), "clocks": clocks, "numa_node_rank0": env.numa,
         }

@@ -99,29 +99,27 @@ constexpr int F_W1G0 = b_image_bytes(64, 48);      // 6144
 constexpr int F_LUT = 64 * 64 * 2;                 // 8192 per axis
 constexpr int F_IMG = F_W1G0 + b_image_bytes(64, TC_K2) + b_image_bytes(16, TC_K2) + 2 * F_LUT;
 
-// R[node][n] = sum_c W1[n][4C + c] * G1[c][node], stored [x][y][64] 16-bit (128 B per node).  Blocks of 8 (x) x 16 (y) nodes;
-// a thread owns 16 of the 64 outputs of TWO nodes that are neighbours along y (32 accumulators: four blocks per SM).  The patch
-// of the channel-major source grid ([c][y][x], x fastest) goes through shared memory, and the four threads of a node together
-// with their neighbours along y — the fast axis of R — write runs of 2 KB.  (The first version had one thread per node with 64
-// accumulators, 128 threads along x: every 16-byte store of a warp went to 32 different lines 64 KB apart and two warps per
-// scheduler could not hide the shared-memory weight loads: 52 us for a 513 x 513 grid, half of the table build of a 4096^2 frame.)
-// Persistent blocks (the 64 x 12 weights are fetched once per block, not once per 128 nodes), and a block's next patch is
-// in flight in registers while it works on the current one.
+// R[node][n] = sum_c W1[n][4C + c] * G1[c][node], stored [x][y][64] 16-bit (128 B per node).  Persistent blocks walk tiles of
+// 8 (x) x 16 (y) nodes.  A thread owns FOUR of the 64 outputs and keeps their 4 x 12 weights in registers for the life of the
+// block; the 16 threads of an output row share a node, whose 12 channels come from a channel-last shared-memory patch as three
+// 16-byte loads (48 FMAs per 3 loads), and together write the node's 128 bytes as one run.  A thread does 8 nodes per tile,
+// two at a time.  The next tile's patch is in flight in registers while the block works on the current one.
+// (History: one thread per node with 64 accumulators, stores 64 KB apart: 52 us for a 513 x 513 grid; four threads per node
+// pair with the weights re-read from shared memory for every channel — 6 loads per 32 FMAs, half of them two-wavefront bank
+// conflicts — 40 us, 30 us without the conflicts: the kernel waited on shared-memory latency.)
 constexpr int G1R_TX = 8, G1R_TY = 16;
 template <int FMT>
-__global__ void __launch_bounds__(256, 3) g1_rows_kernel(MlpDev m, const float* __restrict__ g1, int nx, int ny,
+__global__ void __launch_bounds__(256, 2) g1_rows_kernel(MlpDev m, const float* __restrict__ g1, int nx, int ny,
                                                          uint16_t* __restrict__ R, int code_bits) {
   constexpr int C = 12, PER = C * G1R_TY * G1R_TX / 256;    // patch elements per thread (6)
-  // [c][n / 16][16 + 4]: the four 64-byte output groups of a channel sit 80 bytes apart, so the 16-byte loads of the four
-  // threads of a node hit four different bank groups (a stride of 64 bytes puts groups 0 / 2 and 1 / 3 on the same banks: every
-  // weight load took two wavefronts, and the kernel waits on shared-memory latency — short-scoreboard stall 7.4, profiles/r02m)
-  constexpr int WS = 20, WC = 4 * WS;
-  __shared__ __align__(16) float w[C * WC];
-  __shared__ float patch[C][G1R_TY][G1R_TX + 1];            // [c][y][x]
-  for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) {
-    const int n = i / C, c = i % C;
-    w[c * WC + (n >> 4) * WS + (n & 15)] = m.w1[n * m.cin + 4 * C + c];
-  }
+  constexpr int ROW = G1R_TX * C + 4;                       // floats per y-row of the patch (+4: rows shifted by 4 banks)
+  __shared__ __align__(16) float patch[G1R_TY * ROW];       // [y][x][c], channel-last
+  const int oq = threadIdx.x & 15, ns = threadIdx.x >> 4;   // outputs 4 oq .. 4 oq + 3; node row y = ns of the tile
+  float wr[4][C];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < C; ++c) wr[j][c] = m.w1[(4 * oq + j) * m.cin + 4 * C + c];
   const int tiles_x = (nx + G1R_TX - 1) / G1R_TX, tiles_y = (ny + G1R_TY - 1) / G1R_TY, ntiles = tiles_x * tiles_y;
   const size_t nodes = (size_t)nx * ny;
   float pf[PER];
@@ -135,48 +133,50 @@ __global__ void __launch_bounds__(256, 3) g1_rows_kernel(MlpDev m, const float* 
       pf[k] = (x < nx && y < ny) ? grid_value(g1, (long long)(c * nodes + (size_t)y * nx + x), code_bits) : 0.f;
     }
   };
-  const int oq = threadIdx.x & 3, pair = threadIdx.x >> 2, xl = pair >> 3, yl = 2 * (pair & 7);
   int tile = blockIdx.x;
   if (tile < ntiles) fetch(tile);
   for (; tile < ntiles; tile += gridDim.x) {
 #pragma unroll
-    for (int k = 0; k < PER; ++k) (&patch[0][0][0])[((threadIdx.x + 256 * k) / G1R_TX) * (G1R_TX + 1) + (threadIdx.x + 256 * k) % G1R_TX] = pf[k];
+    for (int k = 0; k < PER; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int c = i / (G1R_TY * G1R_TX), r = i - c * (G1R_TY * G1R_TX), yl = r / G1R_TX, xl = r - yl * G1R_TX;
+      patch[yl * ROW + xl * C + c] = pf[k];
+    }
     __syncthreads();
     if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
-    const int x = (tile / tiles_y) * G1R_TX + xl, y = (tile % tiles_y) * G1R_TY + yl;
-    if (x < nx && y < ny) {
-      float acc[2][16];
+    const int x0 = (tile / tiles_y) * G1R_TX, y = (tile % tiles_y) * G1R_TY + ns;
+    if (y < ny) {
 #pragma unroll
-      for (int n = 0; n < 16; ++n) acc[0][n] = acc[1][n] = 0.f;
+      for (int xl = 0; xl < G1R_TX; xl += 2) {
+        float g[2][C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float ga = patch[c][yl][xl], gb = patch[c][yl + 1][xl];
-        const float4* wr = reinterpret_cast<const float4*>(w + c * WC + WS * oq);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 ww = wr[q];
-          acc[0][4 * q] = fmaf(ga, ww.x, acc[0][4 * q]);
-          acc[0][4 * q + 1] = fmaf(ga, ww.y, acc[0][4 * q + 1]);
-          acc[0][4 * q + 2] = fmaf(ga, ww.z, acc[0][4 * q + 2]);
-          acc[0][4 * q + 3] = fmaf(ga, ww.w, acc[0][4 * q + 3]);
-          acc[1][4 * q] = fmaf(gb, ww.x, acc[1][4 * q]);
-          acc[1][4 * q + 1] = fmaf(gb, ww.y, acc[1][4 * q + 1]);
-          acc[1][4 * q + 2] = fmaf(gb, ww.z, acc[1][4 * q + 2]);
-          acc[1][4 * q + 3] = fmaf(gb, ww.w, acc[1][4 * q + 3]);
+        for (int u = 0; u < 2; ++u) {
+          const float4* p = reinterpret_cast<const float4*>(patch + ns * ROW + (xl + u) * C);
+          const float4 a = p[0], bq = p[1], cq = p[2];
+          g[u][0] = a.x; g[u][1] = a.y; g[u][2] = a.z; g[u][3] = a.w;
+          g[u][4] = bq.x; g[u][5] = bq.y; g[u][6] = bq.z; g[u][7] = bq.w;
+          g[u][8] = cq.x; g[u][9] = cq.y; g[u][10] = cq.z; g[u][11] = cq.w;
         }
-      }
+        float acc[2][4];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (y + k >= ny) break;
-        uint4* dst = reinterpret_cast<uint4*>(R + ((size_t)x * ny + y + k) * 64 + 16 * oq);
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint4 v;
-          v.x = to16<FMT>(acc[k][8 * q]) | ((uint32_t)to16<FMT>(acc[k][8 * q + 1]) << 16);
-          v.y = to16<FMT>(acc[k][8 * q + 2]) | ((uint32_t)to16<FMT>(acc[k][8 * q + 3]) << 16);
-          v.z = to16<FMT>(acc[k][8 * q + 4]) | ((uint32_t)to16<FMT>(acc[k][8 * q + 5]) << 16);
-          v.w = to16<FMT>(acc[k][8 * q + 6]) | ((uint32_t)to16<FMT>(acc[k][8 * q + 7]) << 16);
-          dst[q] = v;
+          for (int j = 0; j < 4; ++j) acc[u][j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[u][j] = fmaf(g[u][c], wr[j][c], acc[u][j]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int x = x0 + xl + u;
+          if (x < nx) {
+            uint2 v;
+            v.x = to16<FMT>(acc[u][0]) | ((uint32_t)to16<FMT>(acc[u][1]) << 16);
+            v.y = to16<FMT>(acc[u][2]) | ((uint32_t)to16<FMT>(acc[u][3]) << 16);
+            *reinterpret_cast<uint2*>(R + ((size_t)x * ny + y) * 64 + 4 * oq) = v;
+          }
         }
       }
     }
@@ -1171,7 +1171,7 @@ static int launch_fast2d(Handle* h, const DevGeom& g, const MlpDev& m, const flo
     e = (cudaError_t)launch_relayout<FMT>(h, g, g0, g.n0, s0, st);
     if (e != cudaSuccess) return (int)e;
     const long long tiles_r = (long long)((g.n1[0] + G1R_TX - 1) / G1R_TX) * ((g.n1[1] + G1R_TY - 1) / G1R_TY);
-    const long long cap_r = 3ll * h->sms;
+    const long long cap_r = 2ll * h->sms;
     g1_rows_kernel<FMT><<<(int)(tiles_r < cap_r ? tiles_r : cap_r), 256, 0, st>>>(m, g1, g.n1[0], g.n1[1], R, h->src_code_bits);
     h->launches++;
     pack_fast_kernel<FMT><<<32, 256, 0, st>>>(m, g.lod, g.step, (uint16_t*)h->tc_weights, npoly);
