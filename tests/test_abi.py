@@ -27,6 +27,13 @@ def test_header_and_binding_agree():
     assert sorted(L.SYMBOLS) == syms          # the ctypes table binds exactly what the header declares
 
 
+def test_exchange_mode_constants_match_the_header():
+    src = open(os.path.join(ROOT, "include", "nic.h")).read()
+    got = {k: int(v) for k, v in re.findall(r"#define\s+(NIC_EXCHANGE_[A-Z_]+)\s+(\d+)", src)}
+    assert got == {"NIC_EXCHANGE_ONE_SHOT": L.EXCHANGE_ONE_SHOT, "NIC_EXCHANGE_SLICED": L.EXCHANGE_SLICED}
+    assert int(re.search(r"#define\s+NIC_MAX_PEERS\s+(\d+)", src).group(1)) == L.MAX_PEERS
+
+
 def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(L.LIB_PATH)
     for s in declared_symbols():
