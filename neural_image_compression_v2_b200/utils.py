@@ -1,7 +1,10 @@
 """Positional encodings, PSNR and dtype maps — host-side mirror of the hot-path functions of the reference's
 `Projects/utils.py` (same names and argument meaning), computed by libnic.so."""
 import ctypes as C
+import glob
 import math
+import os
+import re
 
 import numpy as np
 import torch
@@ -10,7 +13,8 @@ from . import _lib as L
 
 
 # the names `from ... import *` hands to the reference script
-__all__ = ["triangular_positional_encoding", "positional_encoding", "tri", "calculate_psnr", "bits2dtype_torch", "bits2dtype_np"]
+__all__ = ["triangular_positional_encoding", "positional_encoding", "tri", "calculate_psnr", "bits2dtype_torch", "bits2dtype_np",
+           "readClip", "timelaps", "save_result_to_csv", "make_filename_by_seq"]
 
 def _pe(coord, num_channels, device, dtype, kind):
     if isinstance(coord, (tuple, list)):
@@ -85,3 +89,65 @@ def bits2dtype_np(num_bits, dtype="float"):
         return np.float32
     if num_bits == 64:
         return np.float64
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Host-side file helpers of the 3-D / movie / LUT workflows.  They are not on the device path:
+# `readClip` feeds `flatten_movie_to_atlas` / the 3-D trainers with a uint8 array, `timelaps` and `save_result_to_csv`
+# take the decoded uint8 volume.  Same names, arguments and file formats as the reference; OpenCV is imported lazily.
+def make_filename_by_seq(dirname, filename, seq_digit=3):
+    """utils.py:37-62 — `dirname/<stem>_<n+1><ext>` where n is the highest sequence number already present (-1 if none);
+    creates `dirname` if needed."""
+    os.makedirs(dirname, exist_ok=True)
+    stem, ext = os.path.splitext(filename)
+    taken = [-1]
+    for f in glob.glob(os.path.join(dirname, f"{stem}_[0-9]*{ext}")):
+        m = re.match(f"{re.escape(stem)}_([0-9]*){re.escape(ext)}", os.path.basename(f))
+        if m and m.group(1):
+            taken.append(int(m.group(1)))
+    return f"{dirname}/{stem}_{max(taken) + 1:0{seq_digit}}{ext}"
+
+
+def readClip(filepass):
+    """utils.py:67-81 — every frame of a video file as one uint8 array [frames, height, width, 3] (BGR, as OpenCV decodes)."""
+    import cv2
+    cap = cv2.VideoCapture(filepass)
+    try:
+        if not cap.isOpened():
+            raise FileNotFoundError(f"cannot open video {filepass!r}")
+        frames = []
+        while True:
+            ok, frame = cap.read()
+            if not ok:
+                break
+            frames.append(frame)
+    finally:
+        cap.release()
+    if not frames:
+        raise ValueError(f"{filepass!r} holds no decodable frame")
+    return np.stack(frames, axis=0)
+
+
+def timelaps(movie, saved_name, all_frame=64, width=64, height=64, frame_rate=32):
+    """utils.py:86-95 — writes frames movie[0 .. all_frame) (uint8 [height, width, 3]) as an mp4v-coded video."""
+    import cv2
+    video = cv2.VideoWriter(saved_name, cv2.VideoWriter_fourcc("m", "p", "4", "v"), frame_rate, (width, height))
+    try:
+        if not video.isOpened():
+            raise OSError(f"cannot open a video writer for {saved_name!r}")
+        for i in range(all_frame):
+            video.write(np.ascontiguousarray(movie[i]))
+    finally:
+        video.release()
+
+
+def save_result_to_csv(result, filename):
+    """utils.py:98-113 — a [S, S, S, 3] LUT as text: one line per (first, second) index pair holding the 3 S values of
+    that row, each followed by a comma."""
+    arr = result.detach().cpu().numpy() if torch.is_tensor(result) else np.asarray(result)
+    size = arr.shape[0]
+    with open(filename, mode="w") as f:
+        for a in range(size):
+            for b in range(size):
+                f.write("".join(f"{v.item()}," for v in arr[a, b, :size, :3].reshape(-1)))
+                f.write("\n")

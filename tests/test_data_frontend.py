@@ -5,6 +5,7 @@ CPU tests pin the oracle's restatement of Pillow's resample to outputs of the re
 (tests/golden/resize.npz, made by tests/golden/make_golden_data.py with torchvision + Pillow); GPU tests hold the kernels
 to the same fixtures and to the oracle, bit for bit (integer / byte work)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -170,3 +171,54 @@ def test_step_sampled_trains_and_is_reproducible():
     assert min(lods) == 0 and max(lods) >= 2 and lods.count(0) > 60          # P(lod = k) ~ 4^-k, uniform every 20th step
     assert np.mean(losses[-20:]) < 0.5 * np.mean(losses[:20])
     configure()
+
+
+# ------------------------------------------------------------------------------------------------ host file helpers (f4)
+def test_host_file_helpers_formats(tmp_path):
+    """save_result_to_csv / make_filename_by_seq / readClip / timelaps (utils.py:37-113): file formats as the reference
+    writes them — checked against the reference's own functions when /root/reference is present (this container), and
+    against the format spelled out here otherwise.  No device involved."""
+    import importlib.util
+    import sys
+    from neural_image_compression_v2_b200 import utils as U
+    rng = np.random.default_rng(3)
+    lut = rng.integers(0, 256, (5, 5, 5, 3)).astype(np.uint8)
+    U.save_result_to_csv(lut, str(tmp_path / "a.csv"))
+    text = (tmp_path / "a.csv").read_text()
+    want = "".join("".join(f"{int(v)}," for v in lut[a, b].reshape(-1)) + "\n" for a in range(5) for b in range(5))
+    assert text == want
+    flt = torch.tensor(rng.random((3, 3, 3, 3)), dtype=torch.float32)
+    U.save_result_to_csv(flt, str(tmp_path / "b.csv"))
+    assert (tmp_path / "b.csv").read_text().split("\n")[0].split(",")[0] == str(flt[0, 0, 0, 0].item())
+    d = tmp_path / "seq"
+    assert U.make_filename_by_seq(str(d), "run_0.csv") == f"{d}/run_0_000.csv"
+    (d / "run_0_000.csv").write_text("x")
+    (d / "run_0_007.csv").write_text("x")
+    assert U.make_filename_by_seq(str(d), "run_0.csv") == f"{d}/run_0_008.csv"
+    ref_utils = "/root/reference/Projects/utils.py"
+    if os.path.exists(ref_utils):
+        sys.dont_write_bytecode = True
+        spec = importlib.util.spec_from_file_location("ref_utils_host", ref_utils)
+        R = importlib.util.module_from_spec(spec)
+        try:
+            spec.loader.exec_module(R)
+        except Exception:          # a missing optional import of the reference module: the format check above stands
+            R = None
+        if R is not None:
+            R.save_result_to_csv(torch.tensor(lut), str(tmp_path / "ref.csv"))
+            assert (tmp_path / "ref.csv").read_text() == text
+            assert R.make_filename_by_seq(str(d), "run_0.csv") == U.make_filename_by_seq(str(d), "run_0.csv")
+    cv2 = pytest.importorskip("cv2")
+    movie = np.zeros((6, 32, 48, 3), dtype=np.uint8)
+    for i in range(6):
+        movie[i, :, : 8 * (i + 1)] = 200
+    path = str(tmp_path / "m.avi")
+    try:
+        U.timelaps(movie, path, all_frame=6, width=48, height=32, frame_rate=8)
+    except OSError:
+        pytest.skip("this OpenCV build has no mp4v writer")
+    back = U.readClip(path)
+    assert back.shape == movie.shape and back.dtype == np.uint8
+    assert np.abs(back.astype(np.int32) - movie.astype(np.int32)).mean() < 12.0        # lossy codec: same picture
+    with pytest.raises(FileNotFoundError):
+        U.readClip(str(tmp_path / "missing.avi"))
