@@ -13,8 +13,8 @@ from . import _lib as L
 
 
 # the names `from ... import *` hands to the reference script
-__all__ = ["triangular_positional_encoding", "positional_encoding", "tri", "calculate_psnr", "bits2dtype_torch", "bits2dtype_np",
-           "readClip", "timelaps", "save_result_to_csv", "make_filename_by_seq"]
+# (the host file helpers at the end of this module are NOT exported by `*`: inside the reference script its own stay in place)
+__all__ = ["triangular_positional_encoding", "positional_encoding", "tri", "calculate_psnr", "bits2dtype_torch", "bits2dtype_np"]
 
 def _pe(coord, num_channels, device, dtype, kind):
     if isinstance(coord, (tuple, list)):
