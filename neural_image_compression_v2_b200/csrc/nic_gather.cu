@@ -1,18 +1,23 @@
-// nic_gather.cu — K1, the tile-staged decoder-input kernel for the common 2-D shape (C = 12, PE = 6, step <= 1,
+// nic_gather.cu — K1, the tile-staged decoder-input kernels for the common 2-D shape (C = 12, PE = 6, step <= 1,
 // runs of 128 texels along the fast block axis): X [N, 73] in fp32 (bit-exact with the reference), f16 or bf16
 // (each value rounded once from the fp32 value).  Reference: create_decoder_input_2d / finally_decode_input_2d
 // (Projects/image_compression.py:71-100, 170-181) over fp_def.create_g0_g1 (Projects/fp_def.py:115-145).
 //
-// The kernel is HBM-WRITE-bound: 73 * sizeof(X) bytes per texel leave the SM, ~3.7 bytes of grid come in
-// (295.8 B/texel for fp32 X, 149.8 B/texel for 16-bit X).  Design:
+// The kernels are HBM-WRITE-bound: 73 * sizeof(X) bytes per texel leave the SM, ~3.7 bytes of grid come in
+// (295.8 B/texel for fp32 X, 149.8 B/texel for 16-bit X; a pure bulk-store loop reaches 6.3 TB/s on a
+// B200, tools/ubench/write_bw.cu).  Common design:
 //   * a tile = 128 consecutive samples n (one ix, 128 consecutive iy) = ONE contiguous span of 128 * 73 elements of X;
 //     it is assembled in shared memory and leaves with a single TMA bulk store (cp.async.bulk.global.shared::cta),
 //     double-buffered so the store of tile i overlaps the build of tile i+1;
-//   * the grid nodes a tile touches (2 x <=130 nodes of G0, 2 x <=67 of G1) are staged once into shared memory in
-//     channel-LAST order, so a corner is three conflict-free LDS.128 instead of 12 strided global loads;
-//   * thread = texel; texel parity is warp-uniform (warp w owns texels 2*lane + (w & 1) + 64*(w >> 1)), so the
-//     16-bit row (146 bytes: rows alternate 4-byte alignment) is written with aligned 32-bit shared stores whose
-//     pairing depends only on the warp, and lanes stride 73 words (== 9 mod 32): bank-conflict free.
+//   * the grid nodes a super-tile of several x-rows touches are staged once into shared memory in channel-LAST order, so
+//     a corner is a few conflict-free vector loads instead of 12 strided global loads; the next super-tile's nodes are
+//     prefetched into registers while the current rows are built;
+//   * node loads carry an L2 evict_last policy, row stores evict_first: the grids stay L2-resident under the write stream;
+//   * gather_tile_kernel (fp32 X; 16-bit X at steps outside {1/4, 1/2, 1}): thread = texel, run-time patch geometry, rows
+//     written piece by piece through RowWriter (16-bit rows are 146 bytes: rows alternate 4-byte alignment, texel parity
+//     is warp-uniform, lanes stride 73 words == 9 mod 32: bank-conflict free);
+//   * gather_tile16_kernel (16-bit X): patch staged already rounded in two alignments, x-weighted G1 rows, compile-time
+//     geometry — see its header below.
 // Everything else (3-D, other C / PE, step > 1, short rows) takes the flat kernel in nic_f32.cu.
 #include "nic_internal.cuh"
 
